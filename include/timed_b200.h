@@ -1,0 +1,156 @@
+/* timed_b200.h -- C ABI of libtimed_b200.so (B200 / sm_100a only).
+ *
+ * Drop-in boundary for the one hot path of wells-wood-research/timed-design: per-residue
+ * 3D-CNN inference (what `tf.keras.models.load_model(...)` + `frame_model.predict(X_batch)`
+ * do at /root/reference/predict.py:121,142) and the Monte-Carlo sequence sampler
+ * (/root/reference/design_utils/sampling_utils.py:53-90,139-161).  The reference is pure
+ * Python and has no FFI of its own; these entry points are what a ctypes binding placed at
+ * those two call sites would bind.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch/Python types cross this boundary;
+ *   - every function returns 0 on success, a negative code on failure, and
+ *     timed_b200_last_error() then returns a thread-local message;
+ *   - `cuda_stream` is a cudaStream_t passed as void* (NULL = default stream); calls enqueue
+ *     work and return without synchronising unless stated otherwise;
+ *   - the caller owns every buffer it passes; the library owns only what *_create returns;
+ *   - a handle is bound to one device and must be driven by one host thread at a time.
+ */
+#ifndef TIMED_B200_H
+#define TIMED_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIMED_B200_ABI_VERSION 1
+
+/* error codes */
+#define TB_OK 0
+#define TB_ERR_INVALID (-1) /* bad argument / unsupported graph */
+#define TB_ERR_CUDA (-2)    /* a CUDA runtime/driver call failed */
+#define TB_ERR_NO_DEVICE (-3)
+
+/* element types of host/device frame buffers handed to graph_forward */
+#define TB_DTYPE_F32 0
+#define TB_DTYPE_F64 1
+#define TB_DTYPE_U8 2 /* numpy bool / uint8 voxels (voxels_as_gaussian == False) */
+
+/* activation codes */
+#define TB_ACT_NONE 0
+#define TB_ACT_RELU 1
+#define TB_ACT_ELU 2
+#define TB_ACT_SIGMOID 3
+#define TB_ACT_TANH 4
+
+/* fused-op kinds (one tb_op_desc per op; ids are indices into the op array) */
+#define TB_OP_INPUT 0   /* the (n,D,H,W,C) frame tensor                                        */
+#define TB_OP_CONV3D 1  /* Conv3D / Dense / Flatten+Dense: act2(scale*act1(conv(x)+bias)+shift) */
+#define TB_OP_POOL3D 2  /* Max/AveragePooling3D (TF 'same'/'valid' semantics)                  */
+#define TB_OP_AFFINE 3  /* standalone BatchNormalization and/or activation                     */
+#define TB_OP_GPOOL 4   /* GlobalAverage/MaxPooling3D                                          */
+#define TB_OP_SOFTMAX 5 /* softmax over channels                                               */
+#define TB_OP_CONCAT 6  /* channel concatenation                                               */
+#define TB_OP_ADD 7     /* elementwise sum                                                     */
+
+#define TB_MAX_INPUTS 8
+
+/* One fused op of the inference graph.  Mirrors the Keras layer semantics listed in SURVEY.md
+ * App. D (Keras 2.13 defaults): Conv3D is cross-correlation NDHWC x DHWIO, stride 1,
+ * 'same' pads before=(k-1)/2 / after=k-1-before; pooling 'same' pads at the end, max ignores
+ * padding, average divides by the number of valid elements. */
+typedef struct tb_op_desc {
+    int32_t op;                    /* TB_OP_*                                                 */
+    int32_t n_inputs;              /* number of valid entries of inputs[]                     */
+    int32_t inputs[TB_MAX_INPUTS]; /* producer op ids                                         */
+    int32_t kernel[3];             /* CONV3D: (kd,kh,kw);  POOL3D: pool size                  */
+    int32_t stride[3];             /* POOL3D strides (CONV3D: must be 1,1,1)                  */
+    int32_t pad_same;              /* 1 = 'same', 0 = 'valid'                                 */
+    int32_t c_out;                 /* CONV3D: filters / Dense units                           */
+    int32_t pool_kind;             /* POOL3D / GPOOL: 0 = max, 1 = average                    */
+    int32_t act1;                  /* TB_ACT_* applied to conv(x)+bias (AFFINE: before scale) */
+    int32_t act2;                  /* TB_ACT_* applied after scale/shift                      */
+    float alpha1;                  /* ELU alpha of act1                                       */
+    float alpha2;                  /* ELU alpha of act2                                       */
+    /* host float32 arrays, NULL when absent; copied (and re-laid-out) by graph_create:        */
+    const float* kernel_w; /* CONV3D: (kd,kh,kw,C_in,C_out) row-major (Keras DHWIO)            */
+    const float* bias;     /* CONV3D: (C_out)                                                  */
+    const float* scale;    /* CONV3D/AFFINE: per-channel multiplier (folded BN gamma/sqrt(var+eps)) */
+    const float* shift;    /* CONV3D/AFFINE: per-channel offset (folded BN beta - mean*scale)   */
+} tb_op_desc;
+
+typedef struct tb_graph tb_graph;
+
+/* ---- library -------------------------------------------------------------------------------- */
+int timed_b200_abi_version(void);
+const char* timed_b200_last_error(void);
+/* number of CUDA devices visible (0 when none; never fails) */
+int timed_b200_device_count(void);
+
+/* ---- inference graph  (replaces tf.keras.models.load_model / Model.predict,
+ *      /root/reference/predict.py:121 and :142) ------------------------------------------------ */
+/* Build a graph on `device` from `n_ops` fused ops; ops[0] must be TB_OP_INPUT with
+ * kernel = (D,H,W) and c_out = C; the last op is the output (n, classes).  Weights are
+ * packed (bf16 hi/lo planes, K-major) and uploaded here. */
+int timed_b200_graph_create(const tb_op_desc* ops, int32_t n_ops, int32_t device, tb_graph** out);
+void timed_b200_graph_destroy(tb_graph* g);
+/* output width (classes) and algorithmic FLOPs per frame (2*D*H*W*k^3*Cin*Cout summed over
+ * conv/dense ops) */
+int timed_b200_graph_info(const tb_graph* g, int32_t* n_classes, double* flops_per_frame,
+                          int32_t* n_kernel_launches_per_forward);
+/* device workspace needed to run `n_frames` frames in one forward */
+int timed_b200_graph_workspace_bytes(const tb_graph* g, int64_t n_frames, size_t* out);
+/* Forward `n_frames` frames resident on the device.  d_frames: (n,D,H,W,C) of `frames_dtype`
+ * (cast to float32 first, as Keras does); d_probs: (n, classes) float32.  No allocation, no
+ * synchronisation: capturable in a CUDA graph. */
+int timed_b200_graph_forward(tb_graph* g, const void* d_frames, int32_t frames_dtype,
+                             int64_t n_frames, void* d_workspace, size_t workspace_bytes,
+                             float* d_probs, void* cuda_stream);
+/* Same through HOST buffers (the call Model.predict maps to): copies frames host->device in
+ * chunks, runs forward, copies probabilities back, synchronises.  Library-owned staging. */
+int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t frames_dtype,
+                                  int64_t n_frames, float* h_probs, int64_t max_chunk_frames);
+
+/* ---- single-layer entry for unit/parity tests -------------------------------------------------
+ * y = act2(scale*act1(conv3d(x)+bias)+shift) on device buffers.
+ * x: (n,D,H,W,C_in) float32 device; y: (n,Do,Ho,Wo,C_out) float32 device. Synchronises. */
+int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int32_t W,
+                          int32_t c_in, const tb_op_desc* conv, int32_t device, float* d_y);
+
+/* ---- Monte-Carlo sampler  (replaces design_utils/sampling_utils.py:53-90,139-161) ------------ */
+/* p ** (1/t) / rowsum  in float64 (apply_temp_to_probs, sampling_utils.py:159-161).
+ * d_probs_in/out: (n_rows, n_cls) float64 device (may alias). */
+int timed_b200_apply_temperature(const double* d_probs_in, int64_t n_rows, int32_t n_cls,
+                                 double t, double* d_probs_out, void* cuda_stream);
+/* sequential float64 cumsum along axis 1 (probs.cumsum(axis=1), sampling_utils.py:82) */
+int timed_b200_cumsum_rows(const double* d_probs, int64_t n_rows, int32_t n_cls, double* d_cdf,
+                           void* cuda_stream);
+/* Draw n_samples sequences of n_res residues: idx = first j with cdf[res][j] > r, else 0
+ * (the (cumsum > r).argmax quirk, sampling_utils.py:82).  r comes from d_uniforms
+ * ((n_samples,n_res) float64, parity hook for np.random.rand values) when non-NULL, else from
+ * Philox4x32-10 keyed (seed, stream_id) with counter (sample, residue): independent of launch
+ * geometry and of how samples are sharded over GPUs (pass first_sample = global index).
+ * d_cls_to_letter: n_cls ASCII codes; d_seqs: (n_samples,n_res) uint8; d_idx (optional, may be
+ * NULL): (n_samples,n_res) int32. */
+int timed_b200_sample(const double* d_cdf, int64_t n_res, int32_t n_cls, int64_t n_samples,
+                      int64_t first_sample, uint64_t seed, uint64_t stream_id,
+                      const double* d_uniforms, const uint8_t* d_cls_to_letter, uint8_t* d_seqs,
+                      int32_t* d_idx, void* cuda_stream);
+/* Philox uniforms exactly as timed_b200_sample would draw them (test hook). */
+int timed_b200_sample_uniforms(int64_t n_res, int64_t n_samples, int64_t first_sample,
+                               uint64_t seed, uint64_t stream_id, double* d_out,
+                               void* cuda_stream);
+
+/* ---- post-processing on device  (design_utils/utils.py:659,768 + predict.py:163) ------------- */
+/* argmax of float16-rounded probabilities, first index wins ties.  d_probs (n, n_cls) float32;
+ * d_idx (n) int32. */
+int timed_b200_argmax_fp16(const float* d_probs, int64_t n, int32_t n_cls, int32_t* d_idx,
+                           void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIMED_B200_H */

@@ -1,0 +1,965 @@
+// libtimed_b200.so -- C-ABI (include/timed_b200.h): inference-graph executor + sampler entry
+// points.  Host side: shape inference, workspace planning, weight packing (bf16 hi/lo planes,
+// K-major), TMA tensor-map construction, kernel launches.  No CPU compute fallback exists: every
+// entry point either launches CUDA kernels or fails with an error code.
+#include "../../include/timed_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_umma.cuh"
+#include "kernels.cuh"
+
+namespace tb {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+// ----------------------------------------------------------------------------- driver entry points
+// libcuda is NOT linked: the tensor-map encoders are fetched through the runtime so that the
+// library loads (and exports its symbols) on a machine without a GPU driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+
+static int load_driver_fns() {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (g_encode_tiled && g_encode_im2col) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    TB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    TB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    fn = nullptr;
+    TB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+    TB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col unavailable");
+    g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+    TB_CHECK_CUDA(cudaDriverGetVersion(&g_driver_version));
+    return 0;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// TF/Keras 'same' padding for (n, k, s): out = ceil(n/s), total = max((out-1)*s+k-n, 0),
+// before = total/2.
+static void same_pads(int n, int k, int s, int* out, int* before, int* after) {
+    *out = ceil_div(n, s);
+    const int total = std::max((*out - 1) * s + k - n, 0);
+    *before = total / 2;
+    *after = total - total / 2;
+}
+
+static int grid_for(int64_t work_items, int threads) {
+    int64_t b = (work_items + threads - 1) / threads;
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(b, 148 * 32)));
+}
+
+// ----------------------------------------------------------------------------- tensors
+struct TensorInfo {
+    int D = 1, H = 1, W = 1, C = 0;
+    int c_pad = 0;        // stored channels per pixel (SPLIT: round_up(C,16); F32: C)
+    int fmt = FMT_F32;
+    int slack_pix = 0;    // extra readable pixels past the end required by im2col consumers
+    int last_use = -1;    // index of the last op reading this tensor
+    int64_t pix_per_frame() const { return static_cast<int64_t>(D) * H * W; }
+    // frames allocated per plane for n frames (so that a 128-pixel im2col column starting at
+    // any valid pixel stays inside the allocation)
+    int64_t frames_alloc(int64_t n) const {
+        return n + (slack_pix + pix_per_frame() - 1) / pix_per_frame();
+    }
+    size_t bytes(int64_t n) const {
+        const int64_t elems = frames_alloc(n) * pix_per_frame() * c_pad;
+        return static_cast<size_t>(round_up64(fmt == FMT_SPLIT ? elems * 2 * 2 : elems * 4, 1024));
+    }
+};
+
+// ----------------------------------------------------------------------------- conv plan
+struct ConvPlan {
+    // static (graph_create)
+    int kd = 1, kh = 1, kw = 1;
+    int cin = 0, cin_pad = 0, cout = 0;
+    int pad0[3] = {0, 0, 0}, pad1[3] = {0, 0, 0};
+    int Di = 1, Hi = 1, Wi = 1, Do = 1, Ho = 1, Wo = 1;
+    int n_tile = 0, n_tiles = 0, n_alloc = 0;
+    int k_total = 0;
+    __nv_bfloat16* d_w = nullptr;   // [2][n_alloc][k_total]
+    float* d_bias = nullptr;        // [n_alloc]
+    float* d_scale = nullptr;
+    float* d_shift = nullptr;
+    int act1 = 0, act2 = 0;
+    float alpha1 = 1.f, alpha2 = 1.f;
+    // tile configuration (depends on the frame count -> chosen at launch)
+    struct Config {
+        int kc, mt, kg, stages, acc_stages, acc_cols;
+        uint32_t swizzle_code;       // UMMA layout type
+        CUtensorMapSwizzle tma_swz;
+        size_t smem_bytes;
+    };
+    std::map<int, CUtensorMap> w_maps;   // keyed by kc
+    double flops_per_frame() const {
+        return 2.0 * Do * Ho * Wo * kd * kh * kw * static_cast<double>(cin) * cout;
+    }
+};
+
+static void free_conv_plan(ConvPlan& p) {
+    cudaFree(p.d_w);
+    cudaFree(p.d_bias);
+    cudaFree(p.d_scale);
+    cudaFree(p.d_shift);
+    p.d_w = nullptr;
+    p.d_bias = p.d_scale = p.d_shift = nullptr;
+}
+
+static constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic smem minus alignment slack
+
+// Pick (kc, mt, kg, stages) for a conv given the number of output rows.
+static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* cfg) {
+    const int m_tiles = static_cast<int>((m_total + 127) / 128);
+    std::vector<int> kcs;
+    for (int kc : {64, 32, 16})
+        if (p.cin_pad % kc == 0) kcs.push_back(kc);
+    TB_REQUIRE(!kcs.empty(), "conv: padded input channels must be a multiple of 16");
+    const int acc_cols = round_up(p.n_tile, 32);
+    // two M sub-tiles per CTA halve the weight traffic per MAC; only worth it when there are
+    // enough tiles to still fill the machine twice over
+    std::vector<int> mts;
+    if (2 * acc_cols <= 512 && static_cast<int64_t>(ceil_div(m_tiles, 2)) * p.n_tiles >= 2 * 148)
+        mts.push_back(2);
+    mts.push_back(1);
+    int best_score = -1;
+    for (int mt : mts) {
+        for (int kc : kcs) {
+            const size_t a_sub = 128u * kc * 2u, w_sub = static_cast<size_t>(p.n_tile) * kc * 2u;
+            const size_t kb = mt * 2 * a_sub + 2 * w_sub;
+            const int n_kblocks = p.kd * p.kh * p.kw * (p.cin_pad / kc);
+            int kg = std::max(1, 64 / kc);
+            kg = std::min(kg, n_kblocks);
+            while (kg > 1 && kb * kg * 2 > kSmemBudget) --kg;
+            if (kb * kg * 2 > kSmemBudget) continue;   // cannot even double-buffer
+            int stages = static_cast<int>(std::min<size_t>(kConvMaxStages, kSmemBudget / (kb * kg)));
+            // score: prefer >=3 stages, then mt=2, then wider kc
+            const int score = (stages >= 3 ? 100 : 0) + (mt == 2 ? 10 : 0) + kc / 16;
+            if (score > best_score) {
+                best_score = score;
+                cfg->kc = kc;
+                cfg->mt = mt;
+                cfg->kg = kg;
+                cfg->stages = stages;
+                cfg->acc_cols = acc_cols;
+                cfg->acc_stages = std::min(2, 512 / (mt * acc_cols));
+                cfg->swizzle_code = kc == 64 ? 2u : (kc == 32 ? 4u : 6u);
+                cfg->tma_swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                        : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                    : CU_TENSOR_MAP_SWIZZLE_32B);
+                cfg->smem_bytes = kb * kg * stages + 1024;
+            }
+        }
+    }
+    TB_REQUIRE(best_score >= 0, "conv: no tile configuration fits shared memory");
+    return 0;
+}
+
+static int encode_w_map(ConvPlan& p, int kc, CUtensorMapSwizzle swz, CUtensorMap* out) {
+    auto it = p.w_maps.find(kc);
+    if (it != p.w_maps.end()) { *out = it->second; return 0; }
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(p.k_total), static_cast<cuuint64_t>(2 * p.n_alloc)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(p.k_total) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(p.n_tile)};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.d_w, dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(weights) failed, CUresult=" + std::to_string(r));
+        return TB_ERR_CUDA;
+    }
+    p.w_maps[kc] = m;
+    *out = m;
+    return 0;
+}
+
+// Activation tensor map (im2col).  Tensor = (2*frames_alloc, Di, Hi, Wi, cin_pad) bf16, the lo
+// plane stacked after the hi plane along the frame axis.
+static int encode_a_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* base,
+                        int64_t frames_alloc, int64_t ld_channels, CUtensorMap* out) {
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(p.cin_pad), static_cast<cuuint64_t>(p.Wi),
+                          static_cast<cuuint64_t>(p.Hi), static_cast<cuuint64_t>(p.Di),
+                          static_cast<cuuint64_t>(2 * frames_alloc)};
+    const cuuint64_t px = static_cast<cuuint64_t>(ld_channels) * 2;
+    cuuint64_t strides[4] = {px, px * p.Wi, px * p.Wi * p.Hi, px * p.Wi * p.Hi * p.Di};
+    int lower[3] = {-p.pad0[2], -p.pad0[1], -p.pad0[0]};
+    int upper[3] = {p.pad1[2] - (p.kw - 1), p.pad1[1] - (p.kh - 1), p.pad1[0] - (p.kd - 1)};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMap m;
+    CUresult r = g_encode_im2col(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, lower,
+                                 upper, static_cast<cuuint32_t>(cfg.kc), 128u, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, cfg.tma_swz,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeIm2col(activations) failed, CUresult=" + std::to_string(r));
+        return TB_ERR_CUDA;
+    }
+    // Same driver workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): drivers up
+    // to 13.1 mis-set a descriptor bit for im2col maps over tensors smaller than 128 KiB.
+    const uint64_t tensor_bytes = strides[3] * dims[4];
+    if (g_driver_version <= 13010 && tensor_bytes < 131072)
+        reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+    *out = m;
+    return 0;
+}
+
+// Build the static part of a conv plan: geometry, packed weights, epilogue vectors.
+static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, int Wi, int cin,
+                            int cin_pad) {
+    p.kd = d.kernel[0]; p.kh = d.kernel[1]; p.kw = d.kernel[2];
+    TB_REQUIRE(p.kd >= 1 && p.kh >= 1 && p.kw >= 1 && p.kd <= 16 && p.kh <= 16 && p.kw <= 16,
+               "conv: kernel extents must be in [1,16]");
+    TB_REQUIRE(d.stride[0] == 1 && d.stride[1] == 1 && d.stride[2] == 1, "conv: only stride 1");
+    TB_REQUIRE(d.kernel_w != nullptr, "conv: kernel weights missing");
+    TB_REQUIRE(d.c_out >= 1, "conv: c_out must be positive");
+    p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.cin = cin; p.cin_pad = cin_pad; p.cout = d.c_out;
+    const int ks[3] = {p.kd, p.kh, p.kw}, in[3] = {Di, Hi, Wi};
+    int out[3];
+    for (int i = 0; i < 3; ++i) {
+        if (d.pad_same) {
+            same_pads(in[i], ks[i], 1, &out[i], &p.pad0[i], &p.pad1[i]);
+        } else {
+            out[i] = in[i] - ks[i] + 1;
+            p.pad0[i] = p.pad1[i] = 0;
+        }
+        TB_REQUIRE(out[i] >= 1, "conv: kernel larger than input with 'valid' padding");
+    }
+    p.Do = out[0]; p.Ho = out[1]; p.Wo = out[2];
+    const int n_pad = round_up(p.cout, 16);
+    p.n_tiles = ceil_div(n_pad, 256);
+    p.n_tile = round_up(ceil_div(n_pad, p.n_tiles), 16);
+    p.n_alloc = p.n_tile * p.n_tiles;
+    p.k_total = p.kd * p.kh * p.kw * cin_pad;
+    p.act1 = d.act1; p.act2 = d.act2; p.alpha1 = d.alpha1; p.alpha2 = d.alpha2;
+
+    // ---- pack weights: Keras DHWIO fp32 -> [plane][n][tap*cin_pad + c] bf16 hi/lo
+    const size_t plane = static_cast<size_t>(p.n_alloc) * p.k_total;
+    std::vector<__nv_bfloat16> w(2 * plane, __float2bfloat16(0.0f));
+    const int taps = p.kd * p.kh * p.kw;
+    for (int t = 0; t < taps; ++t)
+        for (int c = 0; c < cin; ++c) {
+            const float* src = d.kernel_w + (static_cast<size_t>(t) * cin + c) * p.cout;
+            for (int n = 0; n < p.cout; ++n) {
+                const float v = src[n];
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                const size_t o = static_cast<size_t>(n) * p.k_total + static_cast<size_t>(t) * cin_pad + c;
+                w[o] = hi;
+                w[plane + o] = lo;
+            }
+        }
+    TB_CHECK_CUDA(cudaMalloc(&p.d_w, 2 * plane * sizeof(__nv_bfloat16)));
+    TB_CHECK_CUDA(cudaMemcpy(p.d_w, w.data(), 2 * plane * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    std::vector<float> b(p.n_alloc, 0.f), sc(p.n_alloc, 1.f), sh(p.n_alloc, 0.f);
+    for (int n = 0; n < p.cout; ++n) {
+        if (d.bias) b[n] = d.bias[n];
+        if (d.scale) sc[n] = d.scale[n];
+        if (d.shift) sh[n] = d.shift[n];
+    }
+    // padded output channels must come out as exact zeros: act(0)*1 + 0
+    TB_CHECK_CUDA(cudaMalloc(&p.d_bias, p.n_alloc * sizeof(float)));
+    TB_CHECK_CUDA(cudaMalloc(&p.d_scale, p.n_alloc * sizeof(float)));
+    TB_CHECK_CUDA(cudaMalloc(&p.d_shift, p.n_alloc * sizeof(float)));
+    TB_CHECK_CUDA(cudaMemcpy(p.d_bias, b.data(), p.n_alloc * sizeof(float), cudaMemcpyHostToDevice));
+    TB_CHECK_CUDA(cudaMemcpy(p.d_scale, sc.data(), p.n_alloc * sizeof(float), cudaMemcpyHostToDevice));
+    TB_CHECK_CUDA(cudaMemcpy(p.d_shift, sh.data(), p.n_alloc * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static bool g_conv_attr_set = false;
+
+// Launch one conv over `n_frames` frames.  `in_base`: split tensor base (hi plane first);
+// `in_frames_alloc`: frames per plane in that allocation.
+static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames,
+                       const TView& out, cudaStream_t stream) {
+    const int64_t m_total64 = n_frames * p.Do * p.Ho * p.Wo;
+    TB_REQUIRE(m_total64 > 0 && m_total64 < (1ll << 31) - 512, "conv: too many output pixels per launch");
+    ConvPlan::Config cfg;
+    int rc = choose_config(p, m_total64, &cfg);
+    if (rc) return rc;
+    CUtensorMap map_w, map_a;
+    rc = encode_w_map(p, cfg.kc, cfg.tma_swz, &map_w);
+    if (rc) return rc;
+    rc = encode_a_map(p, cfg, in_base, in_frames_alloc, p.cin_pad, &map_a);
+    if (rc) return rc;
+
+    ConvKernelParams k;
+    std::memset(&k, 0, sizeof(k));
+    k.m_total = static_cast<int32_t>(m_total64);
+    const int m_tiles = static_cast<int>((m_total64 + 127) / 128);
+    k.mt = cfg.mt;
+    k.n_ctile_m = ceil_div(m_tiles, cfg.mt);
+    k.n_tiles = p.n_tiles;
+    k.n_tile = p.n_tile;
+    k.acc_cols = cfg.acc_cols;
+    k.acc_stages = cfg.acc_stages;
+    k.kh = p.kh; k.kw = p.kw;
+    k.n_taps = p.kd * p.kh * p.kw;
+    k.cin_pad = p.cin_pad;
+    k.kc = cfg.kc;
+    k.cin_blocks = p.cin_pad / cfg.kc;
+    k.kg = cfg.kg;
+    k.n_kblocks = k.n_taps * k.cin_blocks;
+    k.stages = cfg.stages;
+    k.Do = p.Do; k.Ho = p.Ho; k.Wo = p.Wo;
+    k.lc_d = -p.pad0[0]; k.lc_h = -p.pad0[1]; k.lc_w = -p.pad0[2];
+    k.lo_plane_frames = static_cast<int32_t>(in_frames_alloc);
+    k.w_lo_rows = p.n_alloc;
+    k.a_sub_bytes = 128u * cfg.kc * 2u;
+    k.w_sub_bytes = static_cast<uint32_t>(p.n_tile) * cfg.kc * 2u;
+    k.row_bytes = cfg.kc * 2u;
+    k.layout_type = cfg.swizzle_code;
+    k.bias = p.d_bias; k.scale = p.d_scale; k.shift = p.d_shift;
+    k.act1 = p.act1; k.act2 = p.act2; k.alpha1 = p.alpha1; k.alpha2 = p.alpha2;
+    k.out_fmt = out.fmt;
+    k.out_f32 = out.f32; k.out_hi = out.hi; k.out_lo = out.lo;
+    k.ldc = out.ld;
+    k.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
+               "conv: split output channel padding mismatch");
+
+    if (!g_conv_attr_set) {
+        TB_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024));
+        g_conv_attr_set = true;
+    }
+    const int total_tiles = k.n_ctile_m * k.n_tiles;
+    int sms = 148;
+    const int grid = std::min(total_tiles, sms);
+    conv_umma_kernel<<<grid, kConvThreads, cfg.smem_bytes, stream>>>(map_a, map_w, k);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- graph
+struct OpNode {
+    tb_op_desc d;
+    ConvPlan conv;
+    float* d_scale = nullptr;   // AFFINE
+    float* d_shift = nullptr;
+    PoolParams pool;
+};
+
+struct Layout {
+    std::vector<size_t> offset;
+    size_t total = 0;
+};
+
+}  // namespace tb
+
+struct tb_graph {
+    int device = 0;
+    std::vector<tb::OpNode> ops;
+    std::vector<tb::TensorInfo> tensors;
+    int n_classes = 0;
+    double flops = 0.0;
+    int launches = 0;
+    std::map<int64_t, tb::Layout> layouts;
+    // host-path staging (predict_host)
+    void* d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    void* d_ws = nullptr;
+    size_t ws_bytes = 0;
+    float* d_probs = nullptr;
+    size_t probs_bytes = 0;
+    cudaStream_t s_copy = nullptr, s_compute = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+};
+
+namespace tb {
+
+static TView make_view(const TensorInfo& t, uint8_t* base, int64_t n_frames) {
+    TView v;
+    v.fmt = t.fmt;
+    v.c = t.C;
+    v.c_pad = t.c_pad;
+    v.ld = t.c_pad;
+    v.f32 = nullptr;
+    v.hi = v.lo = nullptr;
+    if (t.fmt == FMT_F32) {
+        v.f32 = reinterpret_cast<float*>(base);
+    } else {
+        v.hi = reinterpret_cast<__nv_bfloat16*>(base);
+        v.lo = v.hi + t.frames_alloc(n_frames) * t.pix_per_frame() * t.c_pad;
+    }
+    return v;
+}
+
+// Liveness-based first-fit workspace layout for n_frames.
+static const Layout& get_layout(tb_graph* g, int64_t n_frames) {
+    auto it = g->layouts.find(n_frames);
+    if (it != g->layouts.end()) return it->second;
+    Layout L;
+    const int n = static_cast<int>(g->tensors.size());
+    L.offset.assign(n, 0);
+    struct Block { size_t off, size; };
+    std::vector<Block> free_list;
+    size_t top = 0;
+    std::vector<std::pair<size_t, size_t>> live(n, {0, 0});
+    for (int i = 0; i < n; ++i) {
+        // release tensors whose last reader ran before op i
+        for (int j = 0; j < i; ++j)
+            if (live[j].second && g->tensors[j].last_use < i) {
+                free_list.push_back({live[j].first, live[j].second});
+                live[j].second = 0;
+            }
+        // coalesce
+        std::sort(free_list.begin(), free_list.end(), [](const Block& a, const Block& b) { return a.off < b.off; });
+        for (size_t k = 0; k + 1 < free_list.size();) {
+            if (free_list[k].off + free_list[k].size == free_list[k + 1].off) {
+                free_list[k].size += free_list[k + 1].size;
+                free_list.erase(free_list.begin() + k + 1);
+            } else {
+                ++k;
+            }
+        }
+        const size_t need = g->tensors[i].bytes(n_frames);
+        bool placed = false;
+        for (size_t k = 0; k < free_list.size(); ++k)
+            if (free_list[k].size >= need) {
+                L.offset[i] = free_list[k].off;
+                free_list[k].off += need;
+                free_list[k].size -= need;
+                if (!free_list[k].size) free_list.erase(free_list.begin() + k);
+                placed = true;
+                break;
+            }
+        if (!placed) {
+            // grow from the top; merge with a trailing free block if there is one
+            if (!free_list.empty() && free_list.back().off + free_list.back().size == top) {
+                L.offset[i] = free_list.back().off;
+                top = free_list.back().off + need;
+                free_list.pop_back();
+            } else {
+                L.offset[i] = top;
+                top += need;
+            }
+        }
+        live[i] = {L.offset[i], need};
+    }
+    L.total = top;
+    return g->layouts.emplace(n_frames, std::move(L)).first->second;
+}
+
+static int upload_vec(const float* src, int n, float fill, float** dst) {
+    std::vector<float> v(n, fill);
+    if (src) std::copy(src, src + n, v.begin());
+    TB_CHECK_CUDA(cudaMalloc(dst, n * sizeof(float)));
+    TB_CHECK_CUDA(cudaMemcpy(*dst, v.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
+    TB_REQUIRE(n_ops >= 2, "graph needs an input op and at least one more op");
+    TB_REQUIRE(ops[0].op == TB_OP_INPUT, "ops[0] must be TB_OP_INPUT");
+    g->ops.resize(n_ops);
+    g->tensors.resize(n_ops);
+    // consumers decide the storage format: anything a contraction reads lives as bf16 split planes
+    std::vector<bool> feeds_conv(n_ops, false);
+    for (int i = 0; i < n_ops; ++i) {
+        const tb_op_desc& d = ops[i];
+        TB_REQUIRE(d.n_inputs >= 0 && d.n_inputs <= TB_MAX_INPUTS, "bad n_inputs");
+        for (int k = 0; k < d.n_inputs; ++k) {
+            TB_REQUIRE(d.inputs[k] >= 0 && d.inputs[k] < i, "op inputs must reference earlier ops");
+            if (d.op == TB_OP_CONV3D) feeds_conv[d.inputs[k]] = true;
+            g->tensors[d.inputs[k]].last_use = i;
+        }
+    }
+    g->tensors[n_ops - 1].last_use = n_ops;   // graph output stays live
+    g->flops = 0.0;
+    g->launches = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        OpNode& node = g->ops[i];
+        node.d = ops[i];
+        const tb_op_desc& d = ops[i];
+        TensorInfo& t = g->tensors[i];
+        t.fmt = feeds_conv[i] ? FMT_SPLIT : FMT_F32;
+        const TensorInfo* in0 = d.n_inputs > 0 ? &g->tensors[d.inputs[0]] : nullptr;
+        switch (d.op) {
+            case TB_OP_INPUT:
+                TB_REQUIRE(i == 0, "only ops[0] may be TB_OP_INPUT");
+                t.D = d.kernel[0]; t.H = d.kernel[1]; t.W = d.kernel[2]; t.C = d.c_out;
+                TB_REQUIRE(t.D > 0 && t.H > 0 && t.W > 0 && t.C > 0, "input dims must be positive");
+                g->launches += 1;
+                break;
+            case TB_OP_CONV3D: {
+                TB_REQUIRE(d.n_inputs == 1, "conv takes one input");
+                int rc = conv_plan_create(node.conv, d, in0->D, in0->H, in0->W, in0->C, in0->c_pad);
+                if (rc) return rc;
+                t.D = node.conv.Do; t.H = node.conv.Ho; t.W = node.conv.Wo; t.C = d.c_out;
+                g->flops += node.conv.flops_per_frame();
+                g->launches += 1;
+                break;
+            }
+            case TB_OP_POOL3D: {
+                TB_REQUIRE(d.n_inputs == 1, "pool takes one input");
+                PoolParams& pp = node.pool;
+                pp.D = in0->D; pp.H = in0->H; pp.W = in0->W;
+                const int in[3] = {in0->D, in0->H, in0->W};
+                int out[3];
+                for (int a = 0; a < 3; ++a) {
+                    pp.k[a] = d.kernel[a];
+                    pp.s[a] = d.stride[a] > 0 ? d.stride[a] : d.kernel[a];
+                    TB_REQUIRE(pp.k[a] >= 1, "pool size must be positive");
+                    if (d.pad_same) {
+                        int after;
+                        same_pads(in[a], pp.k[a], pp.s[a], &out[a], &pp.pad0[a], &after);
+                    } else {
+                        out[a] = (in[a] - pp.k[a]) / pp.s[a] + 1;
+                        pp.pad0[a] = 0;
+                    }
+                    TB_REQUIRE(out[a] >= 1, "pool window larger than input");
+                }
+                pp.Do = out[0]; pp.Ho = out[1]; pp.Wo = out[2];
+                pp.is_avg = d.pool_kind;
+                t.D = out[0]; t.H = out[1]; t.W = out[2]; t.C = in0->C;
+                g->launches += 1;
+                break;
+            }
+            case TB_OP_AFFINE: {
+                TB_REQUIRE(d.n_inputs == 1, "affine takes one input");
+                t.D = in0->D; t.H = in0->H; t.W = in0->W; t.C = in0->C;
+                int rc = upload_vec(d.scale, t.C, 1.f, &node.d_scale);
+                if (rc) return rc;
+                rc = upload_vec(d.shift, t.C, 0.f, &node.d_shift);
+                if (rc) return rc;
+                g->launches += 1;
+                break;
+            }
+            case TB_OP_GPOOL:
+                TB_REQUIRE(d.n_inputs == 1, "global pool takes one input");
+                t.D = t.H = t.W = 1; t.C = in0->C;
+                g->launches += 1;
+                break;
+            case TB_OP_SOFTMAX:
+                TB_REQUIRE(d.n_inputs == 1, "softmax takes one input");
+                TB_REQUIRE(in0->pix_per_frame() == 1, "softmax is supported on (n, C) tensors only");
+                t.D = t.H = t.W = 1; t.C = in0->C;
+                g->launches += 1;
+                break;
+            case TB_OP_CONCAT: {
+                TB_REQUIRE(d.n_inputs >= 1, "concat needs inputs");
+                t.D = in0->D; t.H = in0->H; t.W = in0->W; t.C = 0;
+                for (int k = 0; k < d.n_inputs; ++k) {
+                    const TensorInfo& s = g->tensors[d.inputs[k]];
+                    TB_REQUIRE(s.D == t.D && s.H == t.H && s.W == t.W, "concat: spatial dims differ");
+                    t.C += s.C;
+                }
+                g->launches += d.n_inputs + 1;
+                break;
+            }
+            case TB_OP_ADD: {
+                TB_REQUIRE(d.n_inputs == 2, "add takes two inputs");
+                const TensorInfo& s = g->tensors[d.inputs[1]];
+                TB_REQUIRE(s.D == in0->D && s.H == in0->H && s.W == in0->W && s.C == in0->C,
+                           "add: shapes differ");
+                t.D = in0->D; t.H = in0->H; t.W = in0->W; t.C = in0->C;
+                g->launches += 1;
+                break;
+            }
+            default:
+                TB_REQUIRE(false, "unknown op kind");
+        }
+        t.c_pad = t.fmt == FMT_SPLIT ? round_up(t.C, 16) : t.C;
+        // pointers are only valid during graph_create
+        node.d.kernel_w = node.d.bias = node.d.scale = node.d.shift = nullptr;
+    }
+    // conv inputs need 127 readable pixels past the last valid one (im2col column of 128)
+    for (int i = 0; i < n_ops; ++i)
+        if (ops[i].op == TB_OP_CONV3D) {
+            TensorInfo& s = g->tensors[ops[i].inputs[0]];
+            const ConvPlan& c = g->ops[i].conv;
+            // base pixels advance through Do*Ho*Wo per frame: express the slack in input pixels
+            const int64_t out_ppf = static_cast<int64_t>(c.Do) * c.Ho * c.Wo;
+            const int64_t frames = (128 + out_ppf - 1) / out_ppf;
+            s.slack_pix = std::max<int64_t>(s.slack_pix, frames * s.pix_per_frame());
+        }
+    const TensorInfo& last = g->tensors[n_ops - 1];
+    TB_REQUIRE(last.pix_per_frame() == 1, "graph output must be (n, classes)");
+    TB_REQUIRE(last.fmt == FMT_F32, "internal: output tensor must be fp32");
+    g->n_classes = last.C;
+    return 0;
+}
+
+template <typename T>
+static void launch_input_convert(const void* x, int64_t n_pix, const TView& out, cudaStream_t s) {
+    const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    input_convert_kernel<T><<<grid_for(n_pix * cw, 256), 256, 0, s>>>(static_cast<const T*>(x), n_pix, out);
+}
+
+static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n_frames, void* ws,
+                         size_t ws_bytes, float* d_probs, cudaStream_t s) {
+    TB_REQUIRE(n_frames > 0, "n_frames must be positive");
+    const Layout& L = get_layout(g, n_frames);
+    TB_REQUIRE(ws_bytes >= L.total, "workspace too small (see timed_b200_graph_workspace_bytes)");
+    TB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
+    uint8_t* base = static_cast<uint8_t*>(ws);
+    const int n_ops = static_cast<int>(g->ops.size());
+    for (int i = 0; i < n_ops; ++i) {
+        OpNode& node = g->ops[i];
+        const tb_op_desc& d = node.d;
+        const TensorInfo& t = g->tensors[i];
+        TView out = make_view(t, base + L.offset[i], n_frames);
+        if (i == n_ops - 1) {   // the graph output goes straight to the caller's buffer
+            out.f32 = d_probs;
+            out.ld = t.C;
+        }
+        const int64_t out_pix = n_frames * t.pix_per_frame();
+        TView in0{};
+        const TensorInfo* ti0 = nullptr;
+        if (d.n_inputs > 0) {
+            ti0 = &g->tensors[d.inputs[0]];
+            in0 = make_view(*ti0, base + L.offset[d.inputs[0]], n_frames);
+        }
+        const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+        switch (d.op) {
+            case TB_OP_INPUT:
+                if (dtype == TB_DTYPE_F32) launch_input_convert<float>(d_frames, out_pix, out, s);
+                else if (dtype == TB_DTYPE_F64) launch_input_convert<double>(d_frames, out_pix, out, s);
+                else if (dtype == TB_DTYPE_U8) launch_input_convert<uint8_t>(d_frames, out_pix, out, s);
+                else TB_REQUIRE(false, "unknown frames dtype");
+                break;
+            case TB_OP_CONV3D: {
+                TB_REQUIRE(ti0->fmt == FMT_SPLIT, "internal: conv input must be split planes");
+                int rc = conv_launch(node.conv, base + L.offset[d.inputs[0]], ti0->frames_alloc(n_frames),
+                                     n_frames, out, s);
+                if (rc) return rc;
+                break;
+            }
+            case TB_OP_POOL3D:
+                if (in0.fmt == FMT_SPLIT && out.fmt == FMT_SPLIT) {
+                    pool3d_split_vec8_kernel<<<grid_for(out_pix * (out.c_pad / 8), 256), 256, 0, s>>>(
+                        in0, out, node.pool, n_frames);
+                } else {
+                    pool3d_kernel<<<grid_for(out_pix * cw, 256), 256, 0, s>>>(in0, out, node.pool, n_frames);
+                }
+                break;
+            case TB_OP_AFFINE:
+                affine_act_kernel<<<grid_for(out_pix * cw, 256), 256, 0, s>>>(
+                    in0, out, out_pix, node.d_scale, node.d_shift, d.act1, d.alpha1, d.act2, d.alpha2);
+                break;
+            case TB_OP_GPOOL:
+                gpool_kernel<<<static_cast<unsigned>(n_frames), 128, 0, s>>>(
+                    in0, out, static_cast<int>(ti0->pix_per_frame()), d.pool_kind);
+                break;
+            case TB_OP_SOFTMAX:
+                softmax_kernel<<<static_cast<unsigned>((n_frames * 32 + 255) / 256), 256, 0, s>>>(in0, out, n_frames);
+                break;
+            case TB_OP_CONCAT: {
+                int c_off = 0;
+                for (int k = 0; k < d.n_inputs; ++k) {
+                    const TensorInfo& ts = g->tensors[d.inputs[k]];
+                    TView src = make_view(ts, base + L.offset[d.inputs[k]], n_frames);
+                    copy_channels_kernel<<<grid_for(out_pix * src.c, 256), 256, 0, s>>>(src, out, out_pix, c_off);
+                    c_off += ts.C;
+                }
+                if (out.fmt == FMT_SPLIT && out.c_pad > out.c)
+                    zero_pad_channels_kernel<<<grid_for(out_pix * (out.c_pad - out.c), 256), 256, 0, s>>>(out, out_pix);
+                break;
+            }
+            case TB_OP_ADD: {
+                TView in1 = make_view(g->tensors[d.inputs[1]], base + L.offset[d.inputs[1]], n_frames);
+                add_kernel<<<grid_for(out_pix * cw, 256), 256, 0, s>>>(in0, in1, out, out_pix);
+                break;
+            }
+            default:
+                TB_REQUIRE(false, "unknown op kind");
+        }
+        TB_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+static void graph_free(tb_graph* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    for (auto& n : g->ops) {
+        free_conv_plan(n.conv);
+        cudaFree(n.d_scale);
+        cudaFree(n.d_shift);
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(g->d_stage[i]);
+        if (g->ev_copied[i]) cudaEventDestroy(g->ev_copied[i]);
+        if (g->ev_consumed[i]) cudaEventDestroy(g->ev_consumed[i]);
+    }
+    cudaFree(g->d_ws);
+    cudaFree(g->d_probs);
+    if (g->s_copy) cudaStreamDestroy(g->s_copy);
+    if (g->s_compute) cudaStreamDestroy(g->s_compute);
+    delete g;
+}
+
+static size_t dtype_size(int dtype) {
+    return dtype == TB_DTYPE_F64 ? 8 : (dtype == TB_DTYPE_F32 ? 4 : 1);
+}
+
+}  // namespace tb
+
+// ================================================================================= C ABI
+using namespace tb;
+
+extern "C" {
+
+int timed_b200_abi_version(void) { return TIMED_B200_ABI_VERSION; }
+
+const char* timed_b200_last_error(void) { return g_last_error.c_str(); }
+
+int timed_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int timed_b200_graph_create(const tb_op_desc* ops, int32_t n_ops, int32_t device, tb_graph** out) {
+    TB_REQUIRE(ops && out, "null argument");
+    *out = nullptr;
+    if (timed_b200_device_count() <= device) {
+        set_error("no CUDA device " + std::to_string(device) + " (libtimed_b200 has no CPU path)");
+        return TB_ERR_NO_DEVICE;
+    }
+    TB_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                  "; libtimed_b200 is built for sm_100a (B200) only");
+        return TB_ERR_NO_DEVICE;
+    }
+    int rc = load_driver_fns();
+    if (rc) return rc;
+    tb_graph* g = new tb_graph();
+    g->device = device;
+    rc = graph_build(g, ops, n_ops);
+    if (rc) {
+        graph_free(g);
+        return rc;
+    }
+    *out = g;
+    return TB_OK;
+}
+
+void timed_b200_graph_destroy(tb_graph* g) { graph_free(g); }
+
+int timed_b200_graph_info(const tb_graph* g, int32_t* n_classes, double* flops_per_frame,
+                          int32_t* n_kernel_launches_per_forward) {
+    TB_REQUIRE(g, "null graph");
+    if (n_classes) *n_classes = g->n_classes;
+    if (flops_per_frame) *flops_per_frame = g->flops;
+    if (n_kernel_launches_per_forward) *n_kernel_launches_per_forward = g->launches;
+    return TB_OK;
+}
+
+int timed_b200_graph_workspace_bytes(const tb_graph* g, int64_t n_frames, size_t* out) {
+    TB_REQUIRE(g && out, "null argument");
+    TB_REQUIRE(n_frames > 0, "n_frames must be positive");
+    *out = get_layout(const_cast<tb_graph*>(g), n_frames).total;
+    return TB_OK;
+}
+
+int timed_b200_graph_forward(tb_graph* g, const void* d_frames, int32_t frames_dtype, int64_t n_frames,
+                             void* d_workspace, size_t workspace_bytes, float* d_probs,
+                             void* cuda_stream) {
+    TB_REQUIRE(g && d_frames && d_workspace && d_probs, "null argument");
+    TB_CHECK_CUDA(cudaSetDevice(g->device));
+    return graph_forward(g, d_frames, frames_dtype, n_frames, d_workspace, workspace_bytes, d_probs,
+                         static_cast<cudaStream_t>(cuda_stream));
+}
+
+int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t frames_dtype,
+                                  int64_t n_frames, float* h_probs, int64_t max_chunk_frames) {
+    TB_REQUIRE(g && h_frames && h_probs, "null argument");
+    TB_REQUIRE(n_frames > 0, "n_frames must be positive");
+    TB_CHECK_CUDA(cudaSetDevice(g->device));
+    const int64_t chunk = std::min<int64_t>(n_frames, max_chunk_frames > 0 ? max_chunk_frames : 1024);
+    const TensorInfo& tin = g->tensors[0];
+    const size_t frame_bytes = static_cast<size_t>(tin.pix_per_frame()) * tin.C * dtype_size(frames_dtype);
+    // (re)size library-owned staging
+    if (!g->s_copy) {
+        TB_CHECK_CUDA(cudaStreamCreateWithFlags(&g->s_copy, cudaStreamNonBlocking));
+        TB_CHECK_CUDA(cudaStreamCreateWithFlags(&g->s_compute, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            TB_CHECK_CUDA(cudaEventCreateWithFlags(&g->ev_copied[i], cudaEventDisableTiming));
+            TB_CHECK_CUDA(cudaEventCreateWithFlags(&g->ev_consumed[i], cudaEventDisableTiming));
+        }
+    }
+    if (g->stage_bytes < chunk * frame_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(g->d_stage[i]);
+            g->d_stage[i] = nullptr;
+            TB_CHECK_CUDA(cudaMalloc(&g->d_stage[i], chunk * frame_bytes));
+        }
+        g->stage_bytes = chunk * frame_bytes;
+    }
+    const size_t ws_need = get_layout(g, chunk).total;
+    if (g->ws_bytes < ws_need) {
+        cudaFree(g->d_ws);
+        g->d_ws = nullptr;
+        TB_CHECK_CUDA(cudaMalloc(&g->d_ws, ws_need));
+        g->ws_bytes = ws_need;
+    }
+    const size_t probs_need = static_cast<size_t>(n_frames) * g->n_classes * sizeof(float);
+    if (g->probs_bytes < probs_need) {
+        cudaFree(g->d_probs);
+        g->d_probs = nullptr;
+        TB_CHECK_CUDA(cudaMalloc(&g->d_probs, probs_need));
+        g->probs_bytes = probs_need;
+    }
+    // double-buffered: H2D of chunk i+1 overlaps the forward of chunk i
+    const uint8_t* src = static_cast<const uint8_t*>(h_frames);
+    int it = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk, ++it) {
+        const int b = it & 1;
+        const int64_t nf = std::min(chunk, n_frames - f0);
+        if (it >= 2) TB_CHECK_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_consumed[b], 0));
+        TB_CHECK_CUDA(cudaMemcpyAsync(g->d_stage[b], src + f0 * frame_bytes, nf * frame_bytes,
+                                      cudaMemcpyHostToDevice, g->s_copy));
+        TB_CHECK_CUDA(cudaEventRecord(g->ev_copied[b], g->s_copy));
+        TB_CHECK_CUDA(cudaStreamWaitEvent(g->s_compute, g->ev_copied[b], 0));
+        // a shorter tail chunk uses its own (smaller) layout inside the same workspace
+        int rc = graph_forward(g, g->d_stage[b], frames_dtype, nf, g->d_ws, g->ws_bytes,
+                               g->d_probs + f0 * g->n_classes, g->s_compute);
+        if (rc) return rc;
+        TB_CHECK_CUDA(cudaEventRecord(g->ev_consumed[b], g->s_compute));
+    }
+    TB_CHECK_CUDA(cudaMemcpyAsync(h_probs, g->d_probs, probs_need, cudaMemcpyDeviceToHost, g->s_compute));
+    TB_CHECK_CUDA(cudaStreamSynchronize(g->s_compute));
+    return TB_OK;
+}
+
+int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int32_t W, int32_t c_in,
+                          const tb_op_desc* conv, int32_t device, float* d_y) {
+    TB_REQUIRE(d_x && conv && d_y, "null argument");
+    TB_REQUIRE(conv->op == TB_OP_CONV3D, "conv descriptor expected");
+    tb_op_desc ops[2];
+    std::memset(ops, 0, sizeof(ops));
+    ops[0].op = TB_OP_INPUT;
+    ops[0].kernel[0] = D; ops[0].kernel[1] = H; ops[0].kernel[2] = W;
+    ops[0].c_out = c_in;
+    ops[1] = *conv;
+    ops[1].n_inputs = 1;
+    ops[1].inputs[0] = 0;
+    // graph_build wants an (n, classes) output; run the two ops by hand instead
+    if (timed_b200_device_count() <= device) {
+        set_error("no CUDA device (libtimed_b200 has no CPU path)");
+        return TB_ERR_NO_DEVICE;
+    }
+    TB_CHECK_CUDA(cudaSetDevice(device));
+    int rc = load_driver_fns();
+    if (rc) return rc;
+    TensorInfo tin;
+    tin.D = D; tin.H = H; tin.W = W; tin.C = c_in;
+    tin.fmt = FMT_SPLIT;
+    tin.c_pad = round_up(c_in, 16);
+    ConvPlan plan;
+    rc = conv_plan_create(plan, ops[1], D, H, W, c_in, tin.c_pad);
+    if (rc) { free_conv_plan(plan); return rc; }
+    const int64_t out_ppf = static_cast<int64_t>(plan.Do) * plan.Ho * plan.Wo;
+    tin.slack_pix = static_cast<int>(((128 + out_ppf - 1) / out_ppf) * tin.pix_per_frame());
+    void* d_in = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, tin.bytes(n));
+    if (e != cudaSuccess) { free_conv_plan(plan); TB_CHECK_CUDA(e); }
+    cudaMemset(d_in, 0, tin.bytes(n));
+    TView vin = make_view(tin, static_cast<uint8_t*>(d_in), n);
+    launch_input_convert<float>(d_x, n * tin.pix_per_frame(), vin, nullptr);
+    TView vout{};
+    vout.fmt = FMT_F32;
+    vout.f32 = d_y;
+    vout.c = plan.cout;
+    vout.c_pad = plan.cout;
+    vout.ld = plan.cout;
+    rc = conv_launch(plan, d_in, tin.frames_alloc(n), n, vout, nullptr);
+    cudaError_t se = cudaDeviceSynchronize();
+    cudaFree(d_in);
+    free_conv_plan(plan);
+    if (rc) return rc;
+    TB_CHECK_CUDA(se);
+    return TB_OK;
+}
+
+// ---------------------------------------------------------------------------------- sampler
+int timed_b200_apply_temperature(const double* d_probs_in, int64_t n_rows, int32_t n_cls, double t,
+                                 double* d_probs_out, void* cuda_stream) {
+    TB_REQUIRE(d_probs_in && d_probs_out, "null argument");
+    TB_REQUIRE(n_rows > 0 && n_cls > 0, "empty probability matrix");
+    TB_REQUIRE(t != 0.0, "temperature must be non-zero");
+    const double inv_t = 1.0 / t;
+    temperature_kernel<<<static_cast<unsigned>((n_rows + 127) / 128), 128, 0,
+                         static_cast<cudaStream_t>(cuda_stream)>>>(d_probs_in, n_rows, n_cls, inv_t, d_probs_out);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+int timed_b200_cumsum_rows(const double* d_probs, int64_t n_rows, int32_t n_cls, double* d_cdf,
+                           void* cuda_stream) {
+    TB_REQUIRE(d_probs && d_cdf, "null argument");
+    TB_REQUIRE(n_rows > 0 && n_cls > 0, "empty probability matrix");
+    cumsum_rows_kernel<<<static_cast<unsigned>((n_rows + 127) / 128), 128, 0,
+                         static_cast<cudaStream_t>(cuda_stream)>>>(d_probs, n_rows, n_cls, d_cdf);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+int timed_b200_sample(const double* d_cdf, int64_t n_res, int32_t n_cls, int64_t n_samples,
+                      int64_t first_sample, uint64_t seed, uint64_t stream_id, const double* d_uniforms,
+                      const uint8_t* d_cls_to_letter, uint8_t* d_seqs, int32_t* d_idx, void* cuda_stream) {
+    TB_REQUIRE(d_cdf && d_cls_to_letter && d_seqs, "null argument");
+    TB_REQUIRE(n_res > 0 && n_samples > 0, "nothing to sample");
+    TB_REQUIRE(n_cls > 0 && n_cls <= 512, "n_cls must be in [1,512]");
+    TB_REQUIRE((reinterpret_cast<uintptr_t>(d_seqs) & 3) == 0, "d_seqs must be 4-byte aligned");
+    TB_REQUIRE(!d_idx || (reinterpret_cast<uintptr_t>(d_idx) & 15) == 0, "d_idx must be 16-byte aligned");
+    const int64_t words = (n_res * n_samples + 3) / 4;
+    sample_kernel<<<grid_for(words, 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        d_cdf, n_res, n_cls, n_samples, first_sample, seed, stream_id, d_uniforms, d_cls_to_letter, d_seqs,
+        d_idx);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+int timed_b200_sample_uniforms(int64_t n_res, int64_t n_samples, int64_t first_sample, uint64_t seed,
+                               uint64_t stream_id, double* d_out, void* cuda_stream) {
+    TB_REQUIRE(d_out, "null argument");
+    TB_REQUIRE(n_res > 0 && n_samples > 0, "nothing to draw");
+    sample_uniforms_kernel<<<grid_for(n_res * n_samples, 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        n_res, n_samples, first_sample, seed, stream_id, d_out);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+int timed_b200_argmax_fp16(const float* d_probs, int64_t n, int32_t n_cls, int32_t* d_idx, void* cuda_stream) {
+    TB_REQUIRE(d_probs && d_idx, "null argument");
+    TB_REQUIRE(n > 0 && n_cls > 0, "empty matrix");
+    argmax_fp16_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0,
+                         static_cast<cudaStream_t>(cuda_stream)>>>(d_probs, n, n_cls, d_idx);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// Conv3D / Dense as an implicit GEMM on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   out[m, n] = act2( scale[n] * act1( sum_k A[m, k] * Wt[n, k] + bias[n] ) + shift[n] )
+//
+//   m = flattened output pixel (frame, z, p, q)          M = n_frames * Do*Ho*Wo
+//   k = (tap, input channel)                              K = kd*kh*kw * C_in_pad
+//   n = output channel                                    N = C_out
+//
+// Operands are bf16 "split planes": every fp32 value v is stored as hi = bf16(v) and
+// lo = bf16(v - hi); the product is accumulated in fp32 TMEM as  A_hi*W_hi + A_lo*W_hi +
+// A_hi*W_lo  (three tcgen05.mma per K-step), which carries ~16 mantissa bits per operand --
+// what the 1e-4 probability / bit-exact-argmax contract needs (DESIGN.md "Numerics";
+// plain bf16 or fp16/tf32 single-pass misses it by 25-100x on the TIMED stand-in).
+//
+// A tiles (128 output pixels x kc channels of one filter tap) are gathered straight from the
+// NDHWC activation tensor by TMA in IM2COL mode (zero-fill supplies the 'same' padding); W tiles
+// by tiled TMA.  Both land in shared memory in the canonical K-major swizzled layout that the
+// UMMA descriptors read.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// allocation), warps 2..5 = epilogue (TMEM -> registers -> bias/act/BN-affine -> HBM).
+#pragma once
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int kConvMaxStages = 8;
+constexpr int kConvThreads = 192;
+
+enum OutFmt : int { FMT_F32 = 0, FMT_SPLIT = 1 };
+
+struct ConvKernelParams {
+    // ---- GEMM tiling
+    int32_t m_total;     // valid output pixels (rows)
+    int32_t n_ctile_m;   // CTA tiles along M (each covers mt*128 rows)
+    int32_t n_tiles;     // CTA tiles along N
+    int32_t n_tile;      // columns per CTA tile (multiple of 16, <= 256) == UMMA N
+    int32_t mt;          // 128-row sub-tiles per CTA tile (1 or 2)
+    int32_t acc_cols;    // TMEM columns reserved per accumulator (n_tile rounded up to 32)
+    int32_t acc_stages;  // accumulator ring depth (1 or 2)
+    // ---- K loop
+    int32_t kh, kw;      // filter extents (kd implied by n_taps)
+    int32_t n_taps;      // kd*kh*kw
+    int32_t cin_pad;     // padded input channels (K stride of one tap in the packed weights)
+    int32_t cin_blocks;  // cin_pad / kc
+    int32_t kc;          // channels per k-block: 16 / 32 / 64  (row = 32 / 64 / 128 bytes)
+    int32_t kg;          // k-blocks per pipeline stage
+    int32_t n_kblocks;   // n_taps * cin_blocks
+    int32_t stages;      // smem ring depth
+    // ---- geometry of the output volume and the im2col lower corner (= -pad_before)
+    int32_t Do, Ho, Wo;
+    int32_t lc_d, lc_h, lc_w;
+    int32_t lo_plane_frames;  // frame offset of the lo plane inside the activation tensor map
+    int32_t w_lo_rows;        // row offset of the lo plane inside the weight tensor map
+    // ---- smem layout
+    uint32_t a_sub_bytes;  // 128 * kc * 2
+    uint32_t w_sub_bytes;  // n_tile * kc * 2
+    uint32_t row_bytes;    // kc * 2
+    uint32_t layout_type;  // UMMA swizzle code (2 / 4 / 6)
+    // ---- epilogue
+    const float* bias;     // [n_tiles*n_tile], zero padded (never NULL)
+    const float* scale;    // idem (ones when absent)
+    const float* shift;    // idem (zeros when absent)
+    int32_t act1, act2;
+    float alpha1, alpha2;
+    int32_t out_fmt;       // FMT_F32 / FMT_SPLIT
+    float* out_f32;        // [m_total][ldc] (FMT_F32)
+    __nv_bfloat16* out_hi; // [m_total][ldc] (FMT_SPLIT)
+    __nv_bfloat16* out_lo;
+    int64_t ldc;           // row pitch of the output in elements
+    int32_t c_store;       // columns < c_store are stored (FMT_SPLIT: multiple of 16)
+};
+
+#if defined(__CUDACC__)
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
+                 const __grid_constant__ CUtensorMap map_w, const ConvKernelParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+    __shared__ __align__(8) uint64_t full_bar[kConvMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kConvMaxStages];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_w);
+    }
+    if (warp == 1) tmem_alloc_512(&tmem_base_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int total_tiles = p.n_ctile_m * p.n_tiles;
+    const uint32_t kb_bytes = static_cast<uint32_t>(p.mt) * 2u * p.a_sub_bytes + 2u * p.w_sub_bytes;
+    const uint32_t stage_bytes = kb_bytes * static_cast<uint32_t>(p.kg);
+    const int n_groups = (p.n_kblocks + p.kg - 1) / p.kg;
+
+    if (warp == 0) {
+        // =============================================================== TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_ct = tile / p.n_tiles;
+                const int n_idx = tile - m_ct * p.n_tiles;
+                int32_t bw[2], bh[2], bd[2], bn[2];
+                for (int mi = 0; mi < p.mt; ++mi) {
+                    int m0 = (m_ct * p.mt + mi) * 128;
+                    if (m0 >= p.m_total) m0 = 0;   // dummy sub-tile: rows are discarded later
+                    const int q = m0 % p.Wo;
+                    int t = m0 / p.Wo;
+                    const int pp = t % p.Ho;
+                    t /= p.Ho;
+                    const int z = t % p.Do;
+                    const int nf = t / p.Do;
+                    bw[mi] = q + p.lc_w;
+                    bh[mi] = pp + p.lc_h;
+                    bd[mi] = z + p.lc_d;
+                    bn[mi] = nf;
+                }
+                for (int g = 0; g < n_groups; ++g) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    const int kb0 = g * p.kg;
+                    const int nkb = min(p.kg, p.n_kblocks - kb0);
+                    mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * kb_bytes);
+                    uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+                    for (int j = 0; j < nkb; ++j) {
+                        const int kb = kb0 + j;
+                        const int tap = kb / p.cin_blocks;
+                        const int cb = kb - tap * p.cin_blocks;
+                        const int tkw = tap % p.kw;
+                        const int t2 = tap / p.kw;
+                        const int tkh = t2 % p.kh;
+                        const int tkd = t2 / p.kh;
+                        uint8_t* base = st + static_cast<size_t>(j) * kb_bytes;
+                        for (int mi = 0; mi < p.mt; ++mi) {
+                            tma_load_im2col_5d(base + mi * p.a_sub_bytes, &map_a, &full_bar[s],
+                                               cb * p.kc, bw[mi], bh[mi], bd[mi], bn[mi],
+                                               static_cast<uint16_t>(tkw),
+                                               static_cast<uint16_t>(tkh),
+                                               static_cast<uint16_t>(tkd));
+                            tma_load_im2col_5d(base + (p.mt + mi) * p.a_sub_bytes, &map_a,
+                                               &full_bar[s], cb * p.kc, bw[mi], bh[mi], bd[mi],
+                                               bn[mi] + p.lo_plane_frames,
+                                               static_cast<uint16_t>(tkw),
+                                               static_cast<uint16_t>(tkh),
+                                               static_cast<uint16_t>(tkd));
+                        }
+                        uint8_t* wb = base + 2 * p.mt * p.a_sub_bytes;
+                        const int kcoord = tap * p.cin_pad + cb * p.kc;
+                        tma_load_2d(wb, &map_w, &full_bar[s], kcoord, n_idx * p.n_tile);
+                        tma_load_2d(wb + p.w_sub_bytes, &map_w, &full_bar[s], kcoord,
+                                    p.w_lo_rows + n_idx * p.n_tile);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.n_tile));
+            const int k16_steps = p.kc / 16;
+            int s = 0;
+            uint32_t ph = 0;
+            int acc = 0;
+            uint32_t acc_ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
+                tc_fence_after();
+                uint32_t accumulate = 0;
+                for (int g = 0; g < n_groups; ++g) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const int kb0 = g * p.kg;
+                    const int nkb = min(p.kg, p.n_kblocks - kb0);
+                    const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+                    for (int j = 0; j < nkb; ++j) {
+                        const uint32_t base = st + static_cast<uint32_t>(j) * kb_bytes;
+                        const uint32_t wb = base + 2u * p.mt * p.a_sub_bytes;
+                        for (int kk = 0; kk < k16_steps; ++kk) {
+                            const uint32_t koff = static_cast<uint32_t>(kk) * 32u;
+                            const uint64_t w_hi = umma_smem_desc(wb + koff, p.row_bytes, p.layout_type);
+                            const uint64_t w_lo =
+                                umma_smem_desc(wb + p.w_sub_bytes + koff, p.row_bytes, p.layout_type);
+                            for (int mi = 0; mi < p.mt; ++mi) {
+                                const uint64_t a_hi = umma_smem_desc(
+                                    base + mi * p.a_sub_bytes + koff, p.row_bytes, p.layout_type);
+                                const uint64_t a_lo = umma_smem_desc(
+                                    base + (p.mt + mi) * p.a_sub_bytes + koff, p.row_bytes,
+                                    p.layout_type);
+                                const uint32_t d =
+                                    tmem_base + static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);
+                                umma_bf16(d, a_hi, w_hi, idesc, accumulate);
+                                umma_bf16(d, a_lo, w_hi, idesc, 1u);
+                                umma_bf16(d, a_hi, w_lo, idesc, 1u);
+                            }
+                            accumulate = 1u;
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);       // frees the smem stage when the MMAs retire
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+                if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+            }
+        }
+    } else {
+        // =============================================================== epilogue (warps 2..5)
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int row_in_tile = quad * 32 + lane;
+        const int chunks = p.n_tile / 16;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_ct = tile / p.n_tiles;
+            const int n_idx = tile - m_ct * p.n_tiles;
+            mbar_wait(&tfull_bar[acc], acc_ph);
+            tc_fence_after();
+            for (int mi = 0; mi < p.mt; ++mi) {
+                const int64_t m = static_cast<int64_t>(m_ct * p.mt + mi) * 128 + row_in_tile;
+                const bool row_ok = m < p.m_total;
+                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                       static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);
+                for (int c = 0; c < chunks; ++c) {
+                    uint32_t r[16];
+                    __syncwarp();                      // tcgen05.ld is .sync.aligned
+                    tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), r);
+                    tmem_ld_wait();
+                    const int n0 = n_idx * p.n_tile + c * 16;
+                    if (n0 >= p.c_store) continue;     // warp-uniform
+                    float v[16];
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i4);
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + i4);
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0) + i4);
+                        const float bb[4] = {b.x, b.y, b.z, b.w};
+                        const float ss[4] = {sc.x, sc.y, sc.z, sc.w};
+                        const float hh[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float x = __uint_as_float(r[i4 * 4 + i]) + bb[i];
+                            x = apply_act(x, p.act1, p.alpha1);
+                            x = fmaf(x, ss[i], hh[i]);
+                            v[i4 * 4 + i] = apply_act(x, p.act2, p.alpha2);
+                        }
+                    }
+                    if (row_ok && p.out_fmt == FMT_SPLIT) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(v[2 * i], h0, l0);
+                            split_bf16(v[2 * i + 1], h1, l1);
+                            hi[i] = pack_bf16x2(h0, h1);
+                            lo[i] = pack_bf16x2(l0, l1);
+                        }
+                        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + m * p.ldc + n0);
+                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + m * p.ldc + n0);
+                        dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    } else if (row_ok) {
+                        float* dst = p.out_f32 + m * p.ldc + n0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + i < p.c_store) dst[i] = v[i];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_512(tmem_base);
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace tb

@@ -1,0 +1,438 @@
+// Bandwidth-side kernels of the inference graph (everything that is not a contraction) and
+// the Monte-Carlo sampler kernels.  All HBM-bound: coalesced channel-fastest access, 16-byte
+// vectors on the bf16 split planes, grids sized from the element count.
+#pragma once
+#include "common.cuh"
+#include "conv_umma.cuh"
+
+namespace tb {
+
+// NDHWC view: `pix` rows of `c` logical channels, row pitch `ld` elements.
+// FMT_SPLIT rows hold c_pad (multiple of 16) stored channels; channels >= c are zero.
+struct TView {
+    int32_t fmt;
+    float* f32;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+    int64_t ld;
+    int32_t c;
+    int32_t c_pad;
+};
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ float tv_load(const TView& t, int64_t pix, int ch) {
+    const int64_t o = pix * t.ld + ch;
+    if (t.fmt == FMT_F32) return t.f32[o];
+    return __bfloat162float(t.hi[o]) + __bfloat162float(t.lo[o]);
+}
+__device__ __forceinline__ void tv_store(const TView& t, int64_t pix, int ch, float v) {
+    const int64_t o = pix * t.ld + ch;
+    if (t.fmt == FMT_F32) {
+        t.f32[o] = v;
+    } else {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        t.hi[o] = h;
+        t.lo[o] = l;
+    }
+}
+
+// ------------------------------------------------------------------ input frames -> tensor
+// x: (n_pix, c) of T (float/double/uint8) -> out view; the value is first cast to float32
+// (Keras casts X to the InputLayer dtype), pad channels are zeroed.
+template <typename T>
+__global__ void input_convert_kernel(const T* __restrict__ x, int64_t n_pix, TView out) {
+    const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    const int64_t total = n_pix * cw;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t pix = i / cw;
+        const int ch = static_cast<int>(i - pix * cw);
+        const float v = ch < out.c ? static_cast<float>(x[pix * out.c + ch]) : 0.0f;
+        tv_store(out, pix, ch, v);
+    }
+}
+
+// ------------------------------------------------------------------ pooling (TF semantics)
+struct PoolParams {
+    int32_t D, H, W, Do, Ho, Wo;
+    int32_t k[3], s[3], pad0[3];
+    int32_t is_avg;
+};
+
+// scalar path: one thread per (out pixel, channel)
+__global__ void pool3d_kernel(TView in, TView out, PoolParams pp, int64_t n_frames) {
+    const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    const int64_t opix = static_cast<int64_t>(pp.Do) * pp.Ho * pp.Wo;
+    const int64_t total = n_frames * opix * cw;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % cw);
+        int64_t t = i / cw;
+        const int q = static_cast<int>(t % pp.Wo); t /= pp.Wo;
+        const int p = static_cast<int>(t % pp.Ho); t /= pp.Ho;
+        const int z = static_cast<int>(t % pp.Do);
+        const int64_t nf = t / pp.Do;
+        float acc = pp.is_avg ? 0.0f : -INFINITY;
+        int cnt = 0;
+        if (ch < out.c) {
+            for (int a = 0; a < pp.k[0]; ++a) {
+                const int d = z * pp.s[0] - pp.pad0[0] + a;
+                if (d < 0 || d >= pp.D) continue;
+                for (int b = 0; b < pp.k[1]; ++b) {
+                    const int h = p * pp.s[1] - pp.pad0[1] + b;
+                    if (h < 0 || h >= pp.H) continue;
+                    for (int c = 0; c < pp.k[2]; ++c) {
+                        const int w = q * pp.s[2] - pp.pad0[2] + c;
+                        if (w < 0 || w >= pp.W) continue;
+                        const int64_t ipix = ((nf * pp.D + d) * pp.H + h) * pp.W + w;
+                        const float v = tv_load(in, ipix, ch);
+                        acc = pp.is_avg ? acc + v : fmaxf(acc, v);
+                        ++cnt;
+                    }
+                }
+            }
+            if (pp.is_avg) acc = acc / static_cast<float>(cnt);
+        } else {
+            acc = 0.0f;
+        }
+        const int64_t op = ((nf * pp.Do + z) * pp.Ho + p) * pp.Wo + q;
+        tv_store(out, op, ch, acc);
+    }
+}
+
+// vector path: split planes in and out, one thread per (out pixel, 8 channels), 16-byte loads
+__global__ void pool3d_split_vec8_kernel(TView in, TView out, PoolParams pp, int64_t n_frames) {
+    const int groups = out.c_pad / 8;
+    const int64_t opix = static_cast<int64_t>(pp.Do) * pp.Ho * pp.Wo;
+    const int64_t total = n_frames * opix * groups;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % groups);
+        int64_t t = i / groups;
+        const int q = static_cast<int>(t % pp.Wo); t /= pp.Wo;
+        const int p = static_cast<int>(t % pp.Ho); t /= pp.Ho;
+        const int z = static_cast<int>(t % pp.Do);
+        const int64_t nf = t / pp.Do;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = pp.is_avg ? 0.0f : -INFINITY;
+        int cnt = 0;
+        for (int a = 0; a < pp.k[0]; ++a) {
+            const int d = z * pp.s[0] - pp.pad0[0] + a;
+            if (d < 0 || d >= pp.D) continue;
+            for (int b = 0; b < pp.k[1]; ++b) {
+                const int h = p * pp.s[1] - pp.pad0[1] + b;
+                if (h < 0 || h >= pp.H) continue;
+                for (int c = 0; c < pp.k[2]; ++c) {
+                    const int w = q * pp.s[2] - pp.pad0[2] + c;
+                    if (w < 0 || w >= pp.W) continue;
+                    const int64_t o = (((nf * pp.D + d) * pp.H + h) * pp.W + w) * in.ld + g * 8;
+                    const uint4 vh = *reinterpret_cast<const uint4*>(in.hi + o);
+                    const uint4 vl = *reinterpret_cast<const uint4*>(in.lo + o);
+                    const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w};
+                    const uint32_t lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // bf16 -> fp32 is a 16-bit shift
+                        const float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                        const float v1 = __uint_as_float(hw[e] & 0xFFFF0000u) +
+                                         __uint_as_float(lw[e] & 0xFFFF0000u);
+                        acc[2 * e] = pp.is_avg ? acc[2 * e] + v0 : fmaxf(acc[2 * e], v0);
+                        acc[2 * e + 1] = pp.is_avg ? acc[2 * e + 1] + v1 : fmaxf(acc[2 * e + 1], v1);
+                    }
+                    ++cnt;
+                }
+            }
+        }
+        uint32_t ho[4], lo_[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v0 = acc[2 * e], v1 = acc[2 * e + 1];
+            if (pp.is_avg) { v0 /= static_cast<float>(cnt); v1 /= static_cast<float>(cnt); }
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v0, h0, l0);
+            split_bf16(v1, h1, l1);
+            ho[e] = pack_bf16x2(h0, h1);
+            lo_[e] = pack_bf16x2(l0, l1);
+        }
+        const int64_t oo = ((((nf * pp.Do + z) * pp.Ho + p) * pp.Wo + q)) * out.ld + g * 8;
+        *reinterpret_cast<uint4*>(out.hi + oo) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+        *reinterpret_cast<uint4*>(out.lo + oo) = make_uint4(lo_[0], lo_[1], lo_[2], lo_[3]);
+    }
+}
+
+// ------------------------------------------------------------------ standalone BN / activation
+__global__ void affine_act_kernel(TView in, TView out, int64_t n_pix, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, int act1, float alpha1, int act2,
+                                  float alpha2) {
+    const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    const int64_t total = n_pix * cw;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t pix = i / cw;
+        const int ch = static_cast<int>(i - pix * cw);
+        float v = 0.0f;
+        if (ch < out.c) {
+            v = apply_act(tv_load(in, pix, ch), act1, alpha1);
+            v = fmaf(v, scale[ch], shift[ch]);
+            v = apply_act(v, act2, alpha2);
+        }
+        tv_store(out, pix, ch, v);
+    }
+}
+
+// ------------------------------------------------------------------ channel-slice copy / add
+__global__ void copy_channels_kernel(TView in, TView out, int64_t n_pix, int c_off) {
+    const int64_t total = n_pix * in.c;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t pix = i / in.c;
+        const int ch = static_cast<int>(i - pix * in.c);
+        tv_store(out, pix, c_off + ch, tv_load(in, pix, ch));
+    }
+}
+__global__ void zero_pad_channels_kernel(TView out, int64_t n_pix) {
+    const int npad = out.c_pad - out.c;
+    if (out.fmt != FMT_SPLIT || npad <= 0) return;
+    const int64_t total = n_pix * npad;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t pix = i / npad;
+        const int ch = out.c + static_cast<int>(i - pix * npad);
+        tv_store(out, pix, ch, 0.0f);
+    }
+}
+__global__ void add_kernel(TView a, TView b, TView out, int64_t n_pix) {
+    const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    const int64_t total = n_pix * cw;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t pix = i / cw;
+        const int ch = static_cast<int>(i - pix * cw);
+        const float v = ch < out.c ? tv_load(a, pix, ch) + tv_load(b, pix, ch) : 0.0f;
+        tv_store(out, pix, ch, v);
+    }
+}
+
+// ------------------------------------------------------------------ global pooling
+// one block per frame; thread t owns channels t, t+blockDim, ...; sums in fp32 over the
+// frame's pixels in index order (deterministic).
+__global__ void gpool_kernel(TView in, TView out, int pix_per_frame, int is_avg) {
+    const int64_t nf = blockIdx.x;
+    const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    for (int ch = threadIdx.x; ch < cw; ch += blockDim.x) {
+        float acc = is_avg ? 0.0f : -INFINITY;
+        if (ch < out.c) {
+            for (int px = 0; px < pix_per_frame; ++px) {
+                const float v = tv_load(in, nf * pix_per_frame + px, ch);
+                acc = is_avg ? acc + v : fmaxf(acc, v);
+            }
+            if (is_avg) acc = acc / static_cast<float>(pix_per_frame);
+        } else {
+            acc = 0.0f;
+        }
+        tv_store(out, nf, ch, acc);
+    }
+}
+
+// ------------------------------------------------------------------ softmax over channels
+// one warp per row; max-subtracted, fp32 (Keras Softmax / activation='softmax').
+__global__ void softmax_kernel(TView in, TView out, int64_t n_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const int c = in.c;
+    float mx = -INFINITY;
+    for (int ch = lane; ch < c; ch += 32) mx = fmaxf(mx, tv_load(in, row, ch));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+    for (int ch = lane; ch < c; ch += 32) sum += expf(tv_load(in, row, ch) - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int ch = lane; ch < c; ch += 32) tv_store(out, row, ch, expf(tv_load(in, row, ch) - mx) / sum);
+}
+
+// ------------------------------------------------------------------ argmax of fp16-rounded probs
+__global__ void argmax_fp16_kernel(const float* __restrict__ probs, int64_t n, int n_cls,
+                                   int32_t* __restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    if (row >= n) return;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int ch = lane; ch < n_cls; ch += 32) {
+        // np.float16 cast (RNE), then compare as the reference's np.argmax does
+        const float v = __half2float(__float2half_rn(probs[row * n_cls + ch]));
+        if (v > best || (v == best && ch < bi) || bi == 0x7fffffff) { best = v; bi = ch; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) {
+            best = ob;
+            bi = oi;
+        }
+    }
+    if (lane == 0) idx[row] = bi;
+}
+
+// =================================================================== Monte-Carlo sampler
+// Philox4x32-10 (Salmon et al. 2011), counter = (sample_lo, sample_hi, res_lo, res_hi).
+__device__ __host__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c[0];
+        const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c[2];
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c[1] ^ k0;
+        const uint32_t n1 = static_cast<uint32_t>(p1);
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c[3] ^ k1;
+        const uint32_t n3 = static_cast<uint32_t>(p0);
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+// 53-bit uniform in [0,1) from two 32-bit words, the same construction numpy's legacy
+// random_sample uses: (a>>5, b>>6) -> (a*2^26 + b) / 2^53.
+__device__ __host__ __forceinline__ double philox_uniform(uint64_t sample, uint64_t res,
+                                                          uint64_t seed, uint64_t stream_id) {
+    const uint64_t mix = stream_id * 0x9E3779B97F4A7C15ull;
+    uint32_t c[4] = {static_cast<uint32_t>(sample), static_cast<uint32_t>(sample >> 32),
+                     static_cast<uint32_t>(res), static_cast<uint32_t>(res >> 32)};
+    philox4x32_10(c, static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(mix >> 32),
+                  static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(mix));
+    const uint32_t a = c[0] >> 5, b = c[1] >> 6;
+    return (static_cast<double>(a) * 67108864.0 + static_cast<double>(b)) / 9007199254740992.0;
+}
+
+__global__ void sample_uniforms_kernel(int64_t n_res, int64_t n_samples, int64_t first_sample,
+                                       uint64_t seed, uint64_t stream_id, double* __restrict__ out) {
+    const int64_t total = n_res * n_samples;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t s = i / n_res;
+        out[i] = philox_uniform(static_cast<uint64_t>(first_sample + s),
+                                static_cast<uint64_t>(i - s * n_res), seed, stream_id);
+    }
+}
+
+// numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum),
+// restated so that the row sums of apply_temp_to_probs match np.sum(axis=1) add-for-add.
+__device__ double np_pairwise_sum(const double* a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += a[i];
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+// apply_temp_to_probs (sampling_utils.py:159-161): p ** (1/t), row sum, divide.  One thread
+// per row (rows are short: 20 or 338); fp64 throughout.
+__global__ void temperature_kernel(const double* __restrict__ in, int64_t n_rows, int n_cls,
+                                   double inv_t, double* __restrict__ out) {
+    const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (row >= n_rows) return;
+    const double* src = in + row * n_cls;
+    double* dst = out + row * n_cls;
+    for (int j = 0; j < n_cls; ++j) dst[j] = pow(src[j], inv_t);
+    const double s = np_pairwise_sum(dst, n_cls);
+    for (int j = 0; j < n_cls; ++j) dst[j] = dst[j] / s;
+}
+
+// probs.cumsum(axis=1): strictly sequential fp64 adds, one thread per row (bit-identical to numpy).
+__global__ void cumsum_rows_kernel(const double* __restrict__ in, int64_t n_rows, int n_cls,
+                                   double* __restrict__ out) {
+    const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (row >= n_rows) return;
+    double acc = 0.0;
+    for (int j = 0; j < n_cls; ++j) {
+        acc = j == 0 ? in[row * n_cls] : __dadd_rn(acc, in[row * n_cls + j]);
+        out[row * n_cls + j] = acc;
+    }
+}
+
+// Inverse-CDF draw.  Each thread owns 4 consecutive (sample, residue) cells of the flat
+// (n_samples, n_res) output and writes them as one 32-bit word (and one int4 of indices).
+// idx = first j with cdf[j] > r; none -> 0  ((cumsum > r).argmax(), sampling_utils.py:82).
+// The CDF is nondecreasing (cumsum of non-negative terms), so "first j with cdf[j] > r" ==
+// "number of j with cdf[j] <= r" -- a branch-free count for short rows, a binary search for
+// long ones.  NaN-safe in the same way as the reference: comparisons with NaN are false.
+__global__ void sample_kernel(const double* __restrict__ cdf, int64_t n_res, int n_cls,
+                              int64_t n_samples, int64_t first_sample, uint64_t seed,
+                              uint64_t stream_id, const double* __restrict__ uniforms,
+                              const uint8_t* __restrict__ letters, uint8_t* __restrict__ seqs,
+                              int32_t* __restrict__ idx_out) {
+    __shared__ uint8_t s_letters[512];
+    for (int i = threadIdx.x; i < n_cls && i < 512; i += blockDim.x) s_letters[i] = letters[i];
+    __syncthreads();
+    const int64_t total = n_res * n_samples;
+    const int64_t n_words = (total + 3) / 4;
+    for (int64_t wi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; wi < n_words;
+         wi += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        uint32_t packed = 0;
+        int32_t id4[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t flat = wi * 4 + e;
+            if (flat >= total) break;
+            const int64_t s = flat / n_res;
+            const int64_t res = flat - s * n_res;
+            const double r = uniforms ? uniforms[flat]
+                                      : philox_uniform(static_cast<uint64_t>(first_sample + s),
+                                                       static_cast<uint64_t>(res), seed, stream_id);
+            const double* row = cdf + res * n_cls;
+            int j;
+            if (n_cls <= 32) {
+                int cnt = 0;
+                for (int k = 0; k < n_cls; ++k) cnt += (__ldg(row + k) > r) ? 0 : 1;
+                // rows containing NaN are not monotone: fall back to the literal first-true scan
+                j = cnt;
+                if (cnt < n_cls && !(__ldg(row + cnt) > r)) {
+                    j = n_cls;
+                    for (int k = 0; k < n_cls; ++k)
+                        if (__ldg(row + k) > r) { j = k; break; }
+                }
+            } else {
+                int lo = 0, hi = n_cls;          // first index with cdf > r in [lo, hi]
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldg(row + mid) > r) hi = mid; else lo = mid + 1;
+                }
+                j = lo;
+            }
+            if (j >= n_cls) j = 0;               // no entry exceeds r -> argmax of all-False is 0
+            id4[e] = j;
+            packed |= static_cast<uint32_t>(s_letters[j]) << (8 * e);
+        }
+        if (wi * 4 + 3 < total) {
+            reinterpret_cast<uint32_t*>(seqs)[wi] = packed;
+            if (idx_out) reinterpret_cast<int4*>(idx_out)[wi] = make_int4(id4[0], id4[1], id4[2], id4[3]);
+        } else {
+            for (int e = 0; e < 4 && wi * 4 + e < total; ++e) {
+                seqs[wi * 4 + e] = static_cast<uint8_t>(packed >> (8 * e));
+                if (idx_out) idx_out[wi * 4 + e] = id4[e];
+            }
+        }
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace tb
