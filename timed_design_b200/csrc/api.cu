@@ -128,7 +128,10 @@ static void free_conv_plan(ConvPlan& p) {
     p.d_bias = p.d_scale = p.d_shift = nullptr;
 }
 
-static constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic smem minus alignment slack
+// 227 KB per CTA is the limit for static + dynamic shared memory; the kernel keeps < 1 KB static
+// (barriers), and 1 KB of the dynamic part is alignment slack.
+static constexpr size_t kSmemDynamicMax = 226 * 1024;
+static constexpr size_t kSmemBudget = kSmemDynamicMax - 1024;
 
 // Pick (kc, mt, kg, stages) for a conv given the number of output rows.
 static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* cfg) {
@@ -344,7 +347,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
 
     if (!g_conv_attr_set) {
         TB_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           227 * 1024));
+                                           static_cast<int>(kSmemDynamicMax)));
         g_conv_attr_set = true;
     }
     const int total_tiles = k.n_ctile_m * k.n_tiles;
