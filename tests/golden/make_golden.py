@@ -115,7 +115,12 @@ def main():
             np.random.seed(1000 * c + s)
             r = orig_rand(37)
             if s == 0:
-                r[:4] = [0.99999, 0.999999999, 1.0 - 2 ** -53, 0.0]   # no-true -> index 0 quirk; r = 0
+                # rows whose fp16-rounded probabilities sum to < 1: r just below 1 exceeds every
+                # cumsum entry -> (cumsum > r) is all False -> argmax returns 0 (the quirk)
+                short = np.where(probs.cumsum(axis=1)[:, -1] < 1.0)[0]
+                assert len(short) >= 2
+                r[short] = 1.0 - 2 ** -53
+                r[(short[0] + 1) % 37] = 0.0
             r_all[s] = r
             np.random.rand = lambda n, _r=r: _r.copy()
             try:

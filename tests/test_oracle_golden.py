@@ -32,8 +32,8 @@ def test_oracle_choice_index_matches_reference(sampler, c):
     for s in range(r.shape[0]):
         np.testing.assert_array_equal(so.choice_index(probs, r[s]), idx[s])
     # the "no cumsum entry exceeds r" quirk is in the fixture (sampling_utils.py:82)
-    assert (probs.cumsum(1)[:3, -1] <= r[0, :3]).any()
-    assert (idx[0, :3][probs.cumsum(1)[:3, -1] <= r[0, :3]] == 0).all()
+    no_true = probs.cumsum(1)[:, -1] <= r[0]
+    assert no_true.sum() >= 2 and (idx[0][no_true] == 0).all()
 
 
 def test_oracle_sequences_match_reference(sampler):

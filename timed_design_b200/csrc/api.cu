@@ -619,7 +619,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
     TB_REQUIRE(n_frames > 0, "n_frames must be positive");
     const Layout& L = get_layout(g, n_frames);
     TB_REQUIRE(ws_bytes >= L.total, "workspace too small (see timed_b200_graph_workspace_bytes)");
-    TB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
+    TB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
     uint8_t* base = static_cast<uint8_t*>(ws);
     const int n_ops = static_cast<int>(g->ops.size());
     for (int i = 0; i < n_ops; ++i) {

@@ -1,0 +1,199 @@
+"""Monte-Carlo sequence sampler on the GPU -- same function names and argument meaning as
+``/root/reference/design_utils/sampling_utils.py`` (lines cited per function).
+
+What changes underneath: instead of ``sample_n`` Python iterations per chain, each recomputing
+``probs.cumsum`` and drawing ``n_res`` uniforms from the global legacy numpy RNG inside a forked
+``multiprocessing.Pool``, one chain's whole (sample_n, n_res) block is drawn by a single kernel
+launch through libtimed_b200 (``timed_b200_sample``): the float64 CDF is built once on the
+device by a strictly sequential per-row cumsum (bit-identical to numpy), uniforms come from
+Philox4x32-10 keyed (seed, chain) with counter (sample, residue), and the letters land as one
+(sample_n, n_res) uint8 block.  torch tensors are used only as device-memory containers.
+
+Kept quirks (parity): a row whose cumsum never exceeds r yields class 0 ('A'); temperature 1
+skips renormalisation (that lives in sample.py).  Documented deviations: ``--seed`` is effective
+(the reference discards it, sample.py:21); ``workers`` is accepted and ignored.
+There is no CPU path: without libtimed_b200.so and a B200 these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import typing as t
+
+import numpy as np
+
+from . import _lib, seq_metrics
+from .postprocess import standard_amino_acids
+
+_state = {"seed": 42}
+
+
+def set_seed(seed: int) -> None:
+    """Seed of the counter-based generator used by all subsequent draws."""
+    _state["seed"] = int(seed)
+
+
+def _torch():
+    import torch
+    _lib.require_device()
+    return torch
+
+
+def _ptr(tensor):
+    return C.c_void_p(tensor.data_ptr()) if tensor is not None else None
+
+
+def _stream(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _letters_u8(rotamer_categories) -> np.ndarray:
+    cats = list(rotamer_categories) if rotamer_categories is not None and len(rotamer_categories) else \
+        list(standard_amino_acids.keys())
+    if any(len(c) != 1 for c in cats):
+        raise ValueError("categories must be one-letter codes (sample.py:50 maps rotamers to letters)")
+    return np.frombuffer("".join(cats).encode("ascii"), dtype=np.uint8).copy()
+
+
+# ----------------------------------------------------------------------------- temperature
+def apply_temp_to_probs(probs: np.ndarray, t: float = 1.0) -> np.ndarray:
+    """sampling_utils.py:139-161: ``p ** (1/t)`` renormalised per row, float64, on the device
+    (row sums in numpy's pairwise order).  Agrees with numpy to the last few ulps (CUDA ``pow``
+    is <= 2 ulp)."""
+    torch = _torch()
+    p = np.ascontiguousarray(np.array(probs, dtype=np.float64))
+    if p.ndim != 2:
+        raise ValueError("probs must be 2-D (n_residues, n_categories)")
+    if p.size == 0:
+        return p.copy()
+    d = torch.from_numpy(p).cuda()
+    out = torch.empty_like(d)
+    _lib.check(_lib.load().timed_b200_apply_temperature(_ptr(d), p.shape[0], p.shape[1], float(t),
+                                                        _ptr(out), _stream(torch)))
+    return out.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------- draws
+def sample_block(probs: np.ndarray, sample_n: int, rotamer_categories=None, *,
+                 uniforms: t.Optional[np.ndarray] = None, seed: t.Optional[int] = None,
+                 stream_id: int = 0, first_sample: int = 0, return_idx: bool = False,
+                 temperature: t.Optional[float] = None):
+    """Draw ``sample_n`` sequences for one chain in one launch.
+
+    probs: (n_res, C) float64 probabilities.  ``uniforms`` (sample_n, n_res) injects the random
+    numbers (parity hook for ``np.random.rand``); otherwise Philox(seed, stream_id) is used and
+    ``first_sample`` offsets the sample counter so that shards of one chain drawn on different
+    GPUs concatenate to exactly what a single GPU would draw.
+    Returns (letters uint8 (sample_n, n_res), idx int32 (sample_n, n_res) or None)."""
+    torch = _torch()
+    lib = _lib.load()
+    p = np.ascontiguousarray(np.array(probs, dtype=np.float64))
+    if p.ndim != 2:
+        raise ValueError("probs must be 2-D (n_residues, n_categories)")
+    n_res, n_cls = p.shape
+    letters = _letters_u8(rotamer_categories)
+    if len(letters) != n_cls:
+        raise ValueError(f"{n_cls} probability columns but {len(letters)} categories")
+    if n_res == 0 or sample_n == 0:
+        return np.zeros((sample_n, n_res), np.uint8), (np.zeros((sample_n, n_res), np.int32) if return_idx else None)
+    st = _stream(torch)
+    d_p = torch.from_numpy(p).cuda()
+    if temperature is not None and temperature != 1:
+        _lib.check(lib.timed_b200_apply_temperature(_ptr(d_p), n_res, n_cls, float(temperature), _ptr(d_p), st))
+    d_cdf = torch.empty_like(d_p)
+    _lib.check(lib.timed_b200_cumsum_rows(_ptr(d_p), n_res, n_cls, _ptr(d_cdf), st))
+    d_u = None
+    if uniforms is not None:
+        u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64))
+        if u.shape != (sample_n, n_res):
+            raise ValueError(f"uniforms must have shape {(sample_n, n_res)}, got {u.shape}")
+        d_u = torch.from_numpy(u).cuda()
+    d_letters = torch.from_numpy(letters).cuda()
+    n_cells = sample_n * n_res
+    d_seq = torch.empty((n_cells + 3) // 4 * 4, dtype=torch.uint8, device="cuda")
+    d_idx = torch.empty((n_cells + 3) // 4 * 4, dtype=torch.int32, device="cuda") if return_idx else None
+    _lib.check(lib.timed_b200_sample(_ptr(d_cdf), n_res, n_cls, sample_n, int(first_sample),
+                                     int(_state["seed"] if seed is None else seed) & (2 ** 64 - 1),
+                                     int(stream_id) & (2 ** 64 - 1), _ptr(d_u), _ptr(d_letters),
+                                     _ptr(d_seq), _ptr(d_idx), st))
+    seqs = d_seq[:n_cells].cpu().numpy().reshape(sample_n, n_res)
+    idx = d_idx[:n_cells].cpu().numpy().reshape(sample_n, n_res) if return_idx else None
+    return seqs, idx
+
+
+_draw_counter = {"n": 0}
+
+
+def random_choice_prob_index(probs: np.ndarray, axis: int = 1, return_seq: bool = True,
+                             rotamer_categories: t.Optional[t.Sequence[str]] = None, *,
+                             uniforms: t.Optional[np.ndarray] = None) -> np.ndarray:
+    """sampling_utils.py:53-90: one categorical draw per row (``axis=1``) of ``probs``; returns
+    the letters (``return_seq``) or the indices.  Successive calls advance the sample counter,
+    as successive ``np.random.rand`` calls advance the reference's generator."""
+    p = np.asarray(probs, dtype=np.float64)
+    if axis == 0:
+        p = p.T
+    elif axis != 1:
+        raise ValueError("axis must be 0 or 1")
+    u = None if uniforms is None else np.asarray(uniforms, dtype=np.float64).reshape(1, -1)
+    cats = rotamer_categories if (return_seq and rotamer_categories) else None
+    n = _draw_counter["n"]
+    _draw_counter["n"] += 1
+    if not return_seq and p.shape[1] != 20:
+        cats = ["A"] * p.shape[1]            # letters unused: indices requested
+    seqs, idx = sample_block(p, 1, cats, uniforms=u, first_sample=n, return_idx=not return_seq)
+    if return_seq:
+        return np.array(list(seqs[0].tobytes().decode("ascii")))
+    return idx[0].astype(np.int64)
+
+
+def _rows_to_tuples(seqs_u8: np.ndarray, with_metrics: bool = True) -> list:
+    strings = [row.tobytes().decode("ascii") for row in seqs_u8]
+    if not with_metrics or not strings:
+        return [(s,) for s in strings]
+    charge, pi, mw, ext = seq_metrics.metrics_from_composition(seq_metrics.composition(seqs_u8))
+    return [(s, float(c), float(p), float(m), float(e)) for s, c, p, m, e in zip(strings, charge, pi, mw, ext)]
+
+
+def sample_from_sequences(pdb: str, sample_n: int, pdb_to_probability: dict,
+                          rotamer_categories: t.Optional[t.Sequence[str]], *, stream_id: int = 0) -> dict:
+    """sampling_utils.py:93-136: ``{pdb: [(sequence, charge, pI, mw, ext280)] * sample_n}``."""
+    probs = np.array(pdb_to_probability[pdb], dtype=np.float64)
+    seqs, _ = sample_block(probs, int(sample_n), rotamer_categories, stream_id=stream_id)
+    return {pdb: _rows_to_tuples(seqs)}
+
+
+def sample_with_multiprocessing(workers, pdb_codes, sample_n, pdb_to_probability, flat_categories) -> dict:
+    """sampling_utils.py:164-197.  ``workers`` is accepted for compatibility and ignored: the
+    fan-out over chains is a loop of kernel launches, each chain keyed by its index so the
+    draws do not depend on how chains are distributed."""
+    out: dict = {}
+    for i, pdb in enumerate(pdb_codes):
+        out.update(sample_from_sequences(pdb, sample_n, pdb_to_probability, flat_categories, stream_id=i))
+    return out
+
+
+def save_as(pdb_to_sampled: dict, filename: str, mode: str) -> t.List[str]:
+    """sampling_utils.py:12-50: ``.json`` / ``.fasta`` (mode) and always ``_metrics.csv``, written
+    relative to the CWD like the reference."""
+    output_paths = []
+    print(f"Saving sampled sequences in mode {mode}")
+    if mode != "fasta":
+        path = f"{filename}.json"
+        output_paths.append(path)
+        with open(path, "w") as f:
+            json.dump(pdb_to_sampled, f)
+    if mode != "json":
+        path = f"{filename}.fasta"
+        output_paths.append(path)
+        with open(path, "w") as f:
+            for pdb, rows in pdb_to_sampled.items():
+                f.writelines(f">{pdb}_{i}\n{row[0]}\n" for i, row in enumerate(rows))
+    print("Saving Metrics")
+    path = f"{filename}_metrics.csv"
+    output_paths.append(path)
+    with open(path, "w") as f:
+        f.write("pdb,sequence,charge,isoelectric_point,molecular_weight,molar_extinction\n")
+        for pdb, rows in pdb_to_sampled.items():
+            f.writelines(f"{pdb},{r[0]},{r[1]},{r[2]},{r[3]},{r[4]}\n" for r in rows)
+    return output_paths
