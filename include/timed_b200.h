@@ -101,6 +101,16 @@ void timed_b200_graph_destroy(tb_graph* g);
  * conv/dense ops) */
 int timed_b200_graph_info(const tb_graph* g, int32_t* n_classes, double* flops_per_frame,
                           int32_t* n_kernel_launches_per_forward);
+/* number of fused ops in the graph */
+int timed_b200_graph_op_count(const tb_graph* g, int32_t* n_ops);
+/* Per-op device timing for bench.py's roofline line.  While enabled, every graph_forward records
+ * a CUDA event on its stream before the first op and after each op (up to 512 forwards).
+ * read_op_times waits for the recorded forwards, writes the SUM of elapsed milliseconds per op
+ * to ms_per_op[n_ops] (plus op kinds and algorithmic FLOPs/frame per op when non-NULL), the
+ * number of forwards summed to n_forwards, and clears the record. */
+int timed_b200_graph_set_timing(tb_graph* g, int32_t enabled);
+int timed_b200_graph_read_op_times(tb_graph* g, float* ms_per_op, int32_t* op_kinds,
+                                   double* op_flops_per_frame, int32_t* n_forwards);
 /* device workspace needed to run `n_frames` frames in one forward */
 int timed_b200_graph_workspace_bytes(const tb_graph* g, int64_t n_frames, size_t* out);
 /* Forward `n_frames` frames resident on the device.  d_frames: (n,D,H,W,C) of `frames_dtype`

@@ -1,0 +1,81 @@
+"""CPU: the C-ABI library loads without a GPU/driver and exports every symbol the header declares;
+host-side graph lowering and error behaviour."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from timed_design_b200 import _lib, standins
+from timed_design_b200.keras_graph import (OP_CONV3D, OP_GPOOL, OP_POOL3D, OP_SOFTMAX, UnsupportedLayerError,
+                                           parse_model_config)
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = (ROOT / "include" / "timed_b200.h").read_text()
+    declared = set(re.findall(r"\b(timed_b200_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.timed_b200_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device(lib):
+    if lib.timed_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    from timed_design_b200.model import Model
+    cfg, w = standins.tiny_standin(calib_frames=0)
+    with pytest.raises(_lib.TimedB200Error):
+        Model(cfg, w)
+    from timed_design_b200 import sampling_utils
+    with pytest.raises(_lib.TimedB200Error):
+        sampling_utils.apply_temp_to_probs(np.full((2, 20), 0.05), 0.5)
+
+
+def test_timed_standin_lowers_to_fused_ops():
+    cfg, w = standins.timed_standin(calib_frames=0)
+    g = parse_model_config(cfg, w)
+    kinds = [op.kind for op in g.ops]
+    assert kinds.count(OP_CONV3D) == 6 and kinds.count(OP_POOL3D) == 2
+    assert kinds[-2:] == [OP_GPOOL, OP_SOFTMAX]
+    conv = [op for op in g.ops if op.kind == OP_CONV3D]
+    assert all(op.fused == ["Conv3D", "ELU", "BatchNormalization"] for op in conv)
+    assert all(op.act1 == 2 and op.scale is not None and op.act2 == 0 for op in conv)
+    # SURVEY.md App. E / BASELINE.md: algorithmic FLOPs per frame
+    assert abs(g.flops_per_frame() - 2.3692e9) < 1e5
+    cfg, w = standins.timed_standin(338, calib_frames=0)
+    assert abs(parse_model_config(cfg, w).flops_per_frame() - 4.2683e9) < 1e5
+    cfg, w = standins.densecpd_standin(calib_frames=0)
+    assert abs(parse_model_config(cfg, w).flops_per_frame() - 17.0986e9) < 1e5
+
+
+def test_bn_fold_matches_definition():
+    cfg, w = standins.tiny_standin(calib_frames=0)
+    g = parse_model_config(cfg, w)
+    op = [o for o in g.ops if o.kind == OP_CONV3D][0]
+    bn = w["batch_normalization"]
+    x = np.linspace(-2, 2, 7)[:, None]
+    ref = bn["gamma:0"] * (x - bn["moving_mean:0"]) / np.sqrt(bn["moving_variance:0"] + 1e-3) + bn["beta:0"]
+    np.testing.assert_allclose(x * op.scale + op.shift, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_sequential_config_and_unsupported_layers():
+    cfg, w = standins.tiny_standin(calib_frames=0)
+    layers = [{"class_name": l["class_name"], "config": l["config"]} for l in cfg["config"]["layers"]]
+    seq = {"class_name": "Sequential", "config": {"name": "seq", "layers": layers}}
+    g = parse_model_config(seq, w)
+    assert g.n_classes == 20 and len(g.ops) == len(parse_model_config(cfg, w).ops)
+    bad = {"class_name": "Sequential", "config": {"name": "bad", "layers": layers[:2] + [
+        {"class_name": "LSTM", "config": {"name": "lstm"}}]}}
+    with pytest.raises(UnsupportedLayerError):
+        parse_model_config(bad, w)
+    with pytest.raises(KeyError):
+        parse_model_config(cfg, {})            # missing weights fail loudly
+
+
+def test_synthetic_frames_are_index_deterministic():
+    a = standins.synthetic_frames(6, side=9)
+    b = standins.synthetic_frames(3, side=9, first_index=3)
+    np.testing.assert_array_equal(a[3:], b)

@@ -391,6 +391,11 @@ struct tb_graph {
     size_t probs_bytes = 0;
     cudaStream_t s_copy = nullptr, s_compute = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    // per-op device timing (timed_b200_graph_set_timing): one event set per recorded forward
+    bool timing = false;
+    std::vector<std::vector<cudaEvent_t>> timing_sets;   // [forward][n_ops + 1]
+    size_t timing_used = 0;
+    static constexpr size_t kMaxTimedForwards = 512;
 };
 
 namespace tb {
@@ -622,6 +627,16 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
     TB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
     uint8_t* base = static_cast<uint8_t*>(ws);
     const int n_ops = static_cast<int>(g->ops.size());
+    std::vector<cudaEvent_t>* tset = nullptr;
+    if (g->timing && g->timing_used < tb_graph::kMaxTimedForwards) {
+        if (g->timing_used == g->timing_sets.size()) {
+            std::vector<cudaEvent_t> evs(n_ops + 1);
+            for (auto& e : evs) TB_CHECK_CUDA(cudaEventCreate(&e));
+            g->timing_sets.push_back(std::move(evs));
+        }
+        tset = &g->timing_sets[g->timing_used++];
+        TB_CHECK_CUDA(cudaEventRecord((*tset)[0], s));
+    }
     for (int i = 0; i < n_ops; ++i) {
         OpNode& node = g->ops[i];
         const tb_op_desc& d = node.d;
@@ -693,6 +708,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 TB_REQUIRE(false, "unknown op kind");
         }
         TB_CHECK_CUDA(cudaGetLastError());
+        if (tset) TB_CHECK_CUDA(cudaEventRecord((*tset)[i + 1], s));
     }
     return 0;
 }
@@ -700,6 +716,8 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
 static void graph_free(tb_graph* g) {
     if (!g) return;
     cudaSetDevice(g->device);
+    for (auto& set : g->timing_sets)
+        for (auto& e : set) cudaEventDestroy(e);
     for (auto& n : g->ops) {
         free_conv_plan(n.conv);
         cudaFree(n.d_scale);
@@ -777,6 +795,44 @@ int timed_b200_graph_info(const tb_graph* g, int32_t* n_classes, double* flops_p
     if (n_classes) *n_classes = g->n_classes;
     if (flops_per_frame) *flops_per_frame = g->flops;
     if (n_kernel_launches_per_forward) *n_kernel_launches_per_forward = g->launches;
+    return TB_OK;
+}
+
+int timed_b200_graph_op_count(const tb_graph* g, int32_t* n_ops) {
+    TB_REQUIRE(g && n_ops, "null argument");
+    *n_ops = static_cast<int32_t>(g->ops.size());
+    return TB_OK;
+}
+
+int timed_b200_graph_set_timing(tb_graph* g, int32_t enabled) {
+    TB_REQUIRE(g, "null graph");
+    g->timing = enabled != 0;
+    g->timing_used = 0;
+    return TB_OK;
+}
+
+int timed_b200_graph_read_op_times(tb_graph* g, float* ms_per_op, int32_t* op_kinds,
+                                   double* op_flops_per_frame, int32_t* n_forwards) {
+    TB_REQUIRE(g && ms_per_op && n_forwards, "null argument");
+    TB_CHECK_CUDA(cudaSetDevice(g->device));
+    const int n_ops = static_cast<int>(g->ops.size());
+    for (int i = 0; i < n_ops; ++i) {
+        ms_per_op[i] = 0.f;
+        if (op_kinds) op_kinds[i] = g->ops[i].d.op;
+        if (op_flops_per_frame)
+            op_flops_per_frame[i] = g->ops[i].d.op == TB_OP_CONV3D ? g->ops[i].conv.flops_per_frame() : 0.0;
+    }
+    for (size_t f = 0; f < g->timing_used; ++f) {
+        auto& set = g->timing_sets[f];
+        TB_CHECK_CUDA(cudaEventSynchronize(set[n_ops]));
+        for (int i = 0; i < n_ops; ++i) {
+            float ms = 0.f;
+            TB_CHECK_CUDA(cudaEventElapsedTime(&ms, set[i], set[i + 1]));
+            ms_per_op[i] += ms;
+        }
+    }
+    *n_forwards = static_cast<int32_t>(g->timing_used);
+    g->timing_used = 0;
     return TB_OK;
 }
 

@@ -87,6 +87,22 @@ class Model:
             workspace.numel() * workspace.element_size(), C.c_void_p(probs.data_ptr()),
             C.c_void_p(stream)))
 
+    def set_timing(self, enabled: bool) -> None:
+        """Record CUDA events around every fused op of subsequent forwards (bench roofline)."""
+        _lib.check(_lib.load().timed_b200_graph_set_timing(self._h, int(bool(enabled))))
+
+    def read_op_times(self):
+        """-> (list of dicts per op: kind, name, ms (summed), flops_per_frame), n_forwards)."""
+        n = len(self.graph.ops)
+        ms = (C.c_float * n)()
+        kinds = (C.c_int32 * n)()
+        flops = (C.c_double * n)()
+        nf = C.c_int32()
+        _lib.check(_lib.load().timed_b200_graph_read_op_times(self._h, ms, kinds, flops, C.byref(nf)))
+        ops = [{"index": i, "kind": int(kinds[i]), "name": self.graph.ops[i].name, "ms": float(ms[i]),
+                "flops_per_frame": float(flops[i])} for i in range(n)]
+        return ops, nf.value
+
     def close(self) -> None:
         if self._h:
             _lib.load().timed_b200_graph_destroy(self._h)

@@ -337,9 +337,9 @@ def prodconn_standin(n_classes: int = 20, c_in: int = 6, seed: int = 13, side: i
 
 
 def tiny_standin(n_classes: int = 20, c_in: int = 6, seed: int = 3, side: int = 9,
-                 filters=(16, 32)):
+                 filters=(16, 32), **kw):
     """Small TIMED-shaped graph for fast parity tests (oracle runs in milliseconds)."""
-    return timed_standin(n_classes, c_in, seed, filters, side)
+    return timed_standin(n_classes, c_in, seed, filters, side, **kw)
 
 
 def conv_flops_per_frame(model_config: dict) -> float:
@@ -357,6 +357,7 @@ def synthetic_frames(n: int, side: int = 21, c: int = 6, seed: int = 1234,
     sigma ~0.6 voxel, channel uniform over ``c``."""
     out = np.zeros((n, side, side, side, c), dtype=dtype)
     ax = np.arange(side, dtype=np.float64)
+    sig = 0.6
     for i in range(n):
         r = np.random.default_rng([seed, first_index + i])
         na = int(r.integers(40, 121))
@@ -364,11 +365,10 @@ def synthetic_frames(n: int, side: int = 21, c: int = 6, seed: int = 1234,
         # per-frame channel mix (Dirichlet) so frames differ in composition, not just position
         mix = r.dirichlet(np.full(c, 0.7))
         ch = r.choice(c, size=na, p=mix)
-        sig = 0.6
-        gx = np.exp(-0.5 * ((ax[None, :] - pos[:, 0:1]) / sig) ** 2)
-        gy = np.exp(-0.5 * ((ax[None, :] - pos[:, 1:2]) / sig) ** 2)
-        gz = np.exp(-0.5 * ((ax[None, :] - pos[:, 2:3]) / sig) ** 2)
-        for a in range(na):
-            out[i, :, :, :, ch[a]] += (gx[a][:, None, None] * gy[a][None, :, None]
-                                        * gz[a][None, None, :]).astype(dtype)
+        g = np.exp(-0.5 * ((ax[None, None, :] - pos.T[:, :, None]) / sig) ** 2)   # (3, na, side)
+        for k in range(c):
+            m = ch == k
+            if m.any():
+                out[i, :, :, :, k] = np.einsum("ax,ay,az->xyz", g[0, m], g[1, m], g[2, m],
+                                               optimize=True).astype(dtype)
     return out
