@@ -1,0 +1,612 @@
+"""Minimal pure-Python HDF5 reader (no libhdf5 / h5py in this image).
+
+Covers what Keras-2 ``.h5`` model files (predict.py:121) and aposteriori frame datasets
+(design_utils/utils.py:238-251, 487-530) contain when written by h5py with default settings:
+superblock v0/v1 (and v2/v3), v1 and v2 object headers with continuation blocks, old-style
+groups (symbol table: v1 B-tree + local heap + SNOD) and new-style groups with compact link
+messages, contiguous / compact / chunked (v1 B-tree index) datasets, deflate + shuffle +
+fletcher32 filters, attributes (message versions 1-3) of fixed-point, floating-point, enum
+(h5py bool), fixed-length string and variable-length string (global heap) types.
+
+Anything else (dense link/attribute storage in fractal heaps, v4 chunk indexes, compound or
+reference types, external storage) raises ``Hdf5FormatError`` naming the feature -- never a
+silent wrong answer.  Written from the published HDF5 File Format Specification (v3.0); no real
+h5py-written file is available offline, so the reader is validated against this package's own
+writer ("real-file parity unpinned").
+"""
+from __future__ import annotations
+
+import struct
+import zlib
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+SIGNATURE = b"\x89HDF\r\n\x1a\n"
+UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+class Hdf5FormatError(NotImplementedError):
+    pass
+
+
+class _Type:
+    """Decoded datatype message."""
+
+    def __init__(self, cls, size, dtype=None, vlen_string=False, vlen_base=None, charset="ascii",
+                 enum_base=None, strpad=0):
+        self.cls, self.size, self.dtype = cls, size, dtype
+        self.vlen_string, self.vlen_base, self.charset = vlen_string, vlen_base, charset
+        self.enum_base, self.strpad = enum_base, strpad
+
+
+def _parse_datatype(buf: bytes, off: int = 0) -> Tuple[_Type, int]:
+    """-> (type, bytes consumed)."""
+    cv, b0, b1, b2, size = struct.unpack_from("<BBBBI", buf, off)
+    cls, version = cv & 0x0F, cv >> 4
+    p = off + 8
+    if cls == 0:      # fixed-point
+        order = ">" if b0 & 1 else "<"
+        signed = bool(b0 & 0x08)
+        if size not in (1, 2, 4, 8):
+            raise Hdf5FormatError(f"fixed-point size {size}")
+        return _Type(0, size, np.dtype(f"{order}{'i' if signed else 'u'}{size}")), p + 4 - off
+    if cls == 1:      # floating point
+        order = ">" if b0 & 1 else "<"
+        if size not in (2, 4, 8):
+            raise Hdf5FormatError(f"float size {size}")
+        return _Type(1, size, np.dtype(f"{order}f{size}")), p + 12 - off
+    if cls == 3:      # fixed-length string
+        charset = "utf-8" if (b0 >> 4) & 0x0F == 1 else "ascii"
+        return _Type(3, size, np.dtype(f"S{size}"), charset=charset, strpad=b0 & 0x0F), p - off
+    if cls == 9:      # variable length
+        kind = b0 & 0x0F
+        charset = "utf-8" if b1 & 0x0F == 1 else "ascii"
+        base, used = _parse_datatype(buf, p)
+        return _Type(9, size, None, vlen_string=(kind == 1), vlen_base=base, charset=charset), p + used - off
+    if cls == 8:      # enumeration (h5py stores numpy bool as ENUM{FALSE,TRUE} over int8)
+        n_members = b0 | (b1 << 8)
+        base, used = _parse_datatype(buf, p)
+        q = p + used
+        for _ in range(n_members):
+            end = buf.index(b"\x00", q)
+            name_len = end - q + 1
+            if version < 3:
+                name_len = (name_len + 7) // 8 * 8
+            q += name_len
+        q += n_members * base.size
+        return _Type(8, size, base.dtype, enum_base=base), q - off
+    if cls == 6:
+        raise Hdf5FormatError("compound datatypes are not supported")
+    if cls == 7:
+        raise Hdf5FormatError("reference datatypes are not supported")
+    if cls == 10:     # array
+        raise Hdf5FormatError("array datatypes are not supported")
+    raise Hdf5FormatError(f"datatype class {cls}")
+
+
+def _parse_dataspace(buf: bytes) -> Optional[Tuple[int, ...]]:
+    """-> shape, () for scalar, None for a null dataspace."""
+    version, rank, flags = struct.unpack_from("<BBB", buf, 0)
+    if version == 1:
+        p = 8
+    elif version == 2:
+        if buf[3] == 2:
+            return None
+        p = 4
+    else:
+        raise Hdf5FormatError(f"dataspace message version {version}")
+    return tuple(struct.unpack_from(f"<{rank}Q", buf, p)) if rank else ()
+
+
+class _Message:
+    __slots__ = ("type", "data", "flags")
+
+    def __init__(self, mtype, data, flags):
+        self.type, self.data, self.flags = mtype, data, flags
+
+
+class File:
+    """Read-only view of an HDF5 file held in memory.  ``f["a/b"]`` -> Group or Dataset."""
+
+    def __init__(self, path):
+        with open(path, "rb") as fh:
+            self.buf = fh.read()
+        self.path = str(path)
+        self._gcol_cache: Dict[int, Dict[int, bytes]] = {}
+        self._parse_superblock()
+        self.root = Group(self, self.root_addr, "/")
+
+    # context-manager sugar to read like h5py
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def __getitem__(self, key):
+        return self.root[key]
+
+    def __contains__(self, key):
+        return key in self.root
+
+    def __iter__(self):
+        return iter(self.root)
+
+    def keys(self):
+        return self.root.keys()
+
+    @property
+    def attrs(self):
+        return self.root.attrs
+
+    # ------------------------------------------------------------------ low level
+    def _parse_superblock(self):
+        buf = self.buf
+        base = 0
+        while True:
+            if buf[base:base + 8] == SIGNATURE:
+                break
+            base = 512 if base == 0 else base * 2
+            if base + 8 > len(buf):
+                raise Hdf5FormatError(f"{self.path}: not an HDF5 file (no superblock signature)")
+        version = buf[base + 8]
+        if version in (0, 1):
+            so, sl = buf[base + 13], buf[base + 14]
+            if (so, sl) != (8, 8):
+                raise Hdf5FormatError(f"size of offsets/lengths {so}/{sl} (only 8/8)")
+            p = base + 24 + (4 if version == 1 else 0)
+            self.base_addr = struct.unpack_from("<Q", buf, p)[0]
+            # root group symbol table entry follows the four addresses
+            entry = p + 32
+            self.root_addr = struct.unpack_from("<Q", buf, entry + 8)[0]
+        elif version in (2, 3):
+            so, sl = buf[base + 9], buf[base + 10]
+            if (so, sl) != (8, 8):
+                raise Hdf5FormatError(f"size of offsets/lengths {so}/{sl} (only 8/8)")
+            self.base_addr = struct.unpack_from("<Q", buf, base + 12)[0]
+            self.root_addr = struct.unpack_from("<Q", buf, base + 12 + 24)[0]
+        else:
+            raise Hdf5FormatError(f"superblock version {version}")
+        if self.base_addr not in (0, base):
+            raise Hdf5FormatError("non-zero base address")
+        self.base_addr = base if self.base_addr == base and base else 0
+
+    def _messages(self, addr: int) -> List[_Message]:
+        buf = self.buf
+        addr += self.base_addr
+        msgs: List[_Message] = []
+        if buf[addr:addr + 4] == b"OHDR":
+            if buf[addr + 4] != 2:
+                raise Hdf5FormatError(f"object header version {buf[addr + 4]}")
+            flags = buf[addr + 5]
+            p = addr + 6
+            if flags & 0x20:
+                p += 16
+            if flags & 0x10:
+                p += 4
+            szw = 1 << (flags & 0x03)
+            chunk0 = int.from_bytes(buf[p:p + szw], "little")
+            p += szw
+            blocks = [(p, chunk0)]
+            track_order = bool(flags & 0x04)
+            while blocks:
+                start, length = blocks.pop(0)
+                q, end = start, start + length
+                while q + 4 <= end:
+                    mtype = buf[q]
+                    msize = struct.unpack_from("<H", buf, q + 1)[0]
+                    mflags = buf[q + 3]
+                    q += 4 + (2 if track_order else 0)
+                    data = buf[q:q + msize]
+                    q += msize
+                    if mtype == 0x10:
+                        off, ln = struct.unpack_from("<QQ", data, 0)
+                        off += self.base_addr
+                        if buf[off:off + 4] != b"OCHK":
+                            raise Hdf5FormatError("bad object header continuation block")
+                        blocks.append((off + 4, ln - 8))      # minus signature and checksum
+                    elif mtype != 0:
+                        msgs.append(_Message(mtype, data, mflags))
+            return msgs
+        version = buf[addr]
+        if version != 1:
+            raise Hdf5FormatError(f"object header version {version} at {addr}")
+        n_msgs = struct.unpack_from("<H", buf, addr + 2)[0]
+        hdr_size = struct.unpack_from("<I", buf, addr + 8)[0]
+        blocks = [(addr + 16, hdr_size)]
+        while blocks and len(msgs) < n_msgs + 64:
+            start, length = blocks.pop(0)
+            q, end = start, start + length
+            while q + 8 <= end:
+                mtype, msize, mflags = struct.unpack_from("<HHB", buf, q)
+                data = buf[q + 8:q + 8 + msize]
+                q += 8 + msize
+                if mtype == 0x10:
+                    off, ln = struct.unpack_from("<QQ", data, 0)
+                    blocks.append((off + self.base_addr, ln))
+                elif mtype != 0:
+                    msgs.append(_Message(mtype, data, mflags))
+        return msgs
+
+    def _local_heap_data(self, addr: int) -> int:
+        addr += self.base_addr
+        if self.buf[addr:addr + 4] != b"HEAP":
+            raise Hdf5FormatError("bad local heap signature")
+        return struct.unpack_from("<Q", self.buf, addr + 24)[0] + self.base_addr
+
+    def _cstr(self, off: int) -> str:
+        end = self.buf.index(b"\x00", off)
+        return self.buf[off:end].decode("utf-8")
+
+    def _group_btree_links(self, btree: int, heap_data: int, out: Dict[str, int]):
+        buf = self.buf
+        a = btree + self.base_addr
+        if buf[a:a + 4] != b"TREE":
+            raise Hdf5FormatError("bad group B-tree signature")
+        ntype, level, used = struct.unpack_from("<BBH", buf, a + 4)
+        if ntype != 0:
+            raise Hdf5FormatError("group B-tree node of wrong type")
+        p = a + 8 + 16
+        for i in range(used):
+            child = struct.unpack_from("<Q", buf, p + 8)[0]      # key_i (8) then child_i (8)
+            p += 16
+            if level > 0:
+                self._group_btree_links(child, heap_data, out)
+            else:
+                s = child + self.base_addr
+                if buf[s:s + 4] != b"SNOD":
+                    raise Hdf5FormatError("bad symbol table node signature")
+                n_sym = struct.unpack_from("<H", buf, s + 6)[0]
+                for k in range(n_sym):
+                    e = s + 8 + 40 * k
+                    name_off, obj = struct.unpack_from("<QQ", buf, e)
+                    out[self._cstr(heap_data + name_off)] = obj
+
+    def _global_heap_object(self, addr: int, index: int) -> bytes:
+        col = self._gcol_cache.get(addr)
+        if col is None:
+            buf = self.buf
+            a = addr + self.base_addr
+            if buf[a:a + 4] != b"GCOL":
+                raise Hdf5FormatError("bad global heap signature")
+            size = struct.unpack_from("<Q", buf, a + 8)[0]
+            col = {}
+            p, end = a + 16, a + size
+            while p + 16 <= end:
+                idx, _, _, osz = struct.unpack_from("<HHIQ", buf, p)
+                if idx == 0:
+                    break
+                col[idx] = buf[p + 16:p + 16 + osz]
+                p += 16 + (osz + 7) // 8 * 8
+            self._gcol_cache[addr] = col
+        return col[index]
+
+    def _decode(self, raw: bytes, typ: _Type, shape):
+        """Raw element bytes -> numpy array / python object shaped like `shape`."""
+        n = int(np.prod(shape)) if shape else 1
+        if typ.cls == 9:
+            items = []
+            for i in range(n):
+                ln, gaddr, gidx = struct.unpack_from("<IQI", raw, 16 * i)
+                if ln == 0 and gaddr in (0, UNDEF):
+                    data = b""
+                else:
+                    data = self._global_heap_object(gaddr, gidx)
+                if typ.vlen_string:
+                    items.append(data[:ln].decode("utf-8", "replace"))
+                else:
+                    items.append(np.frombuffer(data, dtype=typ.vlen_base.dtype, count=ln).copy())
+            if shape == ():
+                return items[0]
+            arr = np.empty(n, dtype=object)
+            arr[:] = items
+            return arr.reshape(shape)
+        arr = np.frombuffer(raw, dtype=typ.dtype, count=n)
+        if typ.cls == 8 and typ.enum_base.size == 1:
+            arr = arr.astype(np.bool_)            # h5py bool
+        if typ.cls == 3:
+            if shape == ():
+                return arr[0].rstrip(b"\x00 ") if typ.strpad else arr[0].split(b"\x00")[0]
+            return arr.reshape(shape).copy()
+        if shape == ():
+            return arr.reshape(()).copy()[()]
+        return arr.reshape(shape).copy()
+
+
+class _Attrs:
+    def __init__(self, f: File, msgs: List[_Message]):
+        self._f = f
+        self._raw: Dict[str, Tuple[_Type, tuple, bytes]] = {}
+        for m in msgs:
+            if m.type == 0x15:
+                info_flags = m.data[1]
+                p = 2 + (2 if info_flags & 1 else 0)
+                heap = struct.unpack_from("<Q", m.data, p)[0]
+                if heap != UNDEF:
+                    raise Hdf5FormatError("dense attribute storage (fractal heap) is not supported")
+            if m.type != 0x0C:
+                continue
+            d = m.data
+            version = d[0]
+            nsz, tsz, ssz = struct.unpack_from("<HHH", d, 2)
+            if version == 1:
+                p = 8
+                pad = lambda x: (x + 7) // 8 * 8
+            elif version == 2:
+                p = 8
+                pad = lambda x: x
+            elif version == 3:
+                p = 9
+                pad = lambda x: x
+            else:
+                raise Hdf5FormatError(f"attribute message version {version}")
+            if version >= 2 and d[1] & 0x03:
+                raise Hdf5FormatError("shared attribute datatype/dataspace")
+            name = d[p:p + nsz].split(b"\x00")[0].decode("utf-8")
+            p += pad(nsz)
+            typ, _ = _parse_datatype(d, p)
+            p += pad(tsz)
+            shape = _parse_dataspace(d[p:p + ssz])
+            p += pad(ssz)
+            self._raw[name] = (typ, shape, d[p:])
+
+    def keys(self):
+        return self._raw.keys()
+
+    def items(self):
+        return [(k, self[k]) for k in self._raw]
+
+    def __iter__(self):
+        return iter(self._raw)
+
+    def __contains__(self, k):
+        return k in self._raw
+
+    def get(self, k, default=None):
+        return self[k] if k in self._raw else default
+
+    def __getitem__(self, k):
+        if k not in self._raw:
+            raise KeyError(f"no attribute '{k}' (has {list(self._raw)})")
+        typ, shape, raw = self._raw[k]
+        if shape is None:
+            return None
+        return self._f._decode(raw, typ, shape)
+
+
+class _Object:
+    def __init__(self, f: File, addr: int, name: str):
+        self._f, self._addr, self.name = f, addr, name
+        self._msgs = f._messages(addr)
+        self._attrs = None
+
+    @property
+    def attrs(self) -> _Attrs:
+        if self._attrs is None:
+            self._attrs = _Attrs(self._f, self._msgs)
+        return self._attrs
+
+
+class Group(_Object):
+    def __init__(self, f, addr, name):
+        super().__init__(f, addr, name)
+        self._links: Optional[Dict[str, int]] = None
+
+    def _load(self) -> Dict[str, int]:
+        if self._links is not None:
+            return self._links
+        links: Dict[str, int] = {}
+        for m in self._msgs:
+            if m.type == 0x11:        # symbol table
+                btree, heap = struct.unpack_from("<QQ", m.data, 0)
+                self._f._group_btree_links(btree, self._f._local_heap_data(heap), links)
+            elif m.type == 0x02:      # link info
+                flags = m.data[1]
+                p = 2 + (8 if flags & 1 else 0)
+                fheap = struct.unpack_from("<Q", m.data, p)[0]
+                if fheap != UNDEF:
+                    raise Hdf5FormatError("dense link storage (fractal heap) is not supported")
+            elif m.type == 0x06:      # link message
+                d = m.data
+                flags = d[1]
+                p = 2
+                ltype = 0
+                if flags & 0x08:
+                    ltype = d[p]
+                    p += 1
+                if flags & 0x04:
+                    p += 8
+                if flags & 0x10:
+                    p += 1
+                lsz = 1 << (flags & 0x03)
+                nlen = int.from_bytes(d[p:p + lsz], "little")
+                p += lsz
+                name = d[p:p + nlen].decode("utf-8")
+                p += nlen
+                if ltype != 0:
+                    raise Hdf5FormatError("soft/external links are not supported")
+                links[name] = struct.unpack_from("<Q", d, p)[0]
+        # h5py iterates old-style groups in name order (B-tree order); keep that for new-style too
+        self._links = dict(sorted(links.items()))
+        return self._links
+
+    def keys(self):
+        return list(self._load().keys())
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self._load())
+
+    def __contains__(self, key):
+        try:
+            self[key]
+            return True
+        except KeyError:
+            return False
+
+    def __getitem__(self, key: str):
+        node = self
+        for part in [p for p in str(key).split("/") if p]:
+            if not isinstance(node, Group):
+                raise KeyError(key)
+            links = node._load()
+            if part not in links:
+                raise KeyError(f"'{part}' not found in group {node.name} of {self._f.path}")
+            addr = links[part]
+            child_name = (node.name.rstrip("/") + "/" + part)
+            msgs = self._f._messages(addr)
+            is_dataset = any(m.type == 0x08 for m in msgs)
+            node = Dataset(self._f, addr, child_name) if is_dataset else Group(self._f, addr, child_name)
+        return node
+
+
+class Dataset(_Object):
+    def __init__(self, f, addr, name):
+        super().__init__(f, addr, name)
+        self._type = self._shape = self._layout = None
+        self._filters: List[Tuple[int, Tuple[int, ...]]] = []
+        for m in self._msgs:
+            if m.type == 0x03:
+                self._type, _ = _parse_datatype(m.data, 0)
+            elif m.type == 0x01:
+                self._shape = _parse_dataspace(m.data)
+            elif m.type == 0x08:
+                self._layout = m.data
+            elif m.type == 0x0B:
+                self._filters = self._parse_filters(m.data)
+        if self._type is None or self._layout is None:
+            raise Hdf5FormatError(f"{name}: dataset without datatype/layout message")
+
+    @staticmethod
+    def _parse_filters(d: bytes):
+        version, n = d[0], d[1]
+        out = []
+        p = 8 if version == 1 else 2
+        for _ in range(n):
+            fid = struct.unpack_from("<H", d, p)[0]
+            p += 2
+            if version == 1 or fid >= 256:
+                nlen = struct.unpack_from("<H", d, p)[0]
+                p += 2
+            else:
+                nlen = 0
+            _, ncd = struct.unpack_from("<HH", d, p)
+            p += 4
+            if version == 1:
+                nlen = (nlen + 7) // 8 * 8
+            p += nlen
+            cd = struct.unpack_from(f"<{ncd}I", d, p)
+            p += 4 * ncd
+            if version == 1 and ncd % 2:
+                p += 4
+            out.append((fid, cd))
+        return out
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @property
+    def dtype(self):
+        if self._type.cls == 8 and self._type.enum_base.size == 1:
+            return np.dtype(np.bool_)
+        return self._type.dtype if self._type.dtype is not None else np.dtype(object)
+
+    def _unfilter(self, raw: bytes, mask: int) -> bytes:
+        for i in reversed(range(len(self._filters))):
+            if mask & (1 << i):
+                continue
+            fid, cd = self._filters[i]
+            if fid == 1:
+                raw = zlib.decompress(raw)
+            elif fid == 2:
+                esz = cd[0] if cd else self._type.size
+                n = len(raw) // esz
+                body = np.frombuffer(raw[:n * esz], dtype=np.uint8).reshape(esz, n).T.tobytes()
+                raw = body + raw[n * esz:]
+            elif fid == 3:
+                raw = raw[:-4]
+            else:
+                raise Hdf5FormatError(f"filter id {fid} is not supported (deflate/shuffle/fletcher32 only)")
+        return raw
+
+    def _chunks(self, addr: int, rank: int, out: list):
+        buf = self._f.buf
+        a = addr + self._f.base_addr
+        if buf[a:a + 4] != b"TREE":
+            raise Hdf5FormatError("bad chunk B-tree signature")
+        ntype, level, used = struct.unpack_from("<BBH", buf, a + 4)
+        if ntype != 1:
+            raise Hdf5FormatError("chunk B-tree node of wrong type")
+        key_size = 8 + 8 * (rank + 1)
+        p = a + 24
+        for _ in range(used):
+            csize, mask = struct.unpack_from("<II", buf, p)
+            offs = struct.unpack_from(f"<{rank}Q", buf, p + 8)
+            child = struct.unpack_from("<Q", buf, p + key_size)[0]
+            p += key_size + 8
+            if level > 0:
+                self._chunks(child, rank, out)
+            else:
+                out.append((offs, csize, mask, child))
+
+    def __getitem__(self, key):
+        arr = self._read()
+        if key == () or key is Ellipsis:
+            return arr
+        return arr[key]
+
+    def _read(self):
+        f, lay, typ = self._f, self._layout, self._type
+        shape = self._shape
+        if shape is None:
+            return None
+        n = int(np.prod(shape)) if shape else 1
+        esz = typ.size
+        version = lay[0]
+        if version == 3:
+            cls = lay[1]
+            if cls == 0:
+                size = struct.unpack_from("<H", lay, 2)[0]
+                return f._decode(lay[4:4 + size], typ, shape)
+            if cls == 1:
+                addr, size = struct.unpack_from("<QQ", lay, 2)
+                if addr == UNDEF:
+                    return f._decode(bytes(n * esz), typ, shape)
+                a = addr + f.base_addr
+                return f._decode(f.buf[a:a + n * esz], typ, shape)
+            if cls == 2:
+                ndim = lay[2]
+                btree = struct.unpack_from("<Q", lay, 3)[0]
+                cdims = struct.unpack_from(f"<{ndim}I", lay, 11)
+                rank = ndim - 1
+                if typ.cls == 9:
+                    raise Hdf5FormatError("chunked variable-length datasets are not supported")
+                out = np.zeros(shape, dtype=typ.dtype)
+                if btree != UNDEF:
+                    chunks: list = []
+                    self._chunks(btree, rank, chunks)
+                    cshape = cdims[:rank]
+                    for offs, csize, mask, caddr in chunks:
+                        a = caddr + f.base_addr
+                        raw = self._unfilter(f.buf[a:a + csize], mask)
+                        block = np.frombuffer(raw, dtype=typ.dtype, count=int(np.prod(cshape))).reshape(cshape)
+                        sl_out = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, cshape, shape))
+                        sl_in = tuple(slice(0, s.stop - s.start) for s in sl_out)
+                        out[sl_out] = block[sl_in]
+                if typ.cls == 8 and typ.enum_base.size == 1:
+                    out = out.astype(np.bool_)
+                return out
+            raise Hdf5FormatError(f"data layout class {cls}")
+        if version in (1, 2):
+            ndim, cls = lay[1], lay[2]
+            p = 8
+            if cls == 1:
+                addr = struct.unpack_from("<Q", lay, p)[0]
+                a = addr + f.base_addr
+                return f._decode(f.buf[a:a + n * esz], typ, shape)
+            raise Hdf5FormatError(f"data layout message v{version} class {cls}")
+        raise Hdf5FormatError(f"data layout message version {version} (v4 chunk indexing is not supported)")
