@@ -1,0 +1,94 @@
+"""CPU: the pure-Python HDF5 writer/reader pair round-trips Keras-style model files and
+aposteriori-style frame datasets (real-file parity is unpinned: no h5py/libhdf5 offline)."""
+import json
+import struct
+
+import numpy as np
+import pytest
+
+from timed_design_b200 import standins
+from timed_design_b200.hdf5 import File, Hdf5FormatError, read_keras_h5, write_frame_dataset, write_keras_h5
+from timed_design_b200.hdf5.writer import Writer
+
+
+def test_keras_h5_roundtrip(tmp_path):
+    cfg, w = standins.tiny_standin(calib_frames=0)
+    p = tmp_path / "TIMED_tiny.h5"
+    write_keras_h5(p, cfg, w)
+    assert p.read_bytes()[:8] == b"\x89HDF\r\n\x1a\n"
+    cfg2, w2 = read_keras_h5(p)
+    assert cfg2 == json.loads(json.dumps(cfg))
+    assert list(w2) == [k for k in (l["name"] for l in cfg["config"]["layers"]) if k in w]
+    for layer, ws in w.items():
+        for k, v in ws.items():
+            np.testing.assert_array_equal(w2[layer][f"{layer}/{k}"], v)
+    f = File(p)
+    assert f.attrs["backend"] == "tensorflow" and f.attrs["keras_version"] == "2.13.1"
+    assert f["model_weights/conv3d/conv3d/kernel:0"].shape == (3, 3, 3, 6, 16)
+    assert f["model_weights"]["conv3d"]["conv3d/bias:0"].dtype == np.float32
+    with pytest.raises(KeyError):
+        f["model_weights/nope"]
+
+
+def test_many_children_and_deep_btree(tmp_path):
+    w = Writer()
+    for i in range(300):                      # > 8 per SNOD and > 32 leaves -> two B-tree levels
+        w.root.dataset(f"g/{i}", np.arange(i % 7 + 1, dtype=np.int64))
+    w.save(tmp_path / "many.h5")
+    f = File(tmp_path / "many.h5")
+    keys = f["g"].keys()
+    assert len(keys) == 300 and keys == sorted(str(i) for i in range(300))
+    for i in (0, 7, 8, 31, 32, 255, 299):
+        np.testing.assert_array_equal(f[f"g/{i}"][()], np.arange(i % 7 + 1))
+
+
+def test_frame_dataset_roundtrip_gzip_and_bool(tmp_path):
+    rng = np.random.default_rng(0)
+    dims = (5, 5, 5, 6)
+    frames = {"1ubq": {"A": {str(i): (rng.random(dims).astype(np.float32), ["MET", "GLN", "ILE"][i % 3])
+                             for i in (1, 2, 10, 11)}},
+              "2abc": {"B": {"7": (rng.random(dims).astype(np.float32), "TRP")}}}
+    p = tmp_path / "data.hdf5"
+    write_frame_dataset(p, frames, dims)
+    with File(p) as f:
+        assert list(f) == ["1ubq", "2abc"] and f["1ubq"].keys() == ["A"]
+        assert sorted(f["1ubq"]["A"].keys(), key=int) == ["1", "2", "10", "11"]
+        assert tuple(f.attrs["frame_dims"]) == dims and f.attrs["voxels_as_gaussian"] == True  # noqa: E712
+        assert f.attrs["make_frame_dataset_ver"] == "2.0.0"
+        assert [bytes(x).decode() for x in f.attrs["atom_encoder"]] == ["C", "N", "O", "CB", "CA", "Q"]
+        for pdb, chains in frames.items():
+            for chain, residues in chains.items():
+                for res, (arr, label) in residues.items():
+                    ds = f[pdb][chain][res]
+                    np.testing.assert_array_equal(ds[()], arr)
+                    assert ds.attrs["label"] == label
+                    assert ds.attrs["encoded_residue"].shape == (20,) and ds.attrs["encoded_residue"].sum() == 1
+    bframes = {"1ubq": {"A": {"1": (rng.random(dims) > 0.5, "MET")}}}
+    write_frame_dataset(tmp_path / "b.hdf5", bframes, dims, voxels_as_gaussian=False, compression=None)
+    f = File(tmp_path / "b.hdf5")
+    assert f.attrs["voxels_as_gaussian"] == False  # noqa: E712
+    got = f["1ubq/A/1"][()]
+    assert got.dtype == np.bool_
+    np.testing.assert_array_equal(got, bframes["1ubq"]["A"]["1"][0])
+
+
+def test_reader_fails_loudly(tmp_path):
+    (tmp_path / "x.h5").write_bytes(b"not hdf5" * 100)
+    with pytest.raises(Hdf5FormatError):
+        File(tmp_path / "x.h5")
+    cfg, w = standins.tiny_standin(calib_frames=0)
+    write_keras_h5(tmp_path / "m.h5", cfg, w)
+    raw = bytearray((tmp_path / "m.h5").read_bytes())
+    raw[8] = 9                                 # unknown superblock version
+    (tmp_path / "bad.h5").write_bytes(bytes(raw))
+    with pytest.raises(Hdf5FormatError):
+        File(tmp_path / "bad.h5")
+
+
+def test_npz_container_roundtrip(tmp_path):
+    from timed_design_b200.model import read_model_file, save_npz
+    cfg, w = standins.tiny_standin(calib_frames=0)
+    save_npz(tmp_path / "m.npz", cfg, w)
+    cfg2, w2 = read_model_file(tmp_path / "m.npz")
+    assert cfg2 == json.loads(json.dumps(cfg))
+    np.testing.assert_array_equal(w2["conv3d"]["kernel:0"], w["conv3d"]["kernel:0"])

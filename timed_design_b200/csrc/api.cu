@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -293,7 +294,19 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
     return 0;
 }
 
-static bool g_conv_attr_set = false;
+template <int A1, int A2, int F>
+static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map_w, const ConvKernelParams& k,
+                                int grid, size_t smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+        TB_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<A1, A2, F>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kSmemDynamicMax)));
+        attr_set = true;
+    }
+    conv_umma_kernel<A1, A2, F><<<grid, kConvThreads, smem_bytes, stream>>>(map_a, map_w, k);
+    return 0;
+}
 
 // Launch one conv over `n_frames` frames.  `in_base`: split tensor base (hi plane first);
 // `in_frames_alloc`: frames per plane in that allocation.
@@ -342,18 +355,38 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.out_f32 = out.f32; k.out_hi = out.hi; k.out_lo = out.lo;
     k.ldc = out.ld;
     k.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    {
+        static const int dbg = [] { const char* e = getenv("TIMED_B200_DBG"); return e ? atoi(e) : 0; }();
+        k.dbg = dbg;
+    }
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "conv: split output channel padding mismatch");
 
-    if (!g_conv_attr_set) {
-        TB_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(kSmemDynamicMax)));
-        g_conv_attr_set = true;
-    }
     const int total_tiles = k.n_ctile_m * k.n_tiles;
-    int sms = 148;
-    const int grid = std::min(total_tiles, sms);
-    conv_umma_kernel<<<grid, kConvThreads, cfg.smem_bytes, stream>>>(map_a, map_w, k);
+    const int grid = std::min(total_tiles, 148);
+    // compile-time specialised epilogues for the activation pairs Keras graphs actually produce;
+    // everything else goes through the runtime-dispatched instance
+    bool launched = false;
+#define TB_CONV_CASE(A1, A2, F)                                                                         \
+    if (!launched && k.act1 == (A1) && k.act2 == (A2) && k.out_fmt == (F)) {                            \
+        rc = launch_conv_instance<A1, A2, F>(map_a, map_w, k, grid, cfg.smem_bytes, stream);            \
+        launched = true;                                                                                \
+    }
+    TB_CONV_CASE(ACT_ELU, ACT_NONE, FMT_SPLIT)
+    TB_CONV_CASE(ACT_ELU, ACT_NONE, FMT_F32)
+    TB_CONV_CASE(ACT_NONE, ACT_NONE, FMT_SPLIT)
+    TB_CONV_CASE(ACT_NONE, ACT_NONE, FMT_F32)
+    TB_CONV_CASE(ACT_RELU, ACT_NONE, FMT_SPLIT)
+    TB_CONV_CASE(ACT_RELU, ACT_NONE, FMT_F32)
+    TB_CONV_CASE(ACT_NONE, ACT_RELU, FMT_SPLIT)
+    TB_CONV_CASE(ACT_NONE, ACT_RELU, FMT_F32)
+    TB_CONV_CASE(ACT_NONE, ACT_ELU, FMT_SPLIT)
+    TB_CONV_CASE(ACT_NONE, ACT_ELU, FMT_F32)
+#undef TB_CONV_CASE
+    if (!launched)
+        rc = k.out_fmt == FMT_SPLIT ? launch_conv_instance<-1, -1, FMT_SPLIT>(map_a, map_w, k, grid, cfg.smem_bytes, stream)
+                                    : launch_conv_instance<-1, -1, FMT_F32>(map_a, map_w, k, grid, cfg.smem_bytes, stream);
+    if (rc) return rc;
     TB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -668,14 +701,26 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 if (rc) return rc;
                 break;
             }
-            case TB_OP_POOL3D:
-                if (in0.fmt == FMT_SPLIT && out.fmt == FMT_SPLIT) {
-                    pool3d_split_vec8_kernel<<<grid_for(out_pix * (out.c_pad / 8), 256), 256, 0, s>>>(
-                        in0, out, node.pool, n_frames);
+            case TB_OP_POOL3D: {
+                // 16-byte vector path when both sides store a multiple of 8 channels per pixel
+                const int in_cw = in0.fmt == FMT_SPLIT ? in0.c_pad : in0.c;
+                const bool vec = (cw % 8 == 0) && (in_cw % 8 == 0) && (in0.ld % 8 == 0) && (out.ld % 8 == 0) &&
+                                 in_cw >= cw;
+                if (vec) {
+                    const int grid = grid_for(out_pix * (cw / 8), 256);
+                    if (in0.fmt == FMT_SPLIT && out.fmt == FMT_SPLIT)
+                        pool3d_vec8_kernel<FMT_SPLIT, FMT_SPLIT><<<grid, 256, 0, s>>>(in0, out, node.pool, n_frames);
+                    else if (in0.fmt == FMT_F32 && out.fmt == FMT_SPLIT)
+                        pool3d_vec8_kernel<FMT_F32, FMT_SPLIT><<<grid, 256, 0, s>>>(in0, out, node.pool, n_frames);
+                    else if (in0.fmt == FMT_SPLIT && out.fmt == FMT_F32)
+                        pool3d_vec8_kernel<FMT_SPLIT, FMT_F32><<<grid, 256, 0, s>>>(in0, out, node.pool, n_frames);
+                    else
+                        pool3d_vec8_kernel<FMT_F32, FMT_F32><<<grid, 256, 0, s>>>(in0, out, node.pool, n_frames);
                 } else {
                     pool3d_kernel<<<grid_for(out_pix * cw, 256), 256, 0, s>>>(in0, out, node.pool, n_frames);
                 }
                 break;
+            }
             case TB_OP_AFFINE:
                 affine_act_kernel<<<grid_for(out_pix * cw, 256), 256, 0, s>>>(
                     in0, out, out_pix, node.d_scale, node.d_shift, d.act1, d.alpha1, d.act2, d.alpha2);

@@ -16,14 +16,18 @@
 // NDHWC activation tensor by TMA in IM2COL mode (zero-fill supplies the 'same' padding); W tiles
 // by tiled TMA.  Both land in shared memory in the canonical K-major swizzled layout that the
 // UMMA descriptors read.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
-// allocation), warps 2..5 = epilogue (TMEM -> registers -> bias/act/BN-affine -> HBM).
+// allocation), warps 2..9 = epilogue (TMEM -> registers -> bias/act/BN-affine -> HBM; two warps per
+// TMEM lane quadrant, alternating 16-column chunks).  The epilogue is specialised at compile
+// time on (act1, act2, output format): a runtime switch per element made it as long as the
+// mainloop (profiles/r1_conv_first_ncu.md).
 #pragma once
 #include "common.cuh"
 
 namespace tb {
 
 constexpr int kConvMaxStages = 8;
-constexpr int kConvThreads = 192;
+constexpr int kConvEpilogueWarps = 8;                       // two per TMEM lane quadrant
+constexpr int kConvThreads = 64 + 32 * kConvEpilogueWarps;  // + TMA producer warp + MMA warp
 
 enum OutFmt : int { FMT_F32 = 0, FMT_SPLIT = 1 };
 
@@ -67,10 +71,23 @@ struct ConvKernelParams {
     __nv_bfloat16* out_lo;
     int64_t ldc;           // row pitch of the output in elements
     int32_t c_store;       // columns < c_store are stored (FMT_SPLIT: multiple of 16)
+    // ---- bring-up / tuning only (env TIMED_B200_DBG): 1 = skip TMA loads, 2 = skip MMA issue,
+    // 4 = skip epilogue math+stores.  Results are garbage; used to time each role in isolation.
+    int32_t dbg;
 };
 
 #if defined(__CUDACC__)
 
+// ACT = -1 selects the runtime-dispatched activation (sigmoid/tanh/mixed cases).
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x, int act_rt, float alpha) {
+    if constexpr (ACT == ACT_NONE) return x;
+    else if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.0f);
+    else if constexpr (ACT == ACT_ELU) return x > 0.0f ? x : alpha * expm1f(x);
+    else return apply_act(x, act_rt, alpha);
+}
+
+template <int ACT1, int ACT2, int FMT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_w, const ConvKernelParams p) {
@@ -94,7 +111,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);
+            mbar_init(&tempty_bar[a], kConvEpilogueWarps);
         }
         mbar_fence_init();
     }
@@ -140,6 +157,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     const int kb0 = g * p.kg;
                     const int nkb = min(p.kg, p.n_kblocks - kb0);
+                    if (p.dbg & 1) {
+                        mbar_arrive(&full_bar[s]);
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * kb_bytes);
                     uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
                     for (int j = 0; j < nkb; ++j) {
@@ -193,7 +215,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                     const int kb0 = g * p.kg;
                     const int nkb = min(p.kg, p.n_kblocks - kb0);
                     const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-                    for (int j = 0; j < nkb; ++j) {
+                    for (int j = 0; j < nkb && !(p.dbg & 2); ++j) {
                         const uint32_t base = st + static_cast<uint32_t>(j) * kb_bytes;
                         const uint32_t wb = base + 2u * p.mt * p.a_sub_bytes;
                         for (int kk = 0; kk < k16_steps; ++kk) {
@@ -224,8 +246,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             }
         }
     } else {
-        // =============================================================== epilogue (warps 2..5)
+        // =============================================================== epilogue (warps 2..9)
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;             // which of the quadrant's two warps
         const int row_in_tile = quad * 32 + lane;
         const int chunks = p.n_tile / 16;
         int acc = 0;
@@ -235,12 +258,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             const int n_idx = tile - m_ct * p.n_tiles;
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
-            for (int mi = 0; mi < p.mt; ++mi) {
+            for (int mi = 0; mi < p.mt && !(p.dbg & 4); ++mi) {
                 const int64_t m = static_cast<int64_t>(m_ct * p.mt + mi) * 128 + row_in_tile;
                 const bool row_ok = m < p.m_total;
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                        static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);
-                for (int c = 0; c < chunks; ++c) {
+                for (int c = half; c < chunks; c += 2) {
                     uint32_t r[16];
                     __syncwarp();                      // tcgen05.ld is .sync.aligned
                     tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), r);
@@ -259,12 +282,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             float x = __uint_as_float(r[i4 * 4 + i]) + bb[i];
-                            x = apply_act(x, p.act1, p.alpha1);
+                            x = act_ct<ACT1>(x, p.act1, p.alpha1);
                             x = fmaf(x, ss[i], hh[i]);
-                            v[i4 * 4 + i] = apply_act(x, p.act2, p.alpha2);
+                            v[i4 * 4 + i] = act_ct<ACT2>(x, p.act2, p.alpha2);
                         }
                     }
-                    if (row_ok && p.out_fmt == FMT_SPLIT) {
+                    if (row_ok && FMT == FMT_SPLIT) {
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {

@@ -102,9 +102,50 @@ __global__ void pool3d_kernel(TView in, TView out, PoolParams pp, int64_t n_fram
     }
 }
 
-// vector path: split planes in and out, one thread per (out pixel, 8 channels), 16-byte loads
-__global__ void pool3d_split_vec8_kernel(TView in, TView out, PoolParams pp, int64_t n_frames) {
-    const int groups = out.c_pad / 8;
+// vector path: one thread per (out pixel, 8 channels), 16-byte loads/stores; input and output
+// formats are compile-time (fp32 rows or bf16 split planes).  Requires 8 | channels stored.
+template <int IN_FMT>
+__device__ __forceinline__ void load8(const TView& t, int64_t elem_off, float (&v)[8]) {
+    if constexpr (IN_FMT == FMT_F32) {
+        const float4 a = *reinterpret_cast<const float4*>(t.f32 + elem_off);
+        const float4 b = *reinterpret_cast<const float4*>(t.f32 + elem_off + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 vh = *reinterpret_cast<const uint4*>(t.hi + elem_off);
+        const uint4 vl = *reinterpret_cast<const uint4*>(t.lo + elem_off);
+        const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w};
+        const uint32_t lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {      // bf16 -> fp32 is a 16-bit shift
+            v[2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            v[2 * e + 1] = __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
+        }
+    }
+}
+template <int OUT_FMT>
+__device__ __forceinline__ void store8(const TView& t, int64_t elem_off, const float (&v)[8]) {
+    if constexpr (OUT_FMT == FMT_F32) {
+        *reinterpret_cast<float4*>(t.f32 + elem_off) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(t.f32 + elem_off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        uint32_t ho[4], lo_[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[2 * e], h0, l0);
+            split_bf16(v[2 * e + 1], h1, l1);
+            ho[e] = pack_bf16x2(h0, h1);
+            lo_[e] = pack_bf16x2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(t.hi + elem_off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+        *reinterpret_cast<uint4*>(t.lo + elem_off) = make_uint4(lo_[0], lo_[1], lo_[2], lo_[3]);
+    }
+}
+
+template <int IN_FMT, int OUT_FMT>
+__global__ void pool3d_vec8_kernel(TView in, TView out, PoolParams pp, int64_t n_frames) {
+    const int groups = (OUT_FMT == FMT_SPLIT ? out.c_pad : out.c) / 8;
     const int64_t opix = static_cast<int64_t>(pp.Do) * pp.Ho * pp.Wo;
     const int64_t total = n_frames * opix * groups;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -128,38 +169,19 @@ __global__ void pool3d_split_vec8_kernel(TView in, TView out, PoolParams pp, int
                 for (int c = 0; c < pp.k[2]; ++c) {
                     const int w = q * pp.s[2] - pp.pad0[2] + c;
                     if (w < 0 || w >= pp.W) continue;
-                    const int64_t o = (((nf * pp.D + d) * pp.H + h) * pp.W + w) * in.ld + g * 8;
-                    const uint4 vh = *reinterpret_cast<const uint4*>(in.hi + o);
-                    const uint4 vl = *reinterpret_cast<const uint4*>(in.lo + o);
-                    const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w};
-                    const uint32_t lw[4] = {vl.x, vl.y, vl.z, vl.w};
+                    float v[8];
+                    load8<IN_FMT>(in, (((nf * pp.D + d) * pp.H + h) * pp.W + w) * in.ld + g * 8, v);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        // bf16 -> fp32 is a 16-bit shift
-                        const float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-                        const float v1 = __uint_as_float(hw[e] & 0xFFFF0000u) +
-                                         __uint_as_float(lw[e] & 0xFFFF0000u);
-                        acc[2 * e] = pp.is_avg ? acc[2 * e] + v0 : fmaxf(acc[2 * e], v0);
-                        acc[2 * e + 1] = pp.is_avg ? acc[2 * e + 1] + v1 : fmaxf(acc[2 * e + 1], v1);
-                    }
+                    for (int e = 0; e < 8; ++e) acc[e] = pp.is_avg ? acc[e] + v[e] : fmaxf(acc[e], v[e]);
                     ++cnt;
                 }
             }
         }
-        uint32_t ho[4], lo_[4];
+        if (pp.is_avg) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float v0 = acc[2 * e], v1 = acc[2 * e + 1];
-            if (pp.is_avg) { v0 /= static_cast<float>(cnt); v1 /= static_cast<float>(cnt); }
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v0, h0, l0);
-            split_bf16(v1, h1, l1);
-            ho[e] = pack_bf16x2(h0, h1);
-            lo_[e] = pack_bf16x2(l0, l1);
+            for (int e = 0; e < 8; ++e) acc[e] /= static_cast<float>(cnt);
         }
-        const int64_t oo = ((((nf * pp.Do + z) * pp.Ho + p) * pp.Wo + q)) * out.ld + g * 8;
-        *reinterpret_cast<uint4*>(out.hi + oo) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
-        *reinterpret_cast<uint4*>(out.lo + oo) = make_uint4(lo_[0], lo_[1], lo_[2], lo_[3]);
+        store8<OUT_FMT>(out, ((((nf * pp.Do + z) * pp.Ho + p) * pp.Wo + q)) * out.ld + g * 8, acc);
     }
 }
 

@@ -1,0 +1,98 @@
+"""Frame-dataset input boundary: enumerate and gather 21^3 x C voxel frames from an
+aposteriori ``.hdf5`` file (schema documented at /root/reference/design_utils/utils.py:238-251).
+
+Same names and return conventions as ``create_flat_dataset_map`` (utils.py:318-407) and
+``load_batch`` (utils.py:487-530); the file is parsed by this package's own HDF5 reader (h5py
+is not available) and is opened ONCE per dataset instead of once per batch.
+"""
+from __future__ import annotations
+
+import typing as t
+import warnings
+from pathlib import Path
+
+import numpy as np
+
+from .hdf5 import File
+from .postprocess import standard_amino_acids
+
+# The reference maps non-standard labels through aposteriori.config.UNCOMMON_RESIDUE_DICT
+# (aposteriori==2.4.0, not vendored, not installable here).  This is NOT that table: only the
+# widely documented modified-residue -> parent pairs are listed; anything else fails the same
+# assertion the reference raises (utils.py:385-389).  Extend via ``UNCOMMON_RESIDUE_DICT.update``.
+UNCOMMON_RESIDUE_DICT = {
+    "MSE": "MET", "SEP": "SER", "TPO": "THR", "PTR": "TYR", "HYP": "PRO", "CSO": "CYS", "CME": "CYS",
+    "CSD": "CYS", "OCS": "CYS", "KCX": "LYS", "MLY": "LYS", "M3L": "LYS", "LLP": "LYS", "PCA": "GLU",
+    "FME": "MET", "DAL": "ALA",
+}
+
+_open_files: t.Dict[str, File] = {}
+
+
+def _open(path) -> File:
+    key = str(Path(path).resolve())
+    f = _open_files.get(key)
+    if f is None or Path(key).stat().st_mtime_ns != getattr(f, "_mtime", None):
+        f = File(key)
+        f._mtime = Path(key).stat().st_mtime_ns
+        _open_files[key] = f
+    return f
+
+
+def _as_str(x) -> str:
+    return x.decode("utf-8") if isinstance(x, (bytes, np.bytes_)) else str(x)
+
+
+def create_flat_dataset_map(frame_dataset: Path, filter_list: t.List[str] = [],
+                            remove_blacklist_silently: bool = False):
+    """utils.py:318-407.  Order: pdb codes and chains in the file's (name) order, residue ids
+    sorted as INTEGERS (utils.py:367-371).  Returns ([(pdb, chain, res_id, label)], {pdbs})."""
+    standard = set(standard_amino_acids.values())
+    f = _open(frame_dataset)
+    flat: t.List[t.Tuple[str, str, str, str]] = []
+    pdbs = set()
+    for pdb_code in f:
+        if pdb_code[:4] in filter_list:
+            if remove_blacklist_silently:
+                warnings.warn(f"PDB code {pdb_code} was found in benchmark dataset. It was automatically removed.")
+                continue
+            raise ValueError(
+                f"PDB code {pdb_code} was found in benchmark dataset. Turn on remove_blacklist_silently=True "
+                f"if you want to ignore these structures for training.")
+        for chain_id in f[pdb_code].keys():
+            chain = f[pdb_code][chain_id]
+            for residue_id in sorted(chain.keys(), key=int):
+                label = _as_str(chain[residue_id].attrs["label"])
+                if label not in standard:
+                    if label in UNCOMMON_RESIDUE_DICT:
+                        warnings.warn(f"{label} is not a standard residue.")
+                        label = UNCOMMON_RESIDUE_DICT[label]
+                        warnings.warn(f"Residue converted to {label}.")
+                    assert label in standard, f"Expected natural amino acid, but got {label}."
+                flat.append((pdb_code, chain_id, str(int(residue_id)), label))
+                pdbs.add(pdb_code)
+    return flat, pdbs
+
+
+def dataset_metadata(frame_dataset: Path) -> dict:
+    """Root attributes of the dataset (utils.py:230-281 reads them into DatasetMetadata)."""
+    f = _open(frame_dataset)
+    return {k: f.attrs[k] for k in f.attrs.keys()}
+
+
+def load_batch(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple]) -> t.Tuple[np.ndarray, np.ndarray]:
+    """utils.py:487-530.  X: (B, *frame_dims) float32 when ``voxels_as_gaussian`` else bool --
+    the reference allocates float64 and Keras casts it to float32 on entry (predict.py:142), so
+    the values the network sees are identical; y: (B, 20) float64 labels."""
+    f = _open(dataset_path)
+    dims = tuple(int(d) for d in f.attrs["frame_dims"])
+    gaussian = bool(f.attrs["voxels_as_gaussian"])
+    n = len(data_point_batch)
+    X = np.zeros((n, *dims), dtype=np.float32 if gaussian else np.bool_)
+    y = np.zeros((n, 20), dtype=float)
+    for i, row in enumerate(data_point_batch):
+        pdb_code, chain_id, residue_id = (str(v) for v in row[:3])
+        ds = f[pdb_code][chain_id][residue_id]
+        X[i] = ds[()]
+        y[i] = ds.attrs["encoded_residue"]
+    return X, y

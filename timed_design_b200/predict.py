@@ -1,0 +1,168 @@
+"""``predict.py`` drop-in: same command-line flags, same importable
+``load_dataset_and_predict(...)`` signature and 6-tuple, same output files as
+/root/reference/predict.py -- with the Keras load/predict pair (predict.py:121,142) replaced by
+the B200 graph executor and the per-batch text round trip (predict.py:145-163) kept only as an
+output format, not as the data path.
+
+Files written into ``path_to_output``: ``{model}.csv`` (float16-cast
+probabilities, ``%.18e``), ``encoded_labels.csv``, ``datasetmap.txt``, ``{model}.txt``,
+``{model}.fasta``, ``dataset.fasta``; rotamer mode adds ``{model}_rot.csv`` (raw float32
+338-wide rows) and turns ``{model}.csv`` into residue one-hots; NMR consensus files go to the
+CWD like the reference's.
+
+Deviations, all additive: the rotamer dump is named ``{model}_rot.csv`` (the
+reference's missing f-prefix produces a literal ``{model_name}_rot.csv``); ``--predict_rotamers``
+/ ``--is_structure_nmr`` also accept an explicit ``True``/``False`` as the README writes them;
+``--yes`` creates a missing output directory without the interactive prompt.
+"""
+from __future__ import annotations
+
+import argparse
+from math import ceil
+from pathlib import Path
+
+import numpy as np
+
+from .frames import create_flat_dataset_map, load_batch
+from .model import load_model
+from .postprocess import (convert_dataset_map_for_srb, extract_sequence_from_pred_matrix,
+                          get_pdb_keys_to_filter, get_rotamer_codec, rotamer_class_to_residue,
+                          save_consensus_probs, save_dict_to_fasta, save_outputs_to_file)
+
+
+def load_dataset_and_predict(
+    models: list,
+    dataset_path: Path,
+    batch_size: int = 20,
+    start_batch: int = 0,
+    dataset_map_path: Path = "datasetmap.txt",
+    blacklist: Path = None,
+    predict_rotamers: bool = False,
+    model_name_suffix: str = "",
+    is_consensus: bool = False,
+    path_to_output: Path = Path.cwd(),
+):
+    """predict.py:28-194.  Returns (flat_dataset_map, pdb_to_sequence, pdb_to_probability,
+    pdb_to_real_sequence, pdb_to_consensus, pdb_to_consensus_prob) of the LAST model."""
+    path_to_output = Path(path_to_output)
+    n_classes = 338 if predict_rotamers else 20
+    print(f"Running model on {n_classes} classes. Rotamer Mode is {predict_rotamers}")
+    filter_pdb_list = get_pdb_keys_to_filter(blacklist) if blacklist else []
+    if Path(dataset_map_path).exists():          # a stale map is reused, as the reference does
+        flat_dataset_map = np.genfromtxt(dataset_map_path, delimiter=",", dtype="str")
+        if flat_dataset_map.ndim == 1:
+            flat_dataset_map = flat_dataset_map[None, :]
+    else:
+        flat_dataset_map, _ = create_flat_dataset_map(dataset_path, filter_pdb_list)
+    old_datasetmap = len(flat_dataset_map[0]) == 4
+    flat_categories = get_rotamer_codec()[1] if predict_rotamers else None
+    cls_to_res = rotamer_class_to_residue() if predict_rotamers else None
+    n_batches = ceil(len(flat_dataset_map) / batch_size)
+    out = None
+    for i, m in enumerate(models):
+        model_name = (m.stem if isinstance(m, Path) else str(m)) + model_name_suffix
+        frame_model = load_model(Path(m))
+        if frame_model.n_classes != n_classes:
+            raise ValueError(f"{m}: model has {frame_model.n_classes} outputs but "
+                             f"{'--predict_rotamers' if predict_rotamers else 'residue mode'} expects {n_classes}")
+        rot_out = path_to_output / f"{model_name}_rot.csv"
+        model_out = rot_out if predict_rotamers else path_to_output / f"{model_name}.csv"
+        rows_before = sum(1 for _ in open(model_out)) if model_out.exists() else 0
+        raw_rows = []
+        for index in range(start_batch, n_batches):
+            current_batch_map = flat_dataset_map[index * batch_size:(index + 1) * batch_size]
+            X_batch, y_true_batch = load_batch(dataset_path, current_batch_map)
+            y_pred_batch = frame_model.predict(X_batch)
+            raw_rows.append(y_pred_batch)
+            if predict_rotamers:
+                with open(rot_out, "a") as f:
+                    np.savetxt(f, y_pred_batch, delimiter=",")
+                y_pred_batch = np.eye(20, dtype=int)[cls_to_res[np.argmax(y_pred_batch, axis=1)]]
+            save_outputs_to_file(list(y_true_batch), {i: list(y_pred_batch)}, flat_dataset_map, i, model_name,
+                                 path_to_output)
+        frame_model.close()
+        flat_dataset_map = np.array(flat_dataset_map)
+        convert_dataset_map_for_srb(flat_dataset_map, model_name, path_to_output)
+        # predict.py:163 re-parses the whole CSV as float16.  The rows written above are these
+        # arrays printed with 18 significant digits (already float16-cast in residue mode), so
+        # casting them to float16 reproduces the parsed matrix bit for bit without the text round
+        # trip -- unless the file already held rows (append mode / start_batch): then honour it.
+        if rows_before == 0 and start_batch == 0 and raw_rows:
+            prediction_matrix = np.concatenate(raw_rows).astype(np.float16)
+        else:
+            prediction_matrix = np.genfromtxt(model_out, delimiter=",", dtype=np.float16)
+        if prediction_matrix.ndim == 1:
+            prediction_matrix = prediction_matrix[None, :]
+        out = extract_sequence_from_pred_matrix(
+            flat_dataset_map, prediction_matrix,
+            rotamers_categories=flat_categories if predict_rotamers else None,
+            old_datasetmap=old_datasetmap, is_consensus=is_consensus)
+        save_dict_to_fasta(out[0], model_name, path_to_output)
+        save_dict_to_fasta(out[2], "dataset", path_to_output)
+        if out[3]:
+            save_dict_to_fasta(out[3], model_name + "_consensus")        # CWD, as the reference
+            save_consensus_probs(out[4], model_name, path_to_output)
+    return (flat_dataset_map, *out)
+
+
+def _flag(value):
+    """store_true-compatible flag that also accepts the README's explicit ``True``/``False``."""
+    if value is None or value is True:
+        return True
+    v = str(value).strip().lower()
+    if v in ("true", "1", "yes", "y"):
+        return True
+    if v in ("false", "0", "no", "n"):
+        return False
+    raise argparse.ArgumentTypeError(f"expected True or False, got {value!r}")
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="Predict with TIMED (B200-native path)")
+    p.add_argument("--batch_size", type=int, default=12, help="Frames predicted per batch (default: 12)")
+    p.add_argument("--path_to_dataset", type=str, help="Frame dataset (.hdf5)")
+    p.add_argument("--path_to_datasetmap", default="datasetmap.txt", type=str, help="Dataset map (.txt)")
+    p.add_argument("--path_to_model", type=str, help="Keras model file (.h5) or .npz container")
+    p.add_argument("--path_to_blacklist", type=str, default=None, help="Directory of PDB-code lists to exclude")
+    p.add_argument("--path_to_output", type=str, default=".", help="Output directory (default: CWD)")
+    p.add_argument("--output_analysis", action="store_true", help="Accepted for compatibility; unused")
+    p.add_argument("--predict_rotamers", nargs="?", const=True, default=False, type=_flag,
+                   help="Model predicts 338 rotamer classes instead of 20 residues")
+    p.add_argument("--is_structure_nmr", nargs="?", const=True, default=False, type=_flag,
+                   help="NMR ensemble: also build a consensus over the states")
+    p.add_argument("--yes", action="store_true", help="Create a missing output directory without asking")
+    return p
+
+
+def main(args) -> None:
+    """predict.py:197-247."""
+    args.path_to_dataset = Path(args.path_to_dataset)
+    args.path_to_model = Path(args.path_to_model)
+    args.path_to_datasetmap = Path(args.path_to_datasetmap)
+    args.path_to_output = Path(args.path_to_output)
+    if not args.path_to_output.exists():
+        if not getattr(args, "yes", False):
+            print(f"Output directory at {args.path_to_output} does not exist. Do you want to create it? (y/n)")
+            if input() != "y":
+                print("Exiting...")
+                raise SystemExit(0)
+        args.path_to_output.mkdir(parents=True, exist_ok=True)
+    if args.path_to_blacklist:
+        args.path_to_blacklist = Path(args.path_to_blacklist)
+        assert args.path_to_blacklist.exists(), f"Path to blacklist at {args.path_to_blacklist} does not exists."
+    assert args.path_to_model.exists(), f"Path to model at {args.path_to_model} does not exists."
+    assert args.path_to_dataset.exists(), f"Path to dataset at {args.path_to_dataset} does not exists."
+    assert args.batch_size > 0, f"Batch size must be higher than 0 but got {args.batch_size}"
+    load_dataset_and_predict(
+        [args.path_to_model], args.path_to_dataset, batch_size=args.batch_size, start_batch=0,
+        blacklist=args.path_to_blacklist, dataset_map_path=args.path_to_datasetmap,
+        predict_rotamers=args.predict_rotamers, is_consensus=args.is_structure_nmr,
+        path_to_output=args.path_to_output)
+
+
+def cli(argv=None) -> None:
+    main(build_parser().parse_args(argv))
+
+
+if __name__ == "__main__":
+    cli()
