@@ -80,14 +80,22 @@ struct TensorInfo {
     int fmt = FMT_F32;
     int slack_pix = 0;    // extra readable pixels past the end required by im2col consumers
     int last_use = -1;    // index of the last op reading this tensor
+    // "W-folded" layout of a thin (C <= 8) graph input: 8 stored channels per pixel and W-rows of
+    // wf_pitch pixels (wf_lm zero pixels, the W real ones, zero pixels up to the pitch).  A conv
+    // then reads kwin consecutive pixels (kwin*8 contiguous elements) as ONE im2col "pixel", so the
+    // kw taps of a row collapse into the K dimension: 3x fewer TMA rows and MMAs for TIMED's
+    // first layer (DESIGN.md "First layer").
+    bool wfold = false;
+    int wf_lm = 0, wf_pitch = 0;
     int64_t pix_per_frame() const { return static_cast<int64_t>(D) * H * W; }
+    int64_t stored_pix_per_frame() const { return static_cast<int64_t>(D) * H * (wfold ? wf_pitch : W); }
     // frames allocated per plane for n frames (so that a 128-pixel im2col column starting at
     // any valid pixel stays inside the allocation)
     int64_t frames_alloc(int64_t n) const {
         return n + (slack_pix + pix_per_frame() - 1) / pix_per_frame();
     }
     size_t bytes(int64_t n) const {
-        const int64_t elems = frames_alloc(n) * pix_per_frame() * c_pad;
+        const int64_t elems = frames_alloc(n) * stored_pix_per_frame() * c_pad;
         return static_cast<size_t>(round_up64(fmt == FMT_SPLIT ? elems * 2 * 2 : elems * 4, 1024));
     }
 };
@@ -101,6 +109,10 @@ struct ConvPlan {
     int Di = 1, Hi = 1, Wi = 1, Do = 1, Ho = 1, Wo = 1;
     int n_tile = 0, n_tiles = 0, n_alloc = 0;
     int k_total = 0;
+    // W-folded input (see TensorInfo): kwin pixels x 8 channels form one K-block of a (kd,kh) tap
+    bool wfold = false;
+    int kwin = 0, in_lm = 0, in_pitch = 0;
+    int taps_eff() const { return wfold ? kd * kh : kd * kh * kw; }
     __nv_bfloat16* d_w = nullptr;   // [2][n_alloc][k_total]
     float* d_bias = nullptr;        // [n_alloc]
     float* d_scale = nullptr;
@@ -129,17 +141,21 @@ static void free_conv_plan(ConvPlan& p) {
     p.d_bias = p.d_scale = p.d_shift = nullptr;
 }
 
-// 227 KB per CTA is the limit for static + dynamic shared memory; the kernel keeps < 1 KB static
-// (barriers), and 1 KB of the dynamic part is alignment slack.
-static constexpr size_t kSmemDynamicMax = 226 * 1024;
+// 227 KB per CTA is the limit for static + dynamic shared memory; the kernel keeps ~6.3 KB static
+// (barriers + staged epilogue vectors), and 1 KB of the dynamic part is alignment slack.
+static constexpr size_t kSmemDynamicMax = 220 * 1024;
 static constexpr size_t kSmemBudget = kSmemDynamicMax - 1024;
 
 // Pick (kc, mt, kg, stages) for a conv given the number of output rows.
 static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* cfg) {
     const int m_tiles = static_cast<int>((m_total + 127) / 128);
     std::vector<int> kcs;
-    for (int kc : {64, 32, 16})
-        if (p.cin_pad % kc == 0) kcs.push_back(kc);
+    if (p.wfold) {
+        kcs.push_back(p.cin_pad);            // one K-block per (kd,kh) tap: kwin*8 = 32 or 64
+    } else {
+        for (int kc : {64, 32, 16})
+            if (p.cin_pad % kc == 0) kcs.push_back(kc);
+    }
     TB_REQUIRE(!kcs.empty(), "conv: padded input channels must be a multiple of 16");
     const int acc_cols = round_up(p.n_tile, 32);
     // two M sub-tiles per CTA halve the weight traffic per MAC; only worth it when there are
@@ -153,7 +169,7 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
         for (int kc : kcs) {
             const size_t a_sub = 128u * kc * 2u, w_sub = static_cast<size_t>(p.n_tile) * kc * 2u;
             const size_t kb = mt * 2 * a_sub + 2 * w_sub;
-            const int n_kblocks = p.kd * p.kh * p.kw * (p.cin_pad / kc);
+            const int n_kblocks = p.taps_eff() * (p.cin_pad / kc);
             int kg = std::max(1, 64 / kc);
             kg = std::min(kg, n_kblocks);
             while (kg > 1 && kb * kg * 2 > kSmemBudget) --kg;
@@ -212,6 +228,21 @@ static int encode_a_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* ba
     cuuint64_t strides[4] = {px, px * p.Wi, px * p.Wi * p.Hi, px * p.Wi * p.Hi * p.Di};
     int lower[3] = {-p.pad0[2], -p.pad0[1], -p.pad0[0]};
     int upper[3] = {p.pad1[2] - (p.kw - 1), p.pad1[1] - (p.kh - 1), p.pad1[0] - (p.kd - 1)};
+    if (p.wfold) {
+        // "pixel" = kwin consecutive stored pixels starting pad_w0 to the left of the output
+        // column; consecutive "pixels" overlap in memory (stride = one stored pixel = 16 bytes).
+        // The W extent of the map is the number of output columns; no W padding/filter extent left.
+        dims[0] = static_cast<cuuint64_t>(p.kwin * 8);
+        dims[1] = static_cast<cuuint64_t>(p.Wo);
+        const cuuint64_t row = static_cast<cuuint64_t>(p.in_pitch) * 16;
+        strides[0] = 16;
+        strides[1] = row;
+        strides[2] = row * p.Hi;
+        strides[3] = row * p.Hi * p.Di;
+        lower[0] = 0;
+        upper[0] = 0;
+        base = static_cast<uint8_t*>(base) + static_cast<size_t>(p.in_lm - p.pad0[2]) * 16;
+    }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUtensorMap m;
     CUresult r = g_encode_im2col(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, lower,
@@ -224,7 +255,7 @@ static int encode_a_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* ba
     }
     // Same driver workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): drivers up
     // to 13.1 mis-set a descriptor bit for im2col maps over tensors smaller than 128 KiB.
-    const uint64_t tensor_bytes = strides[3] * dims[4];
+    const uint64_t tensor_bytes = strides[3] * dims[4];   // (wfold: same formula, padded rows)
     if (g_driver_version <= 13010 && tensor_bytes < 131072)
         reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
     *out = m;
@@ -233,7 +264,7 @@ static int encode_a_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* ba
 
 // Build the static part of a conv plan: geometry, packed weights, epilogue vectors.
 static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, int Wi, int cin,
-                            int cin_pad) {
+                            int cin_pad, const TensorInfo* wfold_in = nullptr) {
     p.kd = d.kernel[0]; p.kh = d.kernel[1]; p.kw = d.kernel[2];
     TB_REQUIRE(p.kd >= 1 && p.kh >= 1 && p.kw >= 1 && p.kd <= 16 && p.kh <= 16 && p.kw <= 16,
                "conv: kernel extents must be in [1,16]");
@@ -241,6 +272,13 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
     TB_REQUIRE(d.kernel_w != nullptr, "conv: kernel weights missing");
     TB_REQUIRE(d.c_out >= 1, "conv: c_out must be positive");
     p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.cin = cin; p.cin_pad = cin_pad; p.cout = d.c_out;
+    if (wfold_in && wfold_in->wfold) {
+        p.wfold = true;
+        p.kwin = p.kw <= 4 ? 4 : 8;
+        p.in_lm = wfold_in->wf_lm;
+        p.in_pitch = wfold_in->wf_pitch;
+        p.cin_pad = cin_pad = p.kwin * 8;
+    }
     const int ks[3] = {p.kd, p.kh, p.kw}, in[3] = {Di, Hi, Wi};
     int out[3];
     for (int i = 0; i < 3; ++i) {
@@ -257,7 +295,7 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
     p.n_tiles = ceil_div(n_pad, 256);
     p.n_tile = round_up(ceil_div(n_pad, p.n_tiles), 16);
     p.n_alloc = p.n_tile * p.n_tiles;
-    p.k_total = p.kd * p.kh * p.kw * cin_pad;
+    p.k_total = p.taps_eff() * cin_pad;
     p.act1 = d.act1; p.act2 = d.act2; p.alpha1 = d.alpha1; p.alpha2 = d.alpha2;
 
     // ---- pack weights: Keras DHWIO fp32 -> [plane][n][tap*cin_pad + c] bf16 hi/lo
@@ -271,7 +309,10 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
                 const float v = src[n];
                 const __nv_bfloat16 hi = __float2bfloat16_rn(v);
                 const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-                const size_t o = static_cast<size_t>(n) * p.k_total + static_cast<size_t>(t) * cin_pad + c;
+                // K index: dense = tap*cin_pad + c; W-folded = (kd,kh)-tap * (kwin*8) + kw*8 + c
+                const size_t kidx = p.wfold ? static_cast<size_t>(t / p.kw) * cin_pad + static_cast<size_t>(t % p.kw) * 8 + c
+                                            : static_cast<size_t>(t) * cin_pad + c;
+                const size_t o = static_cast<size_t>(n) * p.k_total + kidx;
                 w[o] = hi;
                 w[plane + o] = lo;
             }
@@ -333,8 +374,8 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.n_tile = p.n_tile;
     k.acc_cols = cfg.acc_cols;
     k.acc_stages = cfg.acc_stages;
-    k.kh = p.kh; k.kw = p.kw;
-    k.n_taps = p.kd * p.kh * p.kw;
+    k.kh = p.kh; k.kw = p.wfold ? 1 : p.kw;
+    k.n_taps = p.taps_eff();
     k.cin_pad = p.cin_pad;
     k.kc = cfg.kc;
     k.cin_blocks = p.cin_pad / cfg.kc;
@@ -342,7 +383,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.n_kblocks = k.n_taps * k.cin_blocks;
     k.stages = cfg.stages;
     k.Do = p.Do; k.Ho = p.Ho; k.Wo = p.Wo;
-    k.lc_d = -p.pad0[0]; k.lc_h = -p.pad0[1]; k.lc_w = -p.pad0[2];
+    k.lc_d = -p.pad0[0]; k.lc_h = -p.pad0[1]; k.lc_w = p.wfold ? 0 : -p.pad0[2];
     k.lo_plane_frames = static_cast<int32_t>(in_frames_alloc);
     k.w_lo_rows = p.n_alloc;
     k.a_sub_bytes = 128u * cfg.kc * 2u;
@@ -445,7 +486,7 @@ static TView make_view(const TensorInfo& t, uint8_t* base, int64_t n_frames) {
         v.f32 = reinterpret_cast<float*>(base);
     } else {
         v.hi = reinterpret_cast<__nv_bfloat16*>(base);
-        v.lo = v.hi + t.frames_alloc(n_frames) * t.pix_per_frame() * t.c_pad;
+        v.lo = v.hi + t.frames_alloc(n_frames) * t.stored_pix_per_frame() * t.c_pad;
     }
     return v;
 }
@@ -531,6 +572,28 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
         }
     }
     g->tensors[n_ops - 1].last_use = n_ops;   // graph output stays live
+    // W-folded input layout: thin input (C <= 8) read only by stride-1 convs with kw <= 8
+    {
+        bool ok = ops[0].c_out <= 8 && !getenv("TIMED_B200_NO_WFOLD");
+        int lm = 0, rm = 0, n_cons = 0;
+        for (int i = 1; i < n_ops && ok; ++i)
+            for (int k = 0; k < ops[i].n_inputs; ++k)
+                if (ops[i].inputs[k] == 0) {
+                    ++n_cons;
+                    if (ops[i].op != TB_OP_CONV3D || ops[i].kernel[2] > 8 || ops[i].kernel[2] < 1) { ok = false; break; }
+                    const int kw = ops[i].kernel[2];
+                    const int pad0 = ops[i].pad_same ? (kw - 1) / 2 : 0;
+                    const int kwin = kw <= 4 ? 4 : 8;
+                    lm = std::max(lm, pad0);
+                    rm = std::max(rm, kwin - 1 - pad0);
+                }
+        if (ok && n_cons > 0) {
+            TensorInfo& t0 = g->tensors[0];
+            t0.wfold = true;
+            t0.wf_lm = lm;
+            t0.wf_pitch = lm + ops[0].kernel[2] + rm;
+        }
+    }
     g->flops = 0.0;
     g->launches = 0;
     for (int i = 0; i < n_ops; ++i) {
@@ -549,7 +612,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 break;
             case TB_OP_CONV3D: {
                 TB_REQUIRE(d.n_inputs == 1, "conv takes one input");
-                int rc = conv_plan_create(node.conv, d, in0->D, in0->H, in0->W, in0->C, in0->c_pad);
+                int rc = conv_plan_create(node.conv, d, in0->D, in0->H, in0->W, in0->C, in0->c_pad, in0);
                 if (rc) return rc;
                 t.D = node.conv.Do; t.H = node.conv.Ho; t.W = node.conv.Wo; t.C = d.c_out;
                 g->flops += node.conv.flops_per_frame();
@@ -626,6 +689,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 TB_REQUIRE(false, "unknown op kind");
         }
         t.c_pad = t.fmt == FMT_SPLIT ? round_up(t.C, 16) : t.C;
+        if (t.wfold) { t.fmt = FMT_SPLIT; t.c_pad = 8; }
         // pointers are only valid during graph_create
         node.d.kernel_w = node.d.bias = node.d.scale = node.d.shift = nullptr;
     }
@@ -644,6 +708,14 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
     TB_REQUIRE(last.fmt == FMT_F32, "internal: output tensor must be fp32");
     g->n_classes = last.C;
     return 0;
+}
+
+template <typename T>
+static void launch_input_convert_wfold(const void* x, const TensorInfo& t, int64_t n_frames, const TView& out,
+                                       cudaStream_t s) {
+    const int64_t rows = n_frames * t.D * t.H;
+    input_convert_wfold_kernel<T><<<grid_for(rows * t.wf_pitch, 256), 256, 0, s>>>(
+        static_cast<const T*>(x), rows, t.W, t.C, t.wf_lm, t.wf_pitch, out.hi, out.lo);
 }
 
 template <typename T>
@@ -689,6 +761,13 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
         const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
         switch (d.op) {
             case TB_OP_INPUT:
+                if (t.wfold) {
+                    if (dtype == TB_DTYPE_F32) launch_input_convert_wfold<float>(d_frames, t, n_frames, out, s);
+                    else if (dtype == TB_DTYPE_F64) launch_input_convert_wfold<double>(d_frames, t, n_frames, out, s);
+                    else if (dtype == TB_DTYPE_U8) launch_input_convert_wfold<uint8_t>(d_frames, t, n_frames, out, s);
+                    else TB_REQUIRE(false, "unknown frames dtype");
+                    break;
+                }
                 if (dtype == TB_DTYPE_F32) launch_input_convert<float>(d_frames, out_pix, out, s);
                 else if (dtype == TB_DTYPE_F64) launch_input_convert<double>(d_frames, out_pix, out, s);
                 else if (dtype == TB_DTYPE_U8) launch_input_convert<uint8_t>(d_frames, out_pix, out, s);
@@ -982,8 +1061,15 @@ int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int
     tin.D = D; tin.H = H; tin.W = W; tin.C = c_in;
     tin.fmt = FMT_SPLIT;
     tin.c_pad = round_up(c_in, 16);
+    if (c_in <= 8 && conv->kernel[2] <= 8 && !getenv("TIMED_B200_NO_WFOLD")) {
+        const int kw = conv->kernel[2], pad0 = conv->pad_same ? (kw - 1) / 2 : 0, kwin = kw <= 4 ? 4 : 8;
+        tin.wfold = true;
+        tin.wf_lm = pad0;
+        tin.wf_pitch = pad0 + W + (kwin - 1 - pad0);
+        tin.c_pad = 8;
+    }
     ConvPlan plan;
-    rc = conv_plan_create(plan, ops[1], D, H, W, c_in, tin.c_pad);
+    rc = conv_plan_create(plan, ops[1], D, H, W, c_in, tin.c_pad, &tin);
     if (rc) { free_conv_plan(plan); return rc; }
     const int64_t out_ppf = static_cast<int64_t>(plan.Do) * plan.Ho * plan.Wo;
     tin.slack_pix = static_cast<int>(((128 + out_ppf - 1) / out_ppf) * tin.pix_per_frame());
@@ -992,7 +1078,8 @@ int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int
     if (e != cudaSuccess) { free_conv_plan(plan); TB_CHECK_CUDA(e); }
     cudaMemset(d_in, 0, tin.bytes(n));
     TView vin = make_view(tin, static_cast<uint8_t*>(d_in), n);
-    launch_input_convert<float>(d_x, n * tin.pix_per_frame(), vin, nullptr);
+    if (tin.wfold) launch_input_convert_wfold<float>(d_x, tin, n, vin, nullptr);
+    else launch_input_convert<float>(d_x, n * tin.pix_per_frame(), vin, nullptr);
     TView vout{};
     vout.fmt = FMT_F32;
     vout.f32 = d_y;

@@ -78,13 +78,48 @@ struct ConvKernelParams {
 
 #if defined(__CUDACC__)
 
+constexpr int kEpiSmemN = 512;   // epilogue vectors are staged in smem when n_alloc <= this
+
 // ACT = -1 selects the runtime-dispatched activation (sigmoid/tanh/mixed cases).
+// ELU is branch-free: a divergent expm1f call per element made the epilogue as long as the
+// mainloop.  exp(x)-1 uses the SFU exp (abs. error ~1e-7) away from zero and a 4-term series
+// within (-1/32, 0] (error < 3e-10) -- both far below the 2^-17 operand-split resolution.
 template <int ACT>
 __device__ __forceinline__ float act_ct(float x, int act_rt, float alpha) {
     if constexpr (ACT == ACT_NONE) return x;
     else if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.0f);
-    else if constexpr (ACT == ACT_ELU) return x > 0.0f ? x : alpha * expm1f(x);
-    else return apply_act(x, act_rt, alpha);
+    else if constexpr (ACT == ACT_ELU) {
+        const float series = x * fmaf(x, fmaf(x, fmaf(x, 0.041666668f, 0.16666667f), 0.5f), 1.0f);
+        const float em1 = x > -0.03125f ? series : __expf(x) - 1.0f;
+        return x > 0.0f ? x : alpha * em1;
+    } else return apply_act(x, act_rt, alpha);
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// D[tmem] (+)= A * B with descriptors given as (lo, shared hi) 32-bit halves; issued by the
+// elected lane only (pred).  Keeping everything else warp-uniform lets ptxas do the address
+// arithmetic on the uniform datapath instead of R2UR-ing per instruction.
+__device__ __forceinline__ void umma_bf16_lohi(bool leader, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                               uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    if (leader) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 
 template <int ACT1, int ACT2, int FMT>
@@ -100,6 +135,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float s_epi[3][kEpiSmemN];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -120,6 +156,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         tma_prefetch_desc(&map_w);
     }
     if (warp == 1) tmem_alloc_512(&tmem_base_slot);
+    const int n_alloc = p.n_tiles * p.n_tile;
+    const bool epi_in_smem = n_alloc <= kEpiSmemN;
+    if (epi_in_smem) {
+        for (int i = threadIdx.x; i < n_alloc; i += blockDim.x) {
+            s_epi[0][i] = p.bias[i];
+            s_epi[1][i] = p.scale[i];
+            s_epi[2][i] = p.shift[i];
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -132,118 +177,123 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
 
     if (warp == 0) {
         // =============================================================== TMA producer
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_ct = tile / p.n_tiles;
-                const int n_idx = tile - m_ct * p.n_tiles;
-                int32_t bw[2], bh[2], bd[2], bn[2];
-                for (int mi = 0; mi < p.mt; ++mi) {
-                    int m0 = (m_ct * p.mt + mi) * 128;
-                    if (m0 >= p.m_total) m0 = 0;   // dummy sub-tile: rows are discarded later
-                    const int q = m0 % p.Wo;
-                    int t = m0 / p.Wo;
-                    const int pp = t % p.Ho;
-                    t /= p.Ho;
-                    const int z = t % p.Do;
-                    const int nf = t / p.Do;
-                    bw[mi] = q + p.lc_w;
-                    bh[mi] = pp + p.lc_h;
-                    bd[mi] = z + p.lc_d;
-                    bn[mi] = nf;
-                }
-                for (int g = 0; g < n_groups; ++g) {
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
-                    const int kb0 = g * p.kg;
-                    const int nkb = min(p.kg, p.n_kblocks - kb0);
+        // The whole warp walks the loops (uniform control flow); one elected lane issues.
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_ct = tile / p.n_tiles;
+            const int n_idx = tile - m_ct * p.n_tiles;
+            int32_t bw[2], bh[2], bd[2], bn[2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                int m0 = (m_ct * p.mt + mi) * 128;
+                if (m0 >= p.m_total) m0 = 0;       // dummy sub-tile: rows are discarded later
+                const int q = m0 % p.Wo;
+                int t = m0 / p.Wo;
+                const int pp = t % p.Ho;
+                t /= p.Ho;
+                const int z = t % p.Do;
+                const int nf = t / p.Do;
+                bw[mi] = q + p.lc_w;
+                bh[mi] = pp + p.lc_h;
+                bd[mi] = z + p.lc_d;
+                bn[mi] = nf;
+            }
+            for (int g = 0; g < n_groups; ++g) {
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                const int kb0 = g * p.kg;
+                const int nkb = min(p.kg, p.n_kblocks - kb0);
+                if (leader) {
                     if (p.dbg & 1) {
                         mbar_arrive(&full_bar[s]);
-                        if (++s == p.stages) { s = 0; ph ^= 1u; }
-                        continue;
-                    }
-                    mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * kb_bytes);
-                    uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-                    for (int j = 0; j < nkb; ++j) {
-                        const int kb = kb0 + j;
-                        const int tap = kb / p.cin_blocks;
-                        const int cb = kb - tap * p.cin_blocks;
-                        const int tkw = tap % p.kw;
-                        const int t2 = tap / p.kw;
-                        const int tkh = t2 % p.kh;
-                        const int tkd = t2 / p.kh;
-                        uint8_t* base = st + static_cast<size_t>(j) * kb_bytes;
-                        for (int mi = 0; mi < p.mt; ++mi) {
-                            tma_load_im2col_5d(base + mi * p.a_sub_bytes, &map_a, &full_bar[s],
-                                               cb * p.kc, bw[mi], bh[mi], bd[mi], bn[mi],
-                                               static_cast<uint16_t>(tkw),
-                                               static_cast<uint16_t>(tkh),
-                                               static_cast<uint16_t>(tkd));
-                            tma_load_im2col_5d(base + (p.mt + mi) * p.a_sub_bytes, &map_a,
-                                               &full_bar[s], cb * p.kc, bw[mi], bh[mi], bd[mi],
-                                               bn[mi] + p.lo_plane_frames,
-                                               static_cast<uint16_t>(tkw),
-                                               static_cast<uint16_t>(tkh),
-                                               static_cast<uint16_t>(tkd));
+                    } else {
+                        mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * kb_bytes);
+                        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+                        int tap = kb0 / p.cin_blocks;
+                        int cb = kb0 - tap * p.cin_blocks;
+                        for (int j = 0; j < nkb; ++j) {
+                            const int tkw = tap % p.kw;
+                            const int t2 = tap / p.kw;
+                            const int tkh = t2 % p.kh;
+                            const int tkd = t2 / p.kh;
+                            uint8_t* base = st + static_cast<size_t>(j) * kb_bytes;
+                            for (int mi = 0; mi < p.mt; ++mi) {
+                                tma_load_im2col_5d(base + mi * p.a_sub_bytes, &map_a, &full_bar[s],
+                                                   cb * p.kc, bw[mi], bh[mi], bd[mi], bn[mi],
+                                                   static_cast<uint16_t>(tkw), static_cast<uint16_t>(tkh),
+                                                   static_cast<uint16_t>(tkd));
+                                tma_load_im2col_5d(base + (p.mt + mi) * p.a_sub_bytes, &map_a, &full_bar[s],
+                                                   cb * p.kc, bw[mi], bh[mi], bd[mi],
+                                                   bn[mi] + p.lo_plane_frames, static_cast<uint16_t>(tkw),
+                                                   static_cast<uint16_t>(tkh), static_cast<uint16_t>(tkd));
+                            }
+                            uint8_t* wb = base + 2 * p.mt * p.a_sub_bytes;
+                            const int kcoord = tap * p.cin_pad + cb * p.kc;
+                            tma_load_2d(wb, &map_w, &full_bar[s], kcoord, n_idx * p.n_tile);
+                            tma_load_2d(wb + p.w_sub_bytes, &map_w, &full_bar[s], kcoord,
+                                        p.w_lo_rows + n_idx * p.n_tile);
+                            if (++cb == p.cin_blocks) { cb = 0; ++tap; }
                         }
-                        uint8_t* wb = base + 2 * p.mt * p.a_sub_bytes;
-                        const int kcoord = tap * p.cin_pad + cb * p.kc;
-                        tma_load_2d(wb, &map_w, &full_bar[s], kcoord, n_idx * p.n_tile);
-                        tma_load_2d(wb + p.w_sub_bytes, &map_w, &full_bar[s], kcoord,
-                                    p.w_lo_rows + n_idx * p.n_tile);
                     }
-                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // =============================================================== MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.n_tile));
-            const int k16_steps = p.kc / 16;
-            int s = 0;
-            uint32_t ph = 0;
-            int acc = 0;
-            uint32_t acc_ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
+        const bool leader = elect_one();
+        const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.n_tile));
+        // descriptor = {lo: start address >> 4 | LBO(=1) << 16, hi: SBO >> 4 | version << 14 | swizzle << 29}
+        const uint32_t desc_hi = ((p.row_bytes * 8u) >> 4) | (1u << 14) | (p.layout_type << 29);
+        const uint32_t lo_flags = 1u << 16;
+        const int k16_steps = p.kc / 16;
+        const uint32_t a_sub16 = p.a_sub_bytes >> 4, w_sub16 = p.w_sub_bytes >> 4, kb16 = kb_bytes >> 4;
+        const uint32_t a_lo_off16 = static_cast<uint32_t>(p.mt) * a_sub16;       // hi plane -> lo plane
+        const uint32_t w_off16 = 2u * static_cast<uint32_t>(p.mt) * a_sub16;     // A block -> W block
+        const uint32_t smem_base16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+        int s = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
+            tc_fence_after();
+            uint32_t accumulate = 0;
+            const uint32_t d0 = tmem_base + static_cast<uint32_t>((acc * p.mt) * p.acc_cols);
+            const uint32_t d1 = d0 + static_cast<uint32_t>(p.acc_cols);
+            for (int g = 0; g < n_groups; ++g) {
+                mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                uint32_t accumulate = 0;
-                for (int g = 0; g < n_groups; ++g) {
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const int kb0 = g * p.kg;
-                    const int nkb = min(p.kg, p.n_kblocks - kb0);
-                    const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-                    for (int j = 0; j < nkb && !(p.dbg & 2); ++j) {
-                        const uint32_t base = st + static_cast<uint32_t>(j) * kb_bytes;
-                        const uint32_t wb = base + 2u * p.mt * p.a_sub_bytes;
+                const int nkb = min(p.kg, p.n_kblocks - g * p.kg);
+                uint32_t base16 = (smem_base16 + static_cast<uint32_t>(s) * (stage_bytes >> 4)) | lo_flags;
+                if (!(p.dbg & 2)) {
+                    for (int j = 0; j < nkb; ++j, base16 += kb16) {
                         for (int kk = 0; kk < k16_steps; ++kk) {
-                            const uint32_t koff = static_cast<uint32_t>(kk) * 32u;
-                            const uint64_t w_hi = umma_smem_desc(wb + koff, p.row_bytes, p.layout_type);
-                            const uint64_t w_lo =
-                                umma_smem_desc(wb + p.w_sub_bytes + koff, p.row_bytes, p.layout_type);
-                            for (int mi = 0; mi < p.mt; ++mi) {
-                                const uint64_t a_hi = umma_smem_desc(
-                                    base + mi * p.a_sub_bytes + koff, p.row_bytes, p.layout_type);
-                                const uint64_t a_lo = umma_smem_desc(
-                                    base + (p.mt + mi) * p.a_sub_bytes + koff, p.row_bytes,
-                                    p.layout_type);
-                                const uint32_t d =
-                                    tmem_base + static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);
-                                umma_bf16(d, a_hi, w_hi, idesc, accumulate);
-                                umma_bf16(d, a_lo, w_hi, idesc, 1u);
-                                umma_bf16(d, a_hi, w_lo, idesc, 1u);
+                            const uint32_t a0 = base16 + static_cast<uint32_t>(kk) * 2u;   // +32 B per K=16
+                            const uint32_t w_hi = a0 + w_off16;
+                            const uint32_t w_lo = w_hi + w_sub16;
+                            umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc, accumulate);
+                            umma_bf16_lohi(leader, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                            umma_bf16_lohi(leader, d0, a0, w_lo, desc_hi, idesc, 1u);
+                            if (p.mt == 2) {
+                                const uint32_t a1 = a0 + a_sub16;
+                                umma_bf16_lohi(leader, d1, a1, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(leader, d1, a1 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(leader, d1, a1, w_lo, desc_hi, idesc, 1u);
                             }
                             accumulate = 1u;
                         }
                     }
-                    umma_commit(&empty_bar[s]);       // frees the smem stage when the MMAs retire
-                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
-                if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+                if (leader) umma_commit(&empty_bar[s]);   // frees the smem stage when the MMAs retire
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
+            if (leader) umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
+            __syncwarp();
+            if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
     } else {
         // =============================================================== epilogue (warps 2..9)
@@ -251,6 +301,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         const int half = (warp - 2) >> 2;             // which of the quadrant's two warps
         const int row_in_tile = quad * 32 + lane;
         const int chunks = p.n_tile / 16;
+        const float* bias_v = epi_in_smem ? s_epi[0] : p.bias;
+        const float* scale_v = epi_in_smem ? s_epi[1] : p.scale;
+        const float* shift_v = epi_in_smem ? s_epi[2] : p.shift;
         int acc = 0;
         uint32_t acc_ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -273,9 +326,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                     float v[16];
 #pragma unroll
                     for (int i4 = 0; i4 < 4; ++i4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i4);
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + i4);
-                        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0) + i4);
+                        const float4 b = *(reinterpret_cast<const float4*>(bias_v + n0) + i4);
+                        const float4 sc = *(reinterpret_cast<const float4*>(scale_v + n0) + i4);
+                        const float4 sh = *(reinterpret_cast<const float4*>(shift_v + n0) + i4);
                         const float bb[4] = {b.x, b.y, b.z, b.w};
                         const float ss[4] = {sc.x, sc.y, sc.z, sc.w};
                         const float hh[4] = {sh.x, sh.y, sh.z, sh.w};
@@ -305,9 +358,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                         dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                     } else if (row_ok) {
                         float* dst = p.out_f32 + m * p.ldc + n0;
+                        if (n0 + 16 <= p.c_store && (p.ldc & 3) == 0) {
+                            float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (n0 + i < p.c_store) dst[i] = v[i];
+                            for (int i = 0; i < 4; ++i)
+                                d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n0 + i < p.c_store) dst[i] = v[i];
+                        }
                     }
                 }
             }

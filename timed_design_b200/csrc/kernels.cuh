@@ -54,6 +54,38 @@ __global__ void input_convert_kernel(const T* __restrict__ x, int64_t n_pix, TVi
     }
 }
 
+// W-folded input layout (api.cu TensorInfo::wfold): rows = (frame, d, h); each row stores `pitch`
+// pixels of 8 channels: `lm` zero pixels, the W real pixels (channels >= c zero), zeros to the pitch.
+// One thread per stored pixel: 16-byte store per plane.
+template <typename T>
+__global__ void input_convert_wfold_kernel(const T* __restrict__ x, int64_t n_rows, int W, int c, int lm,
+                                           int pitch, __nv_bfloat16* __restrict__ hi,
+                                           __nv_bfloat16* __restrict__ lo) {
+    const int64_t total = n_rows * pitch;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = i / pitch;
+        const int w = static_cast<int>(i - row * pitch) - lm;
+        uint32_t h4[4] = {0, 0, 0, 0}, l4[4] = {0, 0, 0, 0};
+        if (w >= 0 && w < W) {
+            const T* src = x + (row * W + w) * c;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = k < c ? static_cast<float>(src[k]) : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v[2 * k], h0, l0);
+                split_bf16(v[2 * k + 1], h1, l1);
+                h4[k] = pack_bf16x2(h0, h1);
+                l4[k] = pack_bf16x2(l0, l1);
+            }
+        }
+        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+        reinterpret_cast<uint4*>(lo)[i] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+    }
+}
+
 // ------------------------------------------------------------------ pooling (TF semantics)
 struct PoolParams {
     int32_t D, H, W, Do, Ho, Wo;
