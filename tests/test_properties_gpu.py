@@ -1,0 +1,103 @@
+"""GPU: size-independent properties of the inference path at BASELINE.json's full batch size
+(4096 frames of 21^3 x 6 through the TIMED-20 stand-in) and edge cases of the boundary."""
+import numpy as np
+import pytest
+
+from oracle import keras_oracle as ko
+from timed_design_b200 import standins
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def timed():
+    from timed_design_b200.model import Model
+    cfg, w = standins.timed_standin(20)
+    return cfg, w, Model(cfg, w)
+
+
+def test_full_batch_properties(timed):
+    """Batch 4096 (the benchmark configuration): rows sum to 1, every frame's probabilities are
+    independent of the batch it travels in (tiles of 128 output pixels cross frame boundaries, so
+    this is the property that would break), repeated frames give bit-identical rows, and a
+    sample of rows matches the CPU oracle."""
+    cfg, w, m = timed
+    uniq = standins.synthetic_frames(256, seed=77)
+    X = np.tile(uniq, (16, 1, 1, 1, 1))                     # 4096 frames
+    p = m.predict(X, batch_size=4096)
+    assert p.shape == (4096, 20) and np.isfinite(p).all()
+    np.testing.assert_allclose(p.sum(1), 1.0, atol=2e-6)
+    for k in range(1, 16):                                   # same frame, different position in the batch
+        np.testing.assert_array_equal(p[k * 256:(k + 1) * 256], p[:256])
+    small = m.predict(uniq[:37])                             # different batch size, different tiling
+    np.testing.assert_array_equal(small, p[:37])
+    one = m.predict(uniq[5:6])
+    np.testing.assert_array_equal(one[0], p[5])
+    ref = ko.forward_torch(cfg, w, uniq[:24])
+    assert np.abs(p[:24] - ref).max() <= 1e-4
+    safe = ~ko.near_tie_rows(ref)
+    assert (ko.fp16_argmax(p[:24])[safe] == ko.fp16_argmax(ref)[safe]).all()
+
+
+def test_chunked_host_path_equals_single_pass(timed):
+    _, _, m = timed
+    X = standins.synthetic_frames(70, seed=3)
+    a = m.predict(X, batch_size=4096)
+    b = m.predict(X, batch_size=16)                          # 5 chunks, ragged tail, double-buffered H2D
+    c = m.predict(X, batch_size=1)
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a, c)
+
+
+def test_edge_inputs(timed):
+    _, _, m = timed
+    assert m.predict(np.zeros((0, 21, 21, 21, 6), np.float32)).shape == (0, 20)
+    z = m.predict(np.zeros((3, 21, 21, 21, 6), np.float32))  # empty voxel grids
+    assert np.isfinite(z).all() and np.abs(z.sum(1) - 1).max() < 1e-6
+    np.testing.assert_array_equal(z[0], z[2])
+    with pytest.raises(ValueError):
+        m.predict(np.zeros((2, 21, 21, 21, 5), np.float32))  # wrong channel count
+    with pytest.raises(ValueError):
+        m.predict(np.zeros((2, 20, 21, 21, 6), np.float32))
+    nc = np.asfortranarray(standins.synthetic_frames(4, seed=9))      # non-contiguous input
+    np.testing.assert_array_equal(m.predict(nc), m.predict(np.ascontiguousarray(nc)))
+
+
+def test_device_resident_forward_matches_host_path(timed):
+    import torch
+    _, _, m = timed
+    X = standins.synthetic_frames(40, seed=21)
+    host = m.predict(X)
+    d = torch.from_numpy(X).cuda()
+    probs = torch.empty((40, 20), dtype=torch.float32, device="cuda")
+    ws = torch.empty(m.workspace_bytes(40), dtype=torch.uint8, device="cuda")
+    m.forward_device(d, probs, ws, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(probs.cpu().numpy(), host)
+    # float64 / bool device inputs go through the same cast-to-float32 as Keras
+    d64 = torch.from_numpy(X.astype(np.float64)).cuda()
+    m.forward_device(d64, probs, ws, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(probs.cpu().numpy(), host)
+    small_ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    from timed_design_b200._lib import TimedB200Error
+    with pytest.raises(TimedB200Error):
+        m.forward_device(d, probs, small_ws)
+
+
+def test_wfold_and_dense_input_layouts_agree(monkeypatch):
+    """The W-folded first-layer path and the generic im2col path are two routes to the same conv."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, sys; sys.path.insert(0, '.');"
+            "from timed_design_b200 import standins; from timed_design_b200.model import Model;"
+            "cfg, w = standins.tiny_standin(); X = standins.synthetic_frames(9, side=9);"
+            "np.save(sys.argv[1], Model(cfg, w).predict(X))")
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        for name, env in (("a.npy", {}), ("b.npy", {"TIMED_B200_NO_WFOLD": "1"})):
+            subprocess.run([sys.executable, "-c", code, os.path.join(d, name)], check=True,
+                           env={**os.environ, **env}, cwd=str(__import__("pathlib").Path(__file__).parents[1]))
+        a, b = np.load(os.path.join(d, "a.npy")), np.load(os.path.join(d, "b.npy"))
+    assert np.abs(a - b).max() <= 2e-5

@@ -112,7 +112,21 @@ struct ConvPlan {
     // W-folded input (see TensorInfo): kwin pixels x 8 channels form one K-block of a (kd,kh) tap
     bool wfold = false;
     int kwin = 0, in_lm = 0, in_pitch = 0;
-    int taps_eff() const { return wfold ? kd * kh : kd * kh * kw; }
+    // "tap-to-N" formulation for convs with few output channels (TIMED's 20-class head): instead of
+    // taps x (C_in/16) thin MMAs of N = C_out per tile, run ONE 1x1x1 GEMM  Z[pixel, (tap, co)] =
+    // sum_c X[pixel, c] * W[tap, c, co]  with N = taps*C_out (wide MMAs, every activation read once)
+    // followed by a col2im gather  out[p, co] = sum_tap Z[p + tap - pad, tap, co]  (+ bias/act/BN).
+    bool tap2n = false;
+    int z_cols = 0, z_ld = 0;
+    float* d_c2i_bias = nullptr;     // [cout] epilogue vectors applied by the col2im kernel
+    float* d_c2i_scale = nullptr;
+    float* d_c2i_shift = nullptr;
+    int taps_eff() const { return tap2n ? 1 : (wfold ? kd * kh : kd * kh * kw); }
+    // geometry of the GEMM rows (output pixels, or input pixels for tap-to-N)
+    int Mo_d() const { return tap2n ? Di : Do; }
+    int Mo_h() const { return tap2n ? Hi : Ho; }
+    int Mo_w() const { return tap2n ? Wi : Wo; }
+    int gemm_n() const { return tap2n ? z_cols : cout; }
     __nv_bfloat16* d_w = nullptr;   // [2][n_alloc][k_total]
     float* d_bias = nullptr;        // [n_alloc]
     float* d_scale = nullptr;
@@ -137,8 +151,12 @@ static void free_conv_plan(ConvPlan& p) {
     cudaFree(p.d_bias);
     cudaFree(p.d_scale);
     cudaFree(p.d_shift);
+    cudaFree(p.d_c2i_bias);
+    cudaFree(p.d_c2i_scale);
+    cudaFree(p.d_c2i_shift);
     p.d_w = nullptr;
     p.d_bias = p.d_scale = p.d_shift = nullptr;
+    p.d_c2i_bias = p.d_c2i_scale = p.d_c2i_shift = nullptr;
 }
 
 // 227 KB per CTA is the limit for static + dynamic shared memory; the kernel keeps ~6.3 KB static
@@ -175,8 +193,12 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
             while (kg > 1 && kb * kg * 2 > kSmemBudget) --kg;
             if (kb * kg * 2 > kSmemBudget) continue;   // cannot even double-buffer
             int stages = static_cast<int>(std::min<size_t>(kConvMaxStages, kSmemBudget / (kb * kg)));
-            // score: prefer >=3 stages, then mt=2, then wider kc
-            const int score = (stages >= 3 ? 100 : 0) + (mt == 2 ? 10 : 0) + kc / 16;
+            // score: prefer >=3 stages, then mt=2, then wider kc; a single accumulator stage
+            // serialises the epilogue with the mainloop, which only a long K loop amortises
+            const int acc_stages_c = std::min(2, 512 / (mt * acc_cols));
+            const int mainloop_mmas = n_kblocks * (kc / 16) * 3 * mt;
+            const int score = (stages >= 3 ? 100 : 0) + (mt == 2 ? 10 : 0) + kc / 16 -
+                              ((acc_stages_c == 1 && mainloop_mmas < 1500) ? 20 : 0);
             if (score > best_score) {
                 best_score = score;
                 cfg->kc = kc;
@@ -228,6 +250,9 @@ static int encode_a_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* ba
     cuuint64_t strides[4] = {px, px * p.Wi, px * p.Wi * p.Hi, px * p.Wi * p.Hi * p.Di};
     int lower[3] = {-p.pad0[2], -p.pad0[1], -p.pad0[0]};
     int upper[3] = {p.pad1[2] - (p.kw - 1), p.pad1[1] - (p.kh - 1), p.pad1[0] - (p.kd - 1)};
+    if (p.tap2n) {
+        for (int i = 0; i < 3; ++i) lower[i] = upper[i] = 0;
+    }
     if (p.wfold) {
         // "pixel" = kwin consecutive stored pixels starting pad_w0 to the left of the output
         // column; consecutive "pixels" overlap in memory (stride = one stored pixel = 16 bytes).
@@ -291,7 +316,16 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
         TB_REQUIRE(out[i] >= 1, "conv: kernel larger than input with 'valid' padding");
     }
     p.Do = out[0]; p.Ho = out[1]; p.Wo = out[2];
-    const int n_pad = round_up(p.cout, 16);
+    {
+        const int taps_all = p.kd * p.kh * p.kw;
+        p.tap2n = !p.wfold && taps_all > 1 && p.cout <= 64 && taps_all * p.cout <= 1024 &&
+                  cin_pad >= 128 && !getenv("TIMED_B200_NO_TAP2N");
+        if (p.tap2n) {
+            p.z_cols = taps_all * p.cout;
+            p.z_ld = round_up(p.z_cols, 4);
+        }
+    }
+    const int n_pad = round_up(p.gemm_n(), 16);
     p.n_tiles = ceil_div(n_pad, 256);
     p.n_tile = round_up(ceil_div(n_pad, p.n_tiles), 16);
     p.n_alloc = p.n_tile * p.n_tiles;
@@ -310,9 +344,12 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
                 const __nv_bfloat16 hi = __float2bfloat16_rn(v);
                 const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
                 // K index: dense = tap*cin_pad + c; W-folded = (kd,kh)-tap * (kwin*8) + kw*8 + c
-                const size_t kidx = p.wfold ? static_cast<size_t>(t / p.kw) * cin_pad + static_cast<size_t>(t % p.kw) * 8 + c
+                const size_t kidx = p.tap2n ? static_cast<size_t>(c)
+                                  : p.wfold ? static_cast<size_t>(t / p.kw) * cin_pad + static_cast<size_t>(t % p.kw) * 8 + c
                                             : static_cast<size_t>(t) * cin_pad + c;
-                const size_t o = static_cast<size_t>(n) * p.k_total + kidx;
+                // GEMM column: the output channel, or (tap, channel) for tap-to-N
+                const size_t ncol = p.tap2n ? static_cast<size_t>(t) * p.cout + n : static_cast<size_t>(n);
+                const size_t o = ncol * p.k_total + kidx;
                 w[o] = hi;
                 w[plane + o] = lo;
             }
@@ -320,6 +357,20 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
     TB_CHECK_CUDA(cudaMalloc(&p.d_w, 2 * plane * sizeof(__nv_bfloat16)));
     TB_CHECK_CUDA(cudaMemcpy(p.d_w, w.data(), 2 * plane * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     std::vector<float> b(p.n_alloc, 0.f), sc(p.n_alloc, 1.f), sh(p.n_alloc, 0.f);
+    if (p.tap2n) {      // the GEMM epilogue is the identity; the col2im kernel applies bias/act/BN
+        std::vector<float> cb(p.cout, 0.f), cs(p.cout, 1.f), ch(p.cout, 0.f);
+        for (int n = 0; n < p.cout; ++n) {
+            if (d.bias) cb[n] = d.bias[n];
+            if (d.scale) cs[n] = d.scale[n];
+            if (d.shift) ch[n] = d.shift[n];
+        }
+        TB_CHECK_CUDA(cudaMalloc(&p.d_c2i_bias, p.cout * sizeof(float)));
+        TB_CHECK_CUDA(cudaMalloc(&p.d_c2i_scale, p.cout * sizeof(float)));
+        TB_CHECK_CUDA(cudaMalloc(&p.d_c2i_shift, p.cout * sizeof(float)));
+        TB_CHECK_CUDA(cudaMemcpy(p.d_c2i_bias, cb.data(), p.cout * sizeof(float), cudaMemcpyHostToDevice));
+        TB_CHECK_CUDA(cudaMemcpy(p.d_c2i_scale, cs.data(), p.cout * sizeof(float), cudaMemcpyHostToDevice));
+        TB_CHECK_CUDA(cudaMemcpy(p.d_c2i_shift, ch.data(), p.cout * sizeof(float), cudaMemcpyHostToDevice));
+    } else
     for (int n = 0; n < p.cout; ++n) {
         if (d.bias) b[n] = d.bias[n];
         if (d.scale) sc[n] = d.scale[n];
@@ -351,9 +402,25 @@ static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map
 
 // Launch one conv over `n_frames` frames.  `in_base`: split tensor base (hi plane first);
 // `in_frames_alloc`: frames per plane in that allocation.
+// bytes of fp32 scratch (the Z matrix) a tap-to-N conv needs for n_frames
+static size_t conv_scratch_bytes(const ConvPlan& p, int64_t n_frames) {
+    if (!p.tap2n) return 0;
+    return static_cast<size_t>(round_up64(n_frames * p.Di * p.Hi * p.Wi * static_cast<int64_t>(p.z_ld) * 4, 1024));
+}
+
 static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames,
-                       const TView& out, cudaStream_t stream) {
-    const int64_t m_total64 = n_frames * p.Do * p.Ho * p.Wo;
+                       const TView& final_out, cudaStream_t stream, void* scratch = nullptr,
+                       size_t scratch_bytes = 0) {
+    TView out = final_out;
+    if (p.tap2n) {
+        TB_REQUIRE(scratch && scratch_bytes >= conv_scratch_bytes(p, n_frames), "conv: scratch too small");
+        out = TView{};
+        out.fmt = FMT_F32;
+        out.f32 = static_cast<float*>(scratch);
+        out.ld = p.z_ld;
+        out.c = out.c_pad = p.z_cols;
+    }
+    const int64_t m_total64 = n_frames * p.Mo_d() * p.Mo_h() * p.Mo_w();
     TB_REQUIRE(m_total64 > 0 && m_total64 < (1ll << 31) - 512, "conv: too many output pixels per launch");
     ConvPlan::Config cfg;
     int rc = choose_config(p, m_total64, &cfg);
@@ -374,7 +441,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.n_tile = p.n_tile;
     k.acc_cols = cfg.acc_cols;
     k.acc_stages = cfg.acc_stages;
-    k.kh = p.kh; k.kw = p.wfold ? 1 : p.kw;
+    k.kh = p.tap2n ? 1 : p.kh; k.kw = (p.wfold || p.tap2n) ? 1 : p.kw;
     k.n_taps = p.taps_eff();
     k.cin_pad = p.cin_pad;
     k.kc = cfg.kc;
@@ -382,8 +449,10 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.kg = cfg.kg;
     k.n_kblocks = k.n_taps * k.cin_blocks;
     k.stages = cfg.stages;
-    k.Do = p.Do; k.Ho = p.Ho; k.Wo = p.Wo;
-    k.lc_d = -p.pad0[0]; k.lc_h = -p.pad0[1]; k.lc_w = p.wfold ? 0 : -p.pad0[2];
+    k.Do = p.Mo_d(); k.Ho = p.Mo_h(); k.Wo = p.Mo_w();
+    k.lc_d = p.tap2n ? 0 : -p.pad0[0];
+    k.lc_h = p.tap2n ? 0 : -p.pad0[1];
+    k.lc_w = (p.wfold || p.tap2n) ? 0 : -p.pad0[2];
     k.lo_plane_frames = static_cast<int32_t>(in_frames_alloc);
     k.w_lo_rows = p.n_alloc;
     k.a_sub_bytes = 128u * cfg.kc * 2u;
@@ -392,6 +461,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.layout_type = cfg.swizzle_code;
     k.bias = p.d_bias; k.scale = p.d_scale; k.shift = p.d_shift;
     k.act1 = p.act1; k.act2 = p.act2; k.alpha1 = p.alpha1; k.alpha2 = p.alpha2;
+    if (p.tap2n) k.act1 = k.act2 = ACT_NONE;     // applied by the col2im kernel
     k.out_fmt = out.fmt;
     k.out_f32 = out.f32; k.out_hi = out.hi; k.out_lo = out.lo;
     k.ldc = out.ld;
@@ -429,6 +499,21 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
                                     : launch_conv_instance<-1, -1, FMT_F32>(map_a, map_w, k, grid, cfg.smem_bytes, stream);
     if (rc) return rc;
     TB_CHECK_CUDA(cudaGetLastError());
+    if (p.tap2n) {
+        Col2imParams cp;
+        cp.Di = p.Di; cp.Hi = p.Hi; cp.Wi = p.Wi; cp.Do = p.Do; cp.Ho = p.Ho; cp.Wo = p.Wo;
+        cp.kd = p.kd; cp.kh = p.kh; cp.kw = p.kw;
+        cp.pd = p.pad0[0]; cp.ph = p.pad0[1]; cp.pw = p.pad0[2];
+        cp.cout = p.cout;
+        cp.z_ld = p.z_ld;
+        cp.act1 = p.act1; cp.act2 = p.act2; cp.alpha1 = p.alpha1; cp.alpha2 = p.alpha2;
+        const int cw = final_out.fmt == FMT_SPLIT ? final_out.c_pad : final_out.c;
+        const int64_t work = n_frames * p.Do * p.Ho * p.Wo * cw;
+        col2im_kernel<<<grid_for(work, 256), 256, 0, stream>>>(static_cast<const float*>(scratch), final_out,
+                                                               n_frames, cp, p.d_c2i_bias, p.d_c2i_scale,
+                                                               p.d_c2i_shift);
+        TB_CHECK_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -443,6 +528,7 @@ struct OpNode {
 
 struct Layout {
     std::vector<size_t> offset;
+    size_t scratch_off = 0, scratch_bytes = 0;   // shared fp32 scratch of the tap-to-N convs
     size_t total = 0;
 };
 
@@ -543,7 +629,10 @@ static const Layout& get_layout(tb_graph* g, int64_t n_frames) {
         }
         live[i] = {L.offset[i], need};
     }
-    L.total = top;
+    L.scratch_off = static_cast<size_t>(round_up64(static_cast<int64_t>(top), 1024));
+    for (const auto& op : g->ops)
+        L.scratch_bytes = std::max(L.scratch_bytes, conv_scratch_bytes(op.conv, n_frames));
+    L.total = L.scratch_off + L.scratch_bytes;
     return g->layouts.emplace(n_frames, std::move(L)).first->second;
 }
 
@@ -616,7 +705,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 if (rc) return rc;
                 t.D = node.conv.Do; t.H = node.conv.Ho; t.W = node.conv.Wo; t.C = d.c_out;
                 g->flops += node.conv.flops_per_frame();
-                g->launches += 1;
+                g->launches += node.conv.tap2n ? 2 : 1;
                 break;
             }
             case TB_OP_POOL3D: {
@@ -776,7 +865,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
             case TB_OP_CONV3D: {
                 TB_REQUIRE(ti0->fmt == FMT_SPLIT, "internal: conv input must be split planes");
                 int rc = conv_launch(node.conv, base + L.offset[d.inputs[0]], ti0->frames_alloc(n_frames),
-                                     n_frames, out, s);
+                                     n_frames, out, s, base + L.scratch_off, L.scratch_bytes);
                 if (rc) return rc;
                 break;
             }
@@ -837,6 +926,18 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
     return 0;
 }
 
+static size_t dtype_size(int dtype) {
+    return dtype == TB_DTYPE_F64 ? 8 : (dtype == TB_DTYPE_F32 ? 4 : 1);
+}
+
+// Largest frame count one pass may take: every tensor's pixel count must stay below 2^31 (the
+// kernels index GEMM rows with 32-bit integers).  Larger requests are run as several passes.
+static int64_t max_frames_per_pass(const tb_graph* g) {
+    int64_t max_ppf = 1;
+    for (const auto& t : g->tensors) max_ppf = std::max<int64_t>(max_ppf, t.stored_pix_per_frame());
+    return std::max<int64_t>(1, ((1ll << 31) - (1 << 20)) / max_ppf);
+}
+
 static void graph_free(tb_graph* g) {
     if (!g) return;
     cudaSetDevice(g->device);
@@ -859,9 +960,6 @@ static void graph_free(tb_graph* g) {
     delete g;
 }
 
-static size_t dtype_size(int dtype) {
-    return dtype == TB_DTYPE_F64 ? 8 : (dtype == TB_DTYPE_F32 ? 4 : 1);
-}
 
 }  // namespace tb
 
@@ -963,7 +1061,7 @@ int timed_b200_graph_read_op_times(tb_graph* g, float* ms_per_op, int32_t* op_ki
 int timed_b200_graph_workspace_bytes(const tb_graph* g, int64_t n_frames, size_t* out) {
     TB_REQUIRE(g && out, "null argument");
     TB_REQUIRE(n_frames > 0, "n_frames must be positive");
-    *out = get_layout(const_cast<tb_graph*>(g), n_frames).total;
+    *out = get_layout(const_cast<tb_graph*>(g), std::min(n_frames, max_frames_per_pass(g))).total;
     return TB_OK;
 }
 
@@ -971,9 +1069,18 @@ int timed_b200_graph_forward(tb_graph* g, const void* d_frames, int32_t frames_d
                              void* d_workspace, size_t workspace_bytes, float* d_probs,
                              void* cuda_stream) {
     TB_REQUIRE(g && d_frames && d_workspace && d_probs, "null argument");
+    TB_REQUIRE(n_frames > 0, "n_frames must be positive");
     TB_CHECK_CUDA(cudaSetDevice(g->device));
-    return graph_forward(g, d_frames, frames_dtype, n_frames, d_workspace, workspace_bytes, d_probs,
-                         static_cast<cudaStream_t>(cuda_stream));
+    const int64_t pass = max_frames_per_pass(g);
+    const TensorInfo& tin = g->tensors[0];
+    const size_t frame_bytes = static_cast<size_t>(tin.pix_per_frame()) * tin.C * dtype_size(frames_dtype);
+    for (int64_t f0 = 0; f0 < n_frames; f0 += pass) {
+        int rc = graph_forward(g, static_cast<const uint8_t*>(d_frames) + f0 * frame_bytes, frames_dtype,
+                               std::min(pass, n_frames - f0), d_workspace, workspace_bytes,
+                               d_probs + f0 * g->n_classes, static_cast<cudaStream_t>(cuda_stream));
+        if (rc) return rc;
+    }
+    return TB_OK;
 }
 
 int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t frames_dtype,
@@ -981,7 +1088,8 @@ int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t fra
     TB_REQUIRE(g && h_frames && h_probs, "null argument");
     TB_REQUIRE(n_frames > 0, "n_frames must be positive");
     TB_CHECK_CUDA(cudaSetDevice(g->device));
-    const int64_t chunk = std::min<int64_t>(n_frames, max_chunk_frames > 0 ? max_chunk_frames : 1024);
+    const int64_t chunk = std::min<int64_t>(std::min<int64_t>(n_frames, max_chunk_frames > 0 ? max_chunk_frames : 1024),
+                                            max_frames_per_pass(g));
     const TensorInfo& tin = g->tensors[0];
     const size_t frame_bytes = static_cast<size_t>(tin.pix_per_frame()) * tin.C * dtype_size(frames_dtype);
     // (re)size library-owned staging
@@ -1086,8 +1194,17 @@ int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int
     vout.c = plan.cout;
     vout.c_pad = plan.cout;
     vout.ld = plan.cout;
-    rc = conv_launch(plan, d_in, tin.frames_alloc(n), n, vout, nullptr);
+    void* d_scratch = nullptr;
+    const size_t sb = conv_scratch_bytes(plan, n);
+    if (sb && cudaMalloc(&d_scratch, sb) != cudaSuccess) {
+        cudaFree(d_in);
+        free_conv_plan(plan);
+        set_error("cudaMalloc(scratch) failed");
+        return TB_ERR_CUDA;
+    }
+    rc = conv_launch(plan, d_in, tin.frames_alloc(n), n, vout, nullptr, d_scratch, sb);
     cudaError_t se = cudaDeviceSynchronize();
+    cudaFree(d_scratch);
     cudaFree(d_in);
     free_conv_plan(plan);
     if (rc) return rc;

@@ -237,6 +237,52 @@ __global__ void affine_act_kernel(TView in, TView out, int64_t n_pix, const floa
     }
 }
 
+// ------------------------------------------------------------------ col2im of the tap-to-N convs
+// Z: (input pixels, z_ld) fp32 with Z[p', tap*cout + co] = sum_c X[p', c] * W[tap, c, co].
+// out[p, co] = act2(scale * act1(bias + sum_tap Z[p + tap - pad, tap, co]) + shift), taps summed in
+// (kd, kh, kw) order (deterministic), out-of-volume taps skipped (= zero padding).
+struct Col2imParams {
+    int32_t Di, Hi, Wi, Do, Ho, Wo, kd, kh, kw, pd, ph, pw, cout, z_ld;
+    int32_t act1, act2;
+    float alpha1, alpha2;
+};
+__global__ void col2im_kernel(const float* __restrict__ Z, TView out, int64_t n_frames, Col2imParams cp,
+                              const float* __restrict__ bias, const float* __restrict__ scale,
+                              const float* __restrict__ shift) {
+    const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    const int64_t total = n_frames * cp.Do * cp.Ho * cp.Wo * cw;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % cw);
+        int64_t t = i / cw;
+        const int q = static_cast<int>(t % cp.Wo); t /= cp.Wo;
+        const int p = static_cast<int>(t % cp.Ho); t /= cp.Ho;
+        const int z = static_cast<int>(t % cp.Do);
+        const int64_t nf = t / cp.Do;
+        float v = 0.0f;
+        if (co < cp.cout) {
+            float acc = 0.0f;
+            int tap = 0;
+            for (int a = 0; a < cp.kd; ++a) {
+                const int d = z + a - cp.pd;
+                for (int b = 0; b < cp.kh; ++b) {
+                    const int h = p + b - cp.ph;
+                    for (int c = 0; c < cp.kw; ++c, ++tap) {
+                        const int w = q + c - cp.pw;
+                        if (d < 0 || d >= cp.Di || h < 0 || h >= cp.Hi || w < 0 || w >= cp.Wi) continue;
+                        const int64_t ip = ((nf * cp.Di + d) * cp.Hi + h) * cp.Wi + w;
+                        acc += __ldg(Z + ip * cp.z_ld + tap * cp.cout + co);
+                    }
+                }
+            }
+            v = apply_act(acc + bias[co], cp.act1, cp.alpha1);
+            v = fmaf(v, scale[co], shift[co]);
+            v = apply_act(v, cp.act2, cp.alpha2);
+        }
+        tv_store(out, ((nf * cp.Do + z) * cp.Ho + p) * cp.Wo + q, co, v);
+    }
+}
+
 // ------------------------------------------------------------------ channel-slice copy / add
 __global__ void copy_channels_kernel(TView in, TView out, int64_t n_pix, int c_off) {
     const int64_t total = n_pix * in.c;
