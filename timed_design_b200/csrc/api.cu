@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
+#include "thin_conv.cuh"
 
 namespace tb {
 
@@ -87,8 +88,15 @@ struct TensorInfo {
     // first layer (DESIGN.md "First layer").
     bool wfold = false;
     int wf_lm = 0, wf_pitch = 0;
+    // "padded volume" layout of a thin graph input read by thin_conv_kernel: 8 stored channels, zero
+    // margins materialised in all three dimensions (pv_*0 before, up to the padded extents after).
+    bool padvol = false;
+    int pv_d0 = 0, pv_h0 = 0, pv_w0 = 0, pv_Dp = 0, pv_Hp = 0, pv_Wp = 0;
     int64_t pix_per_frame() const { return static_cast<int64_t>(D) * H * W; }
-    int64_t stored_pix_per_frame() const { return static_cast<int64_t>(D) * H * (wfold ? wf_pitch : W); }
+    int64_t stored_pix_per_frame() const {
+        if (padvol) return static_cast<int64_t>(pv_Dp) * pv_Hp * pv_Wp;
+        return static_cast<int64_t>(D) * H * (wfold ? wf_pitch : W);
+    }
     // frames allocated per plane for n frames (so that a 128-pixel im2col column starting at
     // any valid pixel stays inside the allocation)
     int64_t frames_alloc(int64_t n) const {
@@ -116,6 +124,10 @@ struct ConvPlan {
     // taps x (C_in/16) thin MMAs of N = C_out per tile, run ONE 1x1x1 GEMM  Z[pixel, (tap, co)] =
     // sum_c X[pixel, c] * W[tap, c, co]  with N = taps*C_out (wide MMAs, every activation read once)
     // followed by a col2im gather  out[p, co] = sum_tap Z[p + tap - pad, tap, co]  (+ bias/act/BN).
+    // thin-input path (thin_conv.cuh): padded-volume input, kw taps aliased by the UMMA descriptor
+    bool thin = false;
+    ThinConvParams thin_params;      // static part, completed per launch
+    uint8_t* d_thin_w = nullptr;
     bool tap2n = false;
     int z_cols = 0, z_ld = 0;
     float* d_c2i_bias = nullptr;     // [cout] epilogue vectors applied by the col2im kernel
@@ -151,6 +163,8 @@ static void free_conv_plan(ConvPlan& p) {
     cudaFree(p.d_bias);
     cudaFree(p.d_scale);
     cudaFree(p.d_shift);
+    cudaFree(p.d_thin_w);
+    p.d_thin_w = nullptr;
     cudaFree(p.d_c2i_bias);
     cudaFree(p.d_c2i_scale);
     cudaFree(p.d_c2i_shift);
@@ -287,6 +301,155 @@ static int encode_a_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* ba
     return 0;
 }
 
+// ----------------------------------------------------------------------------- thin-input conv plan
+// Number of K=16 MMA steps thin_conv_kernel needs for a (kd,kh,kw) filter: kw/2 in-row pixel pairs per
+// filter row plus the left-over odd taps paired across consecutive filter rows.
+static int thin_step_count(int kd, int kh, int kw) {
+    const int rows = kd * kh;
+    return rows * (kw / 2) + ((kw & 1) ? (rows + 1) / 2 : 0);
+}
+
+// thin_conv_kernel applies when the K-step table fits, the output channels fit one N tile and the
+// resident weights plus two pipeline stages fit shared memory.
+static bool thin_fits(int kd, int kh, int kw, int cout) {
+    const int steps = thin_step_count(kd, kh, kw);
+    const int n_tile = round_up(cout, 16);
+    if (steps > kThinMaxSteps || n_tile > 256 || kd < 1 || kh < 1 || kw < 1) return false;
+    const size_t w_smem = (static_cast<size_t>(2 * steps) * n_tile * 8 * 2 * 2 + 127) & ~static_cast<size_t>(127);
+    const size_t span = static_cast<size_t>((128 + kw + 2) & ~1) * 16;
+    return w_smem + 2 * (2u * kd * kh * span) + 128 <= kSmemDynamicMax;
+}
+
+static int thin_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& tin) {
+    p.thin = true;
+    const int rows = p.kd * p.kh;
+    const int n_tile = round_up(p.cout, 16);
+    TB_REQUIRE(n_tile <= 256, "thin conv: too many output channels");
+    p.n_tiles = 1;
+    p.n_tile = p.n_alloc = n_tile;
+    // stored pixels per span: row r of a K step reads pixels r+j and r+j+1 (j <= kw-1, the partner of a
+    // partner-less left-over tap aliases the next pixel), so 128 + kw + 1 pixels, rounded to even.  Every
+    // aliased read must stay inside the stage: an out-of-allocation smem read by the tensor core silently
+    // corrupted the last pipeline stage.
+    const int span_pix = (128 + p.kw + 1 + 1) & ~1;
+    const int span_bytes = span_pix * 16;
+    const int span_stride = round_up(span_bytes, 16);
+    ThinConvParams& t = p.thin_params;
+    std::memset(&t, 0, sizeof(t));
+    // ---- K=16 steps and the matching weight K order
+    struct Half { int row, kwi; };                                  // (filter row, kw index) or row=-1: zero
+    std::vector<std::pair<Half, Half>> steps;
+    for (int r = 0; r < rows; ++r)
+        for (int j = 0; j + 1 < p.kw; j += 2) steps.push_back({{r, j}, {r, j + 1}});
+    if (p.kw & 1)
+        for (int r = 0; r < rows; r += 2)
+            steps.push_back({{r, p.kw - 1}, {r + 1 < rows ? r + 1 : -1, p.kw - 1}});
+    TB_REQUIRE(static_cast<int>(steps.size()) <= kThinMaxSteps, "thin conv: too many K steps");
+    t.n_steps = static_cast<int>(steps.size());
+    for (int k = 0; k < t.n_steps; ++k) {
+        const Half a = steps[k].first, b = steps[k].second;
+        t.step_off16[k] = static_cast<uint32_t>(a.row * span_stride + a.kwi * 16) >> 4;
+        // second K-half: the next pixel of the same span (16 B) or the same pixel of the next span
+        // (a missing partner has zero weights: alias the next pixel, any valid smem will do)
+        t.step_lbo16[k] = (b.row >= 0 && b.row != a.row) ? static_cast<uint32_t>(span_stride) >> 4 : 1u;
+    }
+    // ---- weights: [plane][2*n_steps chunks][n_tile][8]
+    const size_t plane = static_cast<size_t>(2 * t.n_steps) * n_tile * 8;
+    std::vector<__nv_bfloat16> w(2 * plane, __float2bfloat16(0.0f));
+    for (int k = 0; k < t.n_steps; ++k)
+        for (int hsel = 0; hsel < 2; ++hsel) {
+            const Half h = hsel ? steps[k].second : steps[k].first;
+            if (h.row < 0) continue;
+            const int tap = h.row * p.kw + h.kwi;                   // (kd,kh,kw) flattened, kw fastest
+            for (int c = 0; c < p.cin; ++c)
+                for (int n = 0; n < p.cout; ++n) {
+                    const float v = d.kernel_w[(static_cast<size_t>(tap) * p.cin + c) * p.cout + n];
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                    const size_t o = (static_cast<size_t>(2 * k + hsel) * n_tile + n) * 8 + c;
+                    w[o] = hi;
+                    w[plane + o] = lo;
+                }
+        }
+    TB_CHECK_CUDA(cudaMalloc(&p.d_thin_w, 2 * plane * sizeof(__nv_bfloat16)));
+    TB_CHECK_CUDA(cudaMemcpy(p.d_thin_w, w.data(), 2 * plane * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    t.w_packed = p.d_thin_w;
+    t.w_plane_bytes = static_cast<uint32_t>(plane * 2);
+    // ---- geometry
+    t.Do = p.Do; t.Ho = p.Ho; t.Wo = p.Wo; t.Wp = tin.pv_Wp;
+    t.tiles_per_plane = ceil_div(p.Ho * tin.pv_Wp, 128);
+    t.frame_bytes = static_cast<int64_t>(tin.pv_Dp) * tin.pv_Hp * tin.pv_Wp * 16;
+    t.dplane_bytes = static_cast<int64_t>(tin.pv_Hp) * tin.pv_Wp * 16;
+    t.row_bytes = tin.pv_Wp * 16;
+    t.off_d = tin.pv_d0 - p.pad0[0];
+    t.off_h = tin.pv_h0 - p.pad0[1];
+    t.off_w = tin.pv_w0 - p.pad0[2];
+    t.kd = p.kd; t.kh = p.kh;
+    t.span_bytes = span_bytes;
+    t.span_stride = span_stride;
+    t.n_tile = n_tile;
+    t.acc_cols = round_up(n_tile, 32);
+    t.acc_stages = std::max(1, std::min(4, 512 / (2 * t.acc_cols)));
+    const size_t w_smem = (2 * plane * 2 + 127) & ~static_cast<size_t>(127);
+    const size_t stage = 2u * rows * span_stride;
+    TB_REQUIRE(w_smem + 2 * stage + 128 <= kSmemDynamicMax, "thin conv: weights + two stages exceed shared memory");
+    t.stages = static_cast<int>(std::min<size_t>(kConvMaxStages, (kSmemDynamicMax - 128 - w_smem) / stage));
+    if (const char* e = getenv("TIMED_B200_THIN_STAGES")) t.stages = std::max(2, std::min(t.stages, atoi(e)));
+    t.act1 = p.act1; t.act2 = p.act2; t.alpha1 = p.alpha1; t.alpha2 = p.alpha2;
+    return 0;
+}
+
+template <int A1, int A2, int F>
+static int launch_thin_instance(const ThinConvParams& k, int grid, size_t smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB_CHECK_CUDA(cudaFuncSetAttribute(thin_conv_kernel<A1, A2, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kSmemDynamicMax)));
+        attr_set = true;
+    }
+    thin_conv_kernel<A1, A2, F><<<grid, kConvThreads, smem_bytes, stream>>>(k);
+    return 0;
+}
+
+static int thin_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames, const TView& out,
+                       cudaStream_t stream) {
+    ThinConvParams k = p.thin_params;
+    const int64_t tiles = n_frames * k.Do * k.tiles_per_plane;
+    TB_REQUIRE(tiles > 0 && tiles < (1ll << 31), "thin conv: too many tiles per launch");
+    k.n_tiles_total = static_cast<int32_t>(tiles);
+    k.in_hi = static_cast<const uint8_t*>(in_base);
+    k.lo_plane_off = in_frames_alloc * k.frame_bytes;
+    k.bias = p.d_bias; k.scale = p.d_scale; k.shift = p.d_shift;
+    k.out_f32 = out.f32; k.out_hi = out.hi; k.out_lo = out.lo;
+    k.ldc = out.ld;
+    k.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
+               "thin conv: split output channel padding mismatch");
+    const size_t w_smem = (2 * static_cast<size_t>(k.w_plane_bytes) + 127) & ~static_cast<size_t>(127);
+    const size_t smem_bytes = 128 + w_smem + static_cast<size_t>(k.stages) * 2u * (k.kd * k.kh) * k.span_stride;
+    const int grid = static_cast<int>(std::min<int64_t>(tiles, 148));
+    int rc = 0;
+    bool launched = false;
+#define TB_THIN_CASE(A1, A2, F)                                                              \
+    if (!launched && k.act1 == (A1) && k.act2 == (A2) && out.fmt == (F)) {                   \
+        rc = launch_thin_instance<A1, A2, F>(k, grid, smem_bytes, stream);                   \
+        launched = true;                                                                     \
+    }
+    TB_THIN_CASE(ACT_ELU, ACT_NONE, FMT_F32)
+    TB_THIN_CASE(ACT_ELU, ACT_NONE, FMT_SPLIT)
+    TB_THIN_CASE(ACT_RELU, ACT_NONE, FMT_F32)
+    TB_THIN_CASE(ACT_RELU, ACT_NONE, FMT_SPLIT)
+    TB_THIN_CASE(ACT_NONE, ACT_NONE, FMT_F32)
+    TB_THIN_CASE(ACT_NONE, ACT_NONE, FMT_SPLIT)
+#undef TB_THIN_CASE
+    if (!launched)
+        rc = out.fmt == FMT_SPLIT ? launch_thin_instance<-1, -1, FMT_SPLIT>(k, grid, smem_bytes, stream)
+                                  : launch_thin_instance<-1, -1, FMT_F32>(k, grid, smem_bytes, stream);
+    if (rc) return rc;
+    TB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Build the static part of a conv plan: geometry, packed weights, epilogue vectors.
 static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, int Wi, int cin,
                             int cin_pad, const TensorInfo* wfold_in = nullptr) {
@@ -316,6 +479,24 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
         TB_REQUIRE(out[i] >= 1, "conv: kernel larger than input with 'valid' padding");
     }
     p.Do = out[0]; p.Ho = out[1]; p.Wo = out[2];
+    if (wfold_in && wfold_in->padvol) {
+        p.act1 = d.act1; p.act2 = d.act2; p.alpha1 = d.alpha1; p.alpha2 = d.alpha2;
+        int rc = thin_plan_create(p, d, *wfold_in);
+        if (rc) return rc;
+        std::vector<float> b(p.n_alloc, 0.f), sc(p.n_alloc, 1.f), sh(p.n_alloc, 0.f);
+        for (int n = 0; n < p.cout; ++n) {
+            if (d.bias) b[n] = d.bias[n];
+            if (d.scale) sc[n] = d.scale[n];
+            if (d.shift) sh[n] = d.shift[n];
+        }
+        TB_CHECK_CUDA(cudaMalloc(&p.d_bias, p.n_alloc * sizeof(float)));
+        TB_CHECK_CUDA(cudaMalloc(&p.d_scale, p.n_alloc * sizeof(float)));
+        TB_CHECK_CUDA(cudaMalloc(&p.d_shift, p.n_alloc * sizeof(float)));
+        TB_CHECK_CUDA(cudaMemcpy(p.d_bias, b.data(), p.n_alloc * sizeof(float), cudaMemcpyHostToDevice));
+        TB_CHECK_CUDA(cudaMemcpy(p.d_scale, sc.data(), p.n_alloc * sizeof(float), cudaMemcpyHostToDevice));
+        TB_CHECK_CUDA(cudaMemcpy(p.d_shift, sh.data(), p.n_alloc * sizeof(float), cudaMemcpyHostToDevice));
+        return 0;
+    }
     {
         const int taps_all = p.kd * p.kh * p.kw;
         p.tap2n = !p.wfold && taps_all > 1 && p.cout <= 64 && taps_all * p.cout <= 1024 &&
@@ -411,6 +592,7 @@ static size_t conv_scratch_bytes(const ConvPlan& p, int64_t n_frames) {
 static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames,
                        const TView& final_out, cudaStream_t stream, void* scratch = nullptr,
                        size_t scratch_bytes = 0) {
+    if (p.thin) return thin_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream);
     TView out = final_out;
     if (p.tap2n) {
         TB_REQUIRE(scratch && scratch_bytes >= conv_scratch_bytes(p, n_frames), "conv: scratch too small");
@@ -661,8 +843,40 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
         }
     }
     g->tensors[n_ops - 1].last_use = n_ops;   // graph output stays live
-    // W-folded input layout: thin input (C <= 8) read only by stride-1 convs with kw <= 8
+    // padded-volume input layout + thin_conv_kernel: thin input (C <= 8) read only by stride-1 convs
+    // whose K=16 step list fits the kernel's table and whose output channels fit one N tile
     {
+        bool ok = ops[0].c_out <= 8 && !getenv("TIMED_B200_NO_THIN");
+        int d0 = 0, d1 = 0, h0 = 0, h1 = 0, w0 = 0, w1 = 0, n_cons = 0;
+        for (int i = 1; i < n_ops && ok; ++i)
+            for (int k = 0; k < ops[i].n_inputs; ++k)
+                if (ops[i].inputs[k] == 0) {
+                    ++n_cons;
+                    const tb_op_desc& c = ops[i];
+                    if (c.op != TB_OP_CONV3D || !thin_fits(c.kernel[0], c.kernel[1], c.kernel[2], c.c_out)) {
+                        ok = false;
+                        break;
+                    }
+                    int pb[3] = {0, 0, 0}, pa[3] = {0, 0, 0};
+                    for (int a = 0; a < 3 && c.pad_same; ++a) {
+                        int o;
+                        same_pads(ops[0].kernel[a], c.kernel[a], 1, &o, &pb[a], &pa[a]);
+                    }
+                    d0 = std::max(d0, pb[0]); d1 = std::max(d1, pa[0]);
+                    h0 = std::max(h0, pb[1]); h1 = std::max(h1, pa[1]);
+                    w0 = std::max(w0, pb[2]); w1 = std::max(w1, pa[2]);
+                }
+        if (ok && n_cons > 0) {
+            TensorInfo& t0 = g->tensors[0];
+            t0.padvol = true;
+            t0.pv_d0 = d0; t0.pv_h0 = h0; t0.pv_w0 = w0;
+            t0.pv_Dp = d0 + ops[0].kernel[0] + d1;
+            t0.pv_Hp = h0 + ops[0].kernel[1] + h1;
+            t0.pv_Wp = w0 + ops[0].kernel[2] + w1;
+        }
+    }
+    // W-folded input layout: thin input (C <= 8) read only by stride-1 convs with kw <= 8
+    if (!g->tensors[0].padvol) {
         bool ok = ops[0].c_out <= 8 && !getenv("TIMED_B200_NO_WFOLD");
         int lm = 0, rm = 0, n_cons = 0;
         for (int i = 1; i < n_ops && ok; ++i)
@@ -778,7 +992,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 TB_REQUIRE(false, "unknown op kind");
         }
         t.c_pad = t.fmt == FMT_SPLIT ? round_up(t.C, 16) : t.C;
-        if (t.wfold) { t.fmt = FMT_SPLIT; t.c_pad = 8; }
+        if (t.wfold || t.padvol) { t.fmt = FMT_SPLIT; t.c_pad = 8; }
         // pointers are only valid during graph_create
         node.d.kernel_w = node.d.bias = node.d.scale = node.d.shift = nullptr;
     }
@@ -789,7 +1003,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
             const ConvPlan& c = g->ops[i].conv;
             // base pixels advance through Do*Ho*Wo per frame: express the slack in input pixels
             const int64_t out_ppf = static_cast<int64_t>(c.Do) * c.Ho * c.Wo;
-            const int64_t frames = (128 + out_ppf - 1) / out_ppf;
+            const int64_t frames = c.thin ? 1 : (128 + out_ppf - 1) / out_ppf;   // thin: spans overrun < 1 frame
             s.slack_pix = std::max<int64_t>(s.slack_pix, frames * s.pix_per_frame());
         }
     const TensorInfo& last = g->tensors[n_ops - 1];
@@ -805,6 +1019,15 @@ static void launch_input_convert_wfold(const void* x, const TensorInfo& t, int64
     const int64_t rows = n_frames * t.D * t.H;
     input_convert_wfold_kernel<T><<<grid_for(rows * t.wf_pitch, 256), 256, 0, s>>>(
         static_cast<const T*>(x), rows, t.W, t.C, t.wf_lm, t.wf_pitch, out.hi, out.lo);
+}
+
+template <typename T>
+static void launch_input_convert_padvol(const void* x, const TensorInfo& t, int64_t n_frames, const TView& out,
+                                        cudaStream_t s) {
+    const int64_t total = n_frames * t.stored_pix_per_frame();
+    input_convert_padvol_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
+        static_cast<const T*>(x), n_frames, t.D, t.H, t.W, t.C, t.pv_d0, t.pv_h0, t.pv_w0, t.pv_Dp, t.pv_Hp,
+        t.pv_Wp, out.hi, out.lo);
 }
 
 template <typename T>
@@ -850,6 +1073,13 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
         const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
         switch (d.op) {
             case TB_OP_INPUT:
+                if (t.padvol) {
+                    if (dtype == TB_DTYPE_F32) launch_input_convert_padvol<float>(d_frames, t, n_frames, out, s);
+                    else if (dtype == TB_DTYPE_F64) launch_input_convert_padvol<double>(d_frames, t, n_frames, out, s);
+                    else if (dtype == TB_DTYPE_U8) launch_input_convert_padvol<uint8_t>(d_frames, t, n_frames, out, s);
+                    else TB_REQUIRE(false, "unknown frames dtype");
+                    break;
+                }
                 if (t.wfold) {
                     if (dtype == TB_DTYPE_F32) launch_input_convert_wfold<float>(d_frames, t, n_frames, out, s);
                     else if (dtype == TB_DTYPE_F64) launch_input_convert_wfold<double>(d_frames, t, n_frames, out, s);
@@ -1169,7 +1399,19 @@ int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int
     tin.D = D; tin.H = H; tin.W = W; tin.C = c_in;
     tin.fmt = FMT_SPLIT;
     tin.c_pad = round_up(c_in, 16);
-    if (c_in <= 8 && conv->kernel[2] <= 8 && !getenv("TIMED_B200_NO_WFOLD")) {
+    if (c_in <= 8 && !getenv("TIMED_B200_NO_THIN") &&
+        thin_fits(conv->kernel[0], conv->kernel[1], conv->kernel[2], conv->c_out)) {
+        const int in[3] = {D, H, W};
+        int pb[3] = {0, 0, 0}, pa[3] = {0, 0, 0};
+        for (int a = 0; a < 3 && conv->pad_same; ++a) {
+            int o;
+            same_pads(in[a], conv->kernel[a], 1, &o, &pb[a], &pa[a]);
+        }
+        tin.padvol = true;
+        tin.pv_d0 = pb[0]; tin.pv_h0 = pb[1]; tin.pv_w0 = pb[2];
+        tin.pv_Dp = pb[0] + D + pa[0]; tin.pv_Hp = pb[1] + H + pa[1]; tin.pv_Wp = pb[2] + W + pa[2];
+        tin.c_pad = 8;
+    } else if (c_in <= 8 && conv->kernel[2] <= 8 && !getenv("TIMED_B200_NO_WFOLD")) {
         const int kw = conv->kernel[2], pad0 = conv->pad_same ? (kw - 1) / 2 : 0, kwin = kw <= 4 ? 4 : 8;
         tin.wfold = true;
         tin.wf_lm = pad0;
@@ -1180,13 +1422,14 @@ int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int
     rc = conv_plan_create(plan, ops[1], D, H, W, c_in, tin.c_pad, &tin);
     if (rc) { free_conv_plan(plan); return rc; }
     const int64_t out_ppf = static_cast<int64_t>(plan.Do) * plan.Ho * plan.Wo;
-    tin.slack_pix = static_cast<int>(((128 + out_ppf - 1) / out_ppf) * tin.pix_per_frame());
+    tin.slack_pix = static_cast<int>((plan.thin ? 1 : (128 + out_ppf - 1) / out_ppf) * tin.pix_per_frame());
     void* d_in = nullptr;
     cudaError_t e = cudaMalloc(&d_in, tin.bytes(n));
     if (e != cudaSuccess) { free_conv_plan(plan); TB_CHECK_CUDA(e); }
     cudaMemset(d_in, 0, tin.bytes(n));
     TView vin = make_view(tin, static_cast<uint8_t*>(d_in), n);
-    if (tin.wfold) launch_input_convert_wfold<float>(d_x, tin, n, vin, nullptr);
+    if (tin.padvol) launch_input_convert_padvol<float>(d_x, tin, n, vin, nullptr);
+    else if (tin.wfold) launch_input_convert_wfold<float>(d_x, tin, n, vin, nullptr);
     else launch_input_convert<float>(d_x, n * tin.pix_per_frame(), vin, nullptr);
     TView vout{};
     vout.fmt = FMT_F32;

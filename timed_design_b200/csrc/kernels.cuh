@@ -86,6 +86,41 @@ __global__ void input_convert_wfold_kernel(const T* __restrict__ x, int64_t n_ro
     }
 }
 
+// Padded-volume input layout (api.cu TensorInfo::padvol): per frame Dp x Hp x Wp stored pixels of 8
+// channels, the real D x H x W block at offset (d0, h0, w0), everything else zero.  One thread per
+// stored pixel: one 16-byte store per plane.
+template <typename T>
+__global__ void input_convert_padvol_kernel(const T* __restrict__ x, int64_t n_frames, int D, int H, int W, int c,
+                                            int d0, int h0, int w0, int Dp, int Hp, int Wp,
+                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int64_t total = n_frames * Dp * Hp * Wp;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        int64_t t = i;
+        const int w = static_cast<int>(t % Wp) - w0; t /= Wp;
+        const int h = static_cast<int>(t % Hp) - h0; t /= Hp;
+        const int d = static_cast<int>(t % Dp) - d0;
+        const int64_t nf = t / Dp;
+        uint32_t h4[4] = {0, 0, 0, 0}, l4[4] = {0, 0, 0, 0};
+        if (w >= 0 && w < W && h >= 0 && h < H && d >= 0 && d < D) {
+            const T* src = x + ((((nf * D + d) * H + h) * W + w) * static_cast<int64_t>(c));
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = k < c ? static_cast<float>(src[k]) : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                __nv_bfloat16 a0, b0, a1, b1;
+                split_bf16(v[2 * k], a0, b0);
+                split_bf16(v[2 * k + 1], a1, b1);
+                h4[k] = pack_bf16x2(a0, a1);
+                l4[k] = pack_bf16x2(b0, b1);
+            }
+        }
+        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+        reinterpret_cast<uint4*>(lo)[i] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+    }
+}
+
 // ------------------------------------------------------------------ pooling (TF semantics)
 struct PoolParams {
     int32_t D, H, W, Do, Ho, Wo;
