@@ -160,6 +160,9 @@ def main():
     from timed_design_b200.model import Model
 
     torch.cuda.set_device(local_rank)
+    # fixture generation (stand-in calibration, synthetic frames) is CPU work: keep N ranks from
+    # oversubscribing the host cores
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
