@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="frames per GPU per step")
     ap.add_argument("--classes", type=int, default=20)
+    ap.add_argument("--model", default="timed", choices=["timed", "densecpd"],
+                    help="side measurements only: the bench line the driver reads is the default (timed, 20 classes)")
     ap.add_argument("--e2e-chunk", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -167,7 +169,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    cfg, weights = standins.timed_standin(args.classes)
+    cfg, weights = standins.timed_standin(args.classes) if args.model == "timed" else standins.densecpd_standin(args.classes)
     model = Model(cfg, weights, device=local_rank, max_chunk_frames=args.e2e_chunk)
     B = args.batch
     # frames are indexed globally so the data does not depend on the rank count
@@ -249,9 +251,13 @@ def main():
     achieved = top["flops_per_frame"] * B / (top_ms / 1e3) / 1e12
     peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
     step_ms_ops = sum(o["ms"] for o in op_times) / max(n_fw, 1)
+    traffic = None
+    tp = ROOT / "profiles" / "r1_dominant_kernel_ncu.json"
+    if tp.exists() and args.model == "timed" and args.classes == 20 and B == 4096:
+        traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": None, "kernel": f"conv_umma_kernel[{top['name']}]",
+        "traffic": traffic, "kernel": f"conv_umma_kernel[{top['name']}]",
         "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
         "mma_passes": 3,
         "issued_frac": 3 * achieved / peak,
@@ -276,7 +282,7 @@ def main():
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 split operands (hi/lo planes), fp32 accumulate/epilogue",
         "data": "synthetic",
-        "config": {"workload": f"TIMED {args.classes}-class stand-in inference, 21^3x6 synthetic frames",
+        "config": {"workload": f"{'TIMED' if args.model == 'timed' else 'DenseCPD'} {args.classes}-class stand-in inference, 21^3x6 synthetic frames",
                    "batch_per_gpu": B, "global_batch": world * B, "flops_per_frame": model.flops_per_frame,
                    "parallelism": f"frames sharded over {world} GPU(s), all-gather of probabilities" if world > 1
                    else "single GPU",

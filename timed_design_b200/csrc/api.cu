@@ -147,7 +147,7 @@ struct ConvPlan {
     float alpha1 = 1.f, alpha2 = 1.f;
     // tile configuration (depends on the frame count -> chosen at launch)
     struct Config {
-        int kc, mt, kg, stages, acc_stages, acc_cols;
+        int kc, mt, kg, stages, acc_stages, acc_cols, nfold;
         uint32_t swizzle_code;       // UMMA layout type
         CUtensorMapSwizzle tma_swz;
         size_t smem_bytes;
@@ -189,7 +189,8 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
             if (p.cin_pad % kc == 0) kcs.push_back(kc);
     }
     TB_REQUIRE(!kcs.empty(), "conv: padded input channels must be a multiple of 16");
-    const int acc_cols = round_up(p.n_tile, 32);
+    const bool nfold = p.n_tile <= 128 && !getenv("TIMED_B200_NO_NFOLD");
+    const int acc_cols = round_up(nfold ? 2 * p.n_tile : p.n_tile, 32);
     // two M sub-tiles per CTA halve the weight traffic per MAC; only worth it when there are
     // enough tiles to still fill the machine twice over
     std::vector<int> mts;
@@ -220,6 +221,7 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
                 cfg->kg = kg;
                 cfg->stages = stages;
                 cfg->acc_cols = acc_cols;
+                cfg->nfold = nfold ? 1 : 0;
                 cfg->acc_stages = std::min(2, 512 / (mt * acc_cols));
                 cfg->swizzle_code = kc == 64 ? 2u : (kc == 32 ? 4u : 6u);
                 cfg->tma_swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -314,7 +316,7 @@ static int thin_step_count(int kd, int kh, int kw) {
 static bool thin_fits(int kd, int kh, int kw, int cout) {
     const int steps = thin_step_count(kd, kh, kw);
     const int n_tile = round_up(cout, 16);
-    if (steps > kThinMaxSteps || n_tile > 256 || kd < 1 || kh < 1 || kw < 1) return false;
+    if (steps > kThinMaxSteps || n_tile > 128 || kd < 1 || kh < 1 || kw < 1) return false;   // folded MMA: N = 2*n_tile <= 256
     const size_t w_smem = (static_cast<size_t>(2 * steps) * n_tile * 8 * 2 * 2 + 127) & ~static_cast<size_t>(127);
     const size_t span = static_cast<size_t>((128 + kw + 2) & ~1) * 16;
     return w_smem + 2 * (2u * kd * kh * span) + 128 <= kSmemDynamicMax;
@@ -324,7 +326,7 @@ static int thin_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& 
     p.thin = true;
     const int rows = p.kd * p.kh;
     const int n_tile = round_up(p.cout, 16);
-    TB_REQUIRE(n_tile <= 256, "thin conv: too many output channels");
+    TB_REQUIRE(n_tile <= 128, "thin conv: too many output channels");
     p.n_tiles = 1;
     p.n_tile = p.n_alloc = n_tile;
     // stored pixels per span: row r of a K step reads pixels r+j and r+j+1 (j <= kw-1, the partner of a
@@ -353,9 +355,9 @@ static int thin_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& 
         // (a missing partner has zero weights: alias the next pixel, any valid smem will do)
         t.step_lbo16[k] = (b.row >= 0 && b.row != a.row) ? static_cast<uint32_t>(span_stride) >> 4 : 1u;
     }
-    // ---- weights: [plane][2*n_steps chunks][n_tile][8]
-    const size_t plane = static_cast<size_t>(2 * t.n_steps) * n_tile * 8;
-    std::vector<__nv_bfloat16> w(2 * plane, __float2bfloat16(0.0f));
+    // ---- weights: [2*n_steps chunks][2*n_tile rows: hi then lo][8]
+    const size_t w_elems = static_cast<size_t>(2 * t.n_steps) * 2 * n_tile * 8;
+    std::vector<__nv_bfloat16> w(w_elems, __float2bfloat16(0.0f));
     for (int k = 0; k < t.n_steps; ++k)
         for (int hsel = 0; hsel < 2; ++hsel) {
             const Half h = hsel ? steps[k].second : steps[k].first;
@@ -366,15 +368,15 @@ static int thin_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& 
                     const float v = d.kernel_w[(static_cast<size_t>(tap) * p.cin + c) * p.cout + n];
                     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
                     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-                    const size_t o = (static_cast<size_t>(2 * k + hsel) * n_tile + n) * 8 + c;
-                    w[o] = hi;
-                    w[plane + o] = lo;
+                    const size_t chunk = static_cast<size_t>(2 * k + hsel) * 2 * n_tile;
+                    w[(chunk + n) * 8 + c] = hi;
+                    w[(chunk + n_tile + n) * 8 + c] = lo;
                 }
         }
-    TB_CHECK_CUDA(cudaMalloc(&p.d_thin_w, 2 * plane * sizeof(__nv_bfloat16)));
-    TB_CHECK_CUDA(cudaMemcpy(p.d_thin_w, w.data(), 2 * plane * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    TB_CHECK_CUDA(cudaMalloc(&p.d_thin_w, w_elems * sizeof(__nv_bfloat16)));
+    TB_CHECK_CUDA(cudaMemcpy(p.d_thin_w, w.data(), w_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     t.w_packed = p.d_thin_w;
-    t.w_plane_bytes = static_cast<uint32_t>(plane * 2);
+    t.w_bytes = static_cast<uint32_t>(w_elems * 2);
     // ---- geometry
     t.Do = p.Do; t.Ho = p.Ho; t.Wo = p.Wo; t.Wp = tin.pv_Wp;
     t.tiles_per_plane = ceil_div(p.Ho * tin.pv_Wp, 128);
@@ -388,9 +390,9 @@ static int thin_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& 
     t.span_bytes = span_bytes;
     t.span_stride = span_stride;
     t.n_tile = n_tile;
-    t.acc_cols = round_up(n_tile, 32);
-    t.acc_stages = std::max(1, std::min(4, 512 / (2 * t.acc_cols)));
-    const size_t w_smem = (2 * plane * 2 + 127) & ~static_cast<size_t>(127);
+    t.acc_cols = round_up(2 * n_tile, 32);
+    t.acc_stages = std::max(1, std::min(4, 512 / t.acc_cols));
+    const size_t w_smem = (w_elems * 2 + 127) & ~static_cast<size_t>(127);
     const size_t stage = 2u * rows * span_stride;
     TB_REQUIRE(w_smem + 2 * stage + 128 <= kSmemDynamicMax, "thin conv: weights + two stages exceed shared memory");
     t.stages = static_cast<int>(std::min<size_t>(kConvMaxStages, (kSmemDynamicMax - 128 - w_smem) / stage));
@@ -423,9 +425,13 @@ static int thin_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.out_f32 = out.f32; k.out_hi = out.hi; k.out_lo = out.lo;
     k.ldc = out.ld;
     k.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    {
+        static const int dbg = [] { const char* e = getenv("TIMED_B200_DBG"); return e ? atoi(e) : 0; }();
+        k.dbg = dbg;
+    }
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "thin conv: split output channel padding mismatch");
-    const size_t w_smem = (2 * static_cast<size_t>(k.w_plane_bytes) + 127) & ~static_cast<size_t>(127);
+    const size_t w_smem = (static_cast<size_t>(k.w_bytes) + 127) & ~static_cast<size_t>(127);
     const size_t smem_bytes = 128 + w_smem + static_cast<size_t>(k.stages) * 2u * (k.kd * k.kh) * k.span_stride;
     const int grid = static_cast<int>(std::min<int64_t>(tiles, 148));
     int rc = 0;
@@ -499,8 +505,16 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
     }
     {
         const int taps_all = p.kd * p.kh * p.kw;
-        p.tap2n = !p.wfold && taps_all > 1 && p.cout <= 64 && taps_all * p.cout <= 1024 &&
-                  cin_pad >= 128 && !getenv("TIMED_B200_NO_TAP2N");
+        // cost model (cycles per 128-row tile, from profiles/r1_summary.md): a thin-N MMA costs ~65
+        // cycles whatever N is, a wide one ~110; the Z matrix is written and read once through HBM at
+        // ~23 B/cycle/SM.  Take tap-to-N only when it wins clearly (TIMED's head: 68k vs 168k cycles;
+        // DenseCPD's 128->32 growth convs: 68k vs 42k, so they stay on the direct path).
+        const double k16 = cin_pad / 16.0;
+        const double direct_cost = taps_all * k16 * 3 * 65.0 * ceil_div(round_up(p.cout, 16), 256);
+        const double z_cols = static_cast<double>(taps_all) * p.cout;
+        const double t2n_cost = k16 * 3 * std::ceil(z_cols / 256.0) * 110.0 + 8.0 * z_cols * 128 / 23.0 * 1.5;
+        p.tap2n = !p.wfold && taps_all > 1 && p.cout <= 64 && taps_all * p.cout <= 1024 && cin_pad >= 64 &&
+                  t2n_cost < 0.7 * direct_cost && !getenv("TIMED_B200_NO_TAP2N");
         if (p.tap2n) {
             p.z_cols = taps_all * p.cout;
             p.z_ld = round_up(p.z_cols, 4);
@@ -623,6 +637,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.n_tile = p.n_tile;
     k.acc_cols = cfg.acc_cols;
     k.acc_stages = cfg.acc_stages;
+    k.nfold = cfg.nfold;
     k.kh = p.tap2n ? 1 : p.kh; k.kw = (p.wfold || p.tap2n) ? 1 : p.kw;
     k.n_taps = p.taps_eff();
     k.cin_pad = p.cin_pad;

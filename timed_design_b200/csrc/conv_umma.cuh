@@ -38,8 +38,13 @@ struct ConvKernelParams {
     int32_t n_tiles;     // CTA tiles along N
     int32_t n_tile;      // columns per CTA tile (multiple of 16, <= 256) == UMMA N
     int32_t mt;          // 128-row sub-tiles per CTA tile (1 or 2)
-    int32_t acc_cols;    // TMEM columns reserved per accumulator (n_tile rounded up to 32)
+    int32_t acc_cols;    // TMEM columns reserved per accumulator (n_tile, or 2*n_tile when nfold, rounded up to 32)
     int32_t acc_stages;  // accumulator ring depth (1 or 2)
+    // N-folded issue for n_tile <= 128: the W_hi and W_lo sub-tiles are adjacent in shared memory, so ONE
+    // MMA of N = 2*n_tile computes A_hi*[W_hi | W_lo] into columns [0,n) (main) and [n,2n) (correction)
+    // and a second MMA adds A_lo*W_hi into [n,2n): two MMAs per K-step instead of three (a thin-N MMA costs
+    // ~the same whatever N is), and the corrections no longer truncate against the main accumulator.
+    int32_t nfold;
     // ---- K loop
     int32_t kh, kw;      // filter extents (kd implied by n_taps)
     int32_t n_taps;      // kd*kh*kw
@@ -245,6 +250,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         // =============================================================== MMA issuer
         const bool leader = elect_one();
         const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.n_tile));
+        const uint32_t idesc2 = umma_idesc_bf16_m128(static_cast<uint32_t>(2 * p.n_tile));
         // descriptor = {lo: start address >> 4 | LBO(=1) << 16, hi: SBO >> 4 | version << 14 | swizzle << 29}
         const uint32_t desc_hi = ((p.row_bytes * 8u) >> 4) | (1u << 14) | (p.layout_type << 29);
         const uint32_t lo_flags = 1u << 16;
@@ -274,14 +280,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                             const uint32_t a0 = base16 + static_cast<uint32_t>(kk) * 2u;   // +32 B per K=16
                             const uint32_t w_hi = a0 + w_off16;
                             const uint32_t w_lo = w_hi + w_sub16;
-                            umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc, accumulate);
-                            umma_bf16_lohi(leader, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                            umma_bf16_lohi(leader, d0, a0, w_lo, desc_hi, idesc, 1u);
-                            if (p.mt == 2) {
+                            if (p.nfold) {
+                                umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc2, accumulate);
+                                umma_bf16_lohi(leader, d0 + p.n_tile, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                                if (p.mt == 2) {
+                                    const uint32_t a1 = a0 + a_sub16;
+                                    umma_bf16_lohi(leader, d1, a1, w_hi, desc_hi, idesc2, accumulate);
+                                    umma_bf16_lohi(leader, d1 + p.n_tile, a1 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                                }
+                            } else if (p.mt == 2) {
                                 const uint32_t a1 = a0 + a_sub16;
+                                umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc, accumulate);
                                 umma_bf16_lohi(leader, d1, a1, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(leader, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
                                 umma_bf16_lohi(leader, d1, a1 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(leader, d0, a0, w_lo, desc_hi, idesc, 1u);
                                 umma_bf16_lohi(leader, d1, a1, w_lo, desc_hi, idesc, 1u);
+                            } else {
+                                umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(leader, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(leader, d0, a0, w_lo, desc_hi, idesc, 1u);
                             }
                             accumulate = 1u;
                         }
@@ -320,7 +338,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                     uint32_t r[16];
                     __syncwarp();                      // tcgen05.ld is .sync.aligned
                     tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), r);
-                    tmem_ld_wait();
+                    if (p.nfold) {                     // warp-uniform
+                        uint32_t rc[16];
+                        tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.n_tile + c * 16), rc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rc[i]));
+                    } else {
+                        tmem_ld_wait();
+                    }
                     const int n0 = n_idx * p.n_tile + c * 16;
                     if (n0 >= p.c_store) continue;     // warp-uniform
                     float v[16];

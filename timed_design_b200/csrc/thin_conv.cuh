@@ -14,8 +14,11 @@
 // resident in shared memory for the whole kernel.  Rows that fall into the W margin of the padded
 // volume (Wp - Wo of every Wp positions) are computed and dropped by the epilogue.
 //
-// Correction MMAs (A_lo*W_hi, A_hi*W_lo) accumulate into their own TMEM accumulator -- TMEM is
-// plentiful at N <= 256/2 -- which also removes two thirds of the accumulator truncation error.
+// Two MMAs per K step instead of three: the resident weights hold, per K chunk, the n_tile hi rows
+// followed by the n_tile lo rows, so A_hi x [W_hi | W_lo] is ONE MMA of N = 2*n_tile writing the main
+// product to TMEM columns [0,n) and the A_hi*W_lo correction to [n,2n); A_lo x W_hi accumulates into
+// [n,2n) as well (a thin-N MMA costs about the same whatever N is).  Keeping the corrections out of the
+// main accumulator also removes two thirds of the accumulator truncation error; the epilogue adds them.
 #pragma once
 #include "common.cuh"
 #include "conv_umma.cuh"
@@ -43,11 +46,11 @@ struct ThinConvParams {
     int32_t n_steps;
     uint32_t step_off16[kThinMaxSteps];
     uint32_t step_lbo16[kThinMaxSteps];
-    // ---- weights: [plane][2*n_steps K-chunks][n_tile rows][8] bf16, resident in smem
+    // ---- weights: [2*n_steps K-chunks][2*n_tile rows: hi then lo][8] bf16, resident in smem
     const uint8_t* w_packed;
-    uint32_t w_plane_bytes;
-    int32_t n_tile;           // UMMA N
-    int32_t acc_cols;         // TMEM columns per accumulator (n_tile rounded up to 32)
+    uint32_t w_bytes;
+    int32_t n_tile;           // output channels per tile (UMMA N = 2*n_tile for the folded MMA)
+    int32_t acc_cols;         // TMEM columns per accumulator stage (2*n_tile rounded up to 32)
     int32_t acc_stages;
     int32_t stages;
     // ---- epilogue (as ConvKernelParams)
@@ -61,6 +64,7 @@ struct ThinConvParams {
     __nv_bfloat16* out_lo;
     int64_t ldc;
     int32_t c_store;
+    int32_t dbg;              // TIMED_B200_DBG role timing: 1 skip copies, 2 skip MMAs, 4 skip epilogue
 };
 
 #if defined(__CUDACC__)
@@ -131,7 +135,7 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
     const uint32_t tmem_base = tmem_base_slot;
 
     const int taps = p.kd * p.kh;
-    const uint32_t w_bytes = 2u * p.w_plane_bytes;
+    const uint32_t w_bytes = p.w_bytes;
     uint8_t* w_smem = smem;                                            // resident weights
     uint8_t* stage0 = smem + ((w_bytes + 127u) & ~127u);
     const uint32_t plane_region = static_cast<uint32_t>(taps) * p.span_stride;   // hi spans, then lo spans
@@ -153,7 +157,9 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
             const int nf = plane / p.Do;
             const int z = plane - nf * p.Do;
             mbar_wait(&empty_bar[s], ph ^ 1u);
-            if (leader) {
+            if (leader && (p.dbg & 1)) {
+                mbar_arrive(&full_bar[s]);
+            } else if (leader) {
                 mbar_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(taps) * p.span_bytes);
                 uint8_t* st = stage0 + static_cast<size_t>(s) * stage_bytes;
                 const uint8_t* src0 = p.in_hi + nf * p.frame_bytes + static_cast<int64_t>(z + p.off_d) * p.dplane_bytes +
@@ -175,12 +181,12 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
         // =============================================================== MMA issuer
         const bool leader = elect_one();
         const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.n_tile));
+        const uint32_t idesc2 = umma_idesc_bf16_m128(static_cast<uint32_t>(2 * p.n_tile));
         // no-swizzle K-major descriptors: hi word = SBO>>4 | version<<14 (layout type 0)
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-        const uint32_t w_lbo16 = (static_cast<uint32_t>(p.n_tile) * 16u) >> 4;      // K-chunk stride of W
+        const uint32_t w_lbo16 = (static_cast<uint32_t>(2 * p.n_tile) * 16u) >> 4;   // K-chunk stride of W
         const uint32_t w_step16 = 2u * w_lbo16;
         const uint32_t w_base16 = (smem_u32(w_smem) & 0x3FFFFu) >> 4;
-        const uint32_t w_lo_off16 = p.w_plane_bytes >> 4;
         const uint32_t stage0_16 = (smem_u32(stage0) & 0x3FFFFu) >> 4;
         const uint32_t plane16 = plane_region >> 4;
         mbar_wait(&w_bar, 0);
@@ -192,18 +198,15 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
             mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
-            const uint32_t d_main = tmem_base + static_cast<uint32_t>(acc * 2 * p.acc_cols);
-            const uint32_t d_corr = d_main + static_cast<uint32_t>(p.acc_cols);
+            const uint32_t d_main = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
+            const uint32_t d_corr = d_main + static_cast<uint32_t>(p.n_tile);
             const uint32_t a_base16 = stage0_16 + static_cast<uint32_t>(s) * (stage_bytes >> 4);
-            for (int k = 0; k < p.n_steps; ++k) {
+            for (int k = 0; k < p.n_steps && !(p.dbg & 2); ++k) {
                 const uint32_t a_hi = (a_base16 + p.step_off16[k]) | (p.step_lbo16[k] << 16);
                 const uint32_t a_lo = a_hi + plane16;
-                const uint32_t b_hi = (w_base16 + static_cast<uint32_t>(k) * w_step16) | (w_lbo16 << 16);
-                const uint32_t b_lo = b_hi + w_lo_off16;
-                const uint32_t first = k == 0 ? 0u : 1u;
-                umma_bf16_desc(leader, d_main, a_hi, desc_hi, b_hi, desc_hi, idesc, first);
-                umma_bf16_desc(leader, d_corr, a_lo, desc_hi, b_hi, desc_hi, idesc, first);
-                umma_bf16_desc(leader, d_corr, a_hi, desc_hi, b_lo, desc_hi, idesc, 1u);
+                const uint32_t b = (w_base16 + static_cast<uint32_t>(k) * w_step16) | (w_lbo16 << 16);
+                umma_bf16_desc(leader, d_main, a_hi, desc_hi, b, desc_hi, idesc2, k == 0 ? 0u : 1u);
+                umma_bf16_desc(leader, d_corr, a_lo, desc_hi, b, desc_hi, idesc, 1u);
             }
             if (leader) {
                 umma_commit(&empty_bar[s]);
@@ -231,12 +234,12 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                   static_cast<uint32_t>(acc * 2 * p.acc_cols);
-            for (int c = half; c < chunks; c += 2) {
+                                   static_cast<uint32_t>(acc * p.acc_cols);
+            for (int c = half; c < chunks && !(p.dbg & 4); c += 2) {
                 uint32_t r[16], rc[16];
                 __syncwarp();
                 tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), r);
-                tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.acc_cols + c * 16), rc);
+                tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.n_tile + c * 16), rc);
                 tmem_ld_wait();
                 const int n0 = c * 16;
                 if (n0 >= p.c_store) continue;
