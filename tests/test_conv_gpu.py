@@ -1,0 +1,104 @@
+"""GPU parity of single Conv3D launches through the C ABI (timed_b200_conv3d_fwd) against the numpy
+fp64 oracle: every operand layout (64/32/16-channel K blocks, W-folded and padded-volume thin inputs),
+'same' and 'valid' padding, kernel sizes 1-7, one and two M sub-tiles, one and two N tiles, the
+tap-to-N head path and the fused bias/ELU/ReLU/BatchNorm epilogues.
+
+Tolerance: 1e-4 of the output range (the bf16 hi/lo split carries ~16 mantissa bits per operand and the
+tensor core's accumulator adds ~2^-26 per accumulation); typical measured 5e-6..5e-5."""
+import numpy as np
+import pytest
+
+from oracle import keras_oracle as ko
+from tests.helpers import run_conv_gpu
+
+pytestmark = pytest.mark.gpu
+
+# (name, n, side, c_in, c_out, k, padding)
+CASES = [
+    ("k1_c64_n32", 2, 4, 64, 32, 1, "same"),
+    ("k1_c16_n32", 2, 4, 16, 32, 1, "same"),
+    ("k1_c32_n32", 2, 4, 32, 32, 1, "same"),
+    ("k1_c128_n64", 2, 4, 128, 64, 1, "same"),
+    ("k1_c6_n20", 3, 5, 6, 20, 1, "same"),
+    ("k3_c64_n128", 2, 6, 64, 128, 3, "same"),
+    ("k3_c6_n32_21", 1, 21, 6, 32, 3, "same"),
+    ("k3_c5_n32_valid", 2, 9, 5, 32, 3, "valid"),
+    ("k3_c32_n64_11", 2, 11, 32, 64, 3, "same"),
+    ("k3_c256_n512", 4, 6, 256, 512, 3, "same"),
+    ("k3_c512_n20_tap2n", 4, 6, 512, 20, 3, "same"),
+    ("k3_c512_n338", 2, 6, 512, 338, 3, "same"),
+    ("k3_valid_c16", 2, 8, 16, 48, 3, "valid"),
+    ("k5_c6_n16", 1, 9, 6, 16, 5, "same"),
+    ("k7_c6_n16", 1, 9, 6, 16, 7, "same"),
+    ("k4_valid_dense", 5, 4, 64, 128, 4, "valid"),
+    ("k2_even_kernel", 2, 6, 32, 48, 2, "same"),
+    ("k3_c128_n256_mt2", 700, 6, 128, 256, 3, "same"),
+    ("k3_c64_n128_mt2", 700, 6, 64, 128, 3, "same"),
+    ("k3_c6_n32_many_tiles", 40, 13, 6, 32, 3, "same"),
+]
+
+
+def _torch_ref(x, w, b, k, padding):
+    import torch
+    import torch.nn.functional as F
+    xt = torch.from_numpy(x).permute(0, 4, 1, 2, 3).double()
+    wt = torch.from_numpy(w).permute(4, 3, 0, 1, 2).double()
+    if padding == "same":
+        p0, p1 = (k - 1) // 2, k - 1 - (k - 1) // 2
+        xt = F.pad(xt, (p0, p1, p0, p1, p0, p1))
+    return F.conv3d(xt, wt, torch.from_numpy(b).double()).permute(0, 2, 3, 4, 1).numpy()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv3d_matches_oracle(case):
+    name, n, side, ci, co, k, padding = case
+    rng = np.random.default_rng(abs(hash(name)) % 2 ** 31)
+    x = rng.standard_normal((n, side, side, side, ci)).astype(np.float32)
+    w = (rng.standard_normal((k, k, k, ci, co)) * np.sqrt(2.0 / (k ** 3 * ci))).astype(np.float32)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    y = run_conv_gpu(x, w, bias=b, padding=padding)
+    assert np.isfinite(y).all()
+    nref = min(n, 3)
+    ref = ko.np_conv3d(x[:nref].astype(np.float64), w.astype(np.float64), b.astype(np.float64), padding)
+    assert y.shape[1:] == ref.shape[1:]
+    scale = np.abs(ref).max()
+    assert np.abs(y[:nref] - ref).max() <= 1e-4 * scale
+    if n > nref:                       # large batches: middle and tail frames against an independent conv
+        for sl in (slice(n // 2, n // 2 + 4), slice(n - 3, n)):
+            r2 = _torch_ref(x[sl], w, b, k, padding)
+            assert np.abs(y[sl] - r2).max() <= 1e-4 * np.abs(r2).max()
+
+
+def test_onehot_kernel_selects_the_right_taps():
+    """Kernel with a single 1 per output channel: the conv must return shifted copies of the input, which
+    pins the tap <-> coordinate mapping and the zero padding exactly."""
+    rng = np.random.default_rng(5)
+    for ci, side in ((64, 6), (6, 7)):
+        x = rng.standard_normal((2, side, side, side, ci)).astype(np.float32)
+        co = 32
+        w = np.zeros((3, 3, 3, ci, co), np.float32)
+        for o in range(co):
+            t = o % 27
+            w[t // 9, (t // 3) % 3, t % 3, (o * 7) % ci, o] = 1.0
+        y = run_conv_gpu(x, w, padding="same")
+        ref = ko.np_conv3d(x.astype(np.float64), w.astype(np.float64), None, "same")
+        assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("act1,act2,affine", [("elu", None, True), ("relu", None, False), (None, "relu", True),
+                                             (None, None, True), ("tanh", None, True), ("elu", "relu", True)])
+def test_fused_epilogues(act1, act2, affine):
+    rng = np.random.default_rng(11)
+    for ci in (6, 32):
+        x = rng.standard_normal((2, 7, 7, 7, ci)).astype(np.float32)
+        w = (rng.standard_normal((3, 3, 3, ci, 24)) * np.sqrt(2.0 / (27 * ci))).astype(np.float32)
+        b = (rng.standard_normal(24) * 0.2).astype(np.float32)
+        sc = rng.uniform(0.5, 1.5, 24).astype(np.float32) if affine else None
+        sh = (rng.standard_normal(24) * 0.3).astype(np.float32) if affine else None
+        y = run_conv_gpu(x, w, bias=b, scale=sc, shift=sh, padding="same", act1=act1, act2=act2)
+        ref = ko.np_conv3d(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), "same")
+        ref = ko.np_activation(ref, act1) if act1 else ref
+        if affine:
+            ref = ref * sc + sh
+        ref = ko.np_activation(ref, act2) if act2 else ref
+        assert np.abs(y - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1.0)
