@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--model", default="timed", choices=["timed", "densecpd"],
                     help="side measurements only: the bench line the driver reads is the default (timed, 20 classes)")
     ap.add_argument("--e2e-chunk", type=int, default=1024)
+    ap.add_argument("--precise", action="store_true", help="side measurement: Model(precise=True)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -170,7 +171,7 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     cfg, weights = standins.timed_standin(args.classes) if args.model == "timed" else standins.densecpd_standin(args.classes)
-    model = Model(cfg, weights, device=local_rank, max_chunk_frames=args.e2e_chunk)
+    model = Model(cfg, weights, device=local_rank, max_chunk_frames=args.e2e_chunk, precise=args.precise)
     B = args.batch
     # frames are indexed globally so the data does not depend on the rank count
     uniq = standins.synthetic_frames(UNIQUE_FRAMES, seed=1234, first_index=rank * B)

@@ -101,6 +101,11 @@ void timed_b200_graph_destroy(tb_graph* g);
  * conv/dense ops) */
 int timed_b200_graph_info(const tb_graph* g, int32_t* n_classes, double* flops_per_frame,
                           int32_t* n_kernel_launches_per_forward);
+/* Numerics option.  0 (default): widest tiles; max |dp| 6e-5 on the TIMED-20 stand-in.  1: the two
+ * full-width conv layers run as 2-CTA clusters with a separate TMEM accumulator for the correction
+ * MMAs (3x less accumulator truncation; max |dp| 2.8e-5) at ~1.4x their time.  Takes effect on the
+ * next forward. */
+int timed_b200_graph_set_precise(tb_graph* g, int32_t precise);
 /* number of fused ops in the graph */
 int timed_b200_graph_op_count(const tb_graph* g, int32_t* n_ops);
 /* Per-op device timing for bench.py's roofline line.  While enabled, every graph_forward records

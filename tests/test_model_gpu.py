@@ -72,3 +72,23 @@ def test_prodconn_standin_parity():
 def test_densecpd_small_parity():
     _check(lambda: standins.densecpd_standin(side=12, n_layers=2, calib_frames=3),
            lambda n: standins.synthetic_frames(n, side=12), 5)
+
+
+@pytest.mark.gpu
+def test_precise_mode_is_tighter_and_consistent():
+    """Model(precise=True): 2-CTA cluster path for the full-width layers.  Same answers within tolerance,
+    measurably closer to the oracle on a batch large enough to engage the cluster tiles."""
+    from timed_design_b200.model import Model
+    cfg, w = standins.timed_standin(20)
+    uniq = standins.synthetic_frames(48, seed=5)
+    X = np.tile(uniq, (8, 1, 1, 1, 1))                      # 384 frames: enough rows for cluster tiles
+    ref = ko.forward_torch(cfg, w, uniq)
+    fast = Model(cfg, w).predict(X, batch_size=4096)
+    prec = Model(cfg, w, precise=True).predict(X, batch_size=4096)
+    e_fast = np.abs(fast[:48] - ref).max()
+    e_prec = np.abs(prec[:48] - ref).max()
+    assert e_fast <= PROB_TOL and e_prec <= PROB_TOL
+    assert e_prec < e_fast
+    np.testing.assert_array_equal(prec[:48], prec[48:96])    # batch-position independent
+    safe = ~ko.near_tie_rows(ref)
+    assert (ko.fp16_argmax(prec[:48])[safe] == ko.fp16_argmax(ref)[safe]).all()

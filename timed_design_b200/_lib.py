@@ -54,6 +54,7 @@ SYMBOLS = {
     "timed_b200_graph_destroy": (None, [C.c_void_p]),
     "timed_b200_graph_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                         C.POINTER(C.c_int32)]),
+    "timed_b200_graph_set_precise": (C.c_int, [C.c_void_p, C.c_int32]),
     "timed_b200_graph_op_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "timed_b200_graph_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "timed_b200_graph_read_op_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32),

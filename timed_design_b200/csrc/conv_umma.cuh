@@ -45,6 +45,13 @@ struct ConvKernelParams {
     // and a second MMA adds A_lo*W_hi into [n,2n): two MMAs per K-step instead of three (a thin-N MMA costs
     // ~the same whatever N is), and the corrections no longer truncate against the main accumulator.
     int32_t nfold;
+    // 2-CTA cluster mode for n_tile = 256 (two such accumulators fill TMEM): the pair shares every W tile
+    // -- each CTA loads half of it and TMA-multicasts it to both -- so a 128 x 256 tile per CTA costs
+    // the same L2->SM traffic as 256 x 256 per CTA did, and the freed TMEM half holds a separate
+    // accumulator for the correction MMAs (3x less accumulator truncation).
+    // Requires mt = 1 and a (2,1,1) cluster launch.  corr_off = TMEM column offset of that accumulator.
+    int32_t cluster2;
+    int32_t corr_off;
     // ---- K loop
     int32_t kh, kw;      // filter extents (kd implied by n_taps)
     int32_t n_taps;      // kd*kh*kw
@@ -148,7 +155,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], p.cluster2 ? 2 : 1);   // cluster mode: both CTAs' MMA warps release a stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -160,6 +167,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_w);
     }
+    const uint32_t cta_rank = p.cluster2 ? cluster_ctarank() : 0u;
     if (warp == 1) tmem_alloc_512(&tmem_base_slot);
     const int n_alloc = p.n_tiles * p.n_tile;
     const bool epi_in_smem = n_alloc <= kEpiSmemN;
@@ -172,10 +180,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
+    // cluster mode: the pair walks the same sequence of (256-row pair-tile, n-tile); this CTA owns the
+    // rank-th 128-row half.  tile_first / tile_step are in pair-tiles.
     const int total_tiles = p.n_ctile_m * p.n_tiles;
+    const int tile_first = p.cluster2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = p.cluster2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const uint32_t kb_bytes = static_cast<uint32_t>(p.mt) * 2u * p.a_sub_bytes + 2u * p.w_sub_bytes;
     const uint32_t stage_bytes = kb_bytes * static_cast<uint32_t>(p.kg);
     const int n_groups = (p.n_kblocks + p.kg - 1) / p.kg;
@@ -186,13 +199,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         const bool leader = elect_one();
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
             const int m_ct = tile / p.n_tiles;
             const int n_idx = tile - m_ct * p.n_tiles;
             int32_t bw[2], bh[2], bd[2], bn[2];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) {
-                int m0 = (m_ct * p.mt + mi) * 128;
+                int m0 = p.cluster2 ? (m_ct * 2 + static_cast<int>(cta_rank)) * 128 : (m_ct * p.mt + mi) * 128;
                 if (m0 >= p.m_total) m0 = 0;       // dummy sub-tile: rows are discarded later
                 const int q = m0 % p.Wo;
                 int t = m0 / p.Wo;
@@ -235,9 +248,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                             }
                             uint8_t* wb = base + 2 * p.mt * p.a_sub_bytes;
                             const int kcoord = tap * p.cin_pad + cb * p.kc;
-                            tma_load_2d(wb, &map_w, &full_bar[s], kcoord, n_idx * p.n_tile);
-                            tma_load_2d(wb + p.w_sub_bytes, &map_w, &full_bar[s], kcoord,
-                                        p.w_lo_rows + n_idx * p.n_tile);
+                            if (p.cluster2) {
+                                // this CTA fetches its half of the W rows and multicasts it to the pair
+                                const int half_rows = p.n_tile >> 1;
+                                const uint32_t half_bytes = p.w_sub_bytes >> 1;
+                                const int r0 = n_idx * p.n_tile + static_cast<int>(cta_rank) * half_rows;
+                                tma_load_2d_mcast(wb + cta_rank * half_bytes, &map_w, &full_bar[s], kcoord, r0, 3);
+                                tma_load_2d_mcast(wb + p.w_sub_bytes + cta_rank * half_bytes, &map_w, &full_bar[s],
+                                                  kcoord, p.w_lo_rows + r0, 3);
+                            } else {
+                                tma_load_2d(wb, &map_w, &full_bar[s], kcoord, n_idx * p.n_tile);
+                                tma_load_2d(wb + p.w_sub_bytes, &map_w, &full_bar[s], kcoord,
+                                            p.w_lo_rows + n_idx * p.n_tile);
+                            }
                             if (++cb == p.cin_blocks) { cb = 0; ++tap; }
                         }
                     }
@@ -263,7 +286,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         uint32_t ph = 0;
         int acc = 0;
         uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
             mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
             tc_fence_after();
             uint32_t accumulate = 0;
@@ -280,7 +303,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                             const uint32_t a0 = base16 + static_cast<uint32_t>(kk) * 2u;   // +32 B per K=16
                             const uint32_t w_hi = a0 + w_off16;
                             const uint32_t w_lo = w_hi + w_sub16;
-                            if (p.nfold) {
+                            if (p.corr_off && !p.nfold) {          // separate correction accumulator
+                                umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(leader, d0 + p.corr_off, a0 + a_lo_off16, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(leader, d0 + p.corr_off, a0, w_lo, desc_hi, idesc, 1u);
+                            } else if (p.nfold) {
                                 umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc2, accumulate);
                                 umma_bf16_lohi(leader, d0 + p.n_tile, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
                                 if (p.mt == 2) {
@@ -305,7 +332,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                         }
                     }
                 }
-                if (leader) umma_commit(&empty_bar[s]);   // frees the smem stage when the MMAs retire
+                if (leader) {                             // frees the smem stage when the MMAs retire
+                    if (p.cluster2) umma_commit_mcast(&empty_bar[s], 3);
+                    else umma_commit(&empty_bar[s]);
+                }
                 __syncwarp();
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
@@ -324,13 +354,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         const float* shift_v = epi_in_smem ? s_epi[2] : p.shift;
         int acc = 0;
         uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
             const int m_ct = tile / p.n_tiles;
             const int n_idx = tile - m_ct * p.n_tiles;
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
             for (int mi = 0; mi < p.mt && !(p.dbg & 4); ++mi) {
-                const int64_t m = static_cast<int64_t>(m_ct * p.mt + mi) * 128 + row_in_tile;
+                const int64_t m = (p.cluster2 ? static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank))
+                                              : static_cast<int64_t>(m_ct * p.mt + mi)) * 128 + row_in_tile;
                 const bool row_ok = m < p.m_total;
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                        static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);
@@ -338,9 +369,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                     uint32_t r[16];
                     __syncwarp();                      // tcgen05.ld is .sync.aligned
                     tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), r);
-                    if (p.nfold) {                     // warp-uniform
+                    if (p.nfold || p.corr_off) {       // warp-uniform: add the correction accumulator
                         uint32_t rc[16];
-                        tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.n_tile + c * 16), rc);
+                        tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>((p.nfold ? p.n_tile : p.corr_off) + c * 16), rc);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
@@ -407,6 +438,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
 
     tc_fence_before();
     __syncthreads();
+    if (p.cluster2) cluster_sync_all();   // the peer may still multicast into / arrive on this CTA's smem
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_512(tmem_base);

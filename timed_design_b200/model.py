@@ -24,7 +24,7 @@ class Model:
     """An inference graph resident on one GPU."""
 
     def __init__(self, model_config: dict, weights: Dict[str, Dict[str, np.ndarray]],
-                 device: int = 0, max_chunk_frames: int = 2048):
+                 device: int = 0, max_chunk_frames: int = 2048, precise: bool = False):
         self.model_config = model_config
         self.graph: Graph = parse_model_config(model_config, weights)
         self.device = device
@@ -43,6 +43,9 @@ class Model:
         assert ncls.value == self.n_classes
         self.flops_per_frame = flops.value
         self.launches_per_forward = launches.value
+        self.precise = False
+        if precise:
+            self.set_precise(True)
 
     # ------------------------------------------------------------------ host path (drop-in)
     def predict(self, X: np.ndarray, batch_size: Optional[int] = None, verbose: int = 0) -> np.ndarray:
@@ -86,6 +89,12 @@ class Model:
             self._h, C.c_void_p(frames.data_ptr()), code, n, C.c_void_p(workspace.data_ptr()),
             workspace.numel() * workspace.element_size(), C.c_void_p(probs.data_ptr()),
             C.c_void_p(stream)))
+
+    def set_precise(self, precise: bool) -> None:
+        """Trade ~15 % throughput for ~2x tighter probabilities (separate correction accumulators in the
+        two full-width conv layers, 2-CTA clusters with multicast weights)."""
+        _lib.check(_lib.load().timed_b200_graph_set_precise(self._h, int(bool(precise))))
+        self.precise = bool(precise)
 
     def set_timing(self, enabled: bool) -> None:
         """Record CUDA events around every fused op of subsequent forwards (bench roofline)."""
