@@ -34,6 +34,9 @@ CASES = [
     ("k2_even_kernel", 2, 6, 32, 48, 2, "same"),
     ("k3_c128_n256_mt2", 700, 6, 128, 256, 3, "same"),
     ("k3_c64_n128_mt2", 700, 6, 64, 128, 3, "same"),
+    ("k3_c256_n512_pair", 360, 6, 256, 512, 3, "same"),
+    ("k3_c128_n338_pair", 400, 6, 128, 338, 3, "same"),
+    ("k1_c96_n540_pair", 300, 6, 96, 540, 1, "same"),
     ("k3_c6_n32_many_tiles", 40, 13, 6, 32, 3, "same"),
 ]
 
@@ -121,3 +124,25 @@ def test_cluster_mode_conv(ci, co, monkeypatch):
         assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
     rms = lambda a, r: np.sqrt(((a - r) ** 2).mean())
     assert rms(y[:2], ref_head) < 0.8 * rms(y_fast[:2], ref_head)
+
+
+@pytest.mark.parametrize("case", [("small_c256_n512", 4, 6, 256, 512, 3, "same"), ("small_c64_n160_k5", 3, 7, 64, 160, 5, "same"),
+                                  ("small_c32_n192_valid", 2, 9, 32, 192, 3, "valid"), ("one_frame_c64_n256", 1, 4, 64, 256, 3, "same")],
+                         ids=lambda c: c[0])
+def test_pair_mode_small_shapes(case, monkeypatch):
+    """tcgen05.mma.cta_group::2 path (conv_pair.cuh) forced on shapes with fewer tiles than CTAs: ragged last
+    pair-tile (dummy peer half), 64B- and 128B-swizzled K blocks, odd N tiles, and agreement with the single-CTA path."""
+    name, n, side, ci, co, k, padding = case
+    rng = np.random.default_rng(abs(hash(name)) % 2 ** 31)
+    x = rng.standard_normal((n, side, side, side, ci)).astype(np.float32)
+    w = (rng.standard_normal((k, k, k, ci, co)) * np.sqrt(2.0 / (k ** 3 * ci))).astype(np.float32)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    y_single = run_conv_gpu(x, w, bias=b, padding=padding)
+    monkeypatch.setenv("TIMED_B200_FORCE_PAIR", "1")
+    for kc in ("64", "32"):
+        monkeypatch.setenv("TIMED_B200_PAIR_KC", kc)
+        y = run_conv_gpu(x, w, bias=b, padding=padding)
+        ref = ko.np_conv3d(x[:2].astype(np.float64), w.astype(np.float64), b.astype(np.float64), padding)
+        assert np.isfinite(y).all()
+        assert np.abs(y[:2] - ref).max() <= 1e-4 * np.abs(ref).max()
+        assert np.abs(y - y_single).max() <= 1e-4 * np.abs(ref).max()

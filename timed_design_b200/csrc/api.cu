@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "conv_umma.cuh"
+#include "conv_pair.cuh"
 #include "kernels.cuh"
 #include "thin_conv.cuh"
 
@@ -148,7 +149,7 @@ struct ConvPlan {
     float alpha1 = 1.f, alpha2 = 1.f;
     // tile configuration (depends on the frame count -> chosen at launch)
     struct Config {
-        int kc, mt, kg, stages, acc_stages, acc_cols, nfold, cluster2, corr_off;
+        int kc, mt, kg, stages, acc_stages, acc_cols, nfold, cluster2, corr_off, pair;
         uint32_t swizzle_code;       // UMMA layout type
         CUtensorMapSwizzle tma_swz;
         size_t smem_bytes;
@@ -192,6 +193,7 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
     TB_REQUIRE(!kcs.empty(), "conv: padded input channels must be a multiple of 16");
     cfg->cluster2 = 0;
     cfg->corr_off = 0;
+    cfg->pair = 0;
     // "precise" graphs, full-width tiles (n_tile = 256) with plenty of rows: 2-CTA cluster, W tiles
     // multicast, one 128-row sub-tile per CTA with separate main / correction accumulators.  Same L2
     // traffic as mt = 2 and 3x less accumulator truncation, but every CTA now stages the whole W tile for
@@ -212,6 +214,32 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
         cfg->corr_off = 256;
         cfg->swizzle_code = 4u;
         cfg->tma_swz = CU_TENSOR_MAP_SWIZZLE_64B;
+        cfg->smem_bytes = kb * cfg->stages + 1024;
+        return 0;
+    }
+    // Wide tiles (n_tile > 128) with plenty of rows: CTA pair, tcgen05.mma.cta_group::2 (conv_pair.cuh).
+    // Each CTA stages 128 rows of A and half of the W tile, so TMEM holds two accumulator stages (the
+    // epilogue overlaps the next mainloop) and an MMA reads 8 KB instead of 12 KB of shared memory.
+    if (!p.precise && p.n_tile > 128 && p.cin_pad % 32 == 0 && !getenv("TIMED_B200_NO_PAIR") &&
+        (static_cast<int64_t>(ceil_div(m_tiles, 2)) * p.n_tiles >= 2 * 74 || getenv("TIMED_B200_FORCE_PAIR"))) {
+        int kc = p.cin_pad % 64 == 0 ? 64 : 32;
+        if (const char* e = getenv("TIMED_B200_PAIR_KC")) {
+            const int v = atoi(e);
+            if ((v == 32 || v == 64) && p.cin_pad % v == 0) kc = v;
+        }
+        const size_t kb = 2 * (128u * kc * 2u) + 2 * (static_cast<size_t>(p.n_tile / 2) * kc * 2u);
+        const int n_kblocks = p.taps_eff() * (p.cin_pad / kc);
+        cfg->kc = kc;
+        cfg->mt = 1;
+        cfg->kg = 1;
+        cfg->stages = static_cast<int>(std::min<size_t>(kConvMaxStages, kSmemBudget / kb));
+        cfg->stages = std::max(2, std::min(cfg->stages, std::max(2, n_kblocks)));
+        cfg->acc_cols = round_up(p.n_tile, 32);
+        cfg->acc_stages = std::min(2, 512 / cfg->acc_cols);
+        cfg->nfold = 0;
+        cfg->pair = 1;
+        cfg->swizzle_code = kc == 64 ? 2u : 4u;
+        cfg->tma_swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
         cfg->smem_bytes = kb * cfg->stages + 1024;
         return 0;
     }
@@ -639,6 +667,32 @@ static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map
     return 0;
 }
 
+template <int A1, int A2, int F>
+static int launch_pair_instance(const CUtensorMap& map_a, const CUtensorMap& map_w, const ConvKernelParams& k,
+                                int grid, size_t smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+        TB_CHECK_CUDA(cudaFuncSetAttribute(conv_pair_kernel<A1, A2, F>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kSmemDynamicMax)));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kConvThreads);
+    lc.dynamicSmemBytes = smem_bytes;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    TB_CHECK_CUDA(cudaLaunchKernelEx(&lc, conv_pair_kernel<A1, A2, F>, map_a, map_w, k));
+    return 0;
+}
+
 // Launch one conv over `n_frames` frames.  `in_base`: split tensor base (hi plane first);
 // `in_frames_alloc`: frames per plane in that allocation.
 // bytes of fp32 scratch (the Z matrix) a tap-to-N conv needs for n_frames
@@ -666,7 +720,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     int rc = choose_config(p, m_total64, &cfg);
     if (rc) return rc;
     CUtensorMap map_w, map_a;
-    rc = encode_w_map(p, cfg.kc, cfg.tma_swz, &map_w, cfg.cluster2 ? p.n_tile / 2 : p.n_tile);
+    rc = encode_w_map(p, cfg.kc, cfg.tma_swz, &map_w, (cfg.cluster2 || cfg.pair) ? p.n_tile / 2 : p.n_tile);
     if (rc) return rc;
     rc = encode_a_map(p, cfg, in_base, in_frames_alloc, p.cin_pad, &map_a);
     if (rc) return rc;
@@ -676,7 +730,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.m_total = static_cast<int32_t>(m_total64);
     const int m_tiles = static_cast<int>((m_total64 + 127) / 128);
     k.mt = cfg.mt;
-    k.n_ctile_m = ceil_div(m_tiles, cfg.cluster2 ? 2 : cfg.mt);   // cluster mode: tiles are 256-row pair-tiles
+    k.n_ctile_m = ceil_div(m_tiles, (cfg.cluster2 || cfg.pair) ? 2 : cfg.mt);   // cluster / pair mode: tiles are 256-row pair-tiles
     k.cluster2 = cfg.cluster2;
     k.corr_off = cfg.corr_off;
     k.n_tiles = p.n_tiles;
@@ -699,7 +753,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.lo_plane_frames = static_cast<int32_t>(in_frames_alloc);
     k.w_lo_rows = p.n_alloc;
     k.a_sub_bytes = 128u * cfg.kc * 2u;
-    k.w_sub_bytes = static_cast<uint32_t>(p.n_tile) * cfg.kc * 2u;
+    k.w_sub_bytes = static_cast<uint32_t>(cfg.pair ? p.n_tile / 2 : p.n_tile) * cfg.kc * 2u;   // pair: per-CTA half tile
     k.row_bytes = cfg.kc * 2u;
     k.layout_type = cfg.swizzle_code;
     k.bias = p.d_bias; k.scale = p.d_scale; k.shift = p.d_shift;
@@ -717,13 +771,14 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
                "conv: split output channel padding mismatch");
 
     const int total_tiles = k.n_ctile_m * k.n_tiles;
-    const int grid = cfg.cluster2 ? 2 * std::min(total_tiles, 74) : std::min(total_tiles, 148);
+    const int grid = (cfg.cluster2 || cfg.pair) ? 2 * std::min(total_tiles, 74) : std::min(total_tiles, 148);
     // compile-time specialised epilogues for the activation pairs Keras graphs actually produce;
     // everything else goes through the runtime-dispatched instance
     bool launched = false;
 #define TB_CONV_CASE(A1, A2, F)                                                                         \
     if (!launched && k.act1 == (A1) && k.act2 == (A2) && k.out_fmt == (F)) {                            \
-        rc = launch_conv_instance<A1, A2, F>(map_a, map_w, k, grid, cfg.smem_bytes, stream);            \
+        rc = cfg.pair ? launch_pair_instance<A1, A2, F>(map_a, map_w, k, grid, cfg.smem_bytes, stream)  \
+                      : launch_conv_instance<A1, A2, F>(map_a, map_w, k, grid, cfg.smem_bytes, stream); \
         launched = true;                                                                                \
     }
     TB_CONV_CASE(ACT_ELU, ACT_NONE, FMT_SPLIT)
@@ -737,7 +792,10 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     TB_CONV_CASE(ACT_NONE, ACT_ELU, FMT_SPLIT)
     TB_CONV_CASE(ACT_NONE, ACT_ELU, FMT_F32)
 #undef TB_CONV_CASE
-    if (!launched)
+    if (!launched && cfg.pair)
+        rc = k.out_fmt == FMT_SPLIT ? launch_pair_instance<-1, -1, FMT_SPLIT>(map_a, map_w, k, grid, cfg.smem_bytes, stream)
+                                    : launch_pair_instance<-1, -1, FMT_F32>(map_a, map_w, k, grid, cfg.smem_bytes, stream);
+    else if (!launched)
         rc = k.out_fmt == FMT_SPLIT ? launch_conv_instance<-1, -1, FMT_SPLIT>(map_a, map_w, k, grid, cfg.smem_bytes, stream)
                                     : launch_conv_instance<-1, -1, FMT_F32>(map_a, map_w, k, grid, cfg.smem_bytes, stream);
     if (rc) return rc;

@@ -134,6 +134,60 @@ __device__ __forceinline__ void umma_bf16_lohi(bool leader, uint32_t d_tmem, uin
     }
 }
 
+// One 16-column chunk of one accumulator row: bias -> act1 -> folded BatchNorm -> act2 -> store
+// (bf16 hi/lo split planes or fp32).  `r` holds the raw fp32 accumulator bits of columns [n0, n0+16).
+template <int ACT1, int ACT2, int FMT>
+__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&r)[16], int n0,
+                                               int64_t m, bool row_ok, const float* bias_v,
+                                               const float* scale_v, const float* shift_v) {
+    float v[16];
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+        const float4 b = *(reinterpret_cast<const float4*>(bias_v + n0) + i4);
+        const float4 sc = *(reinterpret_cast<const float4*>(scale_v + n0) + i4);
+        const float4 sh = *(reinterpret_cast<const float4*>(shift_v + n0) + i4);
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+        const float ss[4] = {sc.x, sc.y, sc.z, sc.w};
+        const float hh[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float x = __uint_as_float(r[i4 * 4 + i]) + bb[i];
+            x = act_ct<ACT1>(x, p.act1, p.alpha1);
+            x = fmaf(x, ss[i], hh[i]);
+            v[i4 * 4 + i] = act_ct<ACT2>(x, p.act2, p.alpha2);
+        }
+    }
+    if (row_ok && FMT == FMT_SPLIT) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[2 * i], h0, l0);
+            split_bf16(v[2 * i + 1], h1, l1);
+            hi[i] = pack_bf16x2(h0, h1);
+            lo[i] = pack_bf16x2(l0, l1);
+        }
+        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + m * p.ldc + n0);
+        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + m * p.ldc + n0);
+        dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    } else if (row_ok) {
+        float* dst = p.out_f32 + m * p.ldc + n0;
+        if (n0 + 16 <= p.c_store && (p.ldc & 3) == 0) {
+            float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (n0 + i < p.c_store) dst[i] = v[i];
+        }
+    }
+}
+
 template <int ACT1, int ACT2, int FMT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -381,52 +435,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                     }
                     const int n0 = n_idx * p.n_tile + c * 16;
                     if (n0 >= p.c_store) continue;     // warp-uniform
-                    float v[16];
-#pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4) {
-                        const float4 b = *(reinterpret_cast<const float4*>(bias_v + n0) + i4);
-                        const float4 sc = *(reinterpret_cast<const float4*>(scale_v + n0) + i4);
-                        const float4 sh = *(reinterpret_cast<const float4*>(shift_v + n0) + i4);
-                        const float bb[4] = {b.x, b.y, b.z, b.w};
-                        const float ss[4] = {sc.x, sc.y, sc.z, sc.w};
-                        const float hh[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float x = __uint_as_float(r[i4 * 4 + i]) + bb[i];
-                            x = act_ct<ACT1>(x, p.act1, p.alpha1);
-                            x = fmaf(x, ss[i], hh[i]);
-                            v[i4 * 4 + i] = act_ct<ACT2>(x, p.act2, p.alpha2);
-                        }
-                    }
-                    if (row_ok && FMT == FMT_SPLIT) {
-                        uint32_t hi[8], lo[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(v[2 * i], h0, l0);
-                            split_bf16(v[2 * i + 1], h1, l1);
-                            hi[i] = pack_bf16x2(h0, h1);
-                            lo[i] = pack_bf16x2(l0, l1);
-                        }
-                        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + m * p.ldc + n0);
-                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + m * p.ldc + n0);
-                        dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                        dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                    } else if (row_ok) {
-                        float* dst = p.out_f32 + m * p.ldc + n0;
-                        if (n0 + 16 <= p.c_store && (p.ldc & 3) == 0) {
-                            float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n0 + i < p.c_store) dst[i] = v[i];
-                        }
-                    }
+                    epilogue_chunk<ACT1, ACT2, FMT>(p, r, n0, m, row_ok, bias_v, scale_v, shift_v);
                 }
             }
             tc_fence_before();
