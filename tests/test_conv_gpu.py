@@ -146,3 +146,40 @@ def test_pair_mode_small_shapes(case, monkeypatch):
         assert np.isfinite(y).all()
         assert np.abs(y[:2] - ref).max() <= 1e-4 * np.abs(ref).max()
         assert np.abs(y - y_single).max() <= 1e-4 * np.abs(ref).max()
+
+
+SLAB_CASES = [
+    ("slab_c32_n64_11_many", 40, 11, 32, 64, 3, "same"),
+    ("slab_c64_n128_13", 3, 13, 64, 128, 3, "same"),
+    ("slab_c16_n24_k5", 2, 12, 16, 24, 5, "same"),
+    ("slab_c48_n96_k2_even", 2, 10, 48, 96, 2, "same"),
+    ("slab_c20_n40_valid", 3, 10, 20, 40, 3, "valid"),
+    ("slab_c32_n64_k1", 2, 9, 32, 64, 1, "same"),
+    ("slab_c32_n16_small_forced", 2, 5, 32, 16, 3, "same"),
+]
+
+
+@pytest.mark.parametrize("case", SLAB_CASES, ids=[c[0] for c in SLAB_CASES])
+def test_slab_conv_matches_oracle_and_im2col_path(case, monkeypatch):
+    """slab_conv_kernel (chunk-plane padded-volume input, taps as descriptor shifts on one staged slab): parity with
+    the fp64 oracle and agreement with the im2col kernel on the same data; odd/even kernels, 'valid' windows, channel
+    counts that are not a multiple of 16, tiles that straddle frames."""
+    name, n, side, ci, co, k, padding = case
+    rng = np.random.default_rng(abs(hash(name)) % 2 ** 31)
+    x = rng.standard_normal((n, side, side, side, ci)).astype(np.float32)
+    w = (rng.standard_normal((k, k, k, ci, co)) * np.sqrt(2.0 / (k ** 3 * ci))).astype(np.float32)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, co).astype(np.float32)
+    sh = (rng.standard_normal(co) * 0.3).astype(np.float32)
+    monkeypatch.setenv("TIMED_B200_NO_SLAB", "1")
+    y_ref_path = run_conv_gpu(x, w, bias=b, scale=sc, shift=sh, padding=padding, act1="elu")
+    monkeypatch.delenv("TIMED_B200_NO_SLAB")
+    monkeypatch.setenv("TIMED_B200_FORCE_SLAB", "1")
+    y = run_conv_gpu(x, w, bias=b, scale=sc, shift=sh, padding=padding, act1="elu")
+    assert np.isfinite(y).all()
+    nref = min(n, 2)
+    ref = ko.np_conv3d(x[:nref].astype(np.float64), w.astype(np.float64), b.astype(np.float64), padding)
+    ref = ko.np_activation(ref, "elu") * sc + sh
+    scale = max(np.abs(ref).max(), 1.0)
+    assert np.abs(y[:nref] - ref).max() <= 1e-4 * scale
+    assert np.abs(y - y_ref_path).max() <= 1e-4 * scale

@@ -18,6 +18,7 @@
 #include "conv_pair.cuh"
 #include "kernels.cuh"
 #include "thin_conv.cuh"
+#include "slab_conv.cuh"
 
 namespace tb {
 
@@ -93,8 +94,15 @@ struct TensorInfo {
     // margins materialised in all three dimensions (pv_*0 before, up to the padded extents after).
     bool padvol = false;
     int pv_d0 = 0, pv_h0 = 0, pv_w0 = 0, pv_Dp = 0, pv_Hp = 0, pv_Wp = 0;
+    // "chunk-plane padded volume" read by slab_conv_kernel (slab_conv.cuh): plane x 8-channel chunk x position
+    // x 8 bf16, positions = lead + one linearisation of all frames with shared zero margins + tail.
+    bool cpv = false;
+    int cpv_Dp = 0, cpv_Hp = 0, cpv_Wp = 0;
+    int64_t cpv_lead = 0, cpv_tail = 0;
+    int64_t cpv_T(int64_t n) const { return cpv_lead + n * cpv_Dp * cpv_Hp * cpv_Wp + cpv_tail; }
     int64_t pix_per_frame() const { return static_cast<int64_t>(D) * H * W; }
     int64_t stored_pix_per_frame() const {
+        if (cpv) return static_cast<int64_t>(cpv_Dp) * cpv_Hp * cpv_Wp;
         if (padvol) return static_cast<int64_t>(pv_Dp) * pv_Hp * pv_Wp;
         return static_cast<int64_t>(D) * H * (wfold ? wf_pitch : W);
     }
@@ -104,6 +112,7 @@ struct TensorInfo {
         return n + (slack_pix + pix_per_frame() - 1) / pix_per_frame();
     }
     size_t bytes(int64_t n) const {
+        if (cpv) return static_cast<size_t>(round_up64(2 * (c_pad / 8) * cpv_T(n) * 16, 1024));
         const int64_t elems = frames_alloc(n) * stored_pix_per_frame() * c_pad;
         return static_cast<size_t>(round_up64(fmt == FMT_SPLIT ? elems * 2 * 2 : elems * 4, 1024));
     }
@@ -127,6 +136,10 @@ struct ConvPlan {
     // followed by a col2im gather  out[p, co] = sum_tap Z[p + tap - pad, tap, co]  (+ bias/act/BN).
     // thin-input path (thin_conv.cuh): padded-volume input, kw taps aliased by the UMMA descriptor
     bool precise = false;            // graph option: 2-CTA cluster mode with separate correction accumulators
+    bool slab = false;               // chunk-plane padded-volume input, slab_conv_kernel
+    SlabConvParams slab_params;      // static part, completed per launch
+    uint8_t* d_slab_w = nullptr;
+    int64_t slab_lead = 0, slab_tail = 0;
     bool thin = false;
     ThinConvParams thin_params;      // static part, completed per launch
     uint8_t* d_thin_w = nullptr;
@@ -167,6 +180,8 @@ static void free_conv_plan(ConvPlan& p) {
     cudaFree(p.d_shift);
     cudaFree(p.d_thin_w);
     p.d_thin_w = nullptr;
+    cudaFree(p.d_slab_w);
+    p.d_slab_w = nullptr;
     cudaFree(p.d_c2i_bias);
     cudaFree(p.d_c2i_scale);
     cudaFree(p.d_c2i_shift);
@@ -404,13 +419,6 @@ static int thin_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& 
             steps.push_back({{r, p.kw - 1}, {r + 1 < rows ? r + 1 : -1, p.kw - 1}});
     TB_REQUIRE(static_cast<int>(steps.size()) <= kThinMaxSteps, "thin conv: too many K steps");
     t.n_steps = static_cast<int>(steps.size());
-    for (int k = 0; k < t.n_steps; ++k) {
-        const Half a = steps[k].first, b = steps[k].second;
-        t.step_off16[k] = static_cast<uint32_t>(a.row * span_stride + a.kwi * 16) >> 4;
-        // second K-half: the next pixel of the same span (16 B) or the same pixel of the next span
-        // (a missing partner has zero weights: alias the next pixel, any valid smem will do)
-        t.step_lbo16[k] = (b.row >= 0 && b.row != a.row) ? static_cast<uint32_t>(span_stride) >> 4 : 1u;
-    }
     // ---- weights: [2*n_steps chunks][2*n_tile rows: hi then lo][8]
     const size_t w_elems = static_cast<size_t>(2 * t.n_steps) * 2 * n_tile * 8;
     std::vector<__nv_bfloat16> w(w_elems, __float2bfloat16(0.0f));
@@ -442,7 +450,7 @@ static int thin_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& 
     t.off_d = tin.pv_d0 - p.pad0[0];
     t.off_h = tin.pv_h0 - p.pad0[1];
     t.off_w = tin.pv_w0 - p.pad0[2];
-    t.kd = p.kd; t.kh = p.kh;
+    t.kd = p.kd; t.kh = p.kh; t.kw = p.kw;
     t.span_bytes = span_bytes;
     t.span_stride = span_stride;
     t.n_tile = n_tile;
@@ -466,6 +474,178 @@ static int launch_thin_instance(const ThinConvParams& k, int grid, size_t smem_b
         attr_set = true;
     }
     thin_conv_kernel<A1, A2, F><<<grid, kConvThreads, smem_bytes, stream>>>(k);
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- slab conv plan
+struct SlabGeom {
+    int pd, ph, pw;          // shared zero margins per dimension
+    int Dp, Hp, Wp;
+    int neg, pos;            // halo positions before / after a tile
+    int mt, w_stages, acc_stages, acc_cols, slab_pix, slab_stride;
+    size_t smem_bytes;
+};
+
+// Can a stride-1 conv over a (D,H,W,cin) tensor run on slab_conv_kernel?  Fills the geometry when it can.
+static bool slab_geometry(int D, int H, int W, int cin, const tb_op_desc& c, SlabGeom* out, int min_pd = 0,
+                          int min_ph = 0, int min_pw = 0) {
+    if (getenv("TIMED_B200_NO_SLAB")) return false;
+    if (c.op != TB_OP_CONV3D || c.stride[0] != 1 || c.stride[1] != 1 || c.stride[2] != 1) return false;
+    const int c_pad = round_up(cin, 16), n_tile = round_up(c.c_out, 16);
+    if (cin <= 8 || c_pad > 64 || n_tile > 128) return false;
+    const int ks[3] = {c.kernel[0], c.kernel[1], c.kernel[2]}, in[3] = {D, H, W};
+    int pb[3] = {0, 0, 0}, pa[3] = {0, 0, 0};
+    for (int a = 0; a < 3; ++a) {
+        if (ks[a] < 1 || ks[a] > 7) return false;
+        if (c.pad_same) {
+            int o;
+            same_pads(in[a], ks[a], 1, &o, &pb[a], &pa[a]);
+        } else if (in[a] < ks[a]) {
+            return false;
+        }
+    }
+    SlabGeom g;
+    g.pd = std::max({pb[0], pa[0], min_pd}); g.ph = std::max({pb[1], pa[1], min_ph}); g.pw = std::max({pb[2], pa[2], min_pw});
+    g.Dp = D + g.pd; g.Hp = H + g.ph; g.Wp = W + g.pw;
+    // margin positions are computed and dropped: require decent utilisation of the MMA rows
+    const double util = static_cast<double>(D) * H * W / (static_cast<double>(g.Dp) * g.Hp * g.Wp);
+    if (util < 0.70 && !getenv("TIMED_B200_FORCE_SLAB")) return false;
+    g.neg = pb[0] * g.Hp * g.Wp + pb[1] * g.Wp + pb[2];
+    g.pos = (ks[0] - 1 - pb[0]) * g.Hp * g.Wp + (ks[1] - 1 - pb[1]) * g.Wp + (ks[2] - 1 - pb[2]);
+    const int n_chunks = c_pad / 8;
+    g.acc_cols = round_up(2 * n_tile, 32);
+    const size_t w_tap = static_cast<size_t>(n_chunks) * 2 * n_tile * 16;
+    const size_t w_stage = (w_tap + 127) & ~static_cast<size_t>(127);
+    for (int mt : {2, 1}) {
+        if (mt * g.acc_cols > 512) continue;
+        g.mt = mt;
+        g.acc_stages = std::min(2, 512 / (mt * g.acc_cols));
+        g.slab_pix = 128 * mt + g.neg + g.pos;
+        g.slab_stride = g.slab_pix * 16;
+        const size_t slabs = 2u * 2u * n_chunks * g.slab_stride;
+        if (slabs + 2 * w_stage + 128 > kSmemDynamicMax) continue;
+        g.w_stages = static_cast<int>(std::min<size_t>(kSlabWStages, (kSmemDynamicMax - 128 - slabs) / w_stage));
+        g.smem_bytes = 128 + slabs + g.w_stages * w_stage;
+        *out = g;
+        return true;
+    }
+    return false;
+}
+
+static int slab_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& tin) {
+    SlabGeom g;
+    TB_REQUIRE(slab_geometry(p.Di, p.Hi, p.Wi, p.cin, d, &g, tin.cpv_Dp - p.Di, tin.cpv_Hp - p.Hi, tin.cpv_Wp - p.Wi),
+               "internal: slab conv not applicable");
+    TB_REQUIRE(g.Dp == tin.cpv_Dp && g.Hp == tin.cpv_Hp && g.Wp == tin.cpv_Wp, "internal: CPV margins mismatch");
+    p.slab = true;
+    const int n_tile = round_up(p.cout, 16);
+    p.n_tiles = 1;
+    p.n_tile = p.n_alloc = n_tile;
+    const int n_chunks = p.cin_pad / 8;
+    const int taps = p.kd * p.kh * p.kw;
+    // halo in the TENSOR's linearisation (its margins may be wider than this conv needs)
+    const int Hp = tin.cpv_Hp, Wp = tin.cpv_Wp;
+    SlabConvParams& t = p.slab_params;
+    std::memset(&t, 0, sizeof(t));
+    t.mt = g.mt;
+    t.Dp = tin.cpv_Dp; t.Hp = Hp; t.Wp = Wp;
+    t.Do = p.Do; t.Ho = p.Ho; t.Wo = p.Wo;
+    t.n_chunks = n_chunks;
+    t.kd = p.kd; t.kh = p.kh; t.kw = p.kw;
+    t.pd = p.pad0[0]; t.ph = p.pad0[1]; t.pw = p.pad0[2];
+    t.neg_halo = p.pad0[0] * Hp * Wp + p.pad0[1] * Wp + p.pad0[2];
+    t.pos_halo = (p.kd - 1 - p.pad0[0]) * Hp * Wp + (p.kh - 1 - p.pad0[1]) * Wp + (p.kw - 1 - p.pad0[2]);
+    t.slab_pix = 128 * g.mt + t.neg_halo + t.pos_halo;
+    t.slab_stride = t.slab_pix * 16;
+    t.n_tile = n_tile;
+    t.acc_cols = g.acc_cols;
+    t.acc_stages = g.acc_stages;
+    t.w_tap_bytes = static_cast<uint32_t>(n_chunks) * 2u * n_tile * 16u;
+    const size_t w_stage = (static_cast<size_t>(t.w_tap_bytes) + 127) & ~static_cast<size_t>(127);
+    const size_t slabs = 2u * 2u * n_chunks * static_cast<size_t>(t.slab_stride);
+    TB_REQUIRE(slabs + 2 * w_stage + 128 <= kSmemDynamicMax, "slab conv: slabs exceed shared memory");
+    t.w_stages = static_cast<int>(std::min<size_t>(kSlabWStages, (kSmemDynamicMax - 128 - slabs) / w_stage));
+    p.slab_lead = tin.cpv_lead;
+    p.slab_tail = tin.cpv_tail;
+    TB_REQUIRE(tin.cpv_lead >= t.neg_halo && tin.cpv_tail >= t.pos_halo + 128 * g.mt, "internal: CPV lead/tail too small");
+    // ---- weights: [tap][chunk][2*n_tile rows: hi then lo][8]
+    const size_t w_elems = static_cast<size_t>(taps) * n_chunks * 2 * n_tile * 8;
+    std::vector<__nv_bfloat16> w(w_elems, __float2bfloat16(0.0f));
+    for (int tap = 0; tap < taps; ++tap)
+        for (int c = 0; c < p.cin; ++c)
+            for (int n = 0; n < p.cout; ++n) {
+                const float v = d.kernel_w[(static_cast<size_t>(tap) * p.cin + c) * p.cout + n];
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                const size_t blk = (static_cast<size_t>(tap) * n_chunks + c / 8) * 2 * n_tile;
+                w[(blk + n) * 8 + c % 8] = hi;
+                w[(blk + n_tile + n) * 8 + c % 8] = lo;
+            }
+    TB_CHECK_CUDA(cudaMalloc(&p.d_slab_w, w_elems * sizeof(__nv_bfloat16)));
+    TB_CHECK_CUDA(cudaMemcpy(p.d_slab_w, w.data(), w_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    t.w_packed = p.d_slab_w;
+    return 0;
+}
+
+template <int A1, int A2, int F>
+static int launch_slab_instance(const SlabConvParams& k, int grid, size_t smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB_CHECK_CUDA(cudaFuncSetAttribute(slab_conv_kernel<A1, A2, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kSmemDynamicMax)));
+        attr_set = true;
+    }
+    slab_conv_kernel<A1, A2, F><<<grid, kConvThreads, smem_bytes, stream>>>(k);
+    return 0;
+}
+
+static int slab_launch(ConvPlan& p, void* in_base, int64_t n_frames, const TView& out, cudaStream_t stream) {
+    SlabConvParams k = p.slab_params;
+    const int64_t fpos = static_cast<int64_t>(k.Dp) * k.Hp * k.Wp;
+    const int64_t T = p.slab_lead + n_frames * fpos + p.slab_tail;
+    k.t_first = p.slab_lead;
+    k.t_count = n_frames * fpos;
+    const int64_t tiles = (k.t_count + 128 * k.mt - 1) / (128 * k.mt);
+    TB_REQUIRE(tiles > 0 && tiles < (1ll << 31), "slab conv: too many tiles per launch");
+    k.n_tiles_total = static_cast<int32_t>(tiles);
+    k.in_hi = static_cast<const uint8_t*>(in_base);
+    k.chunk_stride = T * 16;
+    k.lo_plane_off = static_cast<int64_t>(k.n_chunks) * T * 16;
+    ConvKernelParams& e = k.epi;
+    e.bias = p.d_bias; e.scale = p.d_scale; e.shift = p.d_shift;
+    e.act1 = p.act1; e.act2 = p.act2; e.alpha1 = p.alpha1; e.alpha2 = p.alpha2;
+    e.out_fmt = out.fmt;
+    e.out_f32 = out.f32; e.out_hi = out.hi; e.out_lo = out.lo;
+    e.ldc = out.ld;
+    e.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    {
+        static const int dbg = [] { const char* e = getenv("TIMED_B200_DBG"); return e ? atoi(e) : 0; }();
+        k.dbg = dbg;
+    }
+    TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
+               "slab conv: split output channel padding mismatch");
+    const size_t w_stage = (static_cast<size_t>(k.w_tap_bytes) + 127) & ~static_cast<size_t>(127);
+    const size_t smem_bytes = 128 + 2u * 2u * k.n_chunks * static_cast<size_t>(k.slab_stride) + k.w_stages * w_stage;
+    const int grid = static_cast<int>(std::min<int64_t>(tiles, 148));
+    int rc = 0;
+    bool launched = false;
+#define TB_SLAB_CASE(A1, A2, F)                                                              \
+    if (!launched && e.act1 == (A1) && e.act2 == (A2) && out.fmt == (F)) {                   \
+        rc = launch_slab_instance<A1, A2, F>(k, grid, smem_bytes, stream);                   \
+        launched = true;                                                                     \
+    }
+    TB_SLAB_CASE(ACT_ELU, ACT_NONE, FMT_F32)
+    TB_SLAB_CASE(ACT_ELU, ACT_NONE, FMT_SPLIT)
+    TB_SLAB_CASE(ACT_RELU, ACT_NONE, FMT_F32)
+    TB_SLAB_CASE(ACT_RELU, ACT_NONE, FMT_SPLIT)
+    TB_SLAB_CASE(ACT_NONE, ACT_NONE, FMT_F32)
+    TB_SLAB_CASE(ACT_NONE, ACT_NONE, FMT_SPLIT)
+#undef TB_SLAB_CASE
+    if (!launched)
+        rc = out.fmt == FMT_SPLIT ? launch_slab_instance<-1, -1, FMT_SPLIT>(k, grid, smem_bytes, stream)
+                                  : launch_slab_instance<-1, -1, FMT_F32>(k, grid, smem_bytes, stream);
+    if (rc) return rc;
+    TB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -541,9 +721,9 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
         TB_REQUIRE(out[i] >= 1, "conv: kernel larger than input with 'valid' padding");
     }
     p.Do = out[0]; p.Ho = out[1]; p.Wo = out[2];
-    if (wfold_in && wfold_in->padvol) {
+    if (wfold_in && (wfold_in->padvol || wfold_in->cpv)) {
         p.act1 = d.act1; p.act2 = d.act2; p.alpha1 = d.alpha1; p.alpha2 = d.alpha2;
-        int rc = thin_plan_create(p, d, *wfold_in);
+        int rc = wfold_in->cpv ? slab_plan_create(p, d, *wfold_in) : thin_plan_create(p, d, *wfold_in);
         if (rc) return rc;
         std::vector<float> b(p.n_alloc, 0.f), sc(p.n_alloc, 1.f), sh(p.n_alloc, 0.f);
         for (int n = 0; n < p.cout; ++n) {
@@ -704,6 +884,7 @@ static size_t conv_scratch_bytes(const ConvPlan& p, int64_t n_frames) {
 static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames,
                        const TView& final_out, cudaStream_t stream, void* scratch = nullptr,
                        size_t scratch_bytes = 0) {
+    if (p.slab) return slab_launch(p, in_base, n_frames, final_out, stream);
     if (p.thin) return thin_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream);
     TView out = final_out;
     if (p.tap2n) {
@@ -871,11 +1052,26 @@ static TView make_view(const TensorInfo& t, uint8_t* base, int64_t n_frames) {
     v.hi = v.lo = nullptr;
     if (t.fmt == FMT_F32) {
         v.f32 = reinterpret_cast<float*>(base);
+    } else if (t.cpv) {
+        v.hi = reinterpret_cast<__nv_bfloat16*>(base);
+        v.lo = v.hi + (t.c_pad / 8) * t.cpv_T(n_frames) * 8;
     } else {
         v.hi = reinterpret_cast<__nv_bfloat16*>(base);
         v.lo = v.hi + t.frames_alloc(n_frames) * t.stored_pix_per_frame() * t.c_pad;
     }
     return v;
+}
+
+static CpvGeom make_cpv_geom(const TensorInfo& t, int64_t n_frames) {
+    CpvGeom g;
+    g.T = t.cpv_T(n_frames);
+    g.lead = t.cpv_lead;
+    g.n_pos = n_frames * t.cpv_Dp * t.cpv_Hp * t.cpv_Wp;
+    g.D = t.D; g.H = t.H; g.W = t.W;
+    g.Dp = t.cpv_Dp; g.Hp = t.cpv_Hp; g.Wp = t.cpv_Wp;
+    g.n_chunks = t.c_pad / 8;
+    g.c = t.C;
+    return g;
 }
 
 // Liveness-based first-fit workspace layout for n_frames.
@@ -943,6 +1139,34 @@ static int upload_vec(const float* src, int n, float fill, float** dst) {
     TB_CHECK_CUDA(cudaMalloc(dst, n * sizeof(float)));
     TB_CHECK_CUDA(cudaMemcpy(*dst, v.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
+}
+
+// Give tensor `ti` (dims known, produced by the input op or a pooling op) the CPV layout when every reader is a
+// conv that slab_conv_kernel can run; margins are the union over the readers.
+static void decide_cpv(TensorInfo& t, int ti, const tb_op_desc* ops, int n_ops) {
+    int pd = 0, ph = 0, pw = 0, n_cons = 0;
+    for (int pass = 0; pass < 2; ++pass)          // second pass: every reader must also fit with the union margins
+        for (int i = ti + 1; i < n_ops; ++i)
+            for (int k = 0; k < ops[i].n_inputs; ++k)
+                if (ops[i].inputs[k] == ti) {
+                    SlabGeom g;
+                    if (!slab_geometry(t.D, t.H, t.W, t.C, ops[i], &g, pd, ph, pw)) return;
+                    pd = g.pd; ph = g.ph; pw = g.pw;
+                    if (pass == 0) ++n_cons;
+                }
+    if (!n_cons) return;
+    int neg = 0, pos = 0, mt = 1;
+    for (int i = ti + 1; i < n_ops; ++i)
+        for (int k = 0; k < ops[i].n_inputs; ++k)
+            if (ops[i].inputs[k] == ti) {
+                SlabGeom g;
+                slab_geometry(t.D, t.H, t.W, t.C, ops[i], &g, pd, ph, pw);
+                neg = std::max(neg, g.neg); pos = std::max(pos, g.pos); mt = std::max(mt, g.mt);
+            }
+    t.cpv = true;
+    t.cpv_Dp = t.D + pd; t.cpv_Hp = t.H + ph; t.cpv_Wp = t.W + pw;
+    t.cpv_lead = round_up(neg, 8);
+    t.cpv_tail = round_up(pos + 128 * mt, 8);
 }
 
 static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
@@ -1030,6 +1254,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 TB_REQUIRE(i == 0, "only ops[0] may be TB_OP_INPUT");
                 t.D = d.kernel[0]; t.H = d.kernel[1]; t.W = d.kernel[2]; t.C = d.c_out;
                 TB_REQUIRE(t.D > 0 && t.H > 0 && t.W > 0 && t.C > 0, "input dims must be positive");
+                if (!t.padvol && !t.wfold) decide_cpv(t, i, ops, n_ops);
                 g->launches += 1;
                 break;
             case TB_OP_CONV3D: {
@@ -1063,6 +1288,9 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 pp.Do = out[0]; pp.Ho = out[1]; pp.Wo = out[2];
                 pp.is_avg = d.pool_kind;
                 t.D = out[0]; t.H = out[1]; t.W = out[2]; t.C = in0->C;
+                // the CPV writer reads 8-channel vectors: the pool input must store >= round_up(C,16) channels
+                if (!in0->cpv && !in0->padvol && !in0->wfold && (in0->fmt == FMT_SPLIT || in0->C % 16 == 0))
+                    decide_cpv(t, i, ops, n_ops);
                 g->launches += 1;
                 break;
             }
@@ -1112,6 +1340,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
         }
         t.c_pad = t.fmt == FMT_SPLIT ? round_up(t.C, 16) : t.C;
         if (t.wfold || t.padvol) { t.fmt = FMT_SPLIT; t.c_pad = 8; }
+        if (t.cpv) { t.fmt = FMT_SPLIT; t.c_pad = round_up(t.C, 16); }
         // pointers are only valid during graph_create
         node.d.kernel_w = node.d.bias = node.d.scale = node.d.shift = nullptr;
     }
@@ -1120,6 +1349,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
         if (ops[i].op == TB_OP_CONV3D) {
             TensorInfo& s = g->tensors[ops[i].inputs[0]];
             const ConvPlan& c = g->ops[i].conv;
+            if (s.cpv) continue;
             // base pixels advance through Do*Ho*Wo per frame: express the slack in input pixels
             const int64_t out_ppf = static_cast<int64_t>(c.Do) * c.Ho * c.Wo;
             const int64_t frames = c.thin ? 1 : (128 + out_ppf - 1) / out_ppf;   // thin: spans overrun < 1 frame
@@ -1192,6 +1422,17 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
         const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
         switch (d.op) {
             case TB_OP_INPUT:
+                if (t.cpv) {
+                    const CpvGeom cg = make_cpv_geom(t, n_frames);
+                    const int grid = grid_for(cg.T * cg.n_chunks, 256);
+                    uint4* oh = reinterpret_cast<uint4*>(out.hi);
+                    uint4* ol = reinterpret_cast<uint4*>(out.lo);
+                    if (dtype == TB_DTYPE_F32) input_convert_cpv_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(d_frames), n_frames, cg, oh, ol);
+                    else if (dtype == TB_DTYPE_F64) input_convert_cpv_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(d_frames), n_frames, cg, oh, ol);
+                    else if (dtype == TB_DTYPE_U8) input_convert_cpv_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(d_frames), n_frames, cg, oh, ol);
+                    else TB_REQUIRE(false, "unknown frames dtype");
+                    break;
+                }
                 if (t.padvol) {
                     if (dtype == TB_DTYPE_F32) launch_input_convert_padvol<float>(d_frames, t, n_frames, out, s);
                     else if (dtype == TB_DTYPE_F64) launch_input_convert_padvol<double>(d_frames, t, n_frames, out, s);
@@ -1219,6 +1460,17 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 break;
             }
             case TB_OP_POOL3D: {
+                if (t.cpv) {
+                    const CpvGeom cg = make_cpv_geom(t, n_frames);
+                    const int grid = grid_for(cg.T * cg.n_chunks, 256);
+                    if (in0.fmt == FMT_SPLIT)
+                        pool3d_cpv_kernel<FMT_SPLIT><<<grid, 256, 0, s>>>(
+                            in0, reinterpret_cast<uint4*>(out.hi), reinterpret_cast<uint4*>(out.lo), cg, node.pool, n_frames);
+                    else
+                        pool3d_cpv_kernel<FMT_F32><<<grid, 256, 0, s>>>(
+                            in0, reinterpret_cast<uint4*>(out.hi), reinterpret_cast<uint4*>(out.lo), cg, node.pool, n_frames);
+                    break;
+                }
                 // 16-byte vector path when both sides store a multiple of 8 channels per pixel
                 const int in_cw = in0.fmt == FMT_SPLIT ? in0.c_pad : in0.c;
                 const bool vec = (cw % 8 == 0) && (in_cw % 8 == 0) && (in0.ld % 8 == 0) && (out.ld % 8 == 0) &&
@@ -1536,6 +1788,10 @@ int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int
         tin.pv_d0 = pb[0]; tin.pv_h0 = pb[1]; tin.pv_w0 = pb[2];
         tin.pv_Dp = pb[0] + D + pa[0]; tin.pv_Hp = pb[1] + H + pa[1]; tin.pv_Wp = pb[2] + W + pa[2];
         tin.c_pad = 8;
+    } else if (c_in > 8) {
+        tb_op_desc two[2] = {ops[0], ops[1]};
+        tin.cpv = false;
+        decide_cpv(tin, 0, two, 2);
     } else if (c_in <= 8 && conv->kernel[2] <= 8 && !getenv("TIMED_B200_NO_WFOLD")) {
         const int kw = conv->kernel[2], pad0 = conv->pad_same ? (kw - 1) / 2 : 0, kwin = kw <= 4 ? 4 : 8;
         tin.wfold = true;
@@ -1554,7 +1810,11 @@ int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int
     if (e != cudaSuccess) { free_conv_plan(plan); TB_CHECK_CUDA(e); }
     cudaMemset(d_in, 0, tin.bytes(n));
     TView vin = make_view(tin, static_cast<uint8_t*>(d_in), n);
-    if (tin.padvol) launch_input_convert_padvol<float>(d_x, tin, n, vin, nullptr);
+    if (tin.cpv) {
+        const CpvGeom cg = make_cpv_geom(tin, n);
+        input_convert_cpv_kernel<float><<<grid_for(cg.T * cg.n_chunks, 256), 256>>>(
+            d_x, n, cg, reinterpret_cast<uint4*>(vin.hi), reinterpret_cast<uint4*>(vin.lo));
+    } else if (tin.padvol) launch_input_convert_padvol<float>(d_x, tin, n, vin, nullptr);
     else if (tin.wfold) launch_input_convert_wfold<float>(d_x, tin, n, vin, nullptr);
     else launch_input_convert<float>(d_x, n * tin.pix_per_frame(), vin, nullptr);
     TView vout{};

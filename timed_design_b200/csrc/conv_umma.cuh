@@ -351,41 +351,48 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                 tc_fence_after();
                 const int nkb = min(p.kg, p.n_kblocks - g * p.kg);
                 uint32_t base16 = (smem_base16 + static_cast<uint32_t>(s) * (stage_bytes >> 4)) | lo_flags;
-                if (!(p.dbg & 2)) {
+                if (leader && !(p.dbg & 2)) {
+                    // one thread issues; the issue pattern is selected outside the K loops so that each loop
+                    // body is a straight run of UTCHMMAs with affine descriptor updates
+                    const int mode = (p.corr_off && !p.nfold) ? 0 : p.nfold ? (p.mt == 2 ? 2 : 1) : (p.mt == 2 ? 4 : 3);
+                    const uint32_t n_t = static_cast<uint32_t>(p.n_tile);
                     for (int j = 0; j < nkb; ++j, base16 += kb16) {
+#pragma unroll 2
                         for (int kk = 0; kk < k16_steps; ++kk) {
                             const uint32_t a0 = base16 + static_cast<uint32_t>(kk) * 2u;   // +32 B per K=16
                             const uint32_t w_hi = a0 + w_off16;
                             const uint32_t w_lo = w_hi + w_sub16;
-                            if (p.corr_off && !p.nfold) {          // separate correction accumulator
-                                umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(leader, d0 + p.corr_off, a0 + a_lo_off16, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(leader, d0 + p.corr_off, a0, w_lo, desc_hi, idesc, 1u);
-                            } else if (p.nfold) {
-                                umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc2, accumulate);
-                                umma_bf16_lohi(leader, d0 + p.n_tile, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                                if (p.mt == 2) {
-                                    const uint32_t a1 = a0 + a_sub16;
-                                    umma_bf16_lohi(leader, d1, a1, w_hi, desc_hi, idesc2, accumulate);
-                                    umma_bf16_lohi(leader, d1 + p.n_tile, a1 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                                }
-                            } else if (p.mt == 2) {
+                            if (mode == 0) {                       // separate correction accumulator
+                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(true, d0 + p.corr_off, a0 + a_lo_off16, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(true, d0 + p.corr_off, a0, w_lo, desc_hi, idesc, 1u);
+                            } else if (mode == 1) {                // N-folded, one sub-tile
+                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc2, accumulate);
+                                umma_bf16_lohi(true, d0 + n_t, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                            } else if (mode == 2) {                // N-folded, two sub-tiles
                                 const uint32_t a1 = a0 + a_sub16;
-                                umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(leader, d1, a1, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(leader, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                                umma_bf16_lohi(leader, d1, a1 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                                umma_bf16_lohi(leader, d0, a0, w_lo, desc_hi, idesc, 1u);
-                                umma_bf16_lohi(leader, d1, a1, w_lo, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc2, accumulate);
+                                umma_bf16_lohi(true, d0 + n_t, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(true, d1, a1, w_hi, desc_hi, idesc2, accumulate);
+                                umma_bf16_lohi(true, d1 + n_t, a1 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                            } else if (mode == 4) {                // two sub-tiles sharing every W tile
+                                const uint32_t a1 = a0 + a_sub16;
+                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(true, d1, a1, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(true, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(true, d1, a1 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(true, d0, a0, w_lo, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(true, d1, a1, w_lo, desc_hi, idesc, 1u);
                             } else {
-                                umma_bf16_lohi(leader, d0, a0, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(leader, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                                umma_bf16_lohi(leader, d0, a0, w_lo, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc, accumulate);
+                                umma_bf16_lohi(true, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(true, d0, a0, w_lo, desc_hi, idesc, 1u);
                             }
                             accumulate = 1u;
                         }
                     }
                 }
+                accumulate = 1u;
                 if (leader) {                             // frees the smem stage when the MMAs retire
                     if (p.cluster2) umma_commit_mcast(&empty_bar[s], 3);
                     else umma_commit(&empty_bar[s]);

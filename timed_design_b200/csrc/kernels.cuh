@@ -252,6 +252,106 @@ __global__ void pool3d_vec8_kernel(TView in, TView out, PoolParams pp, int64_t n
     }
 }
 
+// ------------------------------------------------------------------ chunk-plane padded volume (CPV) writers
+// Layout read by slab_conv_kernel: plane (hi | lo) x chunk of 8 channels x position x 8 bf16, positions =
+// lead zeros, then every frame as a (Dp, Hp, Wp) box whose trailing margins are zero, then tail zeros.
+struct CpvGeom {
+    int64_t T, lead, n_pos;          // stored positions; leading zeros; n_frames * Dp*Hp*Wp
+    int32_t D, H, W, Dp, Hp, Wp;
+    int32_t n_chunks, c;
+};
+
+__device__ __forceinline__ void cpv_store(uint4* hi, uint4* lo, int64_t i, const float (&v)[8]) {
+    uint32_t h4[4], l4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        __nv_bfloat16 a0, b0, a1, b1;
+        split_bf16(v[2 * k], a0, b0);
+        split_bf16(v[2 * k + 1], a1, b1);
+        h4[k] = pack_bf16x2(a0, a1);
+        l4[k] = pack_bf16x2(b0, b1);
+    }
+    hi[i] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+    lo[i] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+}
+
+// position -> (frame, z, p, q); false for lead / tail / margin positions
+__device__ __forceinline__ bool cpv_decode(const CpvGeom& g, int64_t t, int64_t& nf, int& z, int& p, int& q) {
+    const int64_t u = t - g.lead;
+    if (u < 0 || u >= g.n_pos) return false;
+    const int64_t fpos = static_cast<int64_t>(g.Dp) * g.Hp * g.Wp;
+    nf = u / fpos;
+    int rem = static_cast<int>(u - nf * fpos);
+    z = rem / (g.Hp * g.Wp);
+    rem -= z * g.Hp * g.Wp;
+    p = rem / g.Wp;
+    q = rem - p * g.Wp;
+    return z < g.D && p < g.H && q < g.W;
+}
+
+template <typename T>
+__global__ void input_convert_cpv_kernel(const T* __restrict__ x, int64_t n_frames, CpvGeom g, uint4* __restrict__ hi,
+                                         uint4* __restrict__ lo) {
+    const int64_t total = g.T * g.n_chunks;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t t = i / g.n_chunks;            // chunk fastest: a pixel's chunks are read by adjacent threads
+        const int chunk = static_cast<int>(i - t * g.n_chunks);
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int64_t nf;
+        int z, p, q;
+        if (cpv_decode(g, t, nf, z, p, q)) {
+            const T* src = x + (((nf * g.D + z) * g.H + p) * g.W + q) * static_cast<int64_t>(g.c) + chunk * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (chunk * 8 + k < g.c) v[k] = static_cast<float>(src[k]);
+        }
+        cpv_store(hi, lo, chunk * g.T + t, v);
+    }
+}
+
+// pooling straight into the CPV layout (input stores >= n_chunks*8 channels per pixel)
+template <int IN_FMT>
+__global__ void pool3d_cpv_kernel(TView in, uint4* __restrict__ hi, uint4* __restrict__ lo, CpvGeom g, PoolParams pp,
+                                  int64_t n_frames) {
+    const int64_t total = g.T * g.n_chunks;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t t = i / g.n_chunks;            // chunk fastest: a pixel's chunks are read by adjacent threads
+        const int chunk = static_cast<int>(i - t * g.n_chunks);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int64_t nf;
+        int z, p, q;
+        if (cpv_decode(g, t, nf, z, p, q)) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = pp.is_avg ? 0.0f : -INFINITY;
+            int cnt = 0;
+            for (int a = 0; a < pp.k[0]; ++a) {
+                const int d = z * pp.s[0] - pp.pad0[0] + a;
+                if (d < 0 || d >= pp.D) continue;
+                for (int b = 0; b < pp.k[1]; ++b) {
+                    const int h = p * pp.s[1] - pp.pad0[1] + b;
+                    if (h < 0 || h >= pp.H) continue;
+                    for (int c = 0; c < pp.k[2]; ++c) {
+                        const int w = q * pp.s[2] - pp.pad0[2] + c;
+                        if (w < 0 || w >= pp.W) continue;
+                        float v[8];
+                        load8<IN_FMT>(in, (((nf * pp.D + d) * pp.H + h) * pp.W + w) * in.ld + chunk * 8, v);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] = pp.is_avg ? acc[e] + v[e] : fmaxf(acc[e], v[e]);
+                        ++cnt;
+                    }
+                }
+            }
+            if (pp.is_avg) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] /= static_cast<float>(cnt);
+            }
+        }
+        cpv_store(hi, lo, chunk * g.T + t, acc);
+    }
+}
+
 // ------------------------------------------------------------------ standalone BN / activation
 __global__ void affine_act_kernel(TView in, TView out, int64_t n_pix, const float* __restrict__ scale,
                                   const float* __restrict__ shift, int act1, float alpha1, int act2,

@@ -39,13 +39,11 @@ struct ThinConvParams {
     int64_t dplane_bytes;     // Hp*Wp*16
     int32_t row_bytes;        // Wp*16
     int32_t off_d, off_h, off_w;   // stored-coordinate offset of this conv's window origin
-    int32_t kd, kh;
+    int32_t kd, kh, kw;
     int32_t span_bytes;       // bytes copied per (kd,kh) span (multiple of 16)
     int32_t span_stride;      // smem distance between consecutive spans
-    // ---- K=16 steps: A descriptor start (>>4, relative to the stage's hi region) and LBO (>>4)
+    // ---- K=16 steps (the kernel regenerates the order of thin_plan_create with two affine loops)
     int32_t n_steps;
-    uint32_t step_off16[kThinMaxSteps];
-    uint32_t step_lbo16[kThinMaxSteps];
     // ---- weights: [2*n_steps K-chunks][2*n_tile rows: hi then lo][8] bf16, resident in smem
     const uint8_t* w_packed;
     uint32_t w_bytes;
@@ -189,6 +187,8 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
         const uint32_t w_base16 = (smem_u32(w_smem) & 0x3FFFFu) >> 4;
         const uint32_t stage0_16 = (smem_u32(stage0) & 0x3FFFFu) >> 4;
         const uint32_t plane16 = plane_region >> 4;
+        const uint32_t ss16 = static_cast<uint32_t>(p.span_stride) >> 4;
+        const int pairs = p.kw >> 1;
         mbar_wait(&w_bar, 0);
         int s = 0;
         uint32_t ph = 0;
@@ -201,12 +201,34 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
             const uint32_t d_main = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
             const uint32_t d_corr = d_main + static_cast<uint32_t>(p.n_tile);
             const uint32_t a_base16 = stage0_16 + static_cast<uint32_t>(s) * (stage_bytes >> 4);
-            for (int k = 0; k < p.n_steps && !(p.dbg & 2); ++k) {
-                const uint32_t a_hi = (a_base16 + p.step_off16[k]) | (p.step_lbo16[k] << 16);
-                const uint32_t a_lo = a_hi + plane16;
-                const uint32_t b = (w_base16 + static_cast<uint32_t>(k) * w_step16) | (w_lbo16 << 16);
-                umma_bf16_desc(leader, d_main, a_hi, desc_hi, b, desc_hi, idesc2, k == 0 ? 0u : 1u);
-                umma_bf16_desc(leader, d_corr, a_lo, desc_hi, b, desc_hi, idesc, 1u);
+            // K steps in the packing order of thin_plan_create, as two affine loops (no descriptor table:
+            // an indexed constant load per step put ~110 cycles of dependent latency between MMAs):
+            //   (a) filter row r, in-row pixel pair (2jp, 2jp+1): start = span r + 2jp pixels, LBO = one pixel
+            //   (b) left-over odd tap of rows (r, r+1): start = span r + (kw-1) pixels, LBO = span stride
+            if (leader && !(p.dbg & 2)) {
+                uint32_t b = w_base16 | (w_lbo16 << 16);
+                uint32_t accumulate = 0;
+                uint32_t a_row = a_base16;
+                for (int r = 0; r < taps; ++r, a_row += ss16) {
+#pragma unroll 2
+                    for (int jp = 0; jp < pairs; ++jp) {
+                        const uint32_t a_hi = (a_row + 2u * static_cast<uint32_t>(jp)) | (1u << 16);
+                        umma_bf16_desc(true, d_main, a_hi, desc_hi, b, desc_hi, idesc2, accumulate);
+                        umma_bf16_desc(true, d_corr, a_hi + plane16, desc_hi, b, desc_hi, idesc, 1u);
+                        accumulate = 1u;
+                        b += w_step16;
+                    }
+                }
+                if (p.kw & 1) {
+                    a_row = a_base16 + static_cast<uint32_t>(p.kw - 1);
+                    for (int r = 0; r < taps; r += 2, a_row += 2u * ss16) {
+                        const uint32_t a_hi = a_row | ((r + 1 < taps ? ss16 : 1u) << 16);
+                        umma_bf16_desc(true, d_main, a_hi, desc_hi, b, desc_hi, idesc2, accumulate);
+                        umma_bf16_desc(true, d_corr, a_hi + plane16, desc_hi, b, desc_hi, idesc, 1u);
+                        accumulate = 1u;
+                        b += w_step16;
+                    }
+                }
             }
             if (leader) {
                 umma_commit(&empty_bar[s]);
