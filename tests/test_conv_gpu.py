@@ -183,3 +183,25 @@ def test_slab_conv_matches_oracle_and_im2col_path(case, monkeypatch):
     scale = max(np.abs(ref).max(), 1.0)
     assert np.abs(y[:nref] - ref).max() <= 1e-4 * scale
     assert np.abs(y - y_ref_path).max() <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("case", [("zfold_c6_n32_21", 3, 21, 6, 32, 3, "same"), ("zfold_c8_n16_k5", 2, 11, 8, 16, 5, "same"),
+                                  ("zfold_c3_n20_valid", 2, 9, 3, 20, 3, "valid"), ("zfold_c6_n32_ragged_z", 2, 6, 6, 32, 3, "same"),
+                                  ("zfold_c4_n48_k2", 2, 8, 4, 48, 2, "same")], ids=lambda c: c[0])
+def test_zfold_thin_conv(case, monkeypatch):
+    """thinz_conv_kernel (kd filter slices folded into the MMA N dimension, zt output planes per tile): parity with
+    the oracle and with thin_conv_kernel; ragged last z group, 'valid' windows, even kernels, kd = 5."""
+    name, n, side, ci, co, k, padding = case
+    rng = np.random.default_rng(abs(hash(name)) % 2 ** 31)
+    x = rng.standard_normal((n, side, side, side, ci)).astype(np.float32)
+    w = (rng.standard_normal((k, k, k, ci, co)) * np.sqrt(2.0 / (k ** 3 * ci))).astype(np.float32)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    monkeypatch.setenv("TIMED_B200_NO_ZFOLD", "1")
+    y_thin = run_conv_gpu(x, w, bias=b, padding=padding, act1="elu")
+    monkeypatch.delenv("TIMED_B200_NO_ZFOLD")
+    y = run_conv_gpu(x, w, bias=b, padding=padding, act1="elu")
+    ref = ko.np_activation(ko.np_conv3d(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), padding), "elu")
+    scale = max(np.abs(ref).max(), 1.0)
+    assert np.isfinite(y).all()
+    assert np.abs(y - ref).max() <= 1e-4 * scale
+    assert np.abs(y - y_thin).max() <= 1e-4 * scale

@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "thin_conv.cuh"
 #include "slab_conv.cuh"
+#include "thinz_conv.cuh"
 
 namespace tb {
 
@@ -141,6 +142,8 @@ struct ConvPlan {
     uint8_t* d_slab_w = nullptr;
     int64_t slab_lead = 0, slab_tail = 0;
     bool thin = false;
+    bool thinz = false;              // kd taps folded into N (thinz_conv.cuh)
+    ThinZParams thinz_params;
     ThinConvParams thin_params;      // static part, completed per launch
     uint8_t* d_thin_w = nullptr;
     bool tap2n = false;
@@ -649,6 +652,155 @@ static int slab_launch(ConvPlan& p, void* in_base, int64_t n_frames, const TView
     return 0;
 }
 
+// ----------------------------------------------------------------------------- thin-input conv, kd folded into N
+struct ThinZGeom { int zt, n_steps, b1_rows, b2_rows, span_bytes, span_stride, stages, acc_cols, acc_stages; size_t w_bytes; };
+
+static bool thinz_geometry(int kd, int kh, int kw, int cout, int Wp, ThinZGeom* out) {
+    if (getenv("TIMED_B200_NO_ZFOLD")) return false;
+    const int n_tile = round_up(cout, 16);
+    if (kd < 2 || kd * 2 * n_tile > 256) return false;
+    ThinZGeom g;
+    g.zt = std::max(1, 256 / (2 * n_tile));                       // two accumulator stages of zt*2*n_tile columns
+    g.acc_cols = round_up(g.zt * 2 * n_tile, 32);
+    g.acc_stages = std::min(2, 512 / g.acc_cols);
+    g.n_steps = kh * (kw / 2) + ((kw & 1) ? (kh + 1) / 2 : 0);
+    g.b1_rows = kd * 2 * n_tile;
+    g.b2_rows = (2 * kd - 1) * n_tile;
+    g.w_bytes = static_cast<size_t>(g.n_steps) * 2 * 16 * (g.b1_rows + g.b2_rows);
+    const int span_pix = (128 + (kh - 1) * Wp + kw + 1 + 1) & ~1;   // window + filter extent + the aliased next pixel
+    g.span_bytes = span_pix * 16;
+    g.span_stride = g.span_bytes;
+    const size_t w_smem = (g.w_bytes + 127) & ~static_cast<size_t>(127);
+    const size_t stage = 2u * (g.zt + kd - 1) * g.span_stride;
+    if (w_smem + 2 * stage + 128 > kSmemDynamicMax) return false;
+    g.stages = static_cast<int>(std::min<size_t>(kConvMaxStages, (kSmemDynamicMax - 128 - w_smem) / stage));
+    *out = g;
+    return true;
+}
+
+static int thinz_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& tin) {
+    ThinZGeom g;
+    TB_REQUIRE(thinz_geometry(p.kd, p.kh, p.kw, p.cout, tin.pv_Wp, &g), "internal: thinz conv not applicable");
+    p.thin = true;
+    p.thinz = true;
+    const int n_tile = round_up(p.cout, 16);
+    p.n_tiles = 1;
+    p.n_tile = p.n_alloc = n_tile;
+    ThinZParams& t = p.thinz_params;
+    std::memset(&t, 0, sizeof(t));
+    // ---- K steps of one input plane: (kh row, kw pair), then odd kw taps paired across rows
+    struct Half { int row, kwi; };
+    std::vector<std::pair<Half, Half>> steps;
+    for (int r = 0; r < p.kh; ++r)
+        for (int j = 0; j + 1 < p.kw; j += 2) steps.push_back({{r, j}, {r, j + 1}});
+    if (p.kw & 1)
+        for (int r = 0; r < p.kh; r += 2) steps.push_back({{r, p.kw - 1}, {r + 1 < p.kh ? r + 1 : -1, p.kw - 1}});
+    TB_REQUIRE(static_cast<int>(steps.size()) == g.n_steps, "internal: thinz step count");
+    // ---- weights: per step [B1: 2 K-chunks][b1_rows][8] then [B2: 2 K-chunks][b2_rows][8]
+    const size_t step_elems = static_cast<size_t>(2) * 8 * (g.b1_rows + g.b2_rows);
+    std::vector<__nv_bfloat16> w(step_elems * g.n_steps, __float2bfloat16(0.0f));
+    for (int sidx = 0; sidx < g.n_steps; ++sidx)
+        for (int hsel = 0; hsel < 2; ++hsel) {
+            const Half h = hsel ? steps[sidx].second : steps[sidx].first;
+            if (h.row < 0) continue;
+            __nv_bfloat16* b1 = w.data() + sidx * step_elems + static_cast<size_t>(hsel) * g.b1_rows * 8;
+            __nv_bfloat16* b2 = w.data() + sidx * step_elems + static_cast<size_t>(2) * g.b1_rows * 8 +
+                                static_cast<size_t>(hsel) * g.b2_rows * 8;
+            for (int blk = 0; blk < p.kd; ++blk) {                 // block blk holds filter slice kd' = kd-1-blk
+                const int tap = ((p.kd - 1 - blk) * p.kh + h.row) * p.kw + h.kwi;
+                for (int c = 0; c < p.cin; ++c)
+                    for (int n = 0; n < p.cout; ++n) {
+                        const float v = d.kernel_w[(static_cast<size_t>(tap) * p.cin + c) * p.cout + n];
+                        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                        b1[(static_cast<size_t>(blk) * 2 * n_tile + n) * 8 + c] = hi;
+                        b1[(static_cast<size_t>(blk) * 2 * n_tile + n_tile + n) * 8 + c] = lo;
+                        b2[(static_cast<size_t>(blk) * 2 * n_tile + n) * 8 + c] = hi;
+                    }
+            }
+        }
+    TB_CHECK_CUDA(cudaMalloc(&p.d_thin_w, w.size() * sizeof(__nv_bfloat16)));
+    TB_CHECK_CUDA(cudaMemcpy(p.d_thin_w, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    t.w_packed = p.d_thin_w;
+    t.w_bytes = static_cast<uint32_t>(w.size() * 2);
+    t.n_steps = g.n_steps;
+    t.b1_rows = g.b1_rows; t.b2_rows = g.b2_rows;
+    t.zt = g.zt;
+    t.z_groups = ceil_div(p.Do, g.zt);
+    t.windows = ceil_div(p.Ho * tin.pv_Wp, 128);
+    t.Do = p.Do; t.Ho = p.Ho; t.Wo = p.Wo; t.Wp = tin.pv_Wp;
+    t.frame_bytes = static_cast<int64_t>(tin.pv_Dp) * tin.pv_Hp * tin.pv_Wp * 16;
+    t.dplane_bytes = static_cast<int64_t>(tin.pv_Hp) * tin.pv_Wp * 16;
+    t.off_d = tin.pv_d0 - p.pad0[0];
+    t.off_hw = (tin.pv_h0 - p.pad0[1]) * tin.pv_Wp + (tin.pv_w0 - p.pad0[2]);
+    t.kd = p.kd; t.kh = p.kh; t.kw = p.kw;
+    t.span_bytes = g.span_bytes;
+    t.span_stride = g.span_stride;
+    t.n_tile = n_tile;
+    t.acc_cols = g.acc_cols;
+    t.acc_stages = g.acc_stages;
+    t.stages = g.stages;
+    return 0;
+}
+
+template <int A1, int A2, int F>
+static int launch_thinz_instance(const ThinZParams& k, int grid, size_t smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB_CHECK_CUDA(cudaFuncSetAttribute(thinz_conv_kernel<A1, A2, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kSmemDynamicMax)));
+        attr_set = true;
+    }
+    thinz_conv_kernel<A1, A2, F><<<grid, kConvThreads, smem_bytes, stream>>>(k);
+    return 0;
+}
+
+static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames, const TView& out,
+                        cudaStream_t stream) {
+    ThinZParams k = p.thinz_params;
+    const int64_t tiles = n_frames * k.z_groups * k.windows;
+    TB_REQUIRE(tiles > 0 && tiles < (1ll << 31), "thinz conv: too many tiles per launch");
+    k.n_tiles_total = static_cast<int32_t>(tiles);
+    k.in_hi = static_cast<const uint8_t*>(in_base);
+    k.lo_plane_off = in_frames_alloc * k.frame_bytes;
+    ConvKernelParams& e = k.epi;
+    e.bias = p.d_bias; e.scale = p.d_scale; e.shift = p.d_shift;
+    e.act1 = p.act1; e.act2 = p.act2; e.alpha1 = p.alpha1; e.alpha2 = p.alpha2;
+    e.out_fmt = out.fmt;
+    e.out_f32 = out.f32; e.out_hi = out.hi; e.out_lo = out.lo;
+    e.ldc = out.ld;
+    e.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    {
+        static const int dbg = [] { const char* e = getenv("TIMED_B200_DBG"); return e ? atoi(e) : 0; }();
+        k.dbg = dbg;
+    }
+    TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
+               "thinz conv: split output channel padding mismatch");
+    const size_t w_smem = (static_cast<size_t>(k.w_bytes) + 127) & ~static_cast<size_t>(127);
+    const size_t smem_bytes = 128 + w_smem + static_cast<size_t>(k.stages) * 2u * (k.zt + k.kd - 1) * k.span_stride;
+    const int grid = static_cast<int>(std::min<int64_t>(tiles, 148));
+    int rc = 0;
+    bool launched = false;
+#define TB_THINZ_CASE(A1, A2, F)                                                             \
+    if (!launched && e.act1 == (A1) && e.act2 == (A2) && out.fmt == (F)) {                   \
+        rc = launch_thinz_instance<A1, A2, F>(k, grid, smem_bytes, stream);                  \
+        launched = true;                                                                     \
+    }
+    TB_THINZ_CASE(ACT_ELU, ACT_NONE, FMT_F32)
+    TB_THINZ_CASE(ACT_ELU, ACT_NONE, FMT_SPLIT)
+    TB_THINZ_CASE(ACT_RELU, ACT_NONE, FMT_F32)
+    TB_THINZ_CASE(ACT_RELU, ACT_NONE, FMT_SPLIT)
+    TB_THINZ_CASE(ACT_NONE, ACT_NONE, FMT_F32)
+    TB_THINZ_CASE(ACT_NONE, ACT_NONE, FMT_SPLIT)
+#undef TB_THINZ_CASE
+    if (!launched)
+        rc = out.fmt == FMT_SPLIT ? launch_thinz_instance<-1, -1, FMT_SPLIT>(k, grid, smem_bytes, stream)
+                                  : launch_thinz_instance<-1, -1, FMT_F32>(k, grid, smem_bytes, stream);
+    if (rc) return rc;
+    TB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int thin_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames, const TView& out,
                        cudaStream_t stream) {
     ThinConvParams k = p.thin_params;
@@ -723,7 +875,10 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
     p.Do = out[0]; p.Ho = out[1]; p.Wo = out[2];
     if (wfold_in && (wfold_in->padvol || wfold_in->cpv)) {
         p.act1 = d.act1; p.act2 = d.act2; p.alpha1 = d.alpha1; p.alpha2 = d.alpha2;
-        int rc = wfold_in->cpv ? slab_plan_create(p, d, *wfold_in) : thin_plan_create(p, d, *wfold_in);
+        ThinZGeom zg;
+        int rc = wfold_in->cpv ? slab_plan_create(p, d, *wfold_in)
+                 : thinz_geometry(p.kd, p.kh, p.kw, p.cout, wfold_in->pv_Wp, &zg) ? thinz_plan_create(p, d, *wfold_in)
+                                                                                 : thin_plan_create(p, d, *wfold_in);
         if (rc) return rc;
         std::vector<float> b(p.n_alloc, 0.f), sc(p.n_alloc, 1.f), sh(p.n_alloc, 0.f);
         for (int n = 0; n < p.cout; ++n) {
@@ -885,6 +1040,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
                        const TView& final_out, cudaStream_t stream, void* scratch = nullptr,
                        size_t scratch_bytes = 0) {
     if (p.slab) return slab_launch(p, in_base, n_frames, final_out, stream);
+    if (p.thinz) return thinz_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream);
     if (p.thin) return thin_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream);
     TView out = final_out;
     if (p.tap2n) {

@@ -16,7 +16,9 @@ struct ProbeCase {
     int layout;       // 2 = SW128, 4 = SW64, 6 = SW32, 0 = no swizzle (LBO = 16 B aliasing as thin_conv)
     int n2;           // number of accumulators used round-robin (1, 2, 4, 8)
     int reps;         // MMA (pairs) per commit
-    int a_rotate;     // number of distinct A tiles cycled through (1 = same address every time)
+    int a_rotate;     // unused
+    int a_off16;      // extra A start offset in 16-byte units (alignment of the core matrices)
+    int lbo16;        // A leading-dimension offset in 16-byte units (no-swizzle layout only)
 };
 
 __global__ void __launch_bounds__(128, 1) mma_probe_kernel(ProbeCase c, int iters, long long* out_cycles) {
@@ -38,6 +40,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(ProbeCase c, int iter
         const uint32_t desc_hi = c.layout ? (((row_bytes * 8u) >> 4) | (1u << 14) | (static_cast<uint32_t>(c.layout) << 29))
                                           : ((128u >> 4) | (1u << 14));
         const uint32_t lbo = 1u << 16;
+        const uint32_t a_lbo = static_cast<uint32_t>(c.lbo16 ? c.lbo16 : 1) << 16;
         const uint32_t a_tile16 = (128u * (c.layout ? row_bytes : 16u) + 1024u) >> 4;      // distinct A tiles
         const uint32_t a_base = (smem_u32(smem) & 0x3FFFFu) >> 4;
         const uint32_t b_base = a_base + (96u * 1024u >> 4);
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(ProbeCase c, int iter
                 if (leader) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const uint32_t a = (a_base + static_cast<uint32_t>(r & 3) * a_tile16) | lbo;   // 4 distinct A tiles
+                    const uint32_t a = (a_base + static_cast<uint32_t>(r & 3) * a_tile16 + static_cast<uint32_t>(c.a_off16)) | a_lbo;   // 4 distinct A tiles
                     const uint32_t b = b_base | lbo;
                     asm volatile(
                         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
@@ -81,10 +84,10 @@ int main() {
     cudaMalloc(&d_out, 8);
     cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     std::vector<ProbeCase> cases;
-    for (int n : {256, 128, 64, 32, 16})
-        for (int nacc : {1, 2, 4, 8})
-            if (n * nacc <= 512) cases.push_back({n, 2, nacc, 64, 4});
-    for (int n : {64, 32}) for (int nacc : {1, 2, 4}) cases.push_back({n, 0, nacc, 64, 4});
+    for (int n : {128, 64})
+        for (int off : {0, 1, 2, 4, 7})
+            for (int lbo : {1, 570}) cases.push_back({n, 0, 2, 64, 4, off, lbo});
+    for (int n : {128, 64}) for (int off : {0, 2, 4}) cases.push_back({n, 2, 2, 64, 4, off * 8, 0});   // SW128: shift whole rows
     printf("%6s %6s %6s %6s %6s | %12s %14s\n", "N", "layout", "N2", "reps", "rot", "cyc/commit", "cyc/MMA(pair)");
     for (const ProbeCase& c : cases) {
         const int iters = 200;
@@ -95,7 +98,7 @@ int main() {
         }
         long long cyc = 0;
         cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
-        printf("%6d %6d %6d %6d %6d | %12.1f %14.1f\n", c.n, c.layout, c.n2, c.reps, c.a_rotate,
+        printf("%6d %6d %6d %6d off %3d lbo %4d | %12.1f %14.1f\n", c.n, c.layout, c.n2, c.reps, c.a_off16, c.lbo16,
                static_cast<double>(cyc) / iters, static_cast<double>(cyc) / iters / c.reps);
     }
     return 0;
