@@ -253,12 +253,12 @@ def main():
     peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
     step_ms_ops = sum(o["ms"] for o in op_times) / max(n_fw, 1)
     traffic = None
-    tp = ROOT / "profiles" / "r1_dominant_kernel_ncu.json"
+    tp = ROOT / "profiles" / "r1f_dominant_kernel_ncu.json"
     if tp.exists() and args.model == "timed" and args.classes == 20 and B == 4096:
         traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": traffic, "kernel": f"conv_umma_kernel[{top['name']}]",
+        "traffic": traffic, "kernel": f"{model.op_kernel(top['index'], B)}[{top['name']}]",
         "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
         "mma_passes": 3,
         "issued_frac": 3 * achieved / peak,
@@ -267,6 +267,7 @@ def main():
         "whole_graph": {"achieved": model.flops_per_frame * B / (ms_max / args.steps / 1e3) / 1e12,
                         "frac": model.flops_per_frame * B / (ms_max / args.steps / 1e3) / 1e12 / peak},
         "per_op_ms": {f"{o['index']}:{o['name']}": round(o["ms"] / max(n_fw, 1), 4) for o in op_times},
+        "per_op_kernel": {f"{o['index']}:{o['name']}": model.op_kernel(o["index"], B) for o in op_times},
     }
 
     cpu = None

@@ -106,6 +106,9 @@ int timed_b200_graph_info(const tb_graph* g, int32_t* n_classes, double* flops_p
  * MMAs (3x less accumulator truncation; max |dp| 2.8e-5) at ~1.4x their time.  Takes effect on the
  * next forward. */
 int timed_b200_graph_set_precise(tb_graph* g, int32_t precise);
+/* Name of the CUDA kernel(s) op `op` launches for a forward of `n_frames` frames (the tile configuration, and
+ * with it the kernel, depends on the frame count); NUL-terminated into buf. */
+int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, char* buf, int32_t buflen);
 /* number of fused ops in the graph */
 int timed_b200_graph_op_count(const tb_graph* g, int32_t* n_ops);
 /* Per-op device timing for bench.py's roofline line.  While enabled, every graph_forward records

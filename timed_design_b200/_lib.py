@@ -56,6 +56,7 @@ SYMBOLS = {
                                         C.POINTER(C.c_int32)]),
     "timed_b200_graph_set_precise": (C.c_int, [C.c_void_p, C.c_int32]),
     "timed_b200_graph_op_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "timed_b200_graph_op_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_char_p, C.c_int32]),
     "timed_b200_graph_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "timed_b200_graph_read_op_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

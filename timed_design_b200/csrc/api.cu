@@ -1147,9 +1147,15 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
         cp.act1 = p.act1; cp.act2 = p.act2; cp.alpha1 = p.alpha1; cp.alpha2 = p.alpha2;
         const int cw = final_out.fmt == FMT_SPLIT ? final_out.c_pad : final_out.c;
         const int64_t work = n_frames * p.Do * p.Ho * p.Wo * cw;
-        col2im_kernel<<<grid_for(work, 256), 256, 0, stream>>>(static_cast<const float*>(scratch), final_out,
-                                                               n_frames, cp, p.d_c2i_bias, p.d_c2i_scale,
-                                                               p.d_c2i_shift);
+        if (final_out.fmt == FMT_F32 && p.cout % 4 == 0 && p.z_ld % 4 == 0 && final_out.ld % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(final_out.f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0)
+            col2im_vec4_kernel<<<grid_for(work / 4, 256), 256, 0, stream>>>(static_cast<const float*>(scratch), final_out,
+                                                                            n_frames, cp, p.d_c2i_bias, p.d_c2i_scale,
+                                                                            p.d_c2i_shift);
+        else
+            col2im_kernel<<<grid_for(work, 256), 256, 0, stream>>>(static_cast<const float*>(scratch), final_out,
+                                                                   n_frames, cp, p.d_c2i_bias, p.d_c2i_scale,
+                                                                   p.d_c2i_shift);
         TB_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
@@ -1780,6 +1786,39 @@ int timed_b200_graph_info(const tb_graph* g, int32_t* n_classes, double* flops_p
 int timed_b200_graph_op_count(const tb_graph* g, int32_t* n_ops) {
     TB_REQUIRE(g && n_ops, "null argument");
     *n_ops = static_cast<int32_t>(g->ops.size());
+    return TB_OK;
+}
+
+int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, char* buf, int32_t buflen) {
+    TB_REQUIRE(g && buf && buflen > 0, "null argument");
+    TB_REQUIRE(op >= 0 && op < static_cast<int32_t>(g->ops.size()) && n_frames > 0, "op index / frame count out of range");
+    const OpNode& node = g->ops[op];
+    std::string name;
+    switch (node.d.op) {
+        case TB_OP_CONV3D: {
+            const ConvPlan& c = node.conv;
+            if (c.slab) name = "slab_conv_kernel";
+            else if (c.thinz) name = "thinz_conv_kernel";
+            else if (c.thin) name = "thin_conv_kernel";
+            else {
+                ConvPlan::Config cfg;
+                const int rc = choose_config(c, n_frames * c.Mo_d() * c.Mo_h() * c.Mo_w(), &cfg);
+                if (rc) return rc;
+                name = cfg.pair ? "conv_pair_kernel" : (cfg.cluster2 ? "conv_umma_kernel(cluster2)" : "conv_umma_kernel");
+                if (c.tap2n) name += "+col2im_kernel";
+            }
+            break;
+        }
+        case TB_OP_INPUT: name = g->tensors[op].cpv ? "input_convert_cpv_kernel" : g->tensors[op].padvol ? "input_convert_padvol_kernel" : "input_convert_kernel"; break;
+        case TB_OP_POOL3D: name = g->tensors[op].cpv ? "pool3d_cpv_kernel" : "pool3d_vec8_kernel"; break;
+        case TB_OP_AFFINE: name = "affine_act_kernel"; break;
+        case TB_OP_GPOOL: name = "gpool_kernel"; break;
+        case TB_OP_SOFTMAX: name = "softmax_kernel"; break;
+        case TB_OP_CONCAT: name = "copy_channels_kernel"; break;
+        case TB_OP_ADD: name = "add_kernel"; break;
+        default: name = "?";
+    }
+    std::snprintf(buf, static_cast<size_t>(buflen), "%s", name.c_str());
     return TB_OK;
 }
 

@@ -418,6 +418,47 @@ __global__ void col2im_kernel(const float* __restrict__ Z, TView out, int64_t n_
     }
 }
 
+// float4 variant: cout % 4 == 0, z_ld % 4 == 0, fp32 output with ld % 4 == 0; one thread per (pixel, 4 channels)
+__global__ void col2im_vec4_kernel(const float* __restrict__ Z, TView out, int64_t n_frames, Col2imParams cp,
+                                   const float* __restrict__ bias, const float* __restrict__ scale,
+                                   const float* __restrict__ shift) {
+    const int groups = cp.cout / 4;
+    const int64_t total = n_frames * cp.Do * cp.Ho * cp.Wo * groups;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % groups) * 4;
+        int64_t t = i / groups;
+        const int q = static_cast<int>(t % cp.Wo); t /= cp.Wo;
+        const int p = static_cast<int>(t % cp.Ho); t /= cp.Ho;
+        const int z = static_cast<int>(t % cp.Do);
+        const int64_t nf = t / cp.Do;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int tap = 0;
+        for (int a = 0; a < cp.kd; ++a) {
+            const int d = z + a - cp.pd;
+            for (int b = 0; b < cp.kh; ++b) {
+                const int h = p + b - cp.ph;
+                for (int c = 0; c < cp.kw; ++c, ++tap) {
+                    const int w = q + c - cp.pw;
+                    if (d < 0 || d >= cp.Di || h < 0 || h >= cp.Hi || w < 0 || w >= cp.Wi) continue;
+                    const int64_t ip = ((nf * cp.Di + d) * cp.Hi + h) * cp.Wi + w;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(Z + ip * cp.z_ld + tap * cp.cout + co));
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;      // same (kd,kh,kw) order as the scalar path
+                }
+            }
+        }
+        float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v = apply_act(r[e] + bias[co + e], cp.act1, cp.alpha1);
+            v = fmaf(v, scale[co + e], shift[co + e]);
+            r[e] = apply_act(v, cp.act2, cp.alpha2);
+        }
+        const int64_t pix = ((nf * cp.Do + z) * cp.Ho + p) * cp.Wo + q;
+        *reinterpret_cast<float4*>(out.f32 + pix * out.ld + co) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
 // ------------------------------------------------------------------ channel-slice copy / add
 __global__ void copy_channels_kernel(TView in, TView out, int64_t n_pix, int c_off) {
     const int64_t total = n_pix * in.c;

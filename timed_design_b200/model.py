@@ -112,6 +112,12 @@ class Model:
                 "flops_per_frame": float(flops[i])} for i in range(n)]
         return ops, nf.value
 
+    def op_kernel(self, op_index: int, n_frames: int) -> str:
+        """Name of the CUDA kernel(s) fused op `op_index` launches at this batch size."""
+        buf = C.create_string_buffer(96)
+        _lib.check(_lib.load().timed_b200_graph_op_kernel(self._h, int(op_index), int(n_frames), buf, 96))
+        return buf.value.decode()
+
     def close(self) -> None:
         if self._h:
             _lib.load().timed_b200_graph_destroy(self._h)
