@@ -19,7 +19,7 @@
 // allocation), warps 2..9 = epilogue (TMEM -> registers -> bias/act/BN-affine -> HBM; two warps per
 // TMEM lane quadrant, alternating 16-column chunks).  The epilogue is specialised at compile
 // time on (act1, act2, output format): a runtime switch per element made it as long as the
-// mainloop (profiles/r1_conv_first_ncu.md).
+// mainloop (profiles/r1_summary.md, r1a).
 #pragma once
 #include "common.cuh"
 
