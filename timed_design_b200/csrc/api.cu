@@ -485,7 +485,7 @@ struct SlabGeom {
     int pd, ph, pw;          // shared zero margins per dimension
     int Dp, Hp, Wp;
     int neg, pos;            // halo positions before / after a tile
-    int mt, w_stages, acc_stages, acc_cols, slab_pix, slab_stride;
+    int mt, w_stages, w_group, acc_stages, acc_cols, slab_pix, slab_stride;
     size_t smem_bytes;
 };
 
@@ -527,8 +527,15 @@ static bool slab_geometry(int D, int H, int W, int cin, const tb_op_desc& c, Sla
         g.slab_stride = g.slab_pix * 16;
         const size_t slabs = 2u * 2u * n_chunks * g.slab_stride;
         if (slabs + 2 * w_stage + 128 > kSmemDynamicMax) continue;
-        g.w_stages = static_cast<int>(std::min<size_t>(kSlabWStages, (kSmemDynamicMax - 128 - slabs) / w_stage));
-        g.smem_bytes = 128 + slabs + g.w_stages * w_stage;
+        // taps per ring stage: one tcgen05.commit per stage (each costs 100-400 tensor cycles), >= 3 stages kept
+        const size_t avail = kSmemDynamicMax - 128 - slabs;
+        int wg = 2;
+        if (const char* e = getenv("TIMED_B200_SLAB_WG")) wg = std::max(1, atoi(e));
+        while (wg > 1 && avail / (((wg * w_tap) + 127) & ~static_cast<size_t>(127)) < 3) --wg;
+        g.w_group = wg;
+        const size_t w_stage_g = ((wg * w_tap) + 127) & ~static_cast<size_t>(127);
+        g.w_stages = static_cast<int>(std::min<size_t>(kSlabWStages, avail / w_stage_g));
+        g.smem_bytes = 128 + slabs + g.w_stages * w_stage_g;
         *out = g;
         return true;
     }
@@ -564,10 +571,8 @@ static int slab_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo& 
     t.acc_cols = g.acc_cols;
     t.acc_stages = g.acc_stages;
     t.w_tap_bytes = static_cast<uint32_t>(n_chunks) * 2u * n_tile * 16u;
-    const size_t w_stage = (static_cast<size_t>(t.w_tap_bytes) + 127) & ~static_cast<size_t>(127);
-    const size_t slabs = 2u * 2u * n_chunks * static_cast<size_t>(t.slab_stride);
-    TB_REQUIRE(slabs + 2 * w_stage + 128 <= kSmemDynamicMax, "slab conv: slabs exceed shared memory");
-    t.w_stages = static_cast<int>(std::min<size_t>(kSlabWStages, (kSmemDynamicMax - 128 - slabs) / w_stage));
+    t.w_group = g.w_group;
+    t.w_stages = g.w_stages;
     p.slab_lead = tin.cpv_lead;
     p.slab_tail = tin.cpv_tail;
     TB_REQUIRE(tin.cpv_lead >= t.neg_halo && tin.cpv_tail >= t.pos_halo + 128 * g.mt, "internal: CPV lead/tail too small");
@@ -627,7 +632,7 @@ static int slab_launch(ConvPlan& p, void* in_base, int64_t n_frames, const TView
     }
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "slab conv: split output channel padding mismatch");
-    const size_t w_stage = (static_cast<size_t>(k.w_tap_bytes) + 127) & ~static_cast<size_t>(127);
+    const size_t w_stage = (static_cast<size_t>(k.w_group) * k.w_tap_bytes + 127) & ~static_cast<size_t>(127);
     const size_t smem_bytes = 128 + 2u * 2u * k.n_chunks * static_cast<size_t>(k.slab_stride) + k.w_stages * w_stage;
     const int grid = static_cast<int>(std::min<int64_t>(tiles, 148));
     int rc = 0;

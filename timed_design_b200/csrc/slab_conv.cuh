@@ -53,6 +53,7 @@ struct SlabConvParams {
     int32_t acc_cols;         // TMEM columns per M tile (2*n_tile rounded up to 32)
     int32_t acc_stages;
     int32_t w_stages;
+    int32_t w_group;          // taps per ring stage (one commit per stage: a tcgen05.commit costs 100-400 tensor cycles)
     ConvKernelParams epi;     // epilogue fields (bias/scale/shift, activations, output pointers, ldc, c_store)
     int32_t dbg;
 };
@@ -105,7 +106,7 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
     const uint32_t plane_region = static_cast<uint32_t>(p.n_chunks) * static_cast<uint32_t>(p.slab_stride);
     const uint32_t slab_bytes = 2u * plane_region;                       // hi spans, then lo spans
     uint8_t* w_ring = smem + 2u * slab_bytes;
-    const uint32_t w_stage_bytes = (p.w_tap_bytes + 127u) & ~127u;
+    const uint32_t w_stage_bytes = (static_cast<uint32_t>(p.w_group) * p.w_tap_bytes + 127u) & ~127u;
     const int n_taps = p.kd * p.kh * p.kw;
     const int tile_pos = 128 * p.mt;
 
@@ -140,18 +141,21 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
         bool first = true;
         for (int tile = blockIdx.x; tile < p.n_tiles_total; tile += gridDim.x) {
             if (first) { load_slab(tile, sb); first = false; }
-            for (int tap = 0; tap < n_taps; ++tap) {
+            for (int tap = 0; tap < n_taps; tap += p.w_group) {
                 // the next tile's slab is requested early: its buffer was released when the previous tile finished
-                if (tap == prefetch_tap && tile + static_cast<int>(gridDim.x) < p.n_tiles_total)
+                if (tap <= prefetch_tap && prefetch_tap < tap + p.w_group && tile + static_cast<int>(gridDim.x) < p.n_tiles_total)
                     load_slab(tile + gridDim.x, sb ^ 1);
                 mbar_wait(&w_empty[ws], wph ^ 1u);
                 if (leader) {
                     if (p.dbg & 1) {
                         mbar_arrive(&w_full[ws]);
                     } else {
-                        mbar_expect_tx(&w_full[ws], p.w_tap_bytes);
-                        bulk_load_1d(w_ring + static_cast<size_t>(ws) * w_stage_bytes,
-                                     p.w_packed + static_cast<size_t>(tap) * p.w_tap_bytes, p.w_tap_bytes, &w_full[ws]);
+                        const uint32_t bytes = static_cast<uint32_t>(min(p.w_group, n_taps - tap)) * p.w_tap_bytes;
+                        mbar_expect_tx(&w_full[ws], bytes);
+                        for (uint32_t off = 0; off < bytes; off += 16384u)
+                            bulk_load_1d(w_ring + static_cast<size_t>(ws) * w_stage_bytes + off,
+                                         p.w_packed + static_cast<size_t>(tap) * p.w_tap_bytes + off,
+                                         min(16384u, bytes - off), &w_full[ws]);
                     }
                 }
                 __syncwarp();
@@ -183,15 +187,19 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
             // first row of M tile 0 for a tap with position offset 0
             const uint32_t a_tile16 = smem16 + static_cast<uint32_t>(sb) * (slab_bytes >> 4) + static_cast<uint32_t>(p.neg_halo);
             uint32_t accumulate = 0;
+            int tap = 0, in_group = 0;
             for (int a = 0; a < p.kd; ++a)
                 for (int b = 0; b < p.kh; ++b)
-                    for (int c = 0; c < p.kw; ++c) {
-                        mbar_wait(&w_full[ws], wph);
-                        tc_fence_after();
+                    for (int c = 0; c < p.kw; ++c, ++tap) {
+                        if (in_group == 0) {
+                            mbar_wait(&w_full[ws], wph);
+                            tc_fence_after();
+                        }
                         if (leader && !(p.dbg & 2)) {
                             const int off = (a - p.pd) * hw + (b - p.ph) * p.Wp + (c - p.pw);
                             uint32_t a_k = (a_tile16 + static_cast<uint32_t>(off)) | (stride16 << 16);
-                            uint32_t b_k = (w_ring16 + static_cast<uint32_t>(ws) * (w_stage_bytes >> 4)) | (w_lbo16 << 16);
+                            uint32_t b_k = (w_ring16 + static_cast<uint32_t>(ws) * (w_stage_bytes >> 4) +
+                                            static_cast<uint32_t>(in_group) * (p.w_tap_bytes >> 4)) | (w_lbo16 << 16);
                             for (int ks = 0; ks < k_steps; ++ks, a_k += 2u * stride16, b_k += 2u * w_lbo16) {
 #pragma unroll 2
                                 for (int mi = 0; mi < p.mt; ++mi) {
@@ -204,9 +212,12 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
                             }
                         }
                         accumulate = 1u;
-                        if (leader) umma_commit(&w_empty[ws]);
-                        __syncwarp();
-                        if (++ws == p.w_stages) { ws = 0; wph ^= 1u; }
+                        if (++in_group == p.w_group || tap + 1 == n_taps) {
+                            in_group = 0;
+                            if (leader) umma_commit(&w_empty[ws]);
+                            __syncwarp();
+                            if (++ws == p.w_stages) { ws = 0; wph ^= 1u; }
+                        }
                     }
             if (leader) {
                 umma_commit(&slab_empty[sb]);
