@@ -168,6 +168,26 @@ int timed_b200_sample_uniforms(int64_t n_res, int64_t n_samples, int64_t first_s
 int timed_b200_argmax_fp16(const float* d_probs, int64_t n, int32_t n_cls, int32_t* d_idx,
                            void* cuda_stream);
 
+/* NMR consensus (design_utils/utils.py:694-713): the states of one structure are `n_states[g]` consecutive blocks of
+ * `n_res[g]` rows starting at `first_row[g]`; output rows of group g start at `out_row0[g]` (ascending).  Consensus =
+ * running pairwise mean in float16 arithmetic over the fp16-rounded probabilities, c <- fp16(fp16(c + p_s) / 2), exactly
+ * what numpy does on the float16 matrix of predict.py:163; d_idx = its first-index argmax.
+ * d_probs (n_rows, n_cls) float32; d_consensus_fp16 (n_out_rows, n_cls) IEEE half bits; d_idx (n_out_rows) int32. */
+int timed_b200_consensus_fp16(const float* d_probs, int64_t n_rows, int32_t n_cls, const int64_t* d_first_row,
+                              const int32_t* d_n_states, const int32_t* d_n_res, const int64_t* d_out_row0,
+                              int32_t n_groups, int64_t n_out_rows, uint16_t* d_consensus_fp16, int32_t* d_idx,
+                              void* cuda_stream);
+
+/* ---- sequence metrics of sampled sequences  (design_utils/analyse_utils.py:351-371, called at
+ *      sampling_utils.py:132) ------------------------------------------------------------------ */
+/* One warp per sequence: 20-bin composition, then charge at the reference pH, isoelectric point (first grid pH with
+ * minimal |charge|), molecular weight, molar extinction at 280 nm from host-built tables
+ * [mw(20)|ext280(20)|q_ref(20)|term_ref|water|n_grid|grid(n)|term(grid)(n)|q(grid)(n x 20)] (float64, device).
+ * d_seqs (n_seqs, n_res) ASCII; d_letter_lut: 256 entries, letter -> 0..19 or -1; d_out (n_seqs, 4) float64
+ * (NaN row when a sequence holds a letter outside the table). */
+int timed_b200_seq_metrics(const uint8_t* d_seqs, int64_t n_seqs, int64_t n_res, const int8_t* d_letter_lut,
+                           const double* d_tables, int32_t n_table_doubles, double* d_out, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,3 +79,23 @@ def test_synthetic_frames_are_index_deterministic():
     a = standins.synthetic_frames(6, side=9)
     b = standins.synthetic_frames(3, side=9, first_index=3)
     np.testing.assert_array_equal(a[3:], b)
+
+
+def test_device_post_host_helpers():
+    """Host-side pieces of the device post-processing: grouping of NMR states as utils.py:696-705 walks the dict, and the
+    packed metric table layout timed_b200_seq_metrics documents."""
+    from timed_design_b200 import device_post, seq_metrics
+    groups = device_post.consensus_groups(["1abc_0A", "1abc_1A", "2xyzA", "1abc_2A"], [5, 5, 3, 5])
+    assert groups == [("1abc", 0, 2), ("2xyzA", 2, 1), ("1abc", 3, 1)]
+    import pytest
+    with pytest.raises(ValueError):
+        device_post.consensus_groups(["1abc_0A", "1abc_1A"], [5, 6])
+    t = seq_metrics.device_tables()
+    n_grid = int(t[62])
+    assert n_grid == 120 and len(t) == 63 + 2 * n_grid + 20 * n_grid
+    assert abs(t[63] - 1.0) < 1e-12 and abs(t[63 + n_grid - 1] - 12.9) < 1e-9
+    # table-driven charge at pH 7.4 == the restated formula
+    counts = np.arange(20)[None, :]
+    c, pi, mw, ext = seq_metrics.metrics_from_composition(counts)
+    assert abs((counts[0] * t[40:60]).sum() + t[60] - c[0]) < 1e-10
+    assert abs((counts[0] * t[:20]).sum() + t[61] - mw[0]) < 1e-9

@@ -104,3 +104,59 @@ def test_predict_cli_rotamer_mode(workdir, monkeypatch):
     from timed_design_b200.postprocess import rotamer_class_to_residue
     np.testing.assert_array_equal(onehot.argmax(1), rotamer_class_to_residue()[raw.argmax(1)])
     assert len((out / "TIMED_rotamer.fasta").read_text().splitlines()[1]) == 76
+
+
+def test_binary_outputs_and_npy_sampling(workdir, monkeypatch):
+    """predict.py --binary_outputs writes {model}.npy = the float16 matrix of {model}.csv; sample.py on the .npy draws
+    exactly what it draws from the .csv."""
+    d, *_ = workdir
+    from timed_design_b200 import predict, sample
+    out = d / "out_bin"
+    monkeypatch.chdir(d)
+    predict.cli(["--path_to_dataset", str(d / "data.hdf5"), "--path_to_model", str(d / "TIMED.h5"),
+                 "--path_to_output", str(out), "--path_to_datasetmap", str(out / "datasetmap.txt"), "--yes",
+                 "--binary_outputs", "--batch_size", "32"])
+    m = np.load(out / "TIMED.npy")
+    assert m.dtype == np.float16 and m.shape == (76, 20)
+    np.testing.assert_array_equal(m.astype(np.float64), np.genfromtxt(out / "TIMED.csv", delimiter=","))
+    a = sample.cli(["--path_to_pred_matrix", str(out / "TIMED.csv"), "--path_to_datasetmap", str(out / "TIMED.txt"),
+                    "--sample_n", "20", "--temperature", "0.7", "--save_as", "fasta"])
+    from_csv = (d / a[0]).read_text()
+    b = sample.cli(["--path_to_pred_matrix", str(out / "TIMED.npy"), "--path_to_datasetmap", str(out / "TIMED.txt"),
+                    "--sample_n", "20", "--temperature", "0.7", "--save_as", "fasta"])
+    assert a == b and (d / b[0]).read_text() == from_csv
+
+
+def test_predict_cli_nmr_consensus(tmp_path, monkeypatch):
+    """--is_structure_nmr: three states of one structure -> consensus files; the device consensus equals the numpy
+    restatement of utils.py:694-713 on the float16 matrix."""
+    from timed_design_b200 import predict, postprocess
+    ubq = json.loads((G / "1ubq_chainA.json").read_text())
+    n = 24
+    states = {}
+    for s in range(3):
+        frames = standins.synthetic_frames(n, seed=10 + s)
+        states[f"1nmr_{s}"] = {"A": {str(rid): (frames[i], ubq["labels"][i]) for i, rid in enumerate(ubq["residue_ids"][:n])}}
+    write_frame_dataset(tmp_path / "nmr.hdf5", states, (21, 21, 21, 6))
+    cfg, w = standins.timed_standin(20, filters=(8, 16, 16, 24, 32), calib_frames=4)
+    write_keras_h5(tmp_path / "TIMED.h5", cfg, w)
+    out = tmp_path / "out"
+    monkeypatch.chdir(tmp_path)
+    predict.cli(["--path_to_dataset", str(tmp_path / "nmr.hdf5"), "--path_to_model", str(tmp_path / "TIMED.h5"),
+                 "--path_to_output", str(out), "--path_to_datasetmap", str(out / "datasetmap.txt"), "--yes",
+                 "--is_structure_nmr", "True", "--batch_size", "40"])
+    pm = np.genfromtxt(out / "TIMED.csv", delimiter=",", dtype=np.float16)
+    dmap = np.genfromtxt(out / "datasetmap.txt", delimiter=",", dtype=str)
+    ref = postprocess.extract_sequence_from_pred_matrix(dmap, pm, None, is_consensus=True)
+    # the reference's writers default to `Path.cwd()` evaluated at import time (utils.py:595-613): that is where the
+    # consensus .fasta lands; the consensus .csv is a bare relative filename (utils.py:587) -> the CWD at call time
+    import inspect
+    fasta_dir = Path(inspect.signature(postprocess.save_dict_to_fasta).parameters["path_to_output"].default)
+    fasta_path = fasta_dir / "TIMED_consensus.fasta"
+    fasta = fasta_path.read_text().splitlines()
+    fasta_path.unlink()
+    assert len(ref[3]) == 1
+    (name, seq), = ref[3].items()
+    assert fasta == [f">{name}", seq] and len(seq) == n
+    cons_csv = np.genfromtxt(tmp_path / "TIMED_consensus.csv", delimiter=",")
+    np.testing.assert_array_equal(cons_csv, np.asarray(ref[4][name], dtype=np.float64))

@@ -2099,4 +2099,29 @@ int timed_b200_argmax_fp16(const float* d_probs, int64_t n, int32_t n_cls, int32
     return TB_OK;
 }
 
+int timed_b200_consensus_fp16(const float* d_probs, int64_t n_rows, int32_t n_cls, const int64_t* d_first_row,
+                              const int32_t* d_n_states, const int32_t* d_n_res, const int64_t* d_out_row0,
+                              int32_t n_groups, int64_t n_out_rows, uint16_t* d_consensus_fp16, int32_t* d_idx,
+                              void* cuda_stream) {
+    TB_REQUIRE(d_probs && d_first_row && d_n_states && d_n_res && d_out_row0 && d_consensus_fp16 && d_idx, "null argument");
+    TB_REQUIRE(n_rows > 0 && n_cls > 0 && n_groups > 0 && n_out_rows > 0, "empty input");
+    consensus_fp16_kernel<<<static_cast<unsigned>((n_out_rows * 32 + 255) / 256), 256, 0,
+                            static_cast<cudaStream_t>(cuda_stream)>>>(
+        d_probs, d_first_row, d_n_states, d_n_res, d_out_row0, n_groups, n_out_rows, n_cls,
+        reinterpret_cast<__half*>(d_consensus_fp16), d_idx);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+int timed_b200_seq_metrics(const uint8_t* d_seqs, int64_t n_seqs, int64_t n_res, const int8_t* d_letter_lut,
+                           const double* d_tables, int32_t n_table_doubles, double* d_out, void* cuda_stream) {
+    TB_REQUIRE(d_seqs && d_letter_lut && d_tables && d_out, "null argument");
+    TB_REQUIRE(n_seqs > 0 && n_res > 0, "empty input");
+    TB_REQUIRE(n_table_doubles >= 63, "metric table too short");
+    seq_metrics_kernel<<<static_cast<unsigned>((n_seqs + 7) / 8), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        d_seqs, n_seqs, n_res, d_letter_lut, d_tables, d_out);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
 }  // extern "C"

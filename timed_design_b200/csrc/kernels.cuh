@@ -2,6 +2,7 @@
 // the Monte-Carlo sampler kernels.  All HBM-bound: coalesced channel-fastest access, 16-byte
 // vectors on the bf16 split planes, grids sized from the element count.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "conv_umma.cuh"
 
@@ -554,6 +555,106 @@ __global__ void argmax_fp16_kernel(const float* __restrict__ probs, int64_t n, i
         }
     }
     if (lane == 0) idx[row] = bi;
+}
+
+// ------------------------------------------------------------------ NMR consensus (utils.py:694-713)
+// One warp per consensus row.  States of one structure are equally long blocks of rows; the reference folds them
+// with a RUNNING PAIRWISE mean in float16 arithmetic, c <- fp16(fp16(c + p_s) / 2) (numpy float16 ops round after
+// every operation), then takes the first-index argmax.  probs are fp32 and rounded to fp16 on the way in, as
+// save_outputs_to_file / predict.py:163 do.
+__global__ void consensus_fp16_kernel(const float* __restrict__ probs, const int64_t* __restrict__ first_row,
+                                      const int32_t* __restrict__ n_states, const int32_t* __restrict__ n_res,
+                                      const int64_t* __restrict__ out_row0, int n_groups, int64_t n_out_rows, int n_cls,
+                                      __half* __restrict__ cons, int32_t* __restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    if (row >= n_out_rows) return;
+    int lo = 0, hi = n_groups - 1;                    // last group whose first output row is <= row
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (out_row0[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    const int g = lo;
+    const int64_t r = row - out_row0[g];
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int ch = lane; ch < n_cls; ch += 32) {
+        __half c = __float2half_rn(probs[(first_row[g] + r) * n_cls + ch]);
+        for (int s = 1; s < n_states[g]; ++s) {
+            const __half v = __float2half_rn(probs[(first_row[g] + static_cast<int64_t>(s) * n_res[g] + r) * n_cls + ch]);
+            const __half sum = __float2half_rn(__half2float(c) + __half2float(v));
+            c = __float2half_rn(__half2float(sum) * 0.5f);
+        }
+        cons[row * n_cls + ch] = c;
+        const float v = __half2float(c);
+        if (v > best || (v == best && ch < bi) || bi == 0x7fffffff) { best = v; bi = ch; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) {
+            best = ob;
+            bi = oi;
+        }
+    }
+    if (lane == 0) idx[row] = bi;
+}
+
+// ------------------------------------------------------------------ sequence metrics (analyse_utils.py:351-371)
+// One warp per sampled sequence: 20-bin residue histogram, then composition-only closed forms from host-built
+// tables T = [mw(20) | ext280(20) | q(pH_ref)(20) | term(pH_ref) | water | n_grid | grid(n_grid) | term(grid)(n_grid) |
+// q(grid)(n_grid x 20)]: net charge at the reference pH, isoelectric point = first grid pH minimising |charge|,
+// molecular weight, molar extinction at 280 nm.  out: (n_seqs, 4) float64; NaN row when a letter is not in `lut`.
+__global__ void seq_metrics_kernel(const uint8_t* __restrict__ seqs, int64_t n_seqs, int64_t n_res,
+                                   const int8_t* __restrict__ lut, const double* __restrict__ T,
+                                   double* __restrict__ out) {
+    __shared__ int s_cnt[8][21];
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const int64_t seq = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + w;
+    if (seq >= n_seqs) return;
+    if (lane < 21) s_cnt[w][lane] = 0;
+    __syncwarp();
+    const uint8_t* srow = seqs + seq * n_res;
+    for (int64_t i = lane; i < n_res; i += 32) {
+        const int k = lut[srow[i]];
+        atomicAdd(&s_cnt[w][k < 0 ? 20 : k], 1);
+    }
+    __syncwarp();
+    const int n_grid = static_cast<int>(T[62]);
+    const double* grid = T + 63;
+    const double* tgrid = grid + n_grid;
+    const double* qgrid = tgrid + n_grid;
+    double best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int gp = lane; gp < n_grid; gp += 32) {
+        double c = 0.0;
+        for (int i = 0; i < 20; ++i) c += static_cast<double>(s_cnt[w][i]) * qgrid[gp * 20 + i];
+        c = fabs(c + tgrid[gp]);
+        if (c < best) { best = c; bi = gp; }       // ascending gp per lane: first minimum kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+        double q = 0.0, mw = 0.0, ext = 0.0;
+        for (int i = 0; i < 20; ++i) {
+            const double n = static_cast<double>(s_cnt[w][i]);
+            mw += n * T[i];
+            ext += n * T[20 + i];
+            q += n * T[40 + i];
+        }
+        const bool bad = s_cnt[w][20] != 0;
+        double* o = out + seq * 4;
+        o[0] = bad ? NAN : q + T[60];
+        o[1] = bad ? NAN : grid[bi];
+        o[2] = bad ? NAN : mw + T[61];
+        o[3] = bad ? NAN : ext;
+    }
 }
 
 // =================================================================== Monte-Carlo sampler

@@ -41,6 +41,7 @@ def load_dataset_and_predict(
     model_name_suffix: str = "",
     is_consensus: bool = False,
     path_to_output: Path = Path.cwd(),
+    binary_outputs: bool = False,
 ):
     """predict.py:28-194.  Returns (flat_dataset_map, pdb_to_sequence, pdb_to_probability,
     pdb_to_real_sequence, pdb_to_consensus, pdb_to_consensus_prob) of the LAST model."""
@@ -93,10 +94,18 @@ def load_dataset_and_predict(
             prediction_matrix = np.genfromtxt(model_out, delimiter=",", dtype=np.float16)
         if prediction_matrix.ndim == 1:
             prediction_matrix = prediction_matrix[None, :]
+        if binary_outputs:     # the %.18e text costs ~25 bytes per probability; .npy is 2
+            np.save(path_to_output / f"{model_name}.npy", prediction_matrix)
+            if predict_rotamers and raw_rows:
+                np.save(path_to_output / f"{model_name}_rot.npy", np.concatenate(raw_rows).astype(np.float32))
         out = extract_sequence_from_pred_matrix(
             flat_dataset_map, prediction_matrix,
             rotamers_categories=flat_categories if predict_rotamers else None,
-            old_datasetmap=old_datasetmap, is_consensus=is_consensus)
+            old_datasetmap=old_datasetmap, is_consensus=False)
+        if is_consensus:       # NMR ensembles: running float16 mean over the states + argmax, on the device
+            from .device_post import nmr_consensus
+            cons, cons_prob = nmr_consensus(out[1], flat_categories if predict_rotamers else None)
+            out = (out[0], out[1], out[2], cons, cons_prob)
         save_dict_to_fasta(out[0], model_name, path_to_output)
         save_dict_to_fasta(out[2], "dataset", path_to_output)
         if out[3]:
@@ -131,6 +140,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--is_structure_nmr", nargs="?", const=True, default=False, type=_flag,
                    help="NMR ensemble: also build a consensus over the states")
     p.add_argument("--yes", action="store_true", help="Create a missing output directory without asking")
+    p.add_argument("--binary_outputs", action="store_true",
+                   help="Also write {model}.npy (the float16 matrix of {model}.csv; sample.py reads it directly)")
     return p
 
 
@@ -157,7 +168,7 @@ def main(args) -> None:
         [args.path_to_model], args.path_to_dataset, batch_size=args.batch_size, start_batch=0,
         blacklist=args.path_to_blacklist, dataset_map_path=args.path_to_datasetmap,
         predict_rotamers=args.predict_rotamers, is_consensus=args.is_structure_nmr,
-        path_to_output=args.path_to_output)
+        path_to_output=args.path_to_output, binary_outputs=getattr(args, "binary_outputs", False))
 
 
 def cli(argv=None) -> None:

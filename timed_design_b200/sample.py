@@ -28,7 +28,10 @@ def main_sample(args):
     args.path_to_datasetmap = Path(args.path_to_datasetmap)
     assert args.path_to_pred_matrix.exists(), f"Prediction Matrix file {args.path_to_pred_matrix} does not exist"
     assert args.path_to_datasetmap.exists(), f"Dataset Map file {args.path_to_datasetmap} does not exist"
-    prediction_matrix = np.genfromtxt(args.path_to_pred_matrix, delimiter=",", dtype=np.float64)
+    if args.path_to_pred_matrix.suffix == ".npy":      # binary fast path written by predict.py --binary_outputs
+        prediction_matrix = np.load(args.path_to_pred_matrix).astype(np.float64)
+    else:
+        prediction_matrix = np.genfromtxt(args.path_to_pred_matrix, delimiter=",", dtype=np.float64)
     if prediction_matrix.ndim == 1:
         prediction_matrix = prediction_matrix[None, :]
     datasetmap = load_datasetmap(args.path_to_datasetmap, is_old=args.support_old_datasetmap)
@@ -54,7 +57,7 @@ def main_sample(args):
 
 def build_parser() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser(description="Monte-Carlo sequence sampling from TIMED predictions (B200-native)")
-    p.add_argument("--path_to_pred_matrix", type=str, help="Prediction matrix (.csv)")
+    p.add_argument("--path_to_pred_matrix", type=str, help="Prediction matrix ({model}.csv, or {model}.npy from predict.py --binary_outputs)")
     p.add_argument("--path_to_datasetmap", default="datasetmap.txt", type=str, help="Dataset map (.txt)")
     p.add_argument("--predict_rotamers", nargs="?", const=True, default=False, type=_flag,
                    help="The matrix holds 338 rotamer classes instead of 20 residues")

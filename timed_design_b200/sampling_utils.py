@@ -77,14 +77,16 @@ def apply_temp_to_probs(probs: np.ndarray, t: float = 1.0) -> np.ndarray:
 def sample_block(probs: np.ndarray, sample_n: int, rotamer_categories=None, *,
                  uniforms: t.Optional[np.ndarray] = None, seed: t.Optional[int] = None,
                  stream_id: int = 0, first_sample: int = 0, return_idx: bool = False,
-                 temperature: t.Optional[float] = None):
+                 temperature: t.Optional[float] = None, return_metrics: bool = False):
     """Draw ``sample_n`` sequences for one chain in one launch.
 
     probs: (n_res, C) float64 probabilities.  ``uniforms`` (sample_n, n_res) injects the random
     numbers (parity hook for ``np.random.rand``); otherwise Philox(seed, stream_id) is used and
     ``first_sample`` offsets the sample counter so that shards of one chain drawn on different
     GPUs concatenate to exactly what a single GPU would draw.
-    Returns (letters uint8 (sample_n, n_res), idx int32 (sample_n, n_res) or None)."""
+    Returns (letters uint8 (sample_n, n_res), idx int32 (sample_n, n_res) or None); with ``return_metrics`` a third
+    item: (sample_n, 4) float64 [charge, pI, molecular weight, extinction], computed on the device from the letter
+    block before it is copied back (device_post.seq_metrics_device)."""
     torch = _torch()
     lib = _lib.load()
     p = np.ascontiguousarray(np.array(probs, dtype=np.float64))
@@ -95,7 +97,8 @@ def sample_block(probs: np.ndarray, sample_n: int, rotamer_categories=None, *,
     if len(letters) != n_cls:
         raise ValueError(f"{n_cls} probability columns but {len(letters)} categories")
     if n_res == 0 or sample_n == 0:
-        return np.zeros((sample_n, n_res), np.uint8), (np.zeros((sample_n, n_res), np.int32) if return_idx else None)
+        empty = (np.zeros((sample_n, n_res), np.uint8), (np.zeros((sample_n, n_res), np.int32) if return_idx else None))
+        return empty + (np.zeros((sample_n, 4)),) if return_metrics else empty
     st = _stream(torch)
     d_p = torch.from_numpy(p).cuda()
     if temperature is not None and temperature != 1:
@@ -116,9 +119,13 @@ def sample_block(probs: np.ndarray, sample_n: int, rotamer_categories=None, *,
                                      int(_state["seed"] if seed is None else seed) & (2 ** 64 - 1),
                                      int(stream_id) & (2 ** 64 - 1), _ptr(d_u), _ptr(d_letters),
                                      _ptr(d_seq), _ptr(d_idx), st))
+    metrics = None
+    if return_metrics:
+        from . import device_post
+        metrics = device_post.seq_metrics_device(d_seq, sample_n, n_res)
     seqs = d_seq[:n_cells].cpu().numpy().reshape(sample_n, n_res)
     idx = d_idx[:n_cells].cpu().numpy().reshape(sample_n, n_res) if return_idx else None
-    return seqs, idx
+    return (seqs, idx, metrics) if return_metrics else (seqs, idx)
 
 
 _draw_counter = {"n": 0}
@@ -147,20 +154,20 @@ def random_choice_prob_index(probs: np.ndarray, axis: int = 1, return_seq: bool 
     return idx[0].astype(np.int64)
 
 
-def _rows_to_tuples(seqs_u8: np.ndarray, with_metrics: bool = True) -> list:
+def _rows_to_tuples(seqs_u8: np.ndarray, metrics: t.Optional[np.ndarray] = None) -> list:
+    """letters (+ the device-computed (n, 4) metric block) -> the reference's per-sample tuples."""
     strings = [row.tobytes().decode("ascii") for row in seqs_u8]
-    if not with_metrics or not strings:
+    if metrics is None or not strings:
         return [(s,) for s in strings]
-    charge, pi, mw, ext = seq_metrics.metrics_from_composition(seq_metrics.composition(seqs_u8))
-    return [(s, float(c), float(p), float(m), float(e)) for s, c, p, m, e in zip(strings, charge, pi, mw, ext)]
+    return [(s, float(m[0]), float(m[1]), float(m[2]), float(m[3])) for s, m in zip(strings, metrics)]
 
 
 def sample_from_sequences(pdb: str, sample_n: int, pdb_to_probability: dict,
                           rotamer_categories: t.Optional[t.Sequence[str]], *, stream_id: int = 0) -> dict:
     """sampling_utils.py:93-136: ``{pdb: [(sequence, charge, pI, mw, ext280)] * sample_n}``."""
     probs = np.array(pdb_to_probability[pdb], dtype=np.float64)
-    seqs, _ = sample_block(probs, int(sample_n), rotamer_categories, stream_id=stream_id)
-    return {pdb: _rows_to_tuples(seqs)}
+    seqs, _, metrics = sample_block(probs, int(sample_n), rotamer_categories, stream_id=stream_id, return_metrics=True)
+    return {pdb: _rows_to_tuples(seqs, metrics)}
 
 
 def sample_with_multiprocessing(workers, pdb_codes, sample_n, pdb_to_probability, flat_categories) -> dict:

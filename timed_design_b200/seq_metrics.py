@@ -79,3 +79,24 @@ def calculate_seq_metrics(seq: str):
     """Drop-in signature of analyse_utils.calculate_seq_metrics for one sequence."""
     c, p, m, e = metrics_from_composition(composition(np.frombuffer(seq.encode(), dtype=np.uint8)[None, :]))
     return float(c[0]), float(p[0]), float(m[0]), float(e[0])
+
+
+def device_tables() -> np.ndarray:
+    """Packed float64 table for ``timed_b200_seq_metrics`` (include/timed_b200.h):
+    [mw(20) | ext280(20) | q(pH 7.4)(20) | term(pH 7.4) | water | n_grid | grid | term(grid) | q(grid) (n_grid x 20)]
+    where q(pH)[i] = charge_i * partial_charge_i(pH) and term(pH) = N-terminus + C-terminus contribution."""
+    grid = np.arange(1, 13, 0.1)
+
+    def per_res(ph):
+        ph = np.atleast_1d(np.asarray(ph, dtype=np.float64))
+        q = np.zeros((len(ph), 20))
+        ion = CHARGE != 0
+        q[:, ion] = _partial(CHARGE[ion], PKA[ion], ph) * CHARGE[ion]
+        term = np.zeros(len(ph))
+        for sign, pka in (_NTERM, _CTERM):
+            term += (_partial(np.array([sign]), np.array([pka]), ph) * sign)[:, 0]
+        return q, term
+
+    q74, t74 = per_res(7.4)
+    qg, tg = per_res(grid)
+    return np.concatenate([MWT, EXT280, q74[0], t74, [WATER_MASS], [float(len(grid))], grid, tg, qg.ravel()]).astype(np.float64)
