@@ -1933,9 +1933,12 @@ int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t fra
     // double-buffered: H2D of chunk i+1 overlaps the forward of chunk i
     const uint8_t* src = static_cast<const uint8_t*>(h_frames);
     int it = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk, ++it) {
+    // chunk sizes ramp up (chunk/8, chunk/4, chunk/2, chunk, ...): only the first, small copy is not hidden
+    // behind a forward
+    int64_t cur = n_frames > chunk ? std::max<int64_t>(64, chunk / 8) : chunk;
+    for (int64_t f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++it, cur = std::min(chunk, cur * 2)) {
         const int b = it & 1;
-        const int64_t nf = std::min(chunk, n_frames - f0);
+        nf = std::min(cur, n_frames - f0);
         if (it >= 2) TB_CHECK_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_consumed[b], 0));
         TB_CHECK_CUDA(cudaMemcpyAsync(g->d_stage[b], src + f0 * frame_bytes, nf * frame_bytes,
                                       cudaMemcpyHostToDevice, g->s_copy));

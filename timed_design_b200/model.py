@@ -24,7 +24,7 @@ class Model:
     """An inference graph resident on one GPU."""
 
     def __init__(self, model_config: dict, weights: Dict[str, Dict[str, np.ndarray]],
-                 device: int = 0, max_chunk_frames: int = 2048, precise: bool = False):
+                 device: int = 0, max_chunk_frames: int = 1024, precise: bool = False):
         self.model_config = model_config
         self.graph: Graph = parse_model_config(model_config, weights)
         self.device = device
