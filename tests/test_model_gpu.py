@@ -92,3 +92,55 @@ def test_precise_mode_is_tighter_and_consistent():
     np.testing.assert_array_equal(prec[:48], prec[48:96])    # batch-position independent
     safe = ~ko.near_tie_rows(ref)
     assert (ko.fp16_argmax(prec[:48])[safe] == ko.fp16_argmax(ref)[safe]).all()
+
+
+def _pool_graph(side, c1, pool_pad, relu, seed=21):
+    """input(6) -> Conv3D(c1, k3, same)[+ReLU | ELU -> BN] -> MaxPool(2, pool_pad) -> GAP -> Dense softmax: the pooled tensor
+    is plain fp32 (read by the global pool), so the fused conv+pool epilogue's NDHWC output path is exercised."""
+    b = standins._Builder(f"pool_{side}_{c1}_{pool_pad}", (side, side, side, 6), seed, standins.synthetic_frames(3, side, 6, seed=99))
+    if relu:
+        x = b.conv3d(b.input_name, c1, 3, "same", activation="relu")
+    else:
+        x = b.bn(b.elu(b.conv3d(b.input_name, c1, 3, "same")))
+    x = b.pool(x, "max", 2, pool_pad)
+    x = b.gap(x)
+    x = b.dense(x, 20, activation="softmax")
+    return b.finish(x)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("side,c1,pool_pad,relu", [(21, 32, "same", False), (21, 24, "valid", True), (10, 16, "valid", False),
+                                                   (13, 32, "same", True), (4, 8, "same", False)])
+def test_fused_conv_maxpool_epilogue(side, c1, pool_pad, relu, monkeypatch):
+    """MaxPool(2,2,2) fused into thinz_conv_kernel's epilogue (z pairs from TMEM, in-plane 2x2 through a staged tile):
+    odd and even volumes, TF 'same' partial windows and 'valid' truncation, against the oracle and the unfused path."""
+    from timed_design_b200.model import Model
+    X = standins.synthetic_frames(7, side=side, seed=4)
+    cfg, w = _pool_graph(side, c1, pool_pad, relu)
+    ref = ko.forward_torch(cfg, w, X)
+    monkeypatch.setenv("TIMED_B200_POOLFUSE", "1")         # opt-in: no faster than the separate pass on TIMED (DESIGN.md)
+    m = Model(cfg, w)
+    fused = m.predict(X)
+    assert any("thinz" in m.op_kernel(i, 7) for i in range(len(m.graph.ops)))
+    monkeypatch.delenv("TIMED_B200_POOLFUSE")
+    m2 = Model(cfg, w)
+    unfused = m2.predict(X)
+    assert m2.launches_per_forward == m.launches_per_forward + 1
+    assert np.abs(fused - ref).max() <= PROB_TOL and np.abs(unfused - ref).max() <= PROB_TOL
+    assert np.abs(fused - unfused).max() <= 2e-6
+
+
+@pytest.mark.gpu
+def test_fused_pool_into_cpv_matches_unfused(monkeypatch):
+    """TIMED stand-in with the first max-pool fused into the first conv's epilogue, pooled tensor written straight in the
+    chunk-plane padded-volume layout the slab conv reads."""
+    from timed_design_b200.model import Model
+    cfg, w = standins.timed_standin(20)
+    X = standins.synthetic_frames(5, seed=12)
+    base = Model(cfg, w).predict(X)
+    monkeypatch.setenv("TIMED_B200_POOLFUSE", "1")
+    m = Model(cfg, w)
+    fused = m.predict(X)
+    assert "slab" in m.op_kernel(3, 5)
+    assert np.abs(fused - base).max() <= 2e-6
+    assert np.abs(fused - ko.forward_torch(cfg, w, X)).max() <= PROB_TOL

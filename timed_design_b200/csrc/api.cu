@@ -142,6 +142,8 @@ struct ConvPlan {
     uint8_t* d_slab_w = nullptr;
     int64_t slab_lead = 0, slab_tail = 0;
     bool thin = false;
+    bool fuse_pool = false;          // thinz only: the MaxPool(2,2,2;2) that follows runs in the conv epilogue
+    int pool_same = 0, pool_Zo = 0, pool_Po = 0, pool_Qo = 0;
     bool thinz = false;              // kd taps folded into N (thinz_conv.cuh)
     ThinZParams thinz_params;
     ThinConvParams thin_params;      // static part, completed per launch
@@ -660,7 +662,7 @@ static int slab_launch(ConvPlan& p, void* in_base, int64_t n_frames, const TView
 // ----------------------------------------------------------------------------- thin-input conv, kd folded into N
 struct ThinZGeom { int zt, n_steps, b1_rows, b2_rows, span_bytes, span_stride, stages, acc_cols, acc_stages; size_t w_bytes; };
 
-static bool thinz_geometry(int kd, int kh, int kw, int cout, int Wp, ThinZGeom* out) {
+static bool thinz_geometry(int kd, int kh, int kw, int cout, int Wp, ThinZGeom* out, bool pool = false) {
     if (getenv("TIMED_B200_NO_ZFOLD")) return false;
     const int n_tile = round_up(cout, 16);
     if (kd < 2 || kd * 2 * n_tile > 256) return false;
@@ -677,8 +679,10 @@ static bool thinz_geometry(int kd, int kh, int kw, int cout, int Wp, ThinZGeom* 
     g.span_stride = g.span_bytes;
     const size_t w_smem = (g.w_bytes + 127) & ~static_cast<size_t>(127);
     const size_t stage = 2u * (g.zt + kd - 1) * g.span_stride;
-    if (w_smem + 2 * stage + 128 > kSmemDynamicMax) return false;
-    g.stages = static_cast<int>(std::min<size_t>(kConvMaxStages, (kSmemDynamicMax - 128 - w_smem) / stage));
+    const size_t pool_buf = pool ? 2u * 128u * n_tile * sizeof(float) : 0;     // fused max-pool: two staged output tiles
+    if (w_smem + 2 * stage + pool_buf + 128 > kSmemDynamicMax) return false;
+    if (pool && (g.zt & 1)) return false;                                   // z pairs must not straddle tiles
+    g.stages = static_cast<int>(std::min<size_t>(kConvMaxStages, (kSmemDynamicMax - 128 - w_smem - pool_buf) / stage));
     *out = g;
     return true;
 }
@@ -733,6 +737,7 @@ static int thinz_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo&
     t.zt = g.zt;
     t.z_groups = ceil_div(p.Do, g.zt);
     t.windows = ceil_div(p.Ho * tin.pv_Wp, 128);
+    t.win_stride = 128;
     t.Do = p.Do; t.Ho = p.Ho; t.Wo = p.Wo; t.Wp = tin.pv_Wp;
     t.frame_bytes = static_cast<int64_t>(tin.pv_Dp) * tin.pv_Hp * tin.pv_Wp * 16;
     t.dplane_bytes = static_cast<int64_t>(tin.pv_Hp) * tin.pv_Wp * 16;
@@ -748,21 +753,41 @@ static int thinz_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo&
     return 0;
 }
 
-template <int A1, int A2, int F>
+template <int A1, int A2, int F, int POOL>
 static int launch_thinz_instance(const ThinZParams& k, int grid, size_t smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        TB_CHECK_CUDA(cudaFuncSetAttribute(thinz_conv_kernel<A1, A2, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        TB_CHECK_CUDA(cudaFuncSetAttribute(thinz_conv_kernel<A1, A2, F, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(kSmemDynamicMax)));
         attr_set = true;
     }
-    thinz_conv_kernel<A1, A2, F><<<grid, kConvThreads, smem_bytes, stream>>>(k);
+    thinz_conv_kernel<A1, A2, F, POOL><<<grid, kThinzThreads, smem_bytes, stream>>>(k);
     return 0;
 }
 
 static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames, const TView& out,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const TensorInfo* out_info = nullptr) {
     ThinZParams k = p.thinz_params;
+    if (p.fuse_pool) {
+        TB_REQUIRE(out_info != nullptr, "internal: fused pool needs the output tensor description");
+        ThinZGeom zg;
+        TB_REQUIRE(thinz_geometry(k.kd, k.kh, k.kw, p.cout, k.Wp, &zg, true), "internal: fused pool does not fit");
+        k.stages = zg.stages;
+        k.win_stride = 128 - k.Wp - 1;
+        const int max_anchor = 2 * (p.pool_Po - 1) * k.Wp + 2 * (p.pool_Qo - 1);
+        k.windows = max_anchor / k.win_stride + 1;
+        k.pool_same = p.pool_same;
+        k.Zo = p.pool_Zo; k.Po = p.pool_Po; k.Qo = p.pool_Qo;
+        k.pool_cpv = out_info->cpv ? 1 : 0;
+        if (out_info->cpv) {
+            k.cpv_T = out_info->cpv_T(n_frames);
+            k.cpv_lead = out_info->cpv_lead;
+            k.cpv_Dp = out_info->cpv_Dp; k.cpv_Hp = out_info->cpv_Hp; k.cpv_Wp = out_info->cpv_Wp;
+            k.out_hi4 = reinterpret_cast<uint4*>(out.hi);
+            k.out_lo4 = reinterpret_cast<uint4*>(out.lo);
+        }
+        k.pool_out = out;
+    }
     const int64_t tiles = n_frames * k.z_groups * k.windows;
     TB_REQUIRE(tiles > 0 && tiles < (1ll << 31), "thinz conv: too many tiles per launch");
     k.n_tiles_total = static_cast<int32_t>(tiles);
@@ -782,13 +807,15 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "thinz conv: split output channel padding mismatch");
     const size_t w_smem = (static_cast<size_t>(k.w_bytes) + 127) & ~static_cast<size_t>(127);
-    const size_t smem_bytes = 128 + w_smem + static_cast<size_t>(k.stages) * 2u * (k.zt + k.kd - 1) * k.span_stride;
+    const size_t smem_bytes = 128 + w_smem + static_cast<size_t>(k.stages) * 2u * (k.zt + k.kd - 1) * k.span_stride +
+                              (p.fuse_pool ? 2u * 128u * k.n_tile * sizeof(float) : 0);
     const int grid = static_cast<int>(std::min<int64_t>(tiles, 148));
     int rc = 0;
     bool launched = false;
 #define TB_THINZ_CASE(A1, A2, F)                                                             \
     if (!launched && e.act1 == (A1) && e.act2 == (A2) && out.fmt == (F)) {                   \
-        rc = launch_thinz_instance<A1, A2, F>(k, grid, smem_bytes, stream);                  \
+        rc = p.fuse_pool ? launch_thinz_instance<A1, A2, F, 1>(k, grid, smem_bytes, stream)  \
+                         : launch_thinz_instance<A1, A2, F, 0>(k, grid, smem_bytes, stream); \
         launched = true;                                                                     \
     }
     TB_THINZ_CASE(ACT_ELU, ACT_NONE, FMT_F32)
@@ -798,9 +825,12 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
     TB_THINZ_CASE(ACT_NONE, ACT_NONE, FMT_F32)
     TB_THINZ_CASE(ACT_NONE, ACT_NONE, FMT_SPLIT)
 #undef TB_THINZ_CASE
-    if (!launched)
-        rc = out.fmt == FMT_SPLIT ? launch_thinz_instance<-1, -1, FMT_SPLIT>(k, grid, smem_bytes, stream)
-                                  : launch_thinz_instance<-1, -1, FMT_F32>(k, grid, smem_bytes, stream);
+    if (!launched && p.fuse_pool)
+        rc = out.fmt == FMT_SPLIT ? launch_thinz_instance<-1, -1, FMT_SPLIT, 1>(k, grid, smem_bytes, stream)
+                                  : launch_thinz_instance<-1, -1, FMT_F32, 1>(k, grid, smem_bytes, stream);
+    else if (!launched)
+        rc = out.fmt == FMT_SPLIT ? launch_thinz_instance<-1, -1, FMT_SPLIT, 0>(k, grid, smem_bytes, stream)
+                                  : launch_thinz_instance<-1, -1, FMT_F32, 0>(k, grid, smem_bytes, stream);
     if (rc) return rc;
     TB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -1043,9 +1073,9 @@ static size_t conv_scratch_bytes(const ConvPlan& p, int64_t n_frames) {
 
 static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames,
                        const TView& final_out, cudaStream_t stream, void* scratch = nullptr,
-                       size_t scratch_bytes = 0) {
+                       size_t scratch_bytes = 0, const TensorInfo* out_info = nullptr) {
     if (p.slab) return slab_launch(p, in_base, n_frames, final_out, stream);
-    if (p.thinz) return thinz_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream);
+    if (p.thinz) return thinz_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream, out_info);
     if (p.thin) return thin_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream);
     TView out = final_out;
     if (p.tap2n) {
@@ -1168,6 +1198,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
 
 // ----------------------------------------------------------------------------- graph
 struct OpNode {
+    int alias_of = -1;          // pooling op fused into the conv that feeds it: shares that op's output tensor
     tb_op_desc d;
     ConvPlan conv;
     float* d_scale = nullptr;   // AFFINE
@@ -1269,6 +1300,11 @@ static const Layout& get_layout(tb_graph* g, int64_t n_frames) {
                 ++k;
             }
         }
+        if (g->ops[i].alias_of >= 0) {                 // fused pooling op: same storage as the conv output
+            L.offset[i] = L.offset[g->ops[i].alias_of];
+            live[i] = {L.offset[i], 0};
+            continue;
+        }
         const size_t need = g->tensors[i].bytes(n_frames);
         bool placed = false;
         for (size_t k = 0; k < free_list.size(); ++k)
@@ -1310,7 +1346,7 @@ static int upload_vec(const float* src, int n, float fill, float** dst) {
 
 // Give tensor `ti` (dims known, produced by the input op or a pooling op) the CPV layout when every reader is a
 // conv that slab_conv_kernel can run; margins are the union over the readers.
-static void decide_cpv(TensorInfo& t, int ti, const tb_op_desc* ops, int n_ops) {
+static void decide_cpv(TensorInfo& t, int ti, const tb_op_desc* ops, int n_ops) {   // ti: op whose READERS decide
     int pd = 0, ph = 0, pw = 0, n_cons = 0;
     for (int pass = 0; pass < 2; ++pass)          // second pass: every reader must also fit with the union margins
         for (int i = ti + 1; i < n_ops; ++i)
@@ -1431,10 +1467,51 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 t.D = node.conv.Do; t.H = node.conv.Ho; t.W = node.conv.Wo; t.C = d.c_out;
                 g->flops += node.conv.flops_per_frame();
                 g->launches += node.conv.tap2n ? 2 : 1;
+                // thinz conv read only by a MaxPool(2,2,2; stride 2): the pooling runs in the conv epilogue and this
+                // op's tensor IS the pooled tensor (the pooling op becomes an alias of it)
+                // Opt-in (TIMED_B200_POOLFUSE=1): measured on TIMED block 1 the fused epilogue costs what the separate pooling
+                // pass saves (5.0 vs 3.6 + 1.26 ms; the overlapping windows add 25 % MMA work) -- profiles/r1_summary.md.
+                if (node.conv.thinz && getenv("TIMED_B200_POOLFUSE")) {
+                    int j = -1, n_readers = 0;
+                    for (int k = i + 1; k < n_ops; ++k)
+                        for (int q = 0; q < ops[k].n_inputs; ++q)
+                            if (ops[k].inputs[q] == i) { ++n_readers; j = k; }
+                    bool ok = n_readers == 1 && ops[j].op == TB_OP_POOL3D && ops[j].pool_kind == 0 && ops[j].n_inputs == 1;
+                    for (int a = 0; a < 3 && ok; ++a)
+                        ok = ops[j].kernel[a] == 2 && (ops[j].stride[a] == 2 || ops[j].stride[a] <= 0);
+                    ThinZGeom zg;
+                    ok = ok && thinz_geometry(node.conv.kd, node.conv.kh, node.conv.kw, node.conv.cout, in0->pv_Wp, &zg, true);
+                    const bool same = ok && ops[j].pad_same;
+                    const int dims[3] = {t.D, t.H, t.W};
+                    int po[3] = {0, 0, 0};
+                    for (int a = 0; a < 3 && ok; ++a) {
+                        po[a] = same ? (dims[a] + 1) / 2 : dims[a] / 2;
+                        ok = po[a] >= 1;
+                    }
+                    // a plain fp32 pooled tensor is written 8 channels at a time
+                    ok = ok && (feeds_conv[j] || t.C % 8 == 0);
+                    if (ok) {
+                        node.conv.fuse_pool = true;
+                        node.conv.pool_same = same ? 1 : 0;
+                        node.conv.pool_Zo = po[0]; node.conv.pool_Po = po[1]; node.conv.pool_Qo = po[2];
+                        g->ops[j].alias_of = i;
+                        t.D = po[0]; t.H = po[1]; t.W = po[2];
+                        t.fmt = feeds_conv[j] ? FMT_SPLIT : FMT_F32;
+                        t.last_use = std::max(t.last_use, g->tensors[j].last_use);
+                        decide_cpv(t, j, ops, n_ops);
+                        if (t.cpv) g->launches += 1;          // margin zeroing
+                    }
+                }
                 break;
             }
             case TB_OP_POOL3D: {
                 TB_REQUIRE(d.n_inputs == 1, "pool takes one input");
+                if (node.alias_of >= 0) {                     // fused into the producing conv's epilogue
+                    const int lu = t.last_use;
+                    t = g->tensors[node.alias_of];
+                    t.last_use = lu;
+                    break;
+                }
                 PoolParams& pp = node.pool;
                 pp.D = in0->D; pp.H = in0->H; pp.W = in0->W;
                 const int in[3] = {in0->D, in0->H, in0->W};
@@ -1517,10 +1594,12 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
             TensorInfo& s = g->tensors[ops[i].inputs[0]];
             const ConvPlan& c = g->ops[i].conv;
             if (s.cpv) continue;
+            const int owner = g->ops[ops[i].inputs[0]].alias_of;      // fused pooling op: the storage belongs to the conv
             // base pixels advance through Do*Ho*Wo per frame: express the slack in input pixels
             const int64_t out_ppf = static_cast<int64_t>(c.Do) * c.Ho * c.Wo;
             const int64_t frames = c.thin ? 1 : (128 + out_ppf - 1) / out_ppf;   // thin: spans overrun < 1 frame
             s.slack_pix = std::max<int64_t>(s.slack_pix, frames * s.pix_per_frame());
+            if (owner >= 0) g->tensors[owner].slack_pix = std::max(g->tensors[owner].slack_pix, s.slack_pix);
         }
     const TensorInfo& last = g->tensors[n_ops - 1];
     TB_REQUIRE(last.pix_per_frame() == 1, "graph output must be (n, classes)");
@@ -1621,12 +1700,18 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 break;
             case TB_OP_CONV3D: {
                 TB_REQUIRE(ti0->fmt == FMT_SPLIT, "internal: conv input must be split planes");
+                if (node.conv.fuse_pool && t.cpv) {
+                    const CpvGeom cg = make_cpv_geom(t, n_frames);
+                    cpv_zero_margins_kernel<<<grid_for(cg.T * cg.n_chunks, 256), 256, 0, s>>>(
+                        reinterpret_cast<uint4*>(out.hi), reinterpret_cast<uint4*>(out.lo), cg);
+                }
                 int rc = conv_launch(node.conv, base + L.offset[d.inputs[0]], ti0->frames_alloc(n_frames),
-                                     n_frames, out, s, base + L.scratch_off, L.scratch_bytes);
+                                     n_frames, out, s, base + L.scratch_off, L.scratch_bytes, &t);
                 if (rc) return rc;
                 break;
             }
             case TB_OP_POOL3D: {
+                if (node.alias_of >= 0) break;                 // ran inside the producing conv's epilogue
                 if (t.cpv) {
                     const CpvGeom cg = make_cpv_geom(t, n_frames);
                     const int grid = grid_for(cg.T * cg.n_chunks, 256);

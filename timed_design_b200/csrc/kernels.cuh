@@ -311,6 +311,22 @@ __global__ void input_convert_cpv_kernel(const T* __restrict__ x, int64_t n_fram
     }
 }
 
+// zero the lead / tail / margin positions of a CPV tensor whose interior is written by a fused conv+pool epilogue
+__global__ void cpv_zero_margins_kernel(uint4* __restrict__ hi, uint4* __restrict__ lo, CpvGeom g) {
+    const int64_t total = g.T * g.n_chunks;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int chunk = static_cast<int>(i / g.T);
+        const int64_t t = i - chunk * g.T;
+        int64_t nf;
+        int z, p, q;
+        if (!cpv_decode(g, t, nf, z, p, q)) {
+            hi[i] = make_uint4(0, 0, 0, 0);
+            lo[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
 // pooling straight into the CPV layout (input stores >= n_chunks*8 channels per pixel)
 template <int IN_FMT>
 __global__ void pool3d_cpv_kernel(TView in, uint4* __restrict__ hi, uint4* __restrict__ lo, CpvGeom g, PoolParams pp,

@@ -16,9 +16,17 @@
 #pragma once
 #include "common.cuh"
 #include "conv_umma.cuh"
+#include "kernels.cuh"
 #include "thin_conv.cuh"
 
 namespace tb {
+
+// Epilogue warps: kThinzSubs per TMEM lane quadrant.  Measured (profiles/r1_summary.md): 16 warps are no faster than 8
+// (epilogue-only 1.67 vs 1.70 ms) and cost 0.3 ms in the full kernel -- the epilogue is bound by its strided 16-byte
+// stores, not by issue slots.
+constexpr int kThinzEpiWarps = 8;
+constexpr int kThinzSubs = kThinzEpiWarps / 4;
+constexpr int kThinzThreads = 64 + 32 * kThinzEpiWarps;
 
 struct ThinZParams {
     // ---- tiling: tile = (frame, z group of zt output planes, window of 128 in-plane positions u = p*Wp + q)
@@ -48,12 +56,26 @@ struct ThinZParams {
     int32_t stages;
     ConvKernelParams epi;     // epilogue fields
     int32_t dbg;
+    int32_t win_stride;       // in-plane positions between consecutive windows (128, or 128 - Wp - 1 when pooling)
+    // ---- fused MaxPool(2,2,2; stride 2) of the conv output (POOL instantiation).  A window owns the pooled pixels
+    // whose anchor position u = 2P*Wp + 2Q lies in its first win_stride positions (all four in-plane partners are then
+    // inside the window); z pairs are the accumulators (2zp, 2zp+1) of the tile.  The epilogue stages the z-maxed,
+    // activated tile in shared memory and writes the pooled pixels in the consumer's layout.
+    int32_t pool_same;        // TF 'same' (partial windows at the far edge are kept) or 'valid'
+    int32_t Zo, Po, Qo;       // pooled extents
+    int32_t pool_cpv;         // 1: chunk-plane padded volume (out_hi4/out_lo4 + geometry below), 0: plain NDHWC view
+    int64_t cpv_T, cpv_lead;
+    int32_t cpv_Dp, cpv_Hp, cpv_Wp;
+    uint4* out_hi4;
+    uint4* out_lo4;
+    TView pool_out;
 };
 
 #if defined(__CUDACC__)
 
-template <int ACT1, int ACT2, int FMT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+// FMT: format of the conv output (POOL = 0) or of the plain pooled output (POOL = 1, ignored for CPV)
+template <int ACT1, int ACT2, int FMT, int POOL>
+__global__ void __launch_bounds__(kThinzThreads, 1)
 thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -77,7 +99,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], kConvEpilogueWarps);
+            mbar_init(&tempty_bar[a], kThinzEpiWarps);
         }
         mbar_init(&w_bar, 1);
         mbar_fence_init();
@@ -99,6 +121,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
     const uint32_t plane_region = static_cast<uint32_t>(max_planes) * p.span_stride;   // hi spans, then lo spans
     const uint32_t stage_bytes = 2u * plane_region;
     const int tiles_per_frame = p.z_groups * p.windows;
+    float* pool_stage = reinterpret_cast<float*>(stage0 + static_cast<size_t>(p.stages) * stage_bytes);   // POOL: 2 x [128][n_tile]
 
     if (warp == 0) {
         // =============================================================== bulk-copy producer
@@ -124,7 +147,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                 mbar_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(n_planes) * p.span_bytes);
                 uint8_t* st = stage0 + static_cast<size_t>(s) * stage_bytes;
                 const uint8_t* src = p.in_hi + nf * p.frame_bytes + static_cast<int64_t>(z0 + p.off_d) * p.dplane_bytes +
-                                     static_cast<int64_t>(p.off_hw + win * 128) * 16;
+                                     static_cast<int64_t>(p.off_hw + win * p.win_stride) * 16;
                 for (int i = 0; i < n_planes; ++i, src += p.dplane_bytes) {
                     bulk_load_1d(st + i * p.span_stride, src, p.span_bytes, &full_bar[s]);
                     bulk_load_1d(st + plane_region + i * p.span_stride, src + p.lo_plane_off, p.span_bytes, &full_bar[s]);
@@ -209,12 +232,13 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         }
     } else {
         // =============================================================== epilogue (warps 2..9)
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int sub = (warp - 2) >> 2;              // which of the quadrant's kThinzSubs warps
         const int chunks = p.n_tile / 16;
         const int plane_positions = p.Ho * p.Wp;
         int acc = 0;
         uint32_t acc_ph = 0;
+        int pool_buf = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles_total; tile += gridDim.x) {
             const int nf = tile / tiles_per_frame;
             const int r = tile - nf * tiles_per_frame;
@@ -222,32 +246,124 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
             const int win = r - zg * p.windows;
             const int z0 = zg * p.zt;
             const int zt_eff = min(p.zt, p.Do - z0);
-            const int u = win * 128 + quad * 32 + lane;
+            const int u0 = win * p.win_stride;
+            const int u = u0 + quad * 32 + lane;
             const int prow = u / p.Wp;
             const int q = u - prow * p.Wp;
             const bool row_ok = u < plane_positions && q < p.Wo;
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
-            for (int j = 0; j < zt_eff && !(p.dbg & 4); ++j) {
-                const int64_t m = ((static_cast<int64_t>(nf) * p.Do + z0 + j) * p.Ho + prow) * p.Wo + q;
-                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                       static_cast<uint32_t>(acc * p.acc_cols + j * 2 * p.n_tile);
-                for (int c = half; c < chunks; c += 2) {
-                    uint32_t rv[16], rc[16];
-                    __syncwarp();
-                    tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), rv);
-                    tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.n_tile + c * 16), rc);
-                    tmem_ld_wait();
+            if constexpr (POOL == 0) {
+                for (int item = sub; item < zt_eff * chunks && !(p.dbg & 4); item += kThinzSubs) {
+                    const int j = item / chunks;
+                    const int64_t m = ((static_cast<int64_t>(nf) * p.Do + z0 + j) * p.Ho + prow) * p.Wo + q;
+                    const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                           static_cast<uint32_t>(acc * p.acc_cols + j * 2 * p.n_tile);
+                    {
+                        const int c = item - j * chunks;
+                        uint32_t rv[16], rc[16];
+                        __syncwarp();
+                        tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), rv);
+                        tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.n_tile + c * 16), rc);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) rv[i] = __float_as_uint(__uint_as_float(rv[i]) + __uint_as_float(rc[i]));
-                    const int n0 = c * 16;
-                    if (n0 >= p.epi.c_store) continue;
-                    epilogue_chunk<ACT1, ACT2, FMT>(p.epi, rv, n0, m, row_ok, s_epi[0], s_epi[1], s_epi[2]);
+                        for (int i = 0; i < 16; ++i) rv[i] = __float_as_uint(__uint_as_float(rv[i]) + __uint_as_float(rc[i]));
+                        const int n0 = c * 16;
+                        if (n0 < p.epi.c_store)
+                            epilogue_chunk<ACT1, ACT2, FMT>(p.epi, rv, n0, m, row_ok, s_epi[0], s_epi[1], s_epi[2]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            } else {
+                const int et = threadIdx.x - 64;                         // index among the epilogue threads
+                const int n_zp = (zt_eff + 1) >> 1;
+                const int row_f4 = p.n_tile >> 2;                        // float4 slots per staged row
+                for (int zp = 0; zp < n_zp && !(p.dbg & 4); ++zp, pool_buf ^= 1) {
+                    // two staging buffers: one barrier per z pair is enough (a buffer is rewritten two pairs later)
+                    float4* stage4 = reinterpret_cast<float4*>(pool_stage) + pool_buf * 128 * row_f4;
+                    const int Z = (z0 >> 1) + zp;
+                    const bool two = 2 * zp + 1 < zt_eff;                // partner plane exists
+                    const bool z_ok = Z < p.Zo && (two || p.pool_same);  // 'valid' drops a window without its partner
+                    // ---- phase 1: activated conv outputs of the z pair, max over z, into shared memory [row][channel]
+                    for (int unit = sub; unit < (p.n_tile >> 3); unit += kThinzSubs) {       // 8 channels per unit
+                        float v[8];
+#pragma unroll
+                        for (int pl = 0; pl < 2; ++pl) {
+                            if (pl == 1 && !two) break;
+                            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                                   static_cast<uint32_t>(acc * p.acc_cols + (2 * zp + pl) * 2 * p.n_tile);
+                            uint32_t rv[8], rc[8];
+                            __syncwarp();
+                            tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(unit * 8), rv);
+                            tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(p.n_tile + unit * 8), rc);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float x = (__uint_as_float(rv[i]) + __uint_as_float(rc[i])) + s_epi[0][unit * 8 + i];
+                                x = act_ct<ACT1>(x, p.epi.act1, p.epi.alpha1);
+                                x = fmaf(x, s_epi[1][unit * 8 + i], s_epi[2][unit * 8 + i]);
+                                x = act_ct<ACT2>(x, p.epi.act2, p.epi.alpha2);
+                                v[i] = pl == 0 ? x : fmaxf(v[i], x);
+                            }
+                        }
+                        // row-major [128][n_tile] fp32 with the 16-byte slot index XORed by the row: a warp's 32 rows would
+                        // otherwise all land on the same four banks
+                        const int srow = quad * 32 + lane;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            stage4[srow * row_f4 + ((unit * 2 + i) ^ (srow & 7 & (row_f4 - 1)))] =
+                                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                    if (zp + 1 == n_zp) {                                // every accumulator of this stage has been read
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kThinzEpiWarps) : "memory");
+                    // ---- phase 2: in-plane 2x2 max of the pooled pixels this window owns, 8 channels per thread
+                    const int groups = p.n_tile >> 3;
+                    for (int w = et; w < p.win_stride * groups && z_ok; w += 32 * kThinzEpiWarps) {
+                        const int g = w % groups;
+                        const int du = w / groups;                       // anchor offset inside the window
+                        const int ua = u0 + du;
+                        const int pa = ua / p.Wp;
+                        const int qa = ua - pa * p.Wp;
+                        if ((pa & 1) || (qa & 1) || pa >= p.Ho || qa >= p.Wo) continue;
+                        const int P = pa >> 1, Q = qa >> 1;
+                        if (P >= p.Po || Q >= p.Qo) continue;
+                        const bool has_q = qa + 1 < p.Wo, has_p = pa + 1 < p.Ho;
+                        if (!p.pool_same && (!has_q || !has_p)) continue;
+                        float m8[8];
+                        auto take = [&](int row, bool first) {
+                            const int sw = row & 7 & (row_f4 - 1);
+                            const float4 a = stage4[row * row_f4 + ((2 * g) ^ sw)];
+                            const float4 b = stage4[row * row_f4 + ((2 * g + 1) ^ sw)];
+                            const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) m8[e] = first ? x[e] : fmaxf(m8[e], x[e]);
+                        };
+                        take(du, true);
+                        if (has_q) take(du + 1, false);
+                        if (has_p) take(du + p.Wp, false);
+                        if (has_q && has_p) take(du + p.Wp + 1, false);
+                        if (p.pool_cpv) {
+                            const int64_t t = p.cpv_lead + ((static_cast<int64_t>(nf) * p.cpv_Dp + Z) * p.cpv_Hp + P) * p.cpv_Wp + Q;
+                            cpv_store(p.out_hi4, p.out_lo4, g * p.cpv_T + t, m8);
+                        } else {
+                            const int64_t pix = ((static_cast<int64_t>(nf) * p.Zo + Z) * p.Po + P) * p.Qo + Q;
+                            if (g * 8 < (FMT == FMT_SPLIT ? p.pool_out.c_pad : p.pool_out.c))
+                                store8<FMT>(p.pool_out, pix * p.pool_out.ld + g * 8, m8);
+                        }
+                    }
+                }
+                if (p.dbg & 4) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
     }
