@@ -268,7 +268,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
             const int64_t m = static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank)) * 128 + row_in_tile;
-            const bool row_ok = m < p.m_total;
+            const bool row_ok = m < p.m_total && !(p.dbg & 8);
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>(acc * p.acc_cols);
             for (int c = half; c < chunks && !(p.dbg & 4); c += 2) {

@@ -134,6 +134,13 @@ __device__ __forceinline__ void umma_bf16_lohi(bool leader, uint32_t d_tmem, uin
     }
 }
 
+// 256-bit global store (STG.256, sm_100): `dst` must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* dst, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 // One 16-column chunk of one accumulator row: bias -> act1 -> folded BatchNorm -> act2 -> store
 // (bf16 hi/lo split planes or fp32).  `r` holds the raw fp32 accumulator bits of columns [n0, n0+16).
 template <int ACT1, int ACT2, int FMT>
@@ -167,15 +174,19 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
             hi[i] = pack_bf16x2(h0, h1);
             lo[i] = pack_bf16x2(l0, l1);
         }
-        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + m * p.ldc + n0);
-        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + m * p.ldc + n0);
-        dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        // one 256-bit store per plane: a lane's 32 bytes are exactly one L2 sector (two 16-byte stores would each
+        // write half a sector); rows are 32-byte aligned because ldc and n0 are multiples of 16 bf16
+        st_global_256(p.out_hi + m * p.ldc + n0, hi);
+        st_global_256(p.out_lo + m * p.ldc + n0, lo);
     } else if (row_ok) {
         float* dst = p.out_f32 + m * p.ldc + n0;
-        if (n0 + 16 <= p.c_store && (p.ldc & 3) == 0) {
+        if (n0 + 16 <= p.c_store && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(v[i]);
+            st_global_256(dst, *reinterpret_cast<const uint32_t(*)[8]>(&w[0]));
+            st_global_256(dst + 8, *reinterpret_cast<const uint32_t(*)[8]>(&w[8]));
+        } else if (n0 + 16 <= p.c_store && (p.ldc & 3) == 0) {
             float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -423,7 +434,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             for (int mi = 0; mi < p.mt && !(p.dbg & 4); ++mi) {
                 const int64_t m = (p.cluster2 ? static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank))
                                               : static_cast<int64_t>(m_ct * p.mt + mi)) * 128 + row_in_tile;
-                const bool row_ok = m < p.m_total;
+                const bool row_ok = m < p.m_total && !(p.dbg & 8);
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                        static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);
                 for (int c = half; c < chunks; c += 2) {

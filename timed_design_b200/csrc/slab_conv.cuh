@@ -247,7 +247,7 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
                 rem -= z * hw;
                 const int pr = rem / p.Wp;
                 const int q = rem - pr * p.Wp;
-                const bool row_ok = u < p.t_count && z < p.Do && pr < p.Ho && q < p.Wo;
+                const bool row_ok = u < p.t_count && z < p.Do && pr < p.Ho && q < p.Wo && !(p.dbg & 8);
                 const int64_t m = ((f * p.Do + z) * p.Ho + pr) * p.Wo + q;
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                        static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);

@@ -250,7 +250,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
             const int u = u0 + quad * 32 + lane;
             const int prow = u / p.Wp;
             const int q = u - prow * p.Wp;
-            const bool row_ok = u < plane_positions && q < p.Wo;
+            const bool row_ok = u < plane_positions && q < p.Wo && !(p.dbg & 8);   // dbg 8: compute, do not store
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
             if constexpr (POOL == 0) {
