@@ -1742,10 +1742,26 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 }
                 break;
             }
-            case TB_OP_AFFINE:
-                affine_act_kernel<<<grid_for(out_pix * cw, 256), 256, 0, s>>>(
-                    in0, out, out_pix, node.d_scale, node.d_shift, d.act1, d.alpha1, d.act2, d.alpha2);
+            case TB_OP_AFFINE: {
+                const int in_cw = in0.fmt == FMT_SPLIT ? in0.c_pad : in0.c;
+                const bool vec = cw % 8 == 0 && in_cw % 8 == 0 && in0.ld % 8 == 0 && out.ld % 8 == 0 &&
+                                 in_cw >= round_up(out.c, 8);
+                if (vec) {
+                    const int grid = grid_for(out_pix * (cw / 8), 256);
+#define TB_AFFINE_VEC(FI, FO)                                                                                     \
+    affine_act_vec8_kernel<FI, FO><<<grid, 256, 0, s>>>(in0, out, out_pix, node.d_scale, node.d_shift, d.act1,     \
+                                                        d.alpha1, d.act2, d.alpha2)
+                    if (in0.fmt == FMT_SPLIT && out.fmt == FMT_SPLIT) TB_AFFINE_VEC(FMT_SPLIT, FMT_SPLIT);
+                    else if (in0.fmt == FMT_F32 && out.fmt == FMT_SPLIT) TB_AFFINE_VEC(FMT_F32, FMT_SPLIT);
+                    else if (in0.fmt == FMT_SPLIT && out.fmt == FMT_F32) TB_AFFINE_VEC(FMT_SPLIT, FMT_F32);
+                    else TB_AFFINE_VEC(FMT_F32, FMT_F32);
+#undef TB_AFFINE_VEC
+                } else {
+                    affine_act_kernel<<<grid_for(out_pix * cw, 256), 256, 0, s>>>(
+                        in0, out, out_pix, node.d_scale, node.d_shift, d.act1, d.alpha1, d.act2, d.alpha2);
+                }
                 break;
+            }
             case TB_OP_GPOOL:
                 gpool_kernel<<<static_cast<unsigned>(n_frames), 128, 0, s>>>(
                     in0, out, static_cast<int>(ti0->pix_per_frame()), d.pool_kind);
@@ -1758,7 +1774,19 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 for (int k = 0; k < d.n_inputs; ++k) {
                     const TensorInfo& ts = g->tensors[d.inputs[k]];
                     TView src = make_view(ts, base + L.offset[d.inputs[k]], n_frames);
-                    copy_channels_kernel<<<grid_for(out_pix * src.c, 256), 256, 0, s>>>(src, out, out_pix, c_off);
+                    if (src.c % 8 == 0 && c_off % 8 == 0 && src.ld % 8 == 0 && out.ld % 8 == 0) {
+                        const int grid = grid_for(out_pix * (src.c / 8), 256);
+                        if (src.fmt == FMT_SPLIT && out.fmt == FMT_SPLIT)
+                            copy_channels_vec8_kernel<FMT_SPLIT, FMT_SPLIT><<<grid, 256, 0, s>>>(src, out, out_pix, c_off);
+                        else if (src.fmt == FMT_F32 && out.fmt == FMT_SPLIT)
+                            copy_channels_vec8_kernel<FMT_F32, FMT_SPLIT><<<grid, 256, 0, s>>>(src, out, out_pix, c_off);
+                        else if (src.fmt == FMT_SPLIT && out.fmt == FMT_F32)
+                            copy_channels_vec8_kernel<FMT_SPLIT, FMT_F32><<<grid, 256, 0, s>>>(src, out, out_pix, c_off);
+                        else
+                            copy_channels_vec8_kernel<FMT_F32, FMT_F32><<<grid, 256, 0, s>>>(src, out, out_pix, c_off);
+                    } else {
+                        copy_channels_kernel<<<grid_for(out_pix * src.c, 256), 256, 0, s>>>(src, out, out_pix, c_off);
+                    }
                     c_off += ts.C;
                 }
                 if (out.fmt == FMT_SPLIT && out.c_pad > out.c)

@@ -389,6 +389,50 @@ __global__ void affine_act_kernel(TView in, TView out, int64_t n_pix, const floa
     }
 }
 
+// 8 channels per thread (16/32-byte vectors): both sides store a multiple of 8 channels per pixel
+template <int IN_FMT, int OUT_FMT>
+__global__ void affine_act_vec8_kernel(TView in, TView out, int64_t n_pix, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, int act1, float alpha1, int act2,
+                                       float alpha2) {
+    const int groups = (OUT_FMT == FMT_SPLIT ? out.c_pad : out.c) / 8;
+    const int64_t total = n_pix * groups;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t pix = i / groups;
+        const int g = static_cast<int>(i - pix * groups);
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (g * 8 < out.c) {
+            load8<IN_FMT>(in, pix * in.ld + g * 8, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ch = g * 8 + e;
+                if (ch < out.c) {
+                    float x = apply_act(v[e], act1, alpha1);
+                    x = fmaf(x, scale[ch], shift[ch]);
+                    v[e] = apply_act(x, act2, alpha2);
+                } else {
+                    v[e] = 0.0f;
+                }
+            }
+        }
+        store8<OUT_FMT>(out, pix * out.ld + g * 8, v);
+    }
+}
+
+template <int IN_FMT, int OUT_FMT>
+__global__ void copy_channels_vec8_kernel(TView in, TView out, int64_t n_pix, int c_off) {
+    const int groups = in.c / 8;
+    const int64_t total = n_pix * groups;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t pix = i / groups;
+        const int g = static_cast<int>(i - pix * groups);
+        float v[8];
+        load8<IN_FMT>(in, pix * in.ld + g * 8, v);
+        store8<OUT_FMT>(out, pix * out.ld + c_off + g * 8, v);
+    }
+}
+
 // ------------------------------------------------------------------ col2im of the tap-to-N convs
 // Z: (input pixels, z_ld) fp32 with Z[p', tap*cout + co] = sum_c X[p', c] * W[tap, c, co].
 // out[p, co] = act2(scale * act1(bias + sum_tap Z[p + tap - pad, tap, co]) + shift), taps summed in
