@@ -294,7 +294,7 @@ def main():
     peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
     step_ms_ops = sum(o["ms"] for o in op_times) / max(n_fw, 1)
     traffic = None
-    tp = ROOT / "profiles" / "r1f_dominant_kernel_ncu.json"
+    tp = ROOT / "profiles" / "r1i_dominant_kernel_ncu.json"
     if tp.exists() and args.model == "timed" and args.classes == 20 and B == 4096:
         traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
     roofline = {
