@@ -75,6 +75,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Same for waits that are expected to be long (an epilogue warp waiting for a whole tile's mainloop): sleep between
+// polls so the spinning warps do not burn issue slots and power next to a power-capped tensor pipe.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(spins < 8 ? 32 : 256);
+        if (++spins > TB_MBAR_SPIN_LIMIT) {
+            printf("timed_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
 // ---- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
