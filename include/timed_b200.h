@@ -157,6 +157,15 @@ int timed_b200_sample(const double* d_cdf, int64_t n_res, int32_t n_cls, int64_t
                       int64_t first_sample, uint64_t seed, uint64_t stream_id,
                       const double* d_uniforms, const uint8_t* d_cls_to_letter, uint8_t* d_seqs,
                       int32_t* d_idx, void* cuda_stream);
+/* Every chain of a structure set in ONE launch (the reference fans chains out over a process pool,
+ * sampling_utils.py:181-191).  d_cdf: CDFs of all chains concatenated, (row_off[n_chains], n_cls) float64; chain c owns rows
+ * [d_row_off[c], d_row_off[c+1]) and the bytes [d_seq_off[c], d_seq_off[c] + n_samples*n_res_c) of d_seqs, laid out
+ * (n_samples, n_res_c) like a per-chain call; d_seq_off has n_chains+1 ascending multiples of 4, the last one =
+ * total_seq_bytes.  Chain c is keyed (seed, stream_id0 + c): byte-identical to timed_b200_sample with that stream id. */
+int timed_b200_sample_chains(const double* d_cdf, const int64_t* d_row_off, const int64_t* d_seq_off, int32_t n_chains,
+                             int64_t total_seq_bytes, int32_t n_cls, int64_t n_samples, int64_t first_sample,
+                             uint64_t seed, uint64_t stream_id0, const uint8_t* d_cls_to_letter, uint8_t* d_seqs,
+                             void* cuda_stream);
 /* Philox uniforms exactly as timed_b200_sample would draw them (test hook). */
 int timed_b200_sample_uniforms(int64_t n_res, int64_t n_samples, int64_t first_sample,
                                uint64_t seed, uint64_t stream_id, double* d_out,

@@ -155,3 +155,21 @@ def test_argmax_fp16_kernel():
     out = torch.empty(len(p), dtype=torch.int32, device="cuda")
     _lib.check(_lib.load().timed_b200_argmax_fp16(C.c_void_p(d.data_ptr()), len(p), 338, C.c_void_p(out.data_ptr()), None))
     np.testing.assert_array_equal(out.cpu().numpy(), np.argmax(p.astype(np.float16), axis=1))
+
+
+def test_sample_chains_equals_per_chain_launches(su):
+    """One launch over all chains (timed_b200_sample_chains) draws byte-for-byte what per-chain launches keyed
+    (seed, stream_id0 + chain) draw -- ragged lengths, a one-residue chain, blocks that are not multiples of four."""
+    rng = np.random.default_rng(17)
+    for n_cls in (20, 338):
+        cats = None if n_cls == 20 else list(("ACDEFGHIKLMNPQRSTVWY" * 17)[:338])
+        chains = [rng.dirichlet(np.ones(n_cls), size=n).astype(np.float16).astype(np.float64) for n in (57, 1, 130, 3, 76)]
+        got, metrics = su.sample_chains(chains, 11, cats, seed=5, stream_id0=40, return_metrics=True)
+        for i, p in enumerate(chains):
+            ref, _ = su.sample_block(p, 11, cats, seed=5, stream_id=40 + i)
+            np.testing.assert_array_equal(got[i], ref)
+            assert metrics[i].shape == (11, 4)
+        cold = su.sample_chains(chains, 4, cats, seed=5, temperature=0.01)
+        for i, p in enumerate(chains):
+            ref, _ = su.sample_block(p, 4, cats, seed=5, stream_id=i, temperature=0.01)
+            np.testing.assert_array_equal(cold[i], ref)

@@ -2196,6 +2196,21 @@ int timed_b200_sample(const double* d_cdf, int64_t n_res, int32_t n_cls, int64_t
     return TB_OK;
 }
 
+int timed_b200_sample_chains(const double* d_cdf, const int64_t* d_row_off, const int64_t* d_seq_off, int32_t n_chains,
+                             int64_t total_seq_bytes, int32_t n_cls, int64_t n_samples, int64_t first_sample, uint64_t seed,
+                             uint64_t stream_id0, const uint8_t* d_cls_to_letter, uint8_t* d_seqs, void* cuda_stream) {
+    TB_REQUIRE(d_cdf && d_row_off && d_seq_off && d_cls_to_letter && d_seqs, "null argument");
+    TB_REQUIRE(n_chains > 0 && n_samples > 0 && total_seq_bytes > 0, "nothing to sample");
+    TB_REQUIRE(n_cls > 0 && n_cls <= 512, "n_cls must be in [1,512]");
+    TB_REQUIRE((reinterpret_cast<uintptr_t>(d_seqs) & 3) == 0 && (total_seq_bytes & 3) == 0,
+               "d_seqs and the chain offsets must be 4-byte aligned");
+    sample_chains_kernel<<<grid_for(total_seq_bytes / 4, 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        d_cdf, d_row_off, d_seq_off, n_chains, n_cls, n_samples, first_sample, seed, stream_id0, d_cls_to_letter,
+        d_seqs);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
 int timed_b200_sample_uniforms(int64_t n_res, int64_t n_samples, int64_t first_sample, uint64_t seed,
                                uint64_t stream_id, double* d_out, void* cuda_stream) {
     TB_REQUIRE(d_out, "null argument");

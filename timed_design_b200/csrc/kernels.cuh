@@ -811,6 +811,60 @@ __global__ void cumsum_rows_kernel(const double* __restrict__ in, int64_t n_rows
 // The CDF is nondecreasing (cumsum of non-negative terms), so "first j with cdf[j] > r" ==
 // "number of j with cdf[j] <= r" -- a branch-free count for short rows, a binary search for
 // long ones.  NaN-safe in the same way as the reference: comparisons with NaN are false.
+// index drawn for one cell: first j with cdf_row[j] > r, none -> 0.  A CDF built by a sequential cumsum of non-negative
+// probabilities is nondecreasing, so "first j with cdf[j] > r" is a lower-bound search (5 loads for 20 classes, 9 for
+// 338); a row holding a NaN (then its last entry is NaN, cumsum propagates it) is not ordered and takes the literal
+// first-true scan, which is what numpy's (cumsum > r).argmax() evaluates.
+__device__ __forceinline__ int sample_index(const double* __restrict__ row, int n_cls, double r) {
+    const double last = __ldg(row + n_cls - 1);
+    int j;
+    if (last != last) {
+        j = n_cls;
+        for (int k = 0; k < n_cls; ++k)
+            if (__ldg(row + k) > r) { j = k; break; }
+    } else {
+        int lo = 0, hi = n_cls;          // first index with cdf > r in [lo, hi]
+        if (!(last > r)) lo = n_cls;     // nothing exceeds r
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(row + mid) > r) hi = mid; else lo = mid + 1;
+        }
+        j = lo;
+    }
+    return j >= n_cls ? 0 : j;           // no entry exceeds r -> argmax of all-False is 0
+}
+
+// four consecutive cells (word `wi`) of one chain's flat (n_samples, n_res) block
+__device__ __forceinline__ void sample_word(const double* __restrict__ cdf, int64_t n_res, int n_cls, int64_t total,
+                                            int64_t first_sample, uint64_t seed, uint64_t stream_id,
+                                            const double* __restrict__ uniforms, const uint8_t* s_letters,
+                                            uint8_t* __restrict__ seqs, int32_t* __restrict__ idx_out, int64_t wi) {
+    uint32_t packed = 0;
+    int32_t id4[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int64_t flat = wi * 4 + e;
+        if (flat >= total) break;
+        const int64_t s = flat / n_res;
+        const int64_t res = flat - s * n_res;
+        const double r = uniforms ? uniforms[flat]
+                                  : philox_uniform(static_cast<uint64_t>(first_sample + s),
+                                                   static_cast<uint64_t>(res), seed, stream_id);
+        const int j = sample_index(cdf + res * n_cls, n_cls, r);
+        id4[e] = j;
+        packed |= static_cast<uint32_t>(s_letters[j]) << (8 * e);
+    }
+    if (wi * 4 + 3 < total) {
+        reinterpret_cast<uint32_t*>(seqs)[wi] = packed;
+        if (idx_out) reinterpret_cast<int4*>(idx_out)[wi] = make_int4(id4[0], id4[1], id4[2], id4[3]);
+    } else {
+        for (int e = 0; e < 4 && wi * 4 + e < total; ++e) {
+            seqs[wi * 4 + e] = static_cast<uint8_t>(packed >> (8 * e));
+            if (idx_out) idx_out[wi * 4 + e] = id4[e];
+        }
+    }
+}
+
 __global__ void sample_kernel(const double* __restrict__ cdf, int64_t n_res, int n_cls,
                               int64_t n_samples, int64_t first_sample, uint64_t seed,
                               uint64_t stream_id, const double* __restrict__ uniforms,
@@ -822,51 +876,35 @@ __global__ void sample_kernel(const double* __restrict__ cdf, int64_t n_res, int
     const int64_t total = n_res * n_samples;
     const int64_t n_words = (total + 3) / 4;
     for (int64_t wi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; wi < n_words;
-         wi += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        uint32_t packed = 0;
-        int32_t id4[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int64_t flat = wi * 4 + e;
-            if (flat >= total) break;
-            const int64_t s = flat / n_res;
-            const int64_t res = flat - s * n_res;
-            const double r = uniforms ? uniforms[flat]
-                                      : philox_uniform(static_cast<uint64_t>(first_sample + s),
-                                                       static_cast<uint64_t>(res), seed, stream_id);
-            const double* row = cdf + res * n_cls;
-            int j;
-            if (n_cls <= 32) {
-                int cnt = 0;
-                for (int k = 0; k < n_cls; ++k) cnt += (__ldg(row + k) > r) ? 0 : 1;
-                // rows containing NaN are not monotone: fall back to the literal first-true scan
-                j = cnt;
-                if (cnt < n_cls && !(__ldg(row + cnt) > r)) {
-                    j = n_cls;
-                    for (int k = 0; k < n_cls; ++k)
-                        if (__ldg(row + k) > r) { j = k; break; }
-                }
-            } else {
-                int lo = 0, hi = n_cls;          // first index with cdf > r in [lo, hi]
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(row + mid) > r) hi = mid; else lo = mid + 1;
-                }
-                j = lo;
-            }
-            if (j >= n_cls) j = 0;               // no entry exceeds r -> argmax of all-False is 0
-            id4[e] = j;
-            packed |= static_cast<uint32_t>(s_letters[j]) << (8 * e);
+         wi += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        sample_word(cdf, n_res, n_cls, total, first_sample, seed, stream_id, uniforms, s_letters, seqs, idx_out, wi);
+}
+
+// All chains of a structure set in ONE launch.  Chain c owns rows [row_off[c], row_off[c+1]) of the concatenated CDF
+// and the byte range [seq_off[c], seq_off[c] + n_samples*n_res_c) of `seqs` (seq_off multiples of 4, ascending, last
+// entry = total bytes); its draws are keyed (seed, stream_id0 + c) exactly as a per-chain timed_b200_sample call with
+// that stream id, so the letters are byte-identical to per-chain launches.
+__global__ void sample_chains_kernel(const double* __restrict__ cdf, const int64_t* __restrict__ row_off,
+                                     const int64_t* __restrict__ seq_off, int n_chains, int n_cls, int64_t n_samples,
+                                     int64_t first_sample, uint64_t seed, uint64_t stream_id0,
+                                     const uint8_t* __restrict__ letters, uint8_t* __restrict__ seqs) {
+    __shared__ uint8_t s_letters[512];
+    for (int i = threadIdx.x; i < n_cls && i < 512; i += blockDim.x) s_letters[i] = letters[i];
+    __syncthreads();
+    const int64_t n_words = seq_off[n_chains] / 4;
+    for (int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; w < n_words;
+         w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        int lo = 0, hi = n_chains - 1;               // last chain whose block starts at or before this word
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seq_off[mid] <= 4 * w) lo = mid; else hi = mid - 1;
         }
-        if (wi * 4 + 3 < total) {
-            reinterpret_cast<uint32_t*>(seqs)[wi] = packed;
-            if (idx_out) reinterpret_cast<int4*>(idx_out)[wi] = make_int4(id4[0], id4[1], id4[2], id4[3]);
-        } else {
-            for (int e = 0; e < 4 && wi * 4 + e < total; ++e) {
-                seqs[wi * 4 + e] = static_cast<uint8_t>(packed >> (8 * e));
-                if (idx_out) idx_out[wi * 4 + e] = id4[e];
-            }
-        }
+        const int64_t n_res = row_off[lo + 1] - row_off[lo];
+        const int64_t total = n_res * n_samples;
+        const int64_t wl = w - seq_off[lo] / 4;
+        if (wl * 4 >= total) continue;               // alignment padding after the chain's block
+        sample_word(cdf + row_off[lo] * n_cls, n_res, n_cls, total, first_sample, seed, stream_id0 + lo, nullptr,
+                    s_letters, seqs + seq_off[lo], nullptr, wl);
     }
 }
 

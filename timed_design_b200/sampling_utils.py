@@ -128,6 +128,57 @@ def sample_block(probs: np.ndarray, sample_n: int, rotamer_categories=None, *,
     return (seqs, idx, metrics) if return_metrics else (seqs, idx)
 
 
+def sample_chains(prob_list: t.Sequence[np.ndarray], sample_n: int, rotamer_categories=None, *,
+                  seed: t.Optional[int] = None, stream_id0: int = 0, first_sample: int = 0,
+                  temperature: t.Optional[float] = None, return_metrics: bool = False):
+    """Draw ``sample_n`` sequences for EVERY chain in ``prob_list`` with one cumsum launch and one sampling launch
+    (``timed_b200_sample_chains``).  Chain ``i`` is keyed ``(seed, stream_id0 + i)``: the letters are byte-identical to
+    ``sample_block(prob_list[i], ..., stream_id=stream_id0 + i)``.
+    Returns a list of (sample_n, n_res_i) uint8 arrays (and, with ``return_metrics``, a list of (sample_n, 4) arrays)."""
+    torch = _torch()
+    lib = _lib.load()
+    mats = [np.ascontiguousarray(np.array(p, dtype=np.float64)) for p in prob_list]
+    if not mats:
+        return ([], []) if return_metrics else []
+    n_cls = mats[0].shape[1]
+    if any(m.ndim != 2 or m.shape[1] != n_cls for m in mats):
+        raise ValueError("every chain needs a 2-D (n_residues, n_categories) matrix with the same category count")
+    letters = _letters_u8(rotamer_categories)
+    if len(letters) != n_cls:
+        raise ValueError(f"{n_cls} probability columns but {len(letters)} categories")
+    lengths = np.array([m.shape[0] for m in mats], dtype=np.int64)
+    row_off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    blocks = (lengths * int(sample_n) + 3) // 4 * 4                      # per-chain byte blocks, 4-byte aligned
+    seq_off = np.concatenate([[0], np.cumsum(blocks)]).astype(np.int64)
+    total_rows, total_bytes = int(row_off[-1]), int(seq_off[-1])
+    if total_rows == 0 or sample_n == 0:
+        seqs = [np.zeros((sample_n, int(n)), np.uint8) for n in lengths]
+        return (seqs, [np.zeros((sample_n, 4)) for _ in lengths]) if return_metrics else seqs
+    st = _stream(torch)
+    d_p = torch.from_numpy(np.concatenate(mats, axis=0)).cuda()
+    if temperature is not None and temperature != 1:
+        _lib.check(lib.timed_b200_apply_temperature(_ptr(d_p), total_rows, n_cls, float(temperature), _ptr(d_p), st))
+    d_cdf = torch.empty_like(d_p)
+    _lib.check(lib.timed_b200_cumsum_rows(_ptr(d_p), total_rows, n_cls, _ptr(d_cdf), st))
+    d_row = torch.from_numpy(row_off).cuda()
+    d_off = torch.from_numpy(seq_off).cuda()
+    d_letters = torch.from_numpy(letters).cuda()
+    d_seq = torch.empty(total_bytes, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.timed_b200_sample_chains(_ptr(d_cdf), _ptr(d_row), _ptr(d_off), len(mats), total_bytes, n_cls,
+                                            int(sample_n), int(first_sample),
+                                            int(_state["seed"] if seed is None else seed) & (2 ** 64 - 1),
+                                            int(stream_id0) & (2 ** 64 - 1), _ptr(d_letters), _ptr(d_seq), st))
+    metrics = None
+    if return_metrics:
+        from . import device_post
+        metrics = [device_post.seq_metrics_device(d_seq[int(seq_off[i]):], int(sample_n), int(n)) if n else
+                   np.zeros((sample_n, 4)) for i, n in enumerate(lengths)]
+    host = d_seq.cpu().numpy()
+    seqs = [host[int(seq_off[i]):int(seq_off[i]) + int(sample_n) * int(n)].reshape(int(sample_n), int(n))
+            for i, n in enumerate(lengths)]
+    return (seqs, metrics) if return_metrics else seqs
+
+
 _draw_counter = {"n": 0}
 
 
@@ -171,13 +222,13 @@ def sample_from_sequences(pdb: str, sample_n: int, pdb_to_probability: dict,
 
 
 def sample_with_multiprocessing(workers, pdb_codes, sample_n, pdb_to_probability, flat_categories) -> dict:
-    """sampling_utils.py:164-197.  ``workers`` is accepted for compatibility and ignored: the
-    fan-out over chains is a loop of kernel launches, each chain keyed by its index so the
-    draws do not depend on how chains are distributed."""
-    out: dict = {}
-    for i, pdb in enumerate(pdb_codes):
-        out.update(sample_from_sequences(pdb, sample_n, pdb_to_probability, flat_categories, stream_id=i))
-    return out
+    """sampling_utils.py:164-197.  ``workers`` is accepted for compatibility and ignored: the fan-out over chains is ONE
+    sampling launch over the concatenated chains (``sample_chains``), each chain keyed by its index so the draws do not
+    depend on how chains are distributed (and equal ``sample_from_sequences(..., stream_id=index)``)."""
+    pdb_codes = list(pdb_codes)
+    seqs, metrics = sample_chains([pdb_to_probability[p] for p in pdb_codes], int(sample_n), flat_categories,
+                                  return_metrics=True)
+    return {pdb: _rows_to_tuples(s, m) for pdb, s, m in zip(pdb_codes, seqs, metrics)}
 
 
 def save_as(pdb_to_sampled: dict, filename: str, mode: str) -> t.List[str]:

@@ -55,20 +55,48 @@ def main():
                 _lib.check(lib.timed_b200_cumsum_rows(P(src), n, c, P(d_cdf[ci]), st))
                 _lib.check(lib.timed_b200_sample(P(d_cdf[ci]), n, c, args.samples, 0, 42, ci * 1000 + ti, None,
                                                  P(letters), P(d_seq[ci]), None, st))
-    sweep()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    sweep()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    # batched: the chains concatenated, three launches per temperature (temperature, cumsum, sample_chains)
+    lens = np.array([p.shape[0] for p in chains], dtype=np.int64)
+    row_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    blocks = (lens * args.samples + 3) // 4 * 4
+    seq_off = np.concatenate([[0], np.cumsum(blocks)]).astype(np.int64)
+    d_all = torch.from_numpy(np.concatenate(chains, axis=0)).cuda()
+    d_all_tmp, d_all_cdf = torch.empty_like(d_all), torch.empty_like(d_all)
+    d_row, d_off = torch.from_numpy(row_off).cuda(), torch.from_numpy(seq_off).cuda()
+    d_all_seq = torch.empty(int(seq_off[-1]), dtype=torch.uint8, device="cuda")
+
+    def sweep_batched():
+        n, c = d_all.shape
+        for ti, t in enumerate(temps):
+            src = d_all
+            if t != 1:
+                _lib.check(lib.timed_b200_apply_temperature(P(d_all), n, c, float(t), P(d_all_tmp), st))
+                src = d_all_tmp
+            _lib.check(lib.timed_b200_cumsum_rows(P(src), n, c, P(d_all_cdf), st))
+            _lib.check(lib.timed_b200_sample_chains(P(d_all_cdf), P(d_row), P(d_off), len(chains), int(seq_off[-1]), c,
+                                                    args.samples, 0, 42, ti * 1000, P(letters), P(d_all_seq), st))
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    ms_per_chain = timed(sweep)
+    ms = timed(sweep_batched)
     residues = int(lengths.sum()) * args.samples * len(temps)
     seqs = 59 * args.samples * len(temps)
     out = {"classes": args.classes, "chains": 59, "residues_per_chain_total": int(lengths.sum()),
            "samples_per_chain": args.samples, "temperatures": len(temps),
            "device": {"ms": ms, "residues_per_s": residues / ms * 1e3, "sequences_per_s": seqs / ms * 1e3,
-                      "bytes_written_GBps": residues / ms * 1e3 / 1e9}}
+                      "bytes_written_GBps": residues / ms * 1e3 / 1e9, "launches": 3 * len(temps),
+                      "path": "timed_b200_sample_chains: all chains per launch"},
+           "device_per_chain_launches": {"ms": ms_per_chain, "residues_per_s": residues / ms_per_chain * 1e3,
+                                         "launches": 3 * 59 * len(temps)}}
     # host API: one temperature, all chains, letters copied back
     t0 = time.perf_counter()
     for ci, p in enumerate(chains):
