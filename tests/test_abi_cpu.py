@@ -99,3 +99,19 @@ def test_device_post_host_helpers():
     c, pi, mw, ext = seq_metrics.metrics_from_composition(counts)
     assert abs((counts[0] * t[40:60]).sum() + t[60] - c[0]) < 1e-10
     assert abs((counts[0] * t[:20]).sum() + t[61] - mw[0]) < 1e-9
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the CPU port timed on the host cores) needs no GPU and prints one JSON line with the
+    keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
