@@ -27,6 +27,28 @@ UNCOMMON_RESIDUE_DICT = {
 }
 
 _open_files: t.Dict[str, File] = {}
+_MIN_FRAMES_PER_THREAD = 4
+_pool_state: dict = {}
+
+
+def _loader_threads() -> int:
+    """Threads used by ``load_batch`` (env TIMED_B200_LOADER_THREADS; default: the host cores, at most 32)."""
+    import os
+    try:
+        return max(1, int(os.environ.get("TIMED_B200_LOADER_THREADS", min(32, os.cpu_count() or 1))))
+    except ValueError:
+        return 1
+
+
+def _pool():
+    from concurrent.futures import ThreadPoolExecutor
+    n = _loader_threads()
+    if _pool_state.get("n") != n:
+        if "pool" in _pool_state:
+            _pool_state["pool"].shutdown(wait=False)
+        _pool_state["pool"] = ThreadPoolExecutor(max_workers=n, thread_name_prefix="frame-loader")
+        _pool_state["n"] = n
+    return _pool_state["pool"]
 
 
 def _open(path) -> File:
@@ -90,9 +112,16 @@ def load_batch(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple]) -> t.T
     n = len(data_point_batch)
     X = np.zeros((n, *dims), dtype=np.float32 if gaussian else np.bool_)
     y = np.zeros((n, 20), dtype=float)
-    for i, row in enumerate(data_point_batch):
-        pdb_code, chain_id, residue_id = (str(v) for v in row[:3])
+
+    def one(i):
+        pdb_code, chain_id, residue_id = (str(v) for v in data_point_batch[i][:3])
         ds = f[pdb_code][chain_id][residue_id]
-        X[i] = ds[()]
+        X[i] = ds[()]                         # gzip inflate releases the GIL: frames decode in parallel
         y[i] = ds.attrs["encoded_residue"]
+
+    if n >= 2 * _MIN_FRAMES_PER_THREAD and _loader_threads() > 1:
+        list(_pool().map(one, range(n)))
+    else:
+        for i in range(n):
+            one(i)
     return X, y

@@ -16,6 +16,7 @@ writer ("real-file parity unpinned").
 """
 from __future__ import annotations
 
+import mmap
 import struct
 import zlib
 from typing import Dict, List, Optional, Tuple
@@ -107,11 +108,15 @@ class _Message:
 
 
 class File:
-    """Read-only view of an HDF5 file held in memory.  ``f["a/b"]`` -> Group or Dataset."""
+    """Read-only view of a memory-mapped HDF5 file.  ``f["a/b"]`` -> Group or Dataset.  The map is only ever sliced
+    (bytes copies), so objects of one File may be read from several threads (frames.load_batch does)."""
 
     def __init__(self, path):
-        with open(path, "rb") as fh:
-            self.buf = fh.read()
+        self._fh = open(path, "rb")
+        try:
+            self.buf = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
+        except ValueError:                       # empty file: let the superblock check report it
+            self.buf = b""
         self.path = str(path)
         self._gcol_cache: Dict[int, Dict[int, bytes]] = {}
         self._parse_superblock()
@@ -236,7 +241,9 @@ class File:
         return struct.unpack_from("<Q", self.buf, addr + 24)[0] + self.base_addr
 
     def _cstr(self, off: int) -> str:
-        end = self.buf.index(b"\x00", off)
+        end = self.buf.find(b"\x00", off)
+        if end < 0:
+            raise Hdf5FormatError("unterminated string in local heap")
         return self.buf[off:end].decode("utf-8")
 
     def _group_btree_links(self, btree: int, heap_data: int, out: Dict[str, int]):
