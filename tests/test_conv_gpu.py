@@ -26,6 +26,9 @@ CASES = [
     ("k3_c32_n64_11", 2, 11, 32, 64, 3, "same"),
     ("k3_c256_n512", 4, 6, 256, 512, 3, "same"),
     ("k3_c512_n20_tap2n", 4, 6, 512, 20, 3, "same"),
+    ("k3_c128_n16_tap2n_valid", 3, 7, 128, 16, 3, "valid"),
+    ("k5_c64_n8_tap2n", 2, 6, 64, 8, 5, "same"),
+    ("k3_c256_n20_tap2n_many", 300, 6, 256, 20, 3, "same"),
     ("k3_c512_n338", 2, 6, 512, 338, 3, "same"),
     ("k3_valid_c16", 2, 8, 16, 48, 3, "valid"),
     ("k5_c6_n16", 1, 9, 6, 16, 5, "same"),
@@ -205,3 +208,21 @@ def test_zfold_thin_conv(case, monkeypatch):
     assert np.isfinite(y).all()
     assert np.abs(y - ref).max() <= 1e-4 * scale
     assert np.abs(y - y_thin).max() <= 1e-4 * scale
+
+
+def test_tap_to_n_variants_agree(monkeypatch):
+    """Head conv as 1x1 GEMM + col2im: the variant that keeps the kw taps in K (Z matrix kw times smaller) against the
+    all-taps-in-N variant and the oracle."""
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((5, 6, 6, 6, 512)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 3, 512, 20)) * np.sqrt(2.0 / (27 * 512))).astype(np.float32)
+    b = (rng.standard_normal(20) * 0.1).astype(np.float32)
+    y_kw = run_conv_gpu(x, w, bias=b, act1="elu")
+    monkeypatch.setenv("TIMED_B200_TAP2N_FULL", "1")
+    y_full = run_conv_gpu(x, w, bias=b, act1="elu")
+    monkeypatch.setenv("TIMED_B200_NO_TAP2N", "1")
+    y_direct = run_conv_gpu(x, w, bias=b, act1="elu")
+    ref = ko.np_activation(ko.np_conv3d(x[:2].astype(np.float64), w.astype(np.float64), b.astype(np.float64), "same"), "elu")
+    for y in (y_kw, y_full, y_direct):
+        assert np.abs(y[:2] - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.abs(y_kw - y_full).max() <= 5e-5 * np.abs(ref).max()

@@ -153,11 +153,15 @@ struct ConvPlan {
     float* d_c2i_bias = nullptr;     // [cout] epilogue vectors applied by the col2im kernel
     float* d_c2i_scale = nullptr;
     float* d_c2i_shift = nullptr;
-    int taps_eff() const { return tap2n ? 1 : (wfold ? kd * kh : kd * kh * kw); }
+    // tap-to-N with the kw taps kept in K ("t2n_kw"): Z[pixel, (kd,kh), co] = sum_{kw,c} X[pixel + kw - pad_w, c] * W, an
+    // im2col along W only.  Same MMA count and activation traffic as folding all taps into N (three N tiles there, three
+    // K taps here) but a Z matrix kw times smaller to write and to gather from.
+    bool t2n_kw = false;
+    int taps_eff() const { return tap2n ? (t2n_kw ? kw : 1) : (wfold ? kd * kh : kd * kh * kw); }
     // geometry of the GEMM rows (output pixels, or input pixels for tap-to-N)
     int Mo_d() const { return tap2n ? Di : Do; }
     int Mo_h() const { return tap2n ? Hi : Ho; }
-    int Mo_w() const { return tap2n ? Wi : Wo; }
+    int Mo_w() const { return tap2n ? (t2n_kw ? Wo : Wi) : Wo; }
     int gemm_n() const { return tap2n ? z_cols : cout; }
     __nv_bfloat16* d_w = nullptr;   // [2][n_alloc][k_total]
     float* d_bias = nullptr;        // [n_alloc]
@@ -343,7 +347,7 @@ static int encode_a_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* ba
     int lower[3] = {-p.pad0[2], -p.pad0[1], -p.pad0[0]};
     int upper[3] = {p.pad1[2] - (p.kw - 1), p.pad1[1] - (p.kh - 1), p.pad1[0] - (p.kd - 1)};
     if (p.tap2n) {
-        for (int i = 0; i < 3; ++i) lower[i] = upper[i] = 0;
+        for (int i = p.t2n_kw ? 1 : 0; i < 3; ++i) lower[i] = upper[i] = 0;   // t2n_kw keeps the W window
     }
     if (p.wfold) {
         // "pixel" = kwin consecutive stored pixels starting pad_w0 to the left of the output
@@ -942,7 +946,8 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
         p.tap2n = !p.wfold && taps_all > 1 && p.cout <= 64 && taps_all * p.cout <= 1024 && cin_pad >= 64 &&
                   t2n_cost < 0.7 * direct_cost && !getenv("TIMED_B200_NO_TAP2N");
         if (p.tap2n) {
-            p.z_cols = taps_all * p.cout;
+            p.t2n_kw = p.kw > 1 && !getenv("TIMED_B200_TAP2N_FULL");
+            p.z_cols = (p.t2n_kw ? p.kd * p.kh : taps_all) * p.cout;
             p.z_ld = round_up(p.z_cols, 4);
         }
     }
@@ -965,11 +970,11 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
                 const __nv_bfloat16 hi = __float2bfloat16_rn(v);
                 const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
                 // K index: dense = tap*cin_pad + c; W-folded = (kd,kh)-tap * (kwin*8) + kw*8 + c
-                const size_t kidx = p.tap2n ? static_cast<size_t>(c)
+                const size_t kidx = p.tap2n ? (p.t2n_kw ? static_cast<size_t>(t % p.kw) * cin_pad + c : static_cast<size_t>(c))
                                   : p.wfold ? static_cast<size_t>(t / p.kw) * cin_pad + static_cast<size_t>(t % p.kw) * 8 + c
                                             : static_cast<size_t>(t) * cin_pad + c;
                 // GEMM column: the output channel, or (tap, channel) for tap-to-N
-                const size_t ncol = p.tap2n ? static_cast<size_t>(t) * p.cout + n : static_cast<size_t>(n);
+                const size_t ncol = p.tap2n ? static_cast<size_t>(p.t2n_kw ? t / p.kw : t) * p.cout + n : static_cast<size_t>(n);
                 const size_t o = ncol * p.k_total + kidx;
                 w[o] = hi;
                 w[plane + o] = lo;
@@ -1068,7 +1073,7 @@ static int launch_pair_instance(const CUtensorMap& map_a, const CUtensorMap& map
 // bytes of fp32 scratch (the Z matrix) a tap-to-N conv needs for n_frames
 static size_t conv_scratch_bytes(const ConvPlan& p, int64_t n_frames) {
     if (!p.tap2n) return 0;
-    return static_cast<size_t>(round_up64(n_frames * p.Di * p.Hi * p.Wi * static_cast<int64_t>(p.z_ld) * 4, 1024));
+    return static_cast<size_t>(round_up64(n_frames * p.Mo_d() * p.Mo_h() * p.Mo_w() * static_cast<int64_t>(p.z_ld) * 4, 1024));
 }
 
 static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames,
@@ -1110,7 +1115,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.acc_cols = cfg.acc_cols;
     k.acc_stages = cfg.acc_stages;
     k.nfold = cfg.nfold;
-    k.kh = p.tap2n ? 1 : p.kh; k.kw = (p.wfold || p.tap2n) ? 1 : p.kw;
+    k.kh = p.tap2n ? 1 : p.kh; k.kw = (p.wfold || (p.tap2n && !p.t2n_kw)) ? 1 : p.kw;
     k.n_taps = p.taps_eff();
     k.cin_pad = p.cin_pad;
     k.kc = cfg.kc;
@@ -1121,7 +1126,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.Do = p.Mo_d(); k.Ho = p.Mo_h(); k.Wo = p.Mo_w();
     k.lc_d = p.tap2n ? 0 : -p.pad0[0];
     k.lc_h = p.tap2n ? 0 : -p.pad0[1];
-    k.lc_w = (p.wfold || p.tap2n) ? 0 : -p.pad0[2];
+    k.lc_w = (p.wfold || (p.tap2n && !p.t2n_kw)) ? 0 : -p.pad0[2];
     k.lo_plane_frames = static_cast<int32_t>(in_frames_alloc);
     k.w_lo_rows = p.n_alloc;
     k.a_sub_bytes = 128u * cfg.kc * 2u;
@@ -1174,9 +1179,9 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     TB_CHECK_CUDA(cudaGetLastError());
     if (p.tap2n) {
         Col2imParams cp;
-        cp.Di = p.Di; cp.Hi = p.Hi; cp.Wi = p.Wi; cp.Do = p.Do; cp.Ho = p.Ho; cp.Wo = p.Wo;
-        cp.kd = p.kd; cp.kh = p.kh; cp.kw = p.kw;
-        cp.pd = p.pad0[0]; cp.ph = p.pad0[1]; cp.pw = p.pad0[2];
+        cp.Di = p.Di; cp.Hi = p.Hi; cp.Wi = p.Mo_w(); cp.Do = p.Do; cp.Ho = p.Ho; cp.Wo = p.Wo;
+        cp.kd = p.kd; cp.kh = p.kh; cp.kw = p.t2n_kw ? 1 : p.kw;             // t2n_kw: the GEMM already summed over kw
+        cp.pd = p.pad0[0]; cp.ph = p.pad0[1]; cp.pw = p.t2n_kw ? 0 : p.pad0[2];
         cp.cout = p.cout;
         cp.z_ld = p.z_ld;
         cp.act1 = p.act1; cp.act2 = p.act2; cp.alpha1 = p.alpha1; cp.alpha2 = p.alpha2;
