@@ -123,11 +123,14 @@ def test_fused_conv_maxpool_epilogue(side, c1, pool_pad, relu, monkeypatch):
     fused = m.predict(X)
     assert any("thinz" in m.op_kernel(i, 7) for i in range(len(m.graph.ops)))
     monkeypatch.delenv("TIMED_B200_POOLFUSE")
-    m2 = Model(cfg, w)
-    unfused = m2.predict(X)
+    m2 = Model(cfg, w)                                      # default: only the z direction is pooled in the epilogue
+    zfused = m2.predict(X)
     assert m2.launches_per_forward == m.launches_per_forward + 1
-    assert np.abs(fused - ref).max() <= PROB_TOL and np.abs(unfused - ref).max() <= PROB_TOL
-    assert np.abs(fused - unfused).max() <= 2e-6
+    monkeypatch.setenv("TIMED_B200_NO_ZPOOL", "1")
+    unfused = Model(cfg, w).predict(X)
+    for got in (fused, zfused, unfused):
+        assert np.abs(got - ref).max() <= PROB_TOL
+    assert np.abs(fused - unfused).max() <= 2e-6 and np.abs(zfused - unfused).max() <= 2e-6
 
 
 @pytest.mark.gpu

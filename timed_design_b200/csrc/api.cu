@@ -142,6 +142,7 @@ struct ConvPlan {
     uint8_t* d_slab_w = nullptr;
     int64_t slab_lead = 0, slab_tail = 0;
     bool thin = false;
+    bool fuse_zpool = false;         // thinz only: the z direction of the MaxPool(2,2,2;2) that follows runs in the epilogue
     bool fuse_pool = false;          // thinz only: the MaxPool(2,2,2;2) that follows runs in the conv epilogue
     int pool_same = 0, pool_Zo = 0, pool_Po = 0, pool_Qo = 0;
     bool thinz = false;              // kd taps folded into N (thinz_conv.cuh)
@@ -772,6 +773,10 @@ static int launch_thinz_instance(const ThinZParams& k, int grid, size_t smem_byt
 static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames, const TView& out,
                         cudaStream_t stream, const TensorInfo* out_info = nullptr) {
     ThinZParams k = p.thinz_params;
+    if (p.fuse_zpool) {
+        k.pool_same = p.pool_same;
+        k.Zo = p.pool_Zo;
+    }
     if (p.fuse_pool) {
         TB_REQUIRE(out_info != nullptr, "internal: fused pool needs the output tensor description");
         ThinZGeom zg;
@@ -818,8 +823,9 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
     bool launched = false;
 #define TB_THINZ_CASE(A1, A2, F)                                                             \
     if (!launched && e.act1 == (A1) && e.act2 == (A2) && out.fmt == (F)) {                   \
-        rc = p.fuse_pool ? launch_thinz_instance<A1, A2, F, 1>(k, grid, smem_bytes, stream)  \
-                         : launch_thinz_instance<A1, A2, F, 0>(k, grid, smem_bytes, stream); \
+        rc = p.fuse_pool    ? launch_thinz_instance<A1, A2, F, 1>(k, grid, smem_bytes, stream)  \
+             : p.fuse_zpool ? launch_thinz_instance<A1, A2, F, 2>(k, grid, smem_bytes, stream)  \
+                            : launch_thinz_instance<A1, A2, F, 0>(k, grid, smem_bytes, stream); \
         launched = true;                                                                     \
     }
     TB_THINZ_CASE(ACT_ELU, ACT_NONE, FMT_F32)
@@ -832,6 +838,9 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
     if (!launched && p.fuse_pool)
         rc = out.fmt == FMT_SPLIT ? launch_thinz_instance<-1, -1, FMT_SPLIT, 1>(k, grid, smem_bytes, stream)
                                   : launch_thinz_instance<-1, -1, FMT_F32, 1>(k, grid, smem_bytes, stream);
+    else if (!launched && p.fuse_zpool)
+        rc = out.fmt == FMT_SPLIT ? launch_thinz_instance<-1, -1, FMT_SPLIT, 2>(k, grid, smem_bytes, stream)
+                                  : launch_thinz_instance<-1, -1, FMT_F32, 2>(k, grid, smem_bytes, stream);
     else if (!launched)
         rc = out.fmt == FMT_SPLIT ? launch_thinz_instance<-1, -1, FMT_SPLIT, 0>(k, grid, smem_bytes, stream)
                                   : launch_thinz_instance<-1, -1, FMT_F32, 0>(k, grid, smem_bytes, stream);
@@ -1507,6 +1516,24 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                         if (t.cpv) g->launches += 1;          // margin zeroing
                     }
                 }
+                // Default: only the z direction of that max-pool runs in the epilogue (max over accumulator pairs: no
+                // staging, no barrier); the pooling op that follows becomes 1x2x2 over half the data.
+                if (node.conv.thinz && !node.conv.fuse_pool && !getenv("TIMED_B200_NO_ZPOOL")) {
+                    int j = -1, n_readers = 0;
+                    for (int k = i + 1; k < n_ops; ++k)
+                        for (int q = 0; q < ops[k].n_inputs; ++q)
+                            if (ops[k].inputs[q] == i) { ++n_readers; j = k; }
+                    bool ok = n_readers == 1 && ops[j].op == TB_OP_POOL3D && ops[j].pool_kind == 0 && ops[j].n_inputs == 1 &&
+                              ops[j].kernel[0] == 2 && (ops[j].stride[0] == 2 || ops[j].stride[0] <= 0) &&
+                              node.conv.thinz_params.zt % 2 == 0;
+                    const int zo = ok ? (ops[j].pad_same ? (t.D + 1) / 2 : t.D / 2) : 0;
+                    if (ok && zo >= 1) {
+                        node.conv.fuse_zpool = true;
+                        node.conv.pool_same = ops[j].pad_same ? 1 : 0;
+                        node.conv.pool_Zo = zo;
+                        t.D = zo;
+                    }
+                }
                 break;
             }
             case TB_OP_POOL3D: {
@@ -1520,10 +1547,12 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 PoolParams& pp = node.pool;
                 pp.D = in0->D; pp.H = in0->H; pp.W = in0->W;
                 const int in[3] = {in0->D, in0->H, in0->W};
+                const bool z_done = g->ops[d.inputs[0]].d.op == TB_OP_CONV3D && g->ops[d.inputs[0]].conv.fuse_zpool;
                 int out[3];
                 for (int a = 0; a < 3; ++a) {
                     pp.k[a] = d.kernel[a];
                     pp.s[a] = d.stride[a] > 0 ? d.stride[a] : d.kernel[a];
+                    if (a == 0 && z_done) pp.k[a] = pp.s[a] = 1;     // the producing conv's epilogue pooled z already
                     TB_REQUIRE(pp.k[a] >= 1, "pool size must be positive");
                     if (d.pad_same) {
                         int after;

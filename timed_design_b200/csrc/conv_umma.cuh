@@ -141,13 +141,12 @@ __device__ __forceinline__ void st_global_256(void* dst, const uint32_t (&r)[8])
                  : "memory");
 }
 
-// One 16-column chunk of one accumulator row: bias -> act1 -> folded BatchNorm -> act2 -> store
-// (bf16 hi/lo split planes or fp32).  `r` holds the raw fp32 accumulator bits of columns [n0, n0+16).
-template <int ACT1, int ACT2, int FMT>
-__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&r)[16], int n0,
-                                               int64_t m, bool row_ok, const float* bias_v,
-                                               const float* scale_v, const float* shift_v) {
-    float v[16];
+// One 16-column chunk of one accumulator row, in two steps: bias -> act1 -> folded BatchNorm -> act2 (`r` holds the raw
+// fp32 accumulator bits of columns [n0, n0+16)), then the store (bf16 hi/lo split planes or fp32).
+template <int ACT1, int ACT2>
+__device__ __forceinline__ void epilogue_math16(const ConvKernelParams& p, const uint32_t (&r)[16], int n0,
+                                                const float* bias_v, const float* scale_v, const float* shift_v,
+                                                float (&v)[16]) {
 #pragma unroll
     for (int i4 = 0; i4 < 4; ++i4) {
         const float4 b = *(reinterpret_cast<const float4*>(bias_v + n0) + i4);
@@ -164,6 +163,11 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
             v[i4 * 4 + i] = act_ct<ACT2>(x, p.act2, p.alpha2);
         }
     }
+}
+
+template <int FMT>
+__device__ __forceinline__ void epilogue_store16(const ConvKernelParams& p, const float (&v)[16], int n0, int64_t m,
+                                                 bool row_ok) {
     if (row_ok && FMT == FMT_SPLIT) {
         uint32_t hi[8], lo[8];
 #pragma unroll
@@ -197,6 +201,15 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
                 if (n0 + i < p.c_store) dst[i] = v[i];
         }
     }
+}
+
+template <int ACT1, int ACT2, int FMT>
+__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&r)[16], int n0,
+                                               int64_t m, bool row_ok, const float* bias_v,
+                                               const float* scale_v, const float* shift_v) {
+    float v[16];
+    epilogue_math16<ACT1, ACT2>(p, r, n0, bias_v, scale_v, shift_v, v);
+    epilogue_store16<FMT>(p, v, n0, m, row_ok);
 }
 
 template <int ACT1, int ACT2, int FMT>

@@ -73,7 +73,8 @@ struct ThinZParams {
 
 #if defined(__CUDACC__)
 
-// FMT: format of the conv output (POOL = 0) or of the plain pooled output (POOL = 1, ignored for CPV)
+// FMT: format of the conv output (POOL = 0, 2) or of the plain pooled output (POOL = 1, ignored for CPV).
+// POOL: 0 none, 1 whole MaxPool(2,2,2;2) in the epilogue, 2 its z direction only.
 template <int ACT1, int ACT2, int FMT, int POOL>
 __global__ void __launch_bounds__(kThinzThreads, 1)
 thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
@@ -272,6 +273,40 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                         if (n0 < p.epi.c_store)
                             epilogue_chunk<ACT1, ACT2, FMT>(p.epi, rv, n0, m, row_ok, s_epi[0], s_epi[1], s_epi[2]);
                     }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            } else if constexpr (POOL == 2) {
+                // max over the z pairs only: halves what this kernel writes and what the (then 1x2x2) pooling pass reads;
+                // no staging, no barrier, no overlapping windows
+                const int n_zp = (zt_eff + 1) >> 1;
+                for (int item = sub; item < n_zp * chunks && !(p.dbg & 4); item += kThinzSubs) {
+                    const int zp = item / chunks;
+                    const int c = item - zp * chunks;
+                    const int Z = (z0 >> 1) + zp;
+                    const bool two = 2 * zp + 1 < zt_eff;
+                    const bool ok = row_ok && Z < p.Zo && (two || p.pool_same);
+                    float v[16];
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
+                        if (pl == 1 && !two) break;
+                        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                               static_cast<uint32_t>(acc * p.acc_cols + (2 * zp + pl) * 2 * p.n_tile);
+                        uint32_t rv[16], rc[16];
+                        __syncwarp();
+                        tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), rv);
+                        tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.n_tile + c * 16), rc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) rv[i] = __float_as_uint(__uint_as_float(rv[i]) + __uint_as_float(rc[i]));
+                        float x[16];
+                        epilogue_math16<ACT1, ACT2>(p.epi, rv, c * 16, s_epi[0], s_epi[1], s_epi[2], x);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = pl == 0 ? x[i] : fmaxf(v[i], x[i]);
+                    }
+                    const int64_t m = ((static_cast<int64_t>(nf) * p.Zo + Z) * p.Ho + prow) * p.Wo + q;
+                    if (c * 16 < p.epi.c_store) epilogue_store16<FMT>(p.epi, v, c * 16, m, ok);
                 }
                 tc_fence_before();
                 __syncwarp();
