@@ -950,10 +950,14 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
         // DenseCPD's 128->32 growth convs: 68k vs 42k, so they stay on the direct path).
         const double k16 = cin_pad / 16.0;
         const double direct_cost = taps_all * k16 * 3 * 65.0 * ceil_div(round_up(p.cout, 16), 256);
-        const double z_cols = static_cast<double>(taps_all) * p.cout;
-        const double t2n_cost = k16 * 3 * std::ceil(z_cols / 256.0) * 110.0 + 8.0 * z_cols * 128 / 23.0 * 1.5;
+        // (kd,kh) taps in N, kw taps in K (the default variant): kw K-taps, Z of kd*kh*cout columns
+        const bool kw_in_k = p.kw > 1 && !getenv("TIMED_B200_TAP2N_FULL");
+        const double z_cols = static_cast<double>(kw_in_k ? p.kd * p.kh : taps_all) * p.cout;
+        const double t2n_cost = k16 * (kw_in_k ? p.kw : 1) * 3 * std::ceil(z_cols / 256.0) * 110.0 +
+                                8.0 * z_cols * 128 / 23.0 * 1.5;
+        const double margin = getenv("TIMED_B200_TAP2N_MARGIN") ? atof(getenv("TIMED_B200_TAP2N_MARGIN")) : 0.7;
         p.tap2n = !p.wfold && taps_all > 1 && p.cout <= 64 && taps_all * p.cout <= 1024 && cin_pad >= 64 &&
-                  t2n_cost < 0.7 * direct_cost && !getenv("TIMED_B200_NO_TAP2N");
+                  t2n_cost < margin * direct_cost && !getenv("TIMED_B200_NO_TAP2N");
         if (p.tap2n) {
             p.t2n_kw = p.kw > 1 && !getenv("TIMED_B200_TAP2N_FULL");
             p.z_cols = (p.t2n_kw ? p.kd * p.kh : taps_all) * p.cout;
