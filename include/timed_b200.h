@@ -101,10 +101,10 @@ void timed_b200_graph_destroy(tb_graph* g);
  * conv/dense ops) */
 int timed_b200_graph_info(const tb_graph* g, int32_t* n_classes, double* flops_per_frame,
                           int32_t* n_kernel_launches_per_forward);
-/* Numerics option.  0 (default): widest tiles; max |dp| 6e-5 on the TIMED-20 stand-in.  1: the two
- * full-width conv layers run as 2-CTA clusters with a separate TMEM accumulator for the correction
- * MMAs (3x less accumulator truncation; max |dp| 2.8e-5) at ~1.4x their time.  Takes effect on the
- * next forward. */
+/* Numerics option.  0 (default): max |dp| 5.5e-5 on the TIMED-20 stand-in.  1: the wide conv layers (CTA-pair kernel)
+ * keep the two correction products of the bf16 split in their own TMEM accumulator (3x less accumulator truncation;
+ * max |dp| 2.2e-5); TMEM then holds one accumulator stage, so their epilogue no longer overlaps the mainloop:
+ * 0.93x throughput.  Takes effect on the next forward. */
 int timed_b200_graph_set_precise(tb_graph* g, int32_t precise);
 /* Name of the CUDA kernel(s) op `op` launches for a forward of `n_frames` frames (the tile configuration, and
  * with it the kernel, depends on the frame count); NUL-terminated into buf. */

@@ -224,7 +224,7 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
     // traffic as mt = 2 and 3x less accumulator truncation, but every CTA now stages the whole W tile for
     // half the rows, so shared memory covers ~1/3 less latency: measured 1.4x slower on the two big TIMED
     // layers (profiles/r1_summary.md) -- hence opt-in.
-    if (p.precise && p.n_tile == 256 && p.cin_pad % 32 == 0 &&
+    if (p.precise && p.n_tile == 256 && p.cin_pad % 32 == 0 && getenv("TIMED_B200_NO_PAIR") &&
         static_cast<int64_t>(ceil_div(m_tiles, 2)) * p.n_tiles >= 2 * 74) {
         const int kc = 32;
         const size_t kb = 2 * (128u * kc * 2u) + 2 * (static_cast<size_t>(p.n_tile) * kc * 2u);
@@ -245,7 +245,7 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
     // Wide tiles (n_tile > 128) with plenty of rows: CTA pair, tcgen05.mma.cta_group::2 (conv_pair.cuh).
     // Each CTA stages 128 rows of A and half of the W tile, so TMEM holds two accumulator stages (the
     // epilogue overlaps the next mainloop) and an MMA reads 8 KB instead of 12 KB of shared memory.
-    if (!p.precise && p.n_tile > 128 && p.cin_pad % 32 == 0 && !getenv("TIMED_B200_NO_PAIR") &&
+    if (p.n_tile > 128 && p.cin_pad % 32 == 0 && !getenv("TIMED_B200_NO_PAIR") &&
         (static_cast<int64_t>(ceil_div(m_tiles, 2)) * p.n_tiles >= 2 * 74 || getenv("TIMED_B200_FORCE_PAIR"))) {
         int kc = p.cin_pad % 64 == 0 ? 64 : 32;
         if (const char* e = getenv("TIMED_B200_PAIR_KC")) {
@@ -261,6 +261,10 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
         cfg->stages = std::max(2, std::min(cfg->stages, std::max(2, n_kblocks)));
         cfg->acc_cols = round_up(p.n_tile, 32);
         cfg->acc_stages = std::min(2, 512 / cfg->acc_cols);
+        if (p.precise) {             // separate correction accumulator next to the main one: one stage fills TMEM
+            cfg->corr_off = cfg->acc_cols;
+            cfg->acc_stages = 1;
+        }
         cfg->nfold = 0;
         cfg->pair = 1;
         cfg->swizzle_code = kc == 64 ? 2u : 4u;

@@ -235,9 +235,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                                 const uint32_t a_lo = a_hi + a_sub16;
                                 const uint32_t w_hi = a_hi + 2u * a_sub16;
                                 const uint32_t w_lo = w_hi + w_sub16;
+                                // precise graphs (corr_off != 0): the two correction products go to their own accumulator
+                                // (3x less accumulator truncation); TMEM then holds one stage only
+                                const uint32_t dc = d0 + static_cast<uint32_t>(p.corr_off);
                                 umma_bf16_pair(leader, d0, a_hi, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_pair(leader, d0, a_lo, w_hi, desc_hi, idesc, 1u);
-                                umma_bf16_pair(leader, d0, a_hi, w_lo, desc_hi, idesc, 1u);
+                                umma_bf16_pair(leader, dc, a_lo, w_hi, desc_hi, idesc, p.corr_off ? accumulate : 1u);
+                                umma_bf16_pair(leader, dc, a_hi, w_lo, desc_hi, idesc, 1u);
                                 accumulate = 1u;
                             }
                         }
@@ -275,7 +278,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                 uint32_t r[16];
                 __syncwarp();                      // tcgen05.ld is .sync.aligned
                 tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), r);
-                tmem_ld_wait();
+                if (p.corr_off) {                  // warp-uniform: add the correction accumulator
+                    uint32_t rc[16];
+                    tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.corr_off + c * 16), rc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rc[i]));
+                } else {
+                    tmem_ld_wait();
+                }
                 const int n0 = n_idx * p.n_tile + c * 16;
                 if (n0 >= p.c_store) continue;     // warp-uniform
                 epilogue_chunk<ACT1, ACT2, FMT>(p, r, n0, m, row_ok, bias_v, scale_v, shift_v);

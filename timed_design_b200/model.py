@@ -91,8 +91,8 @@ class Model:
             C.c_void_p(stream)))
 
     def set_precise(self, precise: bool) -> None:
-        """Trade ~15 % throughput for ~2x tighter probabilities (separate correction accumulators in the
-        two full-width conv layers, 2-CTA clusters with multicast weights)."""
+        """Trade ~7 % throughput for ~2.5x tighter probabilities (max |dp| 2.2e-5 instead of 5.5e-5 on the TIMED-20
+        stand-in): the wide conv layers accumulate the bf16-split correction products in a separate TMEM accumulator."""
         _lib.check(_lib.load().timed_b200_graph_set_precise(self._h, int(bool(precise))))
         self.precise = bool(precise)
 
