@@ -112,8 +112,8 @@ def test_fused_epilogues(act1, act2, affine):
 
 @pytest.mark.parametrize("ci,co", [(128, 256), (256, 512)])
 def test_cluster_mode_conv(ci, co, monkeypatch):
-    """The opt-in 2-CTA cluster path (W tiles multicast, separate correction accumulator): parity, and a
-    smaller error than the default path on the same data."""
+    """The opt-in precise path (separate TMEM accumulator for the correction MMAs of the bf16 split, CTA-pair kernel):
+    parity, and a smaller error than the default path on the same data."""
     rng = np.random.default_rng(ci)
     x = rng.standard_normal((700, 6, 6, 6, ci)).astype(np.float32)
     w = (rng.standard_normal((3, 3, 3, ci, co)) * np.sqrt(2.0 / (27 * ci))).astype(np.float32)
