@@ -1958,7 +1958,7 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
         case TB_OP_CONV3D: {
             const ConvPlan& c = node.conv;
             if (c.slab) name = "slab_conv_kernel";
-            else if (c.thinz) name = "thinz_conv_kernel";
+            else if (c.thinz) name = c.fuse_pool ? "thinz_conv_kernel(+maxpool)" : c.fuse_zpool ? "thinz_conv_kernel(+z-maxpool)" : "thinz_conv_kernel";
             else if (c.thin) name = "thin_conv_kernel";
             else {
                 ConvPlan::Config cfg;
@@ -1970,7 +1970,7 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
             break;
         }
         case TB_OP_INPUT: name = g->tensors[op].cpv ? "input_convert_cpv_kernel" : g->tensors[op].padvol ? "input_convert_padvol_kernel" : "input_convert_kernel"; break;
-        case TB_OP_POOL3D: name = g->tensors[op].cpv ? "pool3d_cpv_kernel" : "pool3d_vec8_kernel"; break;
+        case TB_OP_POOL3D: name = node.alias_of >= 0 ? "(fused into the producing conv)" : g->tensors[op].cpv ? "pool3d_cpv_kernel" : "pool3d_vec8_kernel"; break;
         case TB_OP_AFFINE: name = "affine_act_kernel"; break;
         case TB_OP_GPOOL: name = "gpool_kernel"; break;
         case TB_OP_SOFTMAX: name = "softmax_kernel"; break;
