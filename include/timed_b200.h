@@ -197,6 +197,19 @@ int timed_b200_consensus_fp16(const float* d_probs, int64_t n_rows, int32_t n_cl
 int timed_b200_seq_metrics(const uint8_t* d_seqs, int64_t n_seqs, int64_t n_res, const int8_t* d_letter_lut,
                            const double* d_tables, int32_t n_table_doubles, double* d_out, void* cuda_stream);
 
+/* ---- host-side frame I/O  (replaces the per-frame h5py reads of design_utils/utils.py:514-529) ------------------
+ * Inflate (zlib) / unshuffle the chunks of many HDF5 frame datasets on `n_threads` host threads and scatter them,
+ * cast to float32 (float64/float32/uint8 sources) or copied (uint8 -> uint8), into a dense (n_frames, *frame_dims)
+ * host array.  No device work.  file_base: the memory-mapped file; chunk c lives at file_base + src_off[c]
+ * (src_size[c] stored bytes), belongs to output frame dst_frame[c] and starts at element coordinates
+ * origin[c*rank .. c*rank+rank) of that frame; chunk_dims / frame_dims have `rank` entries (edge chunks are clipped).
+ * deflate: 1 when the chunks are gzip-compressed; shuffle_elem_size: 0, or the element size when the HDF5 shuffle
+ * filter was applied before deflate. */
+int timed_b200_inflate_chunks(const uint8_t* file_base, int64_t n_chunks, const int64_t* src_off, const int64_t* src_size,
+                              const int64_t* dst_frame, const int32_t* origin, int32_t rank, const int32_t* chunk_dims,
+                              const int32_t* frame_dims, int32_t deflate, int32_t shuffle_elem_size, int32_t src_dtype,
+                              int32_t dst_dtype, void* dst, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,3 +92,70 @@ def test_npz_container_roundtrip(tmp_path):
     cfg2, w2 = read_model_file(tmp_path / "m.npz")
     assert cfg2 == json.loads(json.dumps(cfg))
     np.testing.assert_array_equal(w2["conv3d"]["kernel:0"], w["conv3d"]["kernel:0"])
+
+
+def _frames_file(tmp_path, name, frames, dims, gaussian, compression, chunks, labels_onehot):
+    """aposteriori-style dataset written through the low-level Writer so that chunking can be chosen."""
+    w = Writer()
+    w.root.attrs.update({"make_frame_dataset_ver": "2.0.0", "frame_dims": np.asarray(dims, dtype=np.int64),
+                         "voxels_as_gaussian": bool(gaussian), "frame_edge_length": 21.0})
+    for i, fr in enumerate(frames):
+        ds = w.root.dataset(f"1abc/A/{i + 1}", fr, compression=compression, chunks=chunks)
+        ds.attrs["label"] = "ALA"
+        ds.attrs["encoded_residue"] = labels_onehot[i]
+    p = tmp_path / name
+    w.save(p)
+    return p
+
+
+@pytest.mark.parametrize("dtype,gaussian,compression,chunks", [
+    (np.float64, True, "gzip", None), (np.float32, True, "gzip", (4, 5, 9, 2)), (np.float64, True, None, (5, 5, 5, 3)),
+    (np.bool_, False, "gzip", None), (np.bool_, False, "gzip", (9, 4, 3, 6))])
+def test_native_frame_inflater_matches_python_reader(tmp_path, dtype, gaussian, compression, chunks, monkeypatch):
+    """timed_b200_inflate_chunks (zlib + scatter + cast on host threads, no device needed) fills load_batch's arrays
+    exactly as the pure-Python reader does: whole-frame and ragged multi-chunk layouts, stored float64 / float32 /
+    boolean frames, compressed or not, any thread count."""
+    from timed_design_b200 import frames as F
+    rng = np.random.default_rng(4)
+    dims = (9, 9, 9, 6)
+    n = 23
+    raw = rng.random((n, *dims))
+    data = (raw > 0.7) if dtype is np.bool_ else raw.astype(dtype)
+    onehot = np.eye(20)[rng.integers(0, 20, n)]
+    p = _frames_file(tmp_path, "f.hdf5", data, dims, gaussian, compression, chunks, onehot)
+    rows = [("1abc", "A", str(i + 1), "ALA") for i in range(n)][::-1]             # any order
+    calls = []
+    real = F._native_load
+
+    def spy(*a, **k):
+        calls.append(real(*a, **k))
+        return calls[-1]
+
+    monkeypatch.setattr(F, "_native_load", spy)
+    for threads in ("1", "5"):
+        monkeypatch.setenv("TIMED_B200_LOADER_THREADS", threads)
+        X, y = F.load_batch(p, rows)
+        assert calls[-1] is (compression is not None)     # contiguous (uncompressed) datasets stay on the Python reader
+        assert X.dtype == (np.float32 if gaussian else np.bool_)
+        np.testing.assert_array_equal(X, data[::-1].astype(X.dtype))
+        np.testing.assert_array_equal(y, onehot[::-1])
+    monkeypatch.setattr(F, "_native_load", lambda *a, **k: False)                   # pure-Python reader
+    X2, y2 = F.load_batch(p, rows)
+    np.testing.assert_array_equal(X2, X)
+    np.testing.assert_array_equal(y2, y)
+
+
+def test_native_frame_inflater_reports_corrupt_chunks(tmp_path):
+    from timed_design_b200 import _lib, frames as F
+    dims = (6, 6, 6, 4)
+    data = np.random.default_rng(0).random((3, *dims))
+    p = _frames_file(tmp_path, "c.hdf5", data, dims, True, "gzip", None, np.eye(20)[:3])
+    f = File(p)
+    _, table, *_ = f["1abc/A/2"].chunk_table()
+    blob = bytearray(p.read_bytes())
+    off = table[0][1]
+    blob[off + 8:off + 16] = bytes([255] * 8)                                       # damage the deflate stream
+    bad = tmp_path / "bad.hdf5"
+    bad.write_bytes(bytes(blob))
+    with pytest.raises(_lib.TimedB200Error):
+        F.load_batch(bad, [("1abc", "A", "2", "ALA")])

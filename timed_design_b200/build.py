@@ -28,7 +28,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return OUT
     cmd = ["nvcc", *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
-           *map(str, SOURCES), "-o", str(OUT)]
+           *map(str, SOURCES), "-lz", "-o", str(OUT)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")

@@ -11,6 +11,9 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
+#include <atomic>
+#include <zlib.h>
 #include <vector>
 
 #include "common.cuh"
@@ -2294,6 +2297,101 @@ int timed_b200_seq_metrics(const uint8_t* d_seqs, int64_t n_seqs, int64_t n_res,
     seq_metrics_kernel<<<static_cast<unsigned>((n_seqs + 7) / 8), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
         d_seqs, n_seqs, n_res, d_letter_lut, d_tables, d_out);
     TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+// ---- host-side frame I/O helper: no device work, no Python: inflate + unshuffle + scatter + cast on host threads
+int timed_b200_inflate_chunks(const uint8_t* file_base, int64_t n_chunks, const int64_t* src_off, const int64_t* src_size,
+                              const int64_t* dst_frame, const int32_t* origin, int32_t rank, const int32_t* chunk_dims,
+                              const int32_t* frame_dims, int32_t deflate, int32_t shuffle_elem_size, int32_t src_dtype,
+                              int32_t dst_dtype, void* dst, int32_t n_threads) {
+    TB_REQUIRE(file_base && src_off && src_size && dst_frame && origin && chunk_dims && frame_dims && dst, "null argument");
+    TB_REQUIRE(rank >= 1 && rank <= 8 && n_chunks >= 0, "rank must be in [1,8]");
+    TB_REQUIRE(src_dtype == TB_DTYPE_F32 || src_dtype == TB_DTYPE_F64 || src_dtype == TB_DTYPE_U8, "unknown source dtype");
+    TB_REQUIRE(dst_dtype == TB_DTYPE_F32 || (dst_dtype == TB_DTYPE_U8 && src_dtype == TB_DTYPE_U8),
+               "destination must be float32 (or uint8 for uint8 sources)");
+    const size_t esz = dtype_size(src_dtype), dsz = dtype_size(dst_dtype);
+    TB_REQUIRE(shuffle_elem_size == 0 || shuffle_elem_size == static_cast<int32_t>(esz), "shuffle element size mismatch");
+    int64_t chunk_elems = 1, frame_elems = 1;
+    for (int d = 0; d < rank; ++d) {
+        TB_REQUIRE(chunk_dims[d] > 0 && frame_dims[d] > 0, "dims must be positive");
+        chunk_elems *= chunk_dims[d];
+        frame_elems *= frame_dims[d];
+    }
+    const size_t raw_bytes = static_cast<size_t>(chunk_elems) * esz;
+    std::atomic<int64_t> next{0};
+    std::atomic<int> failed{0};
+    auto worker = [&]() {
+        std::vector<uint8_t> raw(raw_bytes), tmp(shuffle_elem_size ? raw_bytes : 0);
+        for (;;) {
+            const int64_t c = next.fetch_add(1);
+            if (c >= n_chunks || failed.load()) return;
+            const uint8_t* src = file_base + src_off[c];
+            if (deflate) {
+                uLongf got = static_cast<uLongf>(raw_bytes);
+                if (uncompress(raw.data(), &got, src, static_cast<uLong>(src_size[c])) != Z_OK || got != raw_bytes) {
+                    failed.store(1);
+                    return;
+                }
+            } else {
+                if (static_cast<size_t>(src_size[c]) != raw_bytes) { failed.store(2); return; }
+                std::memcpy(raw.data(), src, raw_bytes);
+            }
+            const uint8_t* data = raw.data();
+            if (shuffle_elem_size) {              // HDF5 shuffle: byte k of every element stored contiguously
+                for (size_t b = 0; b < esz; ++b)
+                    for (int64_t e = 0; e < chunk_elems; ++e) tmp[e * esz + b] = raw[b * chunk_elems + e];
+                data = tmp.data();
+            }
+            // scatter the chunk into its frame: runs along the last dimension, odometer over the others
+            const int32_t* org = origin + c * rank;
+            uint8_t* out = static_cast<uint8_t*>(dst) + static_cast<size_t>(dst_frame[c]) * frame_elems * dsz;
+            const int last = rank - 1;
+            const int64_t run = std::min<int64_t>(chunk_dims[last], static_cast<int64_t>(frame_dims[last]) - org[last]);
+            if (run <= 0) continue;
+            int32_t idx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (;;) {
+                bool inside = true;
+                int64_t src_e = 0, dst_e = 0;
+                for (int d = 0; d < last; ++d) {
+                    const int64_t g = static_cast<int64_t>(org[d]) + idx[d];
+                    if (g >= frame_dims[d]) inside = false;
+                    src_e = src_e * chunk_dims[d] + idx[d];
+                    dst_e = dst_e * frame_dims[d] + g;
+                }
+                if (inside) {
+                    src_e = src_e * chunk_dims[last];
+                    dst_e = dst_e * frame_dims[last] + org[last];
+                    if (src_dtype == TB_DTYPE_F64) {
+                        const double* sp = reinterpret_cast<const double*>(data) + src_e;
+                        float* dp = reinterpret_cast<float*>(out) + dst_e;
+                        for (int64_t e = 0; e < run; ++e) dp[e] = static_cast<float>(sp[e]);
+                    } else if (src_dtype == TB_DTYPE_F32) {
+                        std::memcpy(reinterpret_cast<float*>(out) + dst_e, reinterpret_cast<const float*>(data) + src_e,
+                                    static_cast<size_t>(run) * 4);
+                    } else if (dst_dtype == TB_DTYPE_U8) {
+                        std::memcpy(out + dst_e, data + src_e, static_cast<size_t>(run));
+                    } else {
+                        float* dp = reinterpret_cast<float*>(out) + dst_e;
+                        for (int64_t e = 0; e < run; ++e) dp[e] = static_cast<float>(data[src_e + e]);
+                    }
+                }
+                int d = last - 1;
+                for (; d >= 0; --d) {
+                    if (++idx[d] < chunk_dims[d]) break;
+                    idx[d] = 0;
+                }
+                if (d < 0) break;
+            }
+        }
+    };
+    const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_threads > 0 ? n_threads : 1, n_chunks)));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    TB_REQUIRE(failed.load() != 1, "zlib failed to inflate a chunk (corrupt data or wrong chunk size)");
+    TB_REQUIRE(failed.load() != 2, "stored chunk size does not match the chunk dimensions");
     return TB_OK;
 }
 

@@ -102,6 +102,63 @@ def dataset_metadata(frame_dataset: Path) -> dict:
     return {k: f.attrs[k] for k in f.attrs.keys()}
 
 
+def _native_load(f: File, rows, dims, X: np.ndarray, y: np.ndarray) -> bool:
+    """Fast path of ``load_batch``: every frame of the batch is a chunked dataset filtered by deflate (+ shuffle) only ->
+    one call into libtimed_b200's host-side inflater (zlib on a thread pool, scatter + cast to the batch array without the
+    GIL).  Returns False (nothing written) when the file is stored any other way; the Python reader then does the work."""
+    import ctypes as C
+    from . import _lib
+    try:
+        lib = _lib.load()
+    except Exception:
+        return False
+    src_off, src_size, dst_frame, origin = [], [], [], []
+    common = None
+    objs = []
+    for i, row in enumerate(rows):
+        pdb_code, chain_id, residue_id = (str(v) for v in row[:3])
+        ds = f[pdb_code][chain_id][residue_id]
+        objs.append(ds)
+        info = ds.chunk_table() if hasattr(ds, "chunk_table") else None
+        if info is None or tuple(ds.shape) != tuple(dims):
+            return False
+        cdims, table, deflate, shuffle, dtype = info
+        key = (cdims, deflate, shuffle, dtype)
+        if common is None:
+            common = key
+        elif key != common:
+            return False
+        for org, off, size in table:
+            origin.append(org)
+            src_off.append(off)
+            src_size.append(size)
+            dst_frame.append(i)
+    cdims, deflate, shuffle, dtype = common
+    to_bool = X.dtype == np.bool_
+    if to_bool and dtype.itemsize != 1:
+        return False                                   # float frames in a boolean dataset: let the reader decide
+    code = {4: _lib.DTYPE_F32, 8: _lib.DTYPE_F64, 1: _lib.DTYPE_U8}[dtype.itemsize]
+    a_off = np.asarray(src_off, dtype=np.int64)
+    a_size = np.asarray(src_size, dtype=np.int64)
+    a_frame = np.asarray(dst_frame, dtype=np.int64)
+    a_org = np.ascontiguousarray(np.asarray(origin, dtype=np.int32).reshape(len(origin), len(dims)))
+    a_cd = np.asarray(cdims, dtype=np.int32)
+    a_fd = np.asarray(dims, dtype=np.int32)
+    base = np.frombuffer(f.buf, dtype=np.uint8)
+    out = X.view(np.uint8) if to_bool else X
+    rc = lib.timed_b200_inflate_chunks(
+        C.c_void_p(base.ctypes.data), len(a_off), C.c_void_p(a_off.ctypes.data), C.c_void_p(a_size.ctypes.data),
+        C.c_void_p(a_frame.ctypes.data), C.c_void_p(a_org.ctypes.data), len(dims), C.c_void_p(a_cd.ctypes.data),
+        C.c_void_p(a_fd.ctypes.data), int(deflate), int(shuffle), code, _lib.DTYPE_U8 if to_bool else _lib.DTYPE_F32,
+        C.c_void_p(out.ctypes.data), _loader_threads())
+    _lib.check(rc)
+    if to_bool:
+        np.not_equal(out, 0, out=X)                    # stored enum bytes -> booleans
+    for i, ds in enumerate(objs):
+        y[i] = ds.attrs["encoded_residue"]
+    return True
+
+
 def load_batch(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple]) -> t.Tuple[np.ndarray, np.ndarray]:
     """utils.py:487-530.  X: (B, *frame_dims) float32 when ``voxels_as_gaussian`` else bool --
     the reference allocates float64 and Keras casts it to float32 on entry (predict.py:142), so
@@ -112,6 +169,8 @@ def load_batch(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple]) -> t.T
     n = len(data_point_batch)
     X = np.zeros((n, *dims), dtype=np.float32 if gaussian else np.bool_)
     y = np.zeros((n, 20), dtype=float)
+    if n and _native_load(f, data_point_batch, dims, X, y):
+        return X, y
 
     def one(i):
         pdb_code, chain_id, residue_id = (str(v) for v in data_point_batch[i][:3])
