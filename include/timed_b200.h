@@ -210,6 +210,12 @@ int timed_b200_inflate_chunks(const uint8_t* file_base, int64_t n_chunks, const 
                               const int32_t* frame_dims, int32_t deflate, int32_t shuffle_elem_size, int32_t src_dtype,
                               int32_t dst_dtype, void* dst, int32_t n_threads);
 
+/* Text of a (rows, cols) float32/float64 host matrix exactly as numpy.savetxt(..., delimiter=",") prints it ("%.18e",
+ * comma separated, one line per row: the rotamer dump of predict.py:145-146), formatted on `n_threads` host threads.
+ * out must hold 26 bytes per number; *written receives the text length.  No device work. */
+int timed_b200_format_csv_e18(const void* data, int32_t dtype, int64_t rows, int64_t cols, char* out, int64_t out_cap,
+                              int64_t* written, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2395,4 +2395,41 @@ int timed_b200_inflate_chunks(const uint8_t* file_base, int64_t n_chunks, const 
     return TB_OK;
 }
 
+// ---- host-side text writer: rows of "%.18e" numbers (numpy's savetxt default), formatted on host threads
+int timed_b200_format_csv_e18(const void* data, int32_t dtype, int64_t rows, int64_t cols, char* out, int64_t out_cap,
+                              int64_t* written, int32_t n_threads) {
+    TB_REQUIRE(data && out && written, "null argument");
+    TB_REQUIRE(dtype == TB_DTYPE_F32 || dtype == TB_DTYPE_F64, "float32 or float64 data expected");
+    TB_REQUIRE(rows >= 0 && cols > 0, "bad shape");
+    TB_REQUIRE(out_cap >= rows * cols * 26, "output buffer must hold 26 bytes per number");
+    const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_threads > 0 ? n_threads : 1, rows)));
+    std::vector<int64_t> used(nt, 0);
+    std::vector<int64_t> first(nt + 1, 0);
+    for (int t = 0; t <= nt; ++t) first[t] = rows * t / nt;
+    // every thread formats its block of rows at the worst-case offset of that block, then the blocks are compacted
+    auto worker = [&](int t) {
+        char* p = out + first[t] * cols * 26;
+        char* p0 = p;
+        for (int64_t r = first[t]; r < first[t + 1]; ++r)
+            for (int64_t c = 0; c < cols; ++c) {
+                const double v = dtype == TB_DTYPE_F32 ? static_cast<double>(static_cast<const float*>(data)[r * cols + c])
+                                                       : static_cast<const double*>(data)[r * cols + c];
+                p += std::snprintf(p, 26, "%.18e", v);
+                *p++ = c + 1 == cols ? '\n' : ',';
+            }
+        used[t] = p - p0;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool) th.join();
+    int64_t total = used[0];
+    for (int t = 1; t < nt; ++t) {
+        std::memmove(out + total, out + first[t] * cols * 26, static_cast<size_t>(used[t]));
+        total += used[t];
+    }
+    *written = total;
+    return TB_OK;
+}
+
 }  // extern "C"

@@ -14,6 +14,7 @@ Deliberate, documented deviations:
 """
 from __future__ import annotations
 
+import io
 import typing as t
 from itertools import product
 from pathlib import Path
@@ -209,6 +210,80 @@ def save_dict_to_fasta(pdb_to_sequence: dict, model_name: str, path_to_output: P
         f.writelines(f">{pdb}\n{seq}\n" for pdb, seq in pdb_to_sequence.items())
 
 
+_FP16_TEXT: dict = {}
+
+
+def _fp16_text_tables():
+    """'%.18e' text of every float16 bit pattern, once (65 536 strings, ~60 ms): the CSV the reference writes holds
+    float16-cast probabilities (utils.py:768-771), so formatting is a table lookup instead of a Python loop per number."""
+    if not _FP16_TEXT:
+        vals = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float64)
+        with np.errstate(all="ignore"):
+            text = ["%.18e" % v for v in vals]
+        ok = np.array([len(t) == 24 for t in text])              # non-negative finite values: fixed 24 characters
+        _FP16_TEXT["ok"] = ok
+        _FP16_TEXT["comma"] = np.array([(t + ",").encode() if k else b"" for t, k in zip(text, ok)], dtype="S25")
+        _FP16_TEXT["nl"] = np.array([(t + "\n").encode() if k else b"" for t, k in zip(text, ok)], dtype="S25")
+    return _FP16_TEXT
+
+
+def savetxt_fp16(f, arr16: np.ndarray) -> None:
+    """Byte-identical to ``np.savetxt(f, arr16, delimiter=",")`` for a 2-D float16 array (numpy's default '%.18e'), written
+    from a 65 536-entry text table; rows holding negative or non-finite values fall back to ``np.savetxt``."""
+    a = np.ascontiguousarray(arr16, dtype=np.float16)
+    if a.ndim != 2 or a.size == 0:
+        np.savetxt(f, a, delimiter=",")
+        return
+    t = _fp16_text_tables()
+    idx = a.view(np.uint16)
+    if not t["ok"][idx].all():
+        np.savetxt(f, a, delimiter=",")
+        return
+    out = t["comma"][idx]
+    out[:, -1] = t["nl"][idx[:, -1]]
+    data = out.tobytes()
+    f.write(data.decode("ascii") if isinstance(f, io.TextIOBase) else data)
+
+
+def savetxt_e18(f, arr) -> None:
+    """Byte-identical to ``np.savetxt(f, arr, delimiter=",")`` for a 2-D float32/float64 array (the raw 338-wide rotamer
+    dump, predict.py:145-146), formatted by libtimed_b200's host-side writer on all cores; any other input goes through
+    ``np.savetxt``."""
+    import ctypes as C
+    import os
+    a = np.asarray(arr)
+    if a.ndim != 2 or a.size == 0 or a.dtype not in (np.float32, np.float64):
+        np.savetxt(f, a, delimiter=",")
+        return
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except Exception:
+        np.savetxt(f, a, delimiter=",")
+        return
+    a = np.ascontiguousarray(a)
+    buf = np.empty(a.size * 26, dtype=np.uint8)
+    n = C.c_int64()
+    _lib.check(lib.timed_b200_format_csv_e18(C.c_void_p(a.ctypes.data), _lib.np_dtype_code(a), a.shape[0], a.shape[1],
+                                             C.c_void_p(buf.ctypes.data), buf.size, C.byref(n),
+                                             min(32, os.cpu_count() or 1)))
+    data = buf[:n.value].tobytes()
+    f.write(data.decode("ascii") if isinstance(f, io.TextIOBase) else data)
+
+
+def savetxt_onehot(f, arr) -> None:
+    """Byte-identical to ``np.savetxt(f, arr, delimiter=",", fmt="%i")`` when every entry is 0 or 1 (the label one-hots);
+    anything else goes through ``np.savetxt``."""
+    a = np.asarray(arr)
+    if a.ndim != 2 or a.size == 0 or not np.isin(a, (0, 1)).all():
+        np.savetxt(f, a, delimiter=",", fmt="%i")
+        return
+    out = np.where(a.astype(bool), b"1,", b"0,").astype("S2")
+    out[:, -1] = np.where(a[:, -1].astype(bool), b"1\n", b"0\n")
+    data = out.tobytes()
+    f.write(data.decode("ascii") if isinstance(f, io.TextIOBase) else data)
+
+
 def save_outputs_to_file(y_true, y_pred, flat_dataset_map, model: int, model_name: str,
                          path_to_output: Path = Path.cwd()):
     """utils.py:726-771.  Appends labels (``%i``) for model 0, writes ``datasetmap.txt`` once,
@@ -216,10 +291,10 @@ def save_outputs_to_file(y_true, y_pred, flat_dataset_map, model: int, model_nam
     path_to_output = Path(path_to_output)
     if model == 0:
         with open(path_to_output / "encoded_labels.csv", "a") as f:
-            np.savetxt(f, np.asarray(y_true), delimiter=",", fmt="%i")
+            savetxt_onehot(f, np.asarray(y_true))
     map_path = path_to_output / "datasetmap.txt"
     if not map_path.exists():
         with open(map_path, "a") as f:
             np.savetxt(f, np.asarray(flat_dataset_map), delimiter=",", fmt="%s")
     with open(path_to_output / f"{model_name}.csv", "a") as f:
-        np.savetxt(f, np.array(y_pred[model], dtype=np.float16), delimiter=",")
+        savetxt_fp16(f, np.array(y_pred[model], dtype=np.float16))

@@ -27,7 +27,7 @@ from .frames import create_flat_dataset_map, load_batch
 from .model import load_model
 from .postprocess import (convert_dataset_map_for_srb, extract_sequence_from_pred_matrix,
                           get_pdb_keys_to_filter, get_rotamer_codec, rotamer_class_to_residue,
-                          save_consensus_probs, save_dict_to_fasta, save_outputs_to_file)
+                          save_consensus_probs, save_dict_to_fasta, save_outputs_to_file, savetxt_e18)
 
 
 def load_dataset_and_predict(
@@ -77,7 +77,7 @@ def load_dataset_and_predict(
             raw_rows.append(y_pred_batch)
             if predict_rotamers:
                 with open(rot_out, "a") as f:
-                    np.savetxt(f, y_pred_batch, delimiter=",")
+                    savetxt_e18(f, y_pred_batch)
                 y_pred_batch = np.eye(20, dtype=int)[cls_to_res[np.argmax(y_pred_batch, axis=1)]]
             save_outputs_to_file(list(y_true_batch), {i: list(y_pred_batch)}, flat_dataset_map, i, model_name,
                                  path_to_output)
