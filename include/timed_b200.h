@@ -216,6 +216,13 @@ int timed_b200_inflate_chunks(const uint8_t* file_base, int64_t n_chunks, const 
 int timed_b200_format_csv_e18(const void* data, int32_t dtype, int64_t rows, int64_t cols, char* out, int64_t out_cap,
                               int64_t* written, int32_t n_threads);
 
+/* Parse a comma-separated text matrix (the {model}.csv that /root/reference/sample.py:32-34 reads back with
+ * np.genfromtxt) with strtod on `n_threads` host threads.  Call once with out == NULL to obtain rows / cols, then with a
+ * (rows * cols) float64 buffer.  Fails with TB_ERR_INVALID when the text is not a rectangular matrix of numbers.
+ * No device work. */
+int timed_b200_parse_csv(const char* text, int64_t len, double* out, int64_t out_cap, int64_t* rows, int64_t* cols,
+                         int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,26 @@ def test_native_e18_writer_is_byte_identical_to_savetxt(tmp_path):
     f = io.StringIO()
     pp.savetxt_e18(f, np.arange(6).reshape(2, 3))            # integers: numpy path
     assert f.getvalue() == _np_text(np.arange(6).reshape(2, 3))
+
+
+def test_native_csv_reader_matches_genfromtxt(tmp_path):
+    """timed_b200_parse_csv behind load_matrix_csv (what sample.py reads the prediction matrix with) against
+    np.genfromtxt: exact float64 values, specials, CRLF / blank lines, the 1-D result for a single row, and the
+    reference's ValueError for ragged text."""
+    import pytest
+    rng = np.random.default_rng(3)
+    a = rng.dirichlet(np.ones(338), size=300).astype(np.float16)
+    p = tmp_path / "m.csv"
+    with open(p, "w") as f:
+        pp.savetxt_fp16(f, a)
+    got = pp.load_matrix_csv(p)
+    ref = np.genfromtxt(p, delimiter=",", dtype=np.float64)
+    assert got.dtype == np.float64 and got.shape == (300, 338)
+    np.testing.assert_array_equal(got, ref)
+    p.write_text("1.5,nan,inf\\n-2e-3,4,5\\r\\n\\n")
+    np.testing.assert_array_equal(pp.load_matrix_csv(p), np.genfromtxt(p, delimiter=","))
+    p.write_text("1,2,3\\n")
+    assert pp.load_matrix_csv(p).shape == (3,)
+    p.write_text("1,2,3\\n4,5\\n")
+    with pytest.raises(ValueError):
+        pp.load_matrix_csv(p)

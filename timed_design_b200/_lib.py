@@ -84,6 +84,8 @@ SYMBOLS = {
                                             C.c_int32]),
     "timed_b200_format_csv_e18": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                             C.POINTER(C.c_int64), C.c_int32]),
+    "timed_b200_parse_csv": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64), C.c_int32]),
     "timed_b200_sample_uniforms": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64,
                                              C.c_void_p, C.c_void_p]),
     "timed_b200_argmax_fp16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -2432,4 +2432,65 @@ int timed_b200_format_csv_e18(const void* data, int32_t dtype, int64_t rows, int
     return TB_OK;
 }
 
+// ---- host-side text reader: a comma-separated matrix of numbers (the {model}.csv that sample.py reads back,
+// sample.py:32-34) parsed with strtod on host threads.  Call with out == NULL to get the shape first.
+int timed_b200_parse_csv(const char* text, int64_t len, double* out, int64_t out_cap, int64_t* rows, int64_t* cols,
+                         int32_t n_threads) {
+    TB_REQUIRE(text && rows && cols && len >= 0, "null argument");
+    std::vector<int64_t> starts;                       // non-empty lines
+    for (int64_t p = 0; p < len;) {
+        const char* nl = static_cast<const char*>(std::memchr(text + p, '\n', static_cast<size_t>(len - p)));
+        const int64_t end = nl ? nl - text : len;
+        int64_t e = end;
+        while (e > p && (text[e - 1] == '\r' || text[e - 1] == ' ')) --e;
+        if (e > p) starts.push_back(p);
+        p = end + 1;
+    }
+    *rows = static_cast<int64_t>(starts.size());
+    *cols = 0;
+    if (starts.empty()) return TB_OK;
+    {
+        const char* nl = static_cast<const char*>(std::memchr(text + starts[0], '\n', static_cast<size_t>(len - starts[0])));
+        const int64_t end = nl ? nl - text : len;
+        int64_t c = 1;
+        for (int64_t q = starts[0]; q < end; ++q) c += text[q] == ',';
+        *cols = c;
+    }
+    if (!out) return TB_OK;
+    TB_REQUIRE(out_cap >= *rows * *cols, "output buffer too small");
+    const int64_t n_rows = *rows, n_cols = *cols;
+    std::atomic<int> bad{0};
+    const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_threads > 0 ? n_threads : 1, n_rows)));
+    auto worker = [&](int t) {
+        std::string line;
+        for (int64_t r = n_rows * t / nt; r < n_rows * (t + 1) / nt && !bad.load(); ++r) {
+            const char* nl = static_cast<const char*>(std::memchr(text + starts[r], '\n', static_cast<size_t>(len - starts[r])));
+            const int64_t end = nl ? nl - text : len;
+            line.assign(text + starts[r], static_cast<size_t>(end - starts[r]));     // NUL-terminated copy for strtod
+            const char* p = line.c_str();
+            for (int64_t c = 0; c < n_cols; ++c) {
+                char* q = nullptr;
+                const double v = std::strtod(p, &q);
+                if (q == p) { bad.store(1); return; }
+                out[r * n_cols + c] = v;
+                p = q;
+                while (*p == ' ' || *p == '\r') ++p;
+                if (c + 1 < n_cols) {
+                    if (*p != ',') { bad.store(1); return; }
+                    ++p;
+                } else if (*p != '\0') {
+                    bad.store(1);
+                    return;
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool) th.join();
+    TB_REQUIRE(!bad.load(), "not a rectangular comma-separated matrix of numbers");
+    return TB_OK;
+}
+
 }  // extern "C"

@@ -271,6 +271,33 @@ def savetxt_e18(f, arr) -> None:
     f.write(data.decode("ascii") if isinstance(f, io.TextIOBase) else data)
 
 
+def load_matrix_csv(path) -> np.ndarray:
+    """``np.genfromtxt(path, delimiter=",", dtype=np.float64)`` for the prediction matrices this package writes, parsed
+    by libtimed_b200's host-side reader (strtod on all cores); anything it does not accept goes through ``genfromtxt``."""
+    import ctypes as C
+    import mmap
+    import os
+    try:
+        from . import _lib
+        lib = _lib.load()
+        with open(path, "rb") as fh:
+            if os.fstat(fh.fileno()).st_size == 0:
+                raise ValueError("empty file")
+            mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            view = np.frombuffer(mm, dtype=np.uint8)
+            rows, cols = C.c_int64(), C.c_int64()
+            _lib.check(lib.timed_b200_parse_csv(C.c_void_p(view.ctypes.data), view.size, None, 0, C.byref(rows),
+                                                C.byref(cols), 1))
+            out = np.empty((rows.value, cols.value), dtype=np.float64)
+            _lib.check(lib.timed_b200_parse_csv(C.c_void_p(view.ctypes.data), view.size, C.c_void_p(out.ctypes.data),
+                                                out.size, C.byref(rows), C.byref(cols), min(32, os.cpu_count() or 1)))
+            del view
+            mm.close()
+        return out[0] if out.shape[0] == 1 else out              # genfromtxt returns 1-D for a single row
+    except Exception:
+        return np.genfromtxt(path, delimiter=",", dtype=np.float64)
+
+
 def savetxt_onehot(f, arr) -> None:
     """Byte-identical to ``np.savetxt(f, arr, delimiter=",", fmt="%i")`` when every entry is 0 or 1 (the label one-hots);
     anything else goes through ``np.savetxt``."""

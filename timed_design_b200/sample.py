@@ -18,7 +18,7 @@ import numpy as np
 
 from . import sampling_utils
 from .postprocess import (_THREE_TO_ONE, extract_sequence_from_pred_matrix, get_rotamer_codec,
-                          load_datasetmap)
+                          load_datasetmap, load_matrix_csv)
 from .predict import _flag
 
 
@@ -31,7 +31,7 @@ def main_sample(args):
     if args.path_to_pred_matrix.suffix == ".npy":      # binary fast path written by predict.py --binary_outputs
         prediction_matrix = np.load(args.path_to_pred_matrix).astype(np.float64)
     else:
-        prediction_matrix = np.genfromtxt(args.path_to_pred_matrix, delimiter=",", dtype=np.float64)
+        prediction_matrix = load_matrix_csv(args.path_to_pred_matrix)
     if prediction_matrix.ndim == 1:
         prediction_matrix = prediction_matrix[None, :]
     datasetmap = load_datasetmap(args.path_to_datasetmap, is_old=args.support_old_datasetmap)
