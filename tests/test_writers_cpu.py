@@ -94,10 +94,10 @@ def test_native_csv_reader_matches_genfromtxt(tmp_path):
     ref = np.genfromtxt(p, delimiter=",", dtype=np.float64)
     assert got.dtype == np.float64 and got.shape == (300, 338)
     np.testing.assert_array_equal(got, ref)
-    p.write_text("1.5,nan,inf\\n-2e-3,4,5\\r\\n\\n")
+    p.write_text("1.5,nan,inf\n-2e-3,4,5\r\n\n")
     np.testing.assert_array_equal(pp.load_matrix_csv(p), np.genfromtxt(p, delimiter=","))
-    p.write_text("1,2,3\\n")
+    p.write_text("1,2,3\n")
     assert pp.load_matrix_csv(p).shape == (3,)
-    p.write_text("1,2,3\\n4,5\\n")
+    p.write_text("1,2,3\n4,5\n")
     with pytest.raises(ValueError):
         pp.load_matrix_csv(p)
