@@ -399,6 +399,7 @@ class Group(_Object):
     def __init__(self, f, addr, name):
         super().__init__(f, addr, name)
         self._links: Optional[Dict[str, int]] = None
+        self._groups: Dict[str, "Group"] = {}        # child groups already opened (their link tables are parsed once)
 
     def _load(self) -> Dict[str, int]:
         if self._links is not None:
@@ -462,11 +463,18 @@ class Group(_Object):
             links = node._load()
             if part not in links:
                 raise KeyError(f"'{part}' not found in group {node.name} of {self._f.path}")
+            cached = node._groups.get(part)
+            if cached is not None:
+                node = cached
+                continue
             addr = links[part]
             child_name = (node.name.rstrip("/") + "/" + part)
             msgs = self._f._messages(addr)
             is_dataset = any(m.type == 0x08 for m in msgs)
-            node = Dataset(self._f, addr, child_name) if is_dataset else Group(self._f, addr, child_name)
+            child = Dataset(self._f, addr, child_name) if is_dataset else Group(self._f, addr, child_name)
+            if not is_dataset:
+                node._groups[part] = child
+            node = child
         return node
 
 
