@@ -69,3 +69,67 @@ def test_shard_ranges_partition_everything():
 def test_gather_rows_without_process_group_is_identity():
     x = torch.arange(12, dtype=torch.float32).reshape(6, 2)
     assert torch.equal(gather_rows(x, 6), x)
+
+
+# ----------------------------------------------------------------------------- predict driver, world_size 2 (gloo)
+class _FakeModel:
+    """Deterministic stand-in for the device model (the CPU suite has no GPU): probabilities from channel sums."""
+    n_classes = 20
+
+    def predict(self, X, batch_size=None):
+        X = np.asarray(X, dtype=np.float64)
+        z = X.reshape(len(X), -1, X.shape[-1]).sum(1) @ np.sin(np.arange(X.shape[-1] * 20).reshape(X.shape[-1], 20))
+        e = np.exp(z - z.max(1, keepdims=True))
+        return (e / e.sum(1, keepdims=True)).astype(np.float32)
+
+    def close(self):
+        pass
+
+
+def _write_dataset(path, n=37):
+    from timed_design_b200 import standins
+    from timed_design_b200.hdf5 import write_frame_dataset
+    frames = standins.synthetic_frames(n, side=7, seed=3)
+    labels = ["ALA", "GLY", "LEU", "LYS", "SER"]
+    chains = {"A": {str(i + 1): (frames[i], labels[i % 5]) for i in range(n - 10)},
+              "B": {str(i + 1): (frames[n - 10 + i], labels[i % 5]) for i in range(10)}}
+    write_frame_dataset(path, {"1abc": chains}, (7, 7, 7, 6))
+
+
+def _predict_worker(rank, world, port, data, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world), TIMED_B200_DIST_BACKEND="gloo")
+    from timed_design_b200 import predict
+    predict.load_model = lambda path, device=0, **kw: _FakeModel()
+    predict.load_dataset_and_predict([__import__("pathlib").Path("TIMED.h5")], data, batch_size=8,
+                                     dataset_map_path=os.path.join(out_dir, "datasetmap.txt"), path_to_output=out_dir)
+    dist.destroy_process_group()
+
+
+def test_predict_driver_world2_writes_the_single_process_files(tmp_path, monkeypatch):
+    """torchrun-style launch of load_dataset_and_predict with two ranks (gloo): frames sharded by flat index, one
+    all-gather, rank 0 writes -- every output file is byte-identical to the single-process run."""
+    from pathlib import Path
+    from timed_design_b200 import predict
+    data = tmp_path / "d.hdf5"
+    _write_dataset(data)
+    single = tmp_path / "single"
+    single.mkdir()
+    monkeypatch.setattr(predict, "load_model", lambda path, device=0, **kw: _FakeModel())
+    monkeypatch.chdir(tmp_path)
+    predict.load_dataset_and_predict([Path("TIMED.h5")], data, batch_size=8,
+                                     dataset_map_path=single / "datasetmap.txt", path_to_output=single)
+    multi = tmp_path / "multi"
+    multi.mkdir()
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_predict_worker, args=(r, 2, port, str(data), str(multi))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    names = sorted(f.name for f in single.iterdir())
+    assert names == sorted(f.name for f in multi.iterdir()) and "TIMED.csv" in names and "TIMED.fasta" in names
+    for name in names:
+        assert (single / name).read_bytes() == (multi / name).read_bytes(), name

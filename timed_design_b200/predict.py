@@ -30,6 +30,38 @@ from .postprocess import (convert_dataset_map_for_srb, extract_sequence_from_pre
                           save_consensus_probs, save_dict_to_fasta, save_outputs_to_file, savetxt_e18)
 
 
+def _dist_context():
+    """(rank, world, local_rank) under torchrun (one process per GPU); (0, 1, 0) otherwise.  The process
+    group is NCCL unless TIMED_B200_DIST_BACKEND says otherwise (the CPU tests use gloo)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, 0
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    if not dist.is_initialized():
+        backend = os.environ.get("TIMED_B200_DIST_BACKEND", "nccl")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def _gather(arr: np.ndarray, n_total: int, local_rank: int) -> np.ndarray:
+    """All-gather the per-rank row blocks (contiguous frame ranges, dist.shard_range) into the full matrix."""
+    import torch
+    import torch.distributed as dist
+    from .dist import gather_rows
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if dist.get_backend() == "nccl":
+        t = t.cuda(local_rank)
+    return gather_rows(t, n_total).cpu().numpy()
+
+
 def load_dataset_and_predict(
     models: list,
     dataset_path: Path,
@@ -59,10 +91,13 @@ def load_dataset_and_predict(
     flat_categories = get_rotamer_codec()[1] if predict_rotamers else None
     cls_to_res = rotamer_class_to_residue() if predict_rotamers else None
     n_batches = ceil(len(flat_dataset_map) / batch_size)
+    rank, world, local_rank = _dist_context()
+    if world > 1 and start_batch != 0:
+        raise ValueError("start_batch is not supported when frames are sharded over several GPUs")
     out = None
     for i, m in enumerate(models):
         model_name = (m.stem if isinstance(m, Path) else str(m)) + model_name_suffix
-        frame_model = load_model(Path(m))
+        frame_model = load_model(Path(m), device=local_rank)
         if frame_model.n_classes != n_classes:
             raise ValueError(f"{m}: model has {frame_model.n_classes} outputs but "
                              f"{'--predict_rotamers' if predict_rotamers else 'residue mode'} expects {n_classes}")
@@ -70,11 +105,32 @@ def load_dataset_and_predict(
         model_out = rot_out if predict_rotamers else path_to_output / f"{model_name}.csv"
         rows_before = sum(1 for _ in open(model_out)) if model_out.exists() else 0
         raw_rows = []
+        gathered = None
+        if world > 1:
+            # frames shard by flat index into contiguous per-rank ranges (each chain's rows stay adjacent); every rank
+            # predicts its range, ONE all-gather reassembles probabilities and labels, rank 0 writes the reference's files
+            from .dist import shard_range
+            n_total = len(flat_dataset_map)
+            lo, hi = shard_range(n_total, rank, world)
+            preds, labels = [], []
+            for b0 in range(lo, hi, batch_size):
+                X_batch, y_true_batch = load_batch(dataset_path, flat_dataset_map[b0:min(b0 + batch_size, hi)])
+                preds.append(frame_model.predict(X_batch))
+                labels.append(np.asarray(y_true_batch, dtype=np.float64))
+            local_p = np.concatenate(preds) if preds else np.zeros((0, n_classes), np.float32)
+            local_y = np.concatenate(labels) if labels else np.zeros((0, 20), np.float64)
+            gathered = (_gather(local_p.astype(np.float32), n_total, local_rank), _gather(local_y, n_total, local_rank))
         for index in range(start_batch, n_batches):
             current_batch_map = flat_dataset_map[index * batch_size:(index + 1) * batch_size]
-            X_batch, y_true_batch = load_batch(dataset_path, current_batch_map)
-            y_pred_batch = frame_model.predict(X_batch)
+            if gathered is not None:
+                y_pred_batch = gathered[0][index * batch_size:(index + 1) * batch_size]
+                y_true_batch = gathered[1][index * batch_size:(index + 1) * batch_size]
+            else:
+                X_batch, y_true_batch = load_batch(dataset_path, current_batch_map)
+                y_pred_batch = frame_model.predict(X_batch)
             raw_rows.append(y_pred_batch)
+            if rank != 0:
+                continue                               # only rank 0 touches the output directory
             if predict_rotamers:
                 with open(rot_out, "a") as f:
                     savetxt_e18(f, y_pred_batch)
@@ -83,18 +139,19 @@ def load_dataset_and_predict(
                                  path_to_output)
         frame_model.close()
         flat_dataset_map = np.array(flat_dataset_map)
-        convert_dataset_map_for_srb(flat_dataset_map, model_name, path_to_output)
+        if rank == 0:
+            convert_dataset_map_for_srb(flat_dataset_map, model_name, path_to_output)
         # predict.py:163 re-parses the whole CSV as float16.  The rows written above are these
         # arrays printed with 18 significant digits (already float16-cast in residue mode), so
         # casting them to float16 reproduces the parsed matrix bit for bit without the text round
         # trip -- unless the file already held rows (append mode / start_batch): then honour it.
-        if rows_before == 0 and start_batch == 0 and raw_rows:
+        if (rows_before == 0 and start_batch == 0 and raw_rows) or rank != 0:
             prediction_matrix = np.concatenate(raw_rows).astype(np.float16)
         else:
             prediction_matrix = np.genfromtxt(model_out, delimiter=",", dtype=np.float16)
         if prediction_matrix.ndim == 1:
             prediction_matrix = prediction_matrix[None, :]
-        if binary_outputs:     # the %.18e text costs ~25 bytes per probability; .npy is 2
+        if binary_outputs and rank == 0:     # the %.18e text costs ~25 bytes per probability; .npy is 2
             np.save(path_to_output / f"{model_name}.npy", prediction_matrix)
             if predict_rotamers and raw_rows:
                 np.save(path_to_output / f"{model_name}_rot.npy", np.concatenate(raw_rows).astype(np.float32))
@@ -106,6 +163,8 @@ def load_dataset_and_predict(
             from .device_post import nmr_consensus
             cons, cons_prob = nmr_consensus(out[1], flat_categories if predict_rotamers else None)
             out = (out[0], out[1], out[2], cons, cons_prob)
+        if rank != 0:
+            continue
         save_dict_to_fasta(out[0], model_name, path_to_output)
         save_dict_to_fasta(out[2], "dataset", path_to_output)
         if out[3]:
