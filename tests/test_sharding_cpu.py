@@ -133,3 +133,50 @@ def test_predict_driver_world2_writes_the_single_process_files(tmp_path, monkeyp
     assert names == sorted(f.name for f in multi.iterdir()) and "TIMED.csv" in names and "TIMED.fasta" in names
     for name in names:
         assert (single / name).read_bytes() == (multi / name).read_bytes(), name
+
+
+# ----------------------------------------------------------------------------- sampler fan-out, world_size 2 (gloo)
+def _fake_sample_chains(prob_list, sample_n, cats=None, *, seed=None, stream_id0=0, first_sample=0, temperature=None,
+                        return_metrics=False):
+    """Counter-based like the device sampler: the letter of (chain, sample, residue) depends on the GLOBAL sample index."""
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    seqs, mets = [], []
+    for c, p in enumerate(prob_list):
+        n = len(p)
+        s_idx = first_sample + np.arange(sample_n)[:, None]
+        seqs.append(letters[(7 * s_idx + 3 * np.arange(n)[None, :] + c) % 20].astype(np.uint8))
+        mets.append(np.stack([s_idx[:, 0] + c, s_idx[:, 0] * 0.5, s_idx[:, 0] + 100.0 * n, s_idx[:, 0] * 0 + c], axis=1).astype(np.float64))
+    return (seqs, mets) if return_metrics else seqs
+
+
+def _sample_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world), TIMED_B200_DIST_BACKEND="gloo")
+    from timed_design_b200 import sampling_utils as su
+    su.sample_chains = _fake_sample_chains
+    probs = {"1abcA": np.ones((11, 20)) / 20, "1abcB": np.ones((4, 20)) / 20, "2xyzA": np.ones((1, 20)) / 20}
+    out = su.sample_with_multiprocessing(8, list(probs), 7, probs, None)
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_sampler_fanout_world2_equals_single_process(monkeypatch):
+    """sample_with_multiprocessing under a two-rank launch: each rank draws a block of the sample index, the gathered
+    result on every rank equals the single-process one (letters and metrics, chain by chain)."""
+    from timed_design_b200 import sampling_utils as su
+    monkeypatch.setattr(su, "sample_chains", _fake_sample_chains)
+    probs = {"1abcA": np.ones((11, 20)) / 20, "1abcB": np.ones((4, 20)) / 20, "2xyzA": np.ones((1, 20)) / 20}
+    ref = su.sample_with_multiprocessing(8, list(probs), 7, probs, None)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sample_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(ref["1abcA"]) == 7 and len(ref["1abcA"][0][0]) == 11
+    for r in range(2):
+        assert results[r] == ref

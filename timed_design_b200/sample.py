@@ -49,6 +49,9 @@ def main_sample(args):
           f"{args.path_to_pred_matrix.stem}.")
     pdb_to_sample = sampling_utils.sample_with_multiprocessing(
         args.workers, pdb_codes, args.sample_n, pdb_to_probability, flat_categories)
+    import os
+    if int(os.environ.get("RANK", "0")) != 0:          # torchrun: every rank holds the gathered samples, rank 0 writes
+        return []
     return sampling_utils.save_as(
         pdb_to_sample,
         filename=f"{args.path_to_pred_matrix.stem}_temp_{args.temperature}_n_{args.sample_n}_{pdb_codes[0]}",

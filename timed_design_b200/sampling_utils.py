@@ -226,9 +226,37 @@ def sample_with_multiprocessing(workers, pdb_codes, sample_n, pdb_to_probability
     sampling launch over the concatenated chains (``sample_chains``), each chain keyed by its index so the draws do not
     depend on how chains are distributed (and equal ``sample_from_sequences(..., stream_id=index)``)."""
     pdb_codes = list(pdb_codes)
-    seqs, metrics = sample_chains([pdb_to_probability[p] for p in pdb_codes], int(sample_n), flat_categories,
-                                  return_metrics=True)
-    return {pdb: _rows_to_tuples(s, m) for pdb, s, m in zip(pdb_codes, seqs, metrics)}
+    probs = [pdb_to_probability[p] for p in pdb_codes]
+    from .predict import _dist_context
+    rank, world, local_rank = _dist_context()
+    if world <= 1:
+        seqs, metrics = sample_chains(probs, int(sample_n), flat_categories, return_metrics=True)
+        return {pdb: _rows_to_tuples(s, m) for pdb, s, m in zip(pdb_codes, seqs, metrics)}
+    # torchrun: every rank draws a contiguous block of the sample index for all chains (the counter-based generator makes
+    # the union identical to one device's draw), one all-gather per output reassembles the blocks on every rank
+    import torch
+    import torch.distributed as dist
+    from .dist import gather_rows, shard_samples
+    if dist.get_backend() == "nccl":
+        torch.cuda.set_device(local_rank)
+    first, count = shard_samples(int(sample_n), rank, world)
+    lengths = [len(p) for p in probs]
+    seqs, metrics = sample_chains(probs, count, flat_categories, first_sample=first, return_metrics=True)
+    local_s = np.concatenate([s.reshape(count, n) for s, n in zip(seqs, lengths)], axis=1) if lengths else np.zeros((count, 0), np.uint8)
+    local_m = np.concatenate([np.asarray(m, dtype=np.float64).reshape(count, 4) for m in metrics], axis=1) if lengths else np.zeros((count, 0))
+
+    def gather(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if dist.get_backend() == "nccl":
+            t = t.cuda(local_rank)
+        return gather_rows(t, int(sample_n)).cpu().numpy()
+
+    all_s, all_m = gather(local_s), gather(local_m)
+    out, col = {}, 0
+    for i, (pdb, n) in enumerate(zip(pdb_codes, lengths)):
+        out[pdb] = _rows_to_tuples(all_s[:, col:col + n], all_m[:, 4 * i:4 * i + 4])
+        col += n
+    return out
 
 
 def save_as(pdb_to_sampled: dict, filename: str, mode: str) -> t.List[str]:
