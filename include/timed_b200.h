@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TIMED_B200_ABI_VERSION 1
+#define TIMED_B200_ABI_VERSION 2 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers (additive) */
 
 /* error codes */
 #define TB_OK 0

@@ -109,7 +109,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)      # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.timed_b200_abi_version() != 1:
+    if lib.timed_b200_abi_version() != 2:
         raise TimedB200Error("libtimed_b200.so ABI version mismatch")
     _lib = lib
     return lib
