@@ -399,7 +399,7 @@ static int thin_step_count(int kd, int kh, int kw) {
     return rows * (kw / 2) + ((kw & 1) ? (rows + 1) / 2 : 0);
 }
 
-// thin_conv_kernel applies when the K-step table fits, the output channels fit one N tile and the
+// thin_conv_kernel applies when the K-step count is bounded (kThinMaxSteps), the output channels fit one N tile and the
 // resident weights plus two pipeline stages fit shared memory.
 static bool thin_fits(int kd, int kh, int kw, int cout) {
     const int steps = thin_step_count(kd, kh, kw);
@@ -1415,7 +1415,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
     }
     g->tensors[n_ops - 1].last_use = n_ops;   // graph output stays live
     // padded-volume input layout + thin_conv_kernel: thin input (C <= 8) read only by stride-1 convs
-    // whose K=16 step list fits the kernel's table and whose output channels fit one N tile
+    // whose K=16 step count is bounded and whose output channels fit one N tile
     {
         bool ok = ops[0].c_out <= 8 && !getenv("TIMED_B200_NO_THIN");
         int d0 = 0, d1 = 0, h0 = 0, h1 = 0, w0 = 0, w1 = 0, n_cons = 0;
