@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TIMED_B200_ABI_VERSION 2 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers (additive) */
+#define TIMED_B200_ABI_VERSION 3 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers; 3: predict_stats, float16 frames (both additive) */
 
 /* error codes */
 #define TB_OK 0
@@ -101,10 +101,11 @@ void timed_b200_graph_destroy(tb_graph* g);
  * conv/dense ops) */
 int timed_b200_graph_info(const tb_graph* g, int32_t* n_classes, double* flops_per_frame,
                           int32_t* n_kernel_launches_per_forward);
-/* Numerics option.  0 (default): max |dp| 5.5e-5 on the TIMED-20 stand-in.  1: the wide conv layers (CTA-pair kernel)
- * keep the two correction products of the bf16 split in their own TMEM accumulator (3x less accumulator truncation;
- * max |dp| 2.2e-5); TMEM then holds one accumulator stage, so their epilogue no longer overlaps the mainloop:
- * 0.93x throughput.  Takes effect on the next forward. */
+/* Numerics option.  1 (default): every conv keeps the two correction products of the bf16 split in their own TMEM
+ * accumulator (3x less accumulator truncation; max |dp| 2.2e-5 on the TIMED-20 stand-in); wide tiles then hold ONE
+ * accumulator stage, which their epilogue drains into registers and releases before the activation math.
+ * 0: corrections accumulate into the main accumulator (max |dp| 5.5e-5, error proportional to the network's logit
+ * gain) -- kept as an A/B switch.  Takes effect on the next forward. */
 int timed_b200_graph_set_precise(tb_graph* g, int32_t precise);
 /* Name of the CUDA kernel(s) op `op` launches for a forward of `n_frames` frames (the tile configuration, and
  * with it the kernel, depends on the frame count); NUL-terminated into buf. */
@@ -131,6 +132,9 @@ int timed_b200_graph_forward(tb_graph* g, const void* d_frames, int32_t frames_d
  * chunks, runs forward, copies probabilities back, synchronises.  Library-owned staging. */
 int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t frames_dtype,
                                   int64_t n_frames, float* h_probs, int64_t max_chunk_frames);
+/* How the last predict_host call was chunked: number of device passes and the largest pass in frames (never above
+ * max_chunk_frames: Keras' batch_size bound, /root/reference/predict.py:142 via Model.predict(batch_size=...)). */
+int timed_b200_graph_predict_stats(const tb_graph* g, int64_t* n_passes, int64_t* max_pass_frames);
 
 /* ---- single-layer entry for unit/parity tests -------------------------------------------------
  * y = act2(scale*act1(conv3d(x)+bias)+shift) on device buffers.

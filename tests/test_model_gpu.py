@@ -51,15 +51,16 @@ def test_tiny_timed_parity_bool_and_f64_inputs():
 
 @pytest.mark.gpu
 def test_timed_standin_parity_20():
-    p, ref = _check(lambda: standins.timed_standin(20), lambda n: standins.synthetic_frames(n), 6,
-                    use_numpy64=False)
+    """TIMED-20 at its benchmark size (21^3 x 6) on 256 frames -- enough rows for the CTA-pair tiles the bench runs."""
+    p, ref = _check(lambda: standins.timed_standin(20), lambda n: standins.synthetic_frames(n, seed=77), 256,
+                    use_numpy64=False, tol=5e-5)
     assert len(set(ko.fp16_argmax(ref))) > 1      # the stand-in is not a constant predictor
 
 
 @pytest.mark.gpu
 def test_timed_standin_parity_338():
-    _check(lambda: standins.timed_standin(338, seed=8), lambda n: standins.synthetic_frames(n), 3,
-           use_numpy64=False)
+    _check(lambda: standins.timed_standin(338, seed=8), lambda n: standins.synthetic_frames(n, seed=77), 256,
+           use_numpy64=False, tol=5e-5)
 
 
 @pytest.mark.gpu
@@ -69,27 +70,53 @@ def test_prodconn_standin_parity():
 
 
 @pytest.mark.gpu
+def test_prodconn_full_size_parity():
+    """ProDCoNN stand-in at 21^3 (k = 3/5/7 branches, Concatenate, valid conv + pools, Flatten, two Dense)."""
+    _check(lambda: standins.prodconn_standin(), lambda n: standins.synthetic_frames(n, seed=31), 8, use_numpy64=False)
+
+
+@pytest.mark.gpu
 def test_densecpd_small_parity():
     _check(lambda: standins.densecpd_standin(side=12, n_layers=2, calib_frames=3),
            lambda n: standins.synthetic_frames(n, side=12), 5)
 
 
 @pytest.mark.gpu
-def test_precise_mode_is_tighter_and_consistent():
-    """Model(precise=True): 2-CTA cluster path for the full-width layers.  Same answers within tolerance,
-    measurably closer to the oracle on a batch large enough to engage the cluster tiles."""
+def test_densecpd_full_size_parity():
+    """The FULL DenseCPD stand-in of BASELINE config 4: 21^3, three dense blocks of six layers, 17.1 GFLOP/frame."""
+    _check(lambda: standins.densecpd_standin(), lambda n: standins.synthetic_frames(n, seed=31), 8, use_numpy64=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gain,tol", [(16.0, 5e-5), (32.0, 1e-4)])
+def test_logit_gain_stress(gain, tol):
+    """Probability errors of any finite-precision evaluation scale with the logit gain of the last BatchNorm (a trained,
+    sharper network = a larger gain).  At 2x and 4x the stand-in's gain the contract must still hold -- with the
+    corrections of the bf16 split in the main accumulator (round 1's default) 2x measured 1.35e-4."""
+    _check(lambda: standins.timed_standin(20, logit_gain=gain), lambda n: standins.synthetic_frames(n, seed=77), 256,
+           use_numpy64=False, tol=tol)
+
+
+@pytest.mark.gpu
+def test_default_accumulation_is_tighter_than_fast_and_consistent():
+    """Default: separate correction accumulator (epilogue drains TMEM into registers before the math).  The A/B switch
+    Model(precise=False) accumulates the corrections into the main accumulator: same answers within tolerance,
+    measurably further from the oracle on a batch large enough to engage the CTA-pair tiles."""
     from timed_design_b200.model import Model
     cfg, w = standins.timed_standin(20)
     uniq = standins.synthetic_frames(48, seed=5)
-    X = np.tile(uniq, (8, 1, 1, 1, 1))                      # 384 frames: enough rows for cluster tiles
+    X = np.tile(uniq, (8, 1, 1, 1, 1))                      # 384 frames: enough rows for pair tiles
     ref = ko.forward_torch(cfg, w, uniq)
-    fast = Model(cfg, w).predict(X, batch_size=4096)
-    prec = Model(cfg, w, precise=True).predict(X, batch_size=4096)
+    m = Model(cfg, w)
+    assert any("pair" in m.op_kernel(i, 384) for i in range(len(m.graph.ops)))
+    prec = m.predict(X, batch_size=4096)
+    fast = Model(cfg, w, precise=False).predict(X, batch_size=4096)
     e_fast = np.abs(fast[:48] - ref).max()
     e_prec = np.abs(prec[:48] - ref).max()
-    assert e_fast <= PROB_TOL and e_prec <= PROB_TOL
+    assert e_fast <= PROB_TOL and e_prec <= 5e-5
     assert e_prec < e_fast
     np.testing.assert_array_equal(prec[:48], prec[48:96])    # batch-position independent
+    np.testing.assert_array_equal(prec[:48], m.predict(uniq))  # ... and tile-configuration independent (pair vs single CTA)
     safe = ~ko.near_tie_rows(ref)
     assert (ko.fp16_argmax(prec[:48])[safe] == ko.fp16_argmax(ref)[safe]).all()
 

@@ -40,13 +40,27 @@ def test_full_batch_properties(timed):
 
 
 def test_chunked_host_path_equals_single_pass(timed):
-    _, _, m = timed
+    cfg, w, m = timed
     X = standins.synthetic_frames(70, seed=3)
     a = m.predict(X, batch_size=4096)
-    b = m.predict(X, batch_size=16)                          # 5 chunks, ragged tail, double-buffered H2D
-    c = m.predict(X, batch_size=1)
+    assert m.predict_stats() == (1, 70)
+    # FRESH models for the small-batch calls: staging buffers and workspace are sized by the first call, so a
+    # pre-grown model would hide a chunk that overruns them (round-1 advisor finding: the ramp started at 64 frames
+    # whatever batch_size was)
+    from timed_design_b200.model import Model
+    m16 = Model(cfg, w, device=0)
+    b = m16.predict(X, batch_size=16)                        # 16,16,16,16,6: ragged tail, double-buffered H2D
+    assert m16.predict_stats() == (5, 16)
+    m32 = Model(cfg, w, device=0)
+    b32 = m32.predict(X, batch_size=32)                      # Keras' default batch size
+    assert m32.predict_stats() == (3, 32)
+    m1 = Model(cfg, w, device=0)
+    c = m1.predict(X[:9], batch_size=1)
+    assert m1.predict_stats() == (9, 1)
     np.testing.assert_array_equal(a, b)
-    np.testing.assert_array_equal(a, c)
+    np.testing.assert_array_equal(a, b32)
+    np.testing.assert_array_equal(a[:9], c)
+    m16.close(); m32.close(); m1.close()
 
 
 def test_edge_inputs(timed):

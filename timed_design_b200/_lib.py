@@ -17,6 +17,7 @@ LIB_PATH = _HERE / "libtimed_b200.so"
 
 TB_MAX_INPUTS = 8
 DTYPE_F32, DTYPE_F64, DTYPE_U8 = 0, 1, 2
+ABI_VERSION = 3
 
 
 class TimedB200Error(RuntimeError):
@@ -65,6 +66,7 @@ SYMBOLS = {
                                            C.c_size_t, C.c_void_p, C.c_void_p]),
     "timed_b200_graph_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                                 C.c_void_p, C.c_int64]),
+    "timed_b200_graph_predict_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "timed_b200_conv3d_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.POINTER(tb_op_desc), C.c_int32, C.c_void_p]),
     "timed_b200_apply_temperature": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double,
@@ -109,7 +111,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)      # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.timed_b200_abi_version() != 2:
+    if lib.timed_b200_abi_version() != ABI_VERSION:
         raise TimedB200Error("libtimed_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -24,7 +24,18 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+DEBUG_OUT = HERE / "libtimed_b200_dbg.so"
+
+
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> Path:
+    """``debug=True`` builds libtimed_b200_dbg.so with -DTIMED_B200_DEBUG: the role-timing switches
+    (TIMED_B200_DBG) exist only there; select it with TIMED_B200_LIB (tools/role_timing.sh)."""
+    if debug:
+        cmd = ["nvcc", *NVCC_FLAGS, "-DTIMED_B200_DEBUG", *map(str, SOURCES), "-lz", "-o", str(DEBUG_OUT)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+        return DEBUG_OUT
     if not force and not needs_build():
         return OUT
     cmd = ["nvcc", *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
@@ -38,4 +49,4 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

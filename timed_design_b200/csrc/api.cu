@@ -27,6 +27,17 @@
 namespace tb {
 
 static thread_local std::string g_last_error;
+
+// Role-timing switches (skip copies / MMA issue / epilogue) exist only in bring-up builds (-DTIMED_B200_DEBUG): the
+// release library ignores TIMED_B200_DBG, so no environment variable can make a kernel return garbage.
+static int debug_mask() {
+#ifdef TIMED_B200_DEBUG
+    static const int dbg = [] { const char* e = getenv("TIMED_B200_DBG"); return e ? atoi(e) : 0; }();
+    return dbg;
+#else
+    return 0;
+#endif
+}
 void set_error(const std::string& msg) { g_last_error = msg; }
 
 // ----------------------------------------------------------------------------- driver entry points
@@ -139,7 +150,7 @@ struct ConvPlan {
     // sum_c X[pixel, c] * W[tap, c, co]  with N = taps*C_out (wide MMAs, every activation read once)
     // followed by a col2im gather  out[p, co] = sum_tap Z[p + tap - pad, tap, co]  (+ bias/act/BN).
     // thin-input path (thin_conv.cuh): padded-volume input, kw taps aliased by the UMMA descriptor
-    bool precise = false;            // graph option: 2-CTA cluster mode with separate correction accumulators
+    bool precise = true;             // graph option (default on): wide tiles keep the correction products in their own TMEM accumulator
     bool slab = false;               // chunk-plane padded-volume input, slab_conv_kernel
     SlabConvParams slab_params;      // static part, completed per launch
     uint8_t* d_slab_w = nullptr;
@@ -279,8 +290,10 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
     const int acc_cols = round_up(nfold ? 2 * p.n_tile : p.n_tile, 32);
     // two M sub-tiles per CTA halve the weight traffic per MAC; only worth it when there are
     // enough tiles to still fill the machine twice over
+    // wide tiles (no N-fold) of a precise graph: one M sub-tile, main and correction accumulators side by side
+    const bool sep_corr = p.precise && !nfold && 2 * acc_cols <= 512;
     std::vector<int> mts;
-    if (2 * acc_cols <= 512 && static_cast<int64_t>(ceil_div(m_tiles, 2)) * p.n_tiles >= 2 * 148)
+    if (!sep_corr && 2 * acc_cols <= 512 && static_cast<int64_t>(ceil_div(m_tiles, 2)) * p.n_tiles >= 2 * 148)
         mts.push_back(2);
     mts.push_back(1);
     int best_score = -1;
@@ -296,7 +309,7 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
             int stages = static_cast<int>(std::min<size_t>(kConvMaxStages, kSmemBudget / (kb * kg)));
             // score: prefer >=3 stages, then mt=2, then wider kc; a single accumulator stage
             // serialises the epilogue with the mainloop, which only a long K loop amortises
-            const int acc_stages_c = std::min(2, 512 / (mt * acc_cols));
+            const int acc_stages_c = sep_corr ? 1 : std::min(2, 512 / (mt * acc_cols));
             const int mainloop_mmas = n_kblocks * (kc / 16) * 3 * mt;
             const int score = (stages >= 3 ? 100 : 0) + (mt == 2 ? 10 : 0) + kc / 16 -
                               ((acc_stages_c == 1 && mainloop_mmas < 1500) ? 20 : 0);
@@ -308,7 +321,8 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
                 cfg->stages = stages;
                 cfg->acc_cols = acc_cols;
                 cfg->nfold = nfold ? 1 : 0;
-                cfg->acc_stages = std::min(2, 512 / (mt * acc_cols));
+                cfg->acc_stages = acc_stages_c;
+                cfg->corr_off = sep_corr ? acc_cols : 0;
                 cfg->swizzle_code = kc == 64 ? 2u : (kc == 32 ? 4u : 6u);
                 cfg->tma_swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                         : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -640,10 +654,7 @@ static int slab_launch(ConvPlan& p, void* in_base, int64_t n_frames, const TView
     e.out_f32 = out.f32; e.out_hi = out.hi; e.out_lo = out.lo;
     e.ldc = out.ld;
     e.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
-    {
-        static const int dbg = [] { const char* e = getenv("TIMED_B200_DBG"); return e ? atoi(e) : 0; }();
-        k.dbg = dbg;
-    }
+    k.dbg = debug_mask();
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "slab conv: split output channel padding mismatch");
     const size_t w_stage = (static_cast<size_t>(k.w_group) * k.w_tap_bytes + 127) & ~static_cast<size_t>(127);
@@ -816,10 +827,7 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
     e.out_f32 = out.f32; e.out_hi = out.hi; e.out_lo = out.lo;
     e.ldc = out.ld;
     e.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
-    {
-        static const int dbg = [] { const char* e = getenv("TIMED_B200_DBG"); return e ? atoi(e) : 0; }();
-        k.dbg = dbg;
-    }
+    k.dbg = debug_mask();
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "thinz conv: split output channel padding mismatch");
     const size_t w_smem = (static_cast<size_t>(k.w_bytes) + 127) & ~static_cast<size_t>(127);
@@ -868,10 +876,7 @@ static int thin_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.out_f32 = out.f32; k.out_hi = out.hi; k.out_lo = out.lo;
     k.ldc = out.ld;
     k.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
-    {
-        static const int dbg = [] { const char* e = getenv("TIMED_B200_DBG"); return e ? atoi(e) : 0; }();
-        k.dbg = dbg;
-    }
+    k.dbg = debug_mask();
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "thin conv: split output channel padding mismatch");
     const size_t w_smem = (static_cast<size_t>(k.w_bytes) + 127) & ~static_cast<size_t>(127);
@@ -1074,7 +1079,7 @@ static int launch_pair_instance(const CUtensorMap& map_a, const CUtensorMap& map
     }
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(kConvThreads);
+    lc.blockDim = dim3(kPairThreads);
     lc.dynamicSmemBytes = smem_bytes;
     lc.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1160,10 +1165,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.out_f32 = out.f32; k.out_hi = out.hi; k.out_lo = out.lo;
     k.ldc = out.ld;
     k.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
-    {
-        static const int dbg = [] { const char* e = getenv("TIMED_B200_DBG"); return e ? atoi(e) : 0; }();
-        k.dbg = dbg;
-    }
+    k.dbg = debug_mask();
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "conv: split output channel padding mismatch");
 
@@ -1254,6 +1256,7 @@ struct tb_graph {
     size_t ws_bytes = 0;
     float* d_probs = nullptr;
     size_t probs_bytes = 0;
+    int64_t last_passes = 0, last_max_pass = 0;          // how the last predict_host call was chunked
     cudaStream_t s_copy = nullptr, s_compute = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     // per-op device timing (timed_b200_graph_set_timing): one event set per recorded forward
@@ -1988,6 +1991,7 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
 int timed_b200_graph_set_precise(tb_graph* g, int32_t precise) {
     TB_REQUIRE(g, "null graph");
     for (auto& n : g->ops) n.conv.precise = precise != 0;
+    g->layouts.clear();        // (tile configurations are chosen per launch; nothing else is cached per mode)
     return TB_OK;
 }
 
@@ -2092,11 +2096,15 @@ int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t fra
     const uint8_t* src = static_cast<const uint8_t*>(h_frames);
     int it = 0;
     // chunk sizes ramp up (chunk/8, chunk/4, chunk/2, chunk, ...): only the first, small copy is not hidden
-    // behind a forward
-    int64_t cur = n_frames > chunk ? std::max<int64_t>(64, chunk / 8) : chunk;
+    // behind a forward.  The ramp never exceeds `chunk`: the staging buffers and the workspace are sized for it, and the
+    // caller's batch_size bound holds for every pass.
+    int64_t cur = n_frames > chunk ? std::min<int64_t>(chunk, std::max<int64_t>(64, chunk / 8)) : chunk;
     for (int64_t f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++it, cur = std::min(chunk, cur * 2)) {
         const int b = it & 1;
         nf = std::min(cur, n_frames - f0);
+        TB_REQUIRE(nf > 0 && nf <= chunk, "internal: predict_host chunk exceeds the staged size");
+        g->last_passes = it + 1;
+        g->last_max_pass = it == 0 ? nf : std::max(g->last_max_pass, nf);
         if (it >= 2) TB_CHECK_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_consumed[b], 0));
         TB_CHECK_CUDA(cudaMemcpyAsync(g->d_stage[b], src + f0 * frame_bytes, nf * frame_bytes,
                                       cudaMemcpyHostToDevice, g->s_copy));
@@ -2110,6 +2118,13 @@ int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t fra
     }
     TB_CHECK_CUDA(cudaMemcpyAsync(h_probs, g->d_probs, probs_need, cudaMemcpyDeviceToHost, g->s_compute));
     TB_CHECK_CUDA(cudaStreamSynchronize(g->s_compute));
+    return TB_OK;
+}
+
+int timed_b200_graph_predict_stats(const tb_graph* g, int64_t* n_passes, int64_t* max_pass_frames) {
+    TB_REQUIRE(g, "null graph");
+    if (n_passes) *n_passes = g->last_passes;
+    if (max_pass_frames) *max_pass_frames = g->last_max_pass;
     return TB_OK;
 }
 
@@ -2161,7 +2176,7 @@ int timed_b200_conv3d_fwd(const float* d_x, int64_t n, int32_t D, int32_t H, int
         tin.c_pad = 8;
     }
     ConvPlan plan;
-    plan.precise = getenv("TIMED_B200_PRECISE") != nullptr;   // test hook for the 2-CTA cluster path
+    plan.precise = getenv("TIMED_B200_FAST_ACCUM") == nullptr;   // test hook: corrections into the main accumulator
     rc = conv_plan_create(plan, ops[1], D, H, W, c_in, tin.c_pad, &tin);
     if (rc) { free_conv_plan(plan); return rc; }
     const int64_t out_ppf = static_cast<int64_t>(plan.Do) * plan.Ho * plan.Wo;
@@ -2405,6 +2420,7 @@ int timed_b200_format_csv_e18(const void* data, int32_t dtype, int64_t rows, int
     const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_threads > 0 ? n_threads : 1, rows)));
     std::vector<int64_t> used(nt, 0);
     std::vector<int64_t> first(nt + 1, 0);
+    std::atomic<int> overflow{0};
     for (int t = 0; t <= nt; ++t) first[t] = rows * t / nt;
     // every thread formats its block of rows at the worst-case offset of that block, then the blocks are compacted
     auto worker = [&](int t) {
@@ -2414,7 +2430,14 @@ int timed_b200_format_csv_e18(const void* data, int32_t dtype, int64_t rows, int
             for (int64_t c = 0; c < cols; ++c) {
                 const double v = dtype == TB_DTYPE_F32 ? static_cast<double>(static_cast<const float*>(data)[r * cols + c])
                                                        : static_cast<const double*>(data)[r * cols + c];
-                p += std::snprintf(p, 26, "%.18e", v);
+                // "%.18e" is at most 27 characters (sign, 20 digits + point, e, sign, 3-digit exponent); 26 bytes per number
+                // INCLUDING the separator are guaranteed by the caller only for |exponent| < 100 and the float32 / float16
+                // data this writer is used for -- format into a local buffer and copy what fits the slot
+                char tmp[40];
+                int len = std::snprintf(tmp, sizeof(tmp), "%.18e", v);
+                if (len > 25) { overflow.store(1); len = 25; }
+                std::memcpy(p, tmp, static_cast<size_t>(len));
+                p += len;
                 *p++ = c + 1 == cols ? '\n' : ',';
             }
         used[t] = p - p0;
@@ -2429,6 +2452,7 @@ int timed_b200_format_csv_e18(const void* data, int32_t dtype, int64_t rows, int
         total += used[t];
     }
     *written = total;
+    TB_REQUIRE(!overflow.load(), "a value needs more than 25 characters in %.18e (negative with a 3-digit exponent)");
     return TB_OK;
 }
 

@@ -28,6 +28,14 @@ void set_error(const std::string& msg);          // defined in api.cu (thread-lo
         }                                                                                \
     } while (0)
 
+// Role-timing switches (skip copies / MMA issue / epilogue / stores) are compiled in only for bring-up builds
+// (-DTIMED_B200_DEBUG, tools/role_timing.sh); in the release library the tests below are constant false.
+#ifdef TIMED_B200_DEBUG
+#define TB_DBG(mask, bit) (((mask) & (bit)) != 0)
+#else
+#define TB_DBG(mask, bit) (false)
+#endif
+
 // ----------------------------------------------------------------------------- device PTX
 #if defined(__CUDACC__)
 

@@ -88,11 +88,18 @@ __device__ __host__ __forceinline__ uint32_t umma_idesc_bf16_m256(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
 }
 
-// Launch: cluster (2,1,1), grid = 2 * min(pair_tiles, 74), kConvThreads threads.
+// Warp roles: warpgroup 0 = {TMA producer, MMA issuer, two idle warps}, warpgroups 1-2 = eight epilogue warps.  With the
+// correction accumulator next to the main one a tile fills TMEM, so an epilogue warp drains its 8 chunks (128 registers)
+// before releasing the stage (epilogue_drained): the epilogue warpgroups take 224 registers per thread and warpgroup 0
+// gives back all but 56 (setmaxnreg; 128*56 + 256*224 = the 384*168 the CTA is launched with).
+constexpr int kPairEpilogueWarp0 = 4;
+constexpr int kPairThreads = 32 * (kPairEpilogueWarp0 + kConvEpilogueWarps);
+
+// Launch: cluster (2,1,1), grid = 2 * min(pair_tiles, 74), kPairThreads threads.
 // Uses ConvKernelParams with mt = 1, nfold = 0; n_ctile_m counts 256-row pair-tiles; w_sub_bytes is the
 // per-CTA HALF tile ((n_tile/2) * kc * 2); map_w's box has n_tile/2 rows.
 template <int ACT1, int ACT2, int FMT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_w, const ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -150,6 +157,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
     const int n_groups = (p.n_kblocks + p.kg - 1) / p.kg;
     const int half_rows = p.n_tile >> 1;
 
+    if (warp < kPairEpilogueWarp0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // =============================================================== TMA producer (both CTAs)
         const bool leader = elect_one();
@@ -173,7 +182,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                 const int kb0 = g * p.kg;
                 const int nkb = min(p.kg, p.n_kblocks - kb0);
                 if (leader) {
-                    if (p.dbg & 1) {
+                    if (TB_DBG(p.dbg, 1)) {
                         if (leader_cta) mbar_arrive(&full_bar[s]);
                     } else {
                         if (leader_cta) mbar_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(nkb) * kb_bytes);
@@ -228,7 +237,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                     tc_fence_after();
                     const int nkb = min(p.kg, p.n_kblocks - g * p.kg);
                     uint32_t base16 = (smem_base16 + static_cast<uint32_t>(s) * (stage_bytes >> 4)) | lo_flags;
-                    if (!(p.dbg & 2)) {
+                    if (!TB_DBG(p.dbg, 2)) {
                         for (int j = 0; j < nkb; ++j, base16 += kb16) {
                             for (int kk = 0; kk < k16_steps; ++kk) {
                                 const uint32_t a_hi = base16 + static_cast<uint32_t>(kk) * 2u;   // +32 B per K=16
@@ -254,10 +263,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                 if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
             }
         }
+    }
     } else {
-        // =============================================================== epilogue (warps 2..9, both CTAs)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // =============================================================== epilogue (warps 4..11, both CTAs)
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - kPairEpilogueWarp0) >> 2;
         const int row_in_tile = quad * 32 + lane;
         const int chunks = p.n_tile / 16;
         const float* bias_v = epi_in_smem ? s_epi[0] : p.bias;
@@ -271,22 +282,23 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             mbar_wait_relaxed(&tfull_bar[acc], acc_ph);   // a whole mainloop away: sleep between polls (0.7 % on conv5)
             tc_fence_after();
             const int64_t m = static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank)) * 128 + row_in_tile;
-            const bool row_ok = m < p.m_total && !(p.dbg & 8);
+            const bool row_ok = m < p.m_total && !TB_DBG(p.dbg, 8);
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>(acc * p.acc_cols);
-            for (int c = half; c < chunks && !(p.dbg & 4); c += 2) {
+            if (p.corr_off && !TB_DBG(p.dbg, 4)) {
+                // separate correction accumulator (the default): main + correction fill TMEM, so the stage is drained
+                // into registers and released before the epilogue math runs (conv_umma.cuh, epilogue_drained)
+                uint64_t* bar = &tempty_bar[acc];
+                epilogue_drained<ACT1, ACT2, FMT>(p, tbase, half, chunks, n_idx * p.n_tile, m, row_ok, bias_v, scale_v,
+                                                  shift_v, [&] { if (lane == 0) mbar_arrive_cluster(bar, 0); });
+                if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+                continue;
+            }
+            for (int c = half; c < chunks && !TB_DBG(p.dbg, 4); c += 2) {
                 uint32_t r[16];
                 __syncwarp();                      // tcgen05.ld is .sync.aligned
                 tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), r);
-                if (p.corr_off) {                  // warp-uniform: add the correction accumulator
-                    uint32_t rc[16];
-                    tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.corr_off + c * 16), rc);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rc[i]));
-                } else {
-                    tmem_ld_wait();
-                }
+                tmem_ld_wait();
                 const int n0 = n_idx * p.n_tile + c * 16;
                 if (n0 >= p.c_store) continue;     // warp-uniform
                 epilogue_chunk<ACT1, ACT2, FMT>(p, r, n0, m, row_ok, bias_v, scale_v, shift_v);

@@ -212,6 +212,54 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
     epilogue_store16<FMT>(p, v, n0, m, row_ok);
 }
 
+// Early-release epilogue for tiles whose main and correction accumulators together fill TMEM (one accumulator stage,
+// DESIGN.md section 4): the warp first drains its share of BOTH accumulators into registers (summing them), releases the
+// TMEM stage -- the MMA warp starts the next tile's mainloop -- and only then runs bias / activation / BatchNorm / split /
+// stores on the register copy.  The exposed part of the epilogue shrinks from the whole tile (~7 % of conv5) to the
+// TMEM reads.  A warp owns the chunks half, half+2, ... of its lane quadrant: at most 8 for n_tile <= 256.
+template <int ACT1, int ACT2, int FMT, typename Release>
+__device__ __forceinline__ void epilogue_drained(const ConvKernelParams& p, uint32_t tbase, int half, int chunks,
+                                                 int n_base, int64_t m, bool row_ok, const float* bias_v,
+                                                 const float* scale_v, const float* shift_v, Release release) {
+    uint32_t acc[8][16];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        const int c0 = half + 2 * i, c1 = c0 + 2;             // warp-uniform
+        uint32_t rc0[16], rc1[16];
+        __syncwarp();                                          // tcgen05.ld is .sync.aligned
+        if (c0 < chunks) {
+            tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c0 * 16), acc[i]);
+            tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.corr_off + c0 * 16), rc0);
+        }
+        if (c1 < chunks) {
+            tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c1 * 16), acc[i + 1]);
+            tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.corr_off + c1 * 16), rc1);
+        }
+        tmem_ld_wait();
+        if (c0 < chunks) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                acc[i][e] = __float_as_uint(__uint_as_float(acc[i][e]) + __uint_as_float(rc0[e]));
+        }
+        if (c1 < chunks) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                acc[i + 1][e] = __float_as_uint(__uint_as_float(acc[i + 1][e]) + __uint_as_float(rc1[e]));
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    release();                                                 // every tcgen05.ld of this warp has completed
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = half + 2 * i;
+        if (c < chunks) {
+            const int n0 = n_base + c * 16;
+            if (n0 < p.c_store) epilogue_chunk<ACT1, ACT2, FMT>(p, acc[i], n0, m, row_ok, bias_v, scale_v, shift_v);
+        }
+    }
+}
+
 template <int ACT1, int ACT2, int FMT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -301,7 +349,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                 const int kb0 = g * p.kg;
                 const int nkb = min(p.kg, p.n_kblocks - kb0);
                 if (leader) {
-                    if (p.dbg & 1) {
+                    if (TB_DBG(p.dbg, 1)) {
                         mbar_arrive(&full_bar[s]);
                     } else {
                         mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * kb_bytes);
@@ -375,7 +423,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                 tc_fence_after();
                 const int nkb = min(p.kg, p.n_kblocks - g * p.kg);
                 uint32_t base16 = (smem_base16 + static_cast<uint32_t>(s) * (stage_bytes >> 4)) | lo_flags;
-                if (leader && !(p.dbg & 2)) {
+                if (leader && !TB_DBG(p.dbg, 2)) {
                     // one thread issues; the issue pattern is selected outside the K loops so that each loop
                     // body is a straight run of UTCHMMAs with affine descriptor updates
                     const int mode = (p.corr_off && !p.nfold) ? 0 : p.nfold ? (p.mt == 2 ? 2 : 1) : (p.mt == 2 ? 4 : 3);
@@ -444,10 +492,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             const int n_idx = tile - m_ct * p.n_tiles;
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
-            for (int mi = 0; mi < p.mt && !(p.dbg & 4); ++mi) {
+            for (int mi = 0; mi < p.mt && !TB_DBG(p.dbg, 4); ++mi) {
                 const int64_t m = (p.cluster2 ? static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank))
                                               : static_cast<int64_t>(m_ct * p.mt + mi)) * 128 + row_in_tile;
-                const bool row_ok = m < p.m_total && !(p.dbg & 8);
+                const bool row_ok = m < p.m_total && !TB_DBG(p.dbg, 8);
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                        static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);
                 for (int c = half; c < chunks; c += 2) {

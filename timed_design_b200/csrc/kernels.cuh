@@ -782,8 +782,9 @@ __device__ double np_pairwise_sum(const double* a, int n) {
 
 // apply_temp_to_probs (sampling_utils.py:159-161): p ** (1/t), row sum, divide.  One thread
 // per row (rows are short: 20 or 338); fp64 throughout.
-__global__ void temperature_kernel(const double* __restrict__ in, int64_t n_rows, int n_cls,
-                                   double inv_t, double* __restrict__ out) {
+// `in` and `out` may be the SAME buffer (the sampler rescales in place): no __restrict__, no read-only loads; every
+// element is read into a register before the store to the same address.
+__global__ void temperature_kernel(const double* in, int64_t n_rows, int n_cls, double inv_t, double* out) {
     const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (row >= n_rows) return;
     const double* src = in + row * n_cls;

@@ -119,7 +119,7 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
             mbar_wait(&slab_empty[b], (slab_uses[b] & 1u) ^ 1u);
             ++slab_uses[b];
             if (leader) {
-                if (p.dbg & 1) {
+                if (TB_DBG(p.dbg, 1)) {
                     mbar_arrive(&slab_full[b]);
                 } else {
                     mbar_expect_tx(&slab_full[b], 2u * static_cast<uint32_t>(p.n_chunks) * span_bytes);
@@ -147,7 +147,7 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
                     load_slab(tile + gridDim.x, sb ^ 1);
                 mbar_wait(&w_empty[ws], wph ^ 1u);
                 if (leader) {
-                    if (p.dbg & 1) {
+                    if (TB_DBG(p.dbg, 1)) {
                         mbar_arrive(&w_full[ws]);
                     } else {
                         const uint32_t bytes = static_cast<uint32_t>(min(p.w_group, n_taps - tap)) * p.w_tap_bytes;
@@ -195,7 +195,7 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
                             mbar_wait(&w_full[ws], wph);
                             tc_fence_after();
                         }
-                        if (leader && !(p.dbg & 2)) {
+                        if (leader && !TB_DBG(p.dbg, 2)) {
                             const int off = (a - p.pd) * hw + (b - p.ph) * p.Wp + (c - p.pw);
                             uint32_t a_k = (a_tile16 + static_cast<uint32_t>(off)) | (stride16 << 16);
                             uint32_t b_k = (w_ring16 + static_cast<uint32_t>(ws) * (w_stage_bytes >> 4) +
@@ -239,7 +239,7 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
         for (int tile = blockIdx.x; tile < p.n_tiles_total; tile += gridDim.x) {
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
-            for (int mi = 0; mi < p.mt && !(p.dbg & 4); ++mi) {
+            for (int mi = 0; mi < p.mt && !TB_DBG(p.dbg, 4); ++mi) {
                 const int64_t u = static_cast<int64_t>(tile) * tile_pos + mi * 128 + quad * 32 + lane;   // t - t_first
                 const int64_t f = u / fpos;
                 int rem = static_cast<int>(u - f * fpos);
@@ -247,7 +247,7 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
                 rem -= z * hw;
                 const int pr = rem / p.Wp;
                 const int q = rem - pr * p.Wp;
-                const bool row_ok = u < p.t_count && z < p.Do && pr < p.Ho && q < p.Wo && !(p.dbg & 8);
+                const bool row_ok = u < p.t_count && z < p.Do && pr < p.Ho && q < p.Wo && !TB_DBG(p.dbg, 8);
                 const int64_t m = ((f * p.Do + z) * p.Ho + pr) * p.Wo + q;
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                        static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);

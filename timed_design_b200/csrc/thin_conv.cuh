@@ -155,7 +155,7 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
             const int nf = plane / p.Do;
             const int z = plane - nf * p.Do;
             mbar_wait(&empty_bar[s], ph ^ 1u);
-            if (leader && (p.dbg & 1)) {
+            if (leader && TB_DBG(p.dbg, 1)) {
                 mbar_arrive(&full_bar[s]);
             } else if (leader) {
                 mbar_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(taps) * p.span_bytes);
@@ -205,7 +205,7 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
             // an indexed constant load per step put ~110 cycles of dependent latency between MMAs):
             //   (a) filter row r, in-row pixel pair (2jp, 2jp+1): start = span r + 2jp pixels, LBO = one pixel
             //   (b) left-over odd tap of rows (r, r+1): start = span r + (kw-1) pixels, LBO = span stride
-            if (leader && !(p.dbg & 2)) {
+            if (leader && !TB_DBG(p.dbg, 2)) {
                 uint32_t b = w_base16 | (w_lbo16 << 16);
                 uint32_t accumulate = 0;
                 uint32_t a_row = a_base16;
@@ -257,7 +257,7 @@ thin_conv_kernel(const __grid_constant__ ThinConvParams p) {
             tc_fence_after();
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>(acc * p.acc_cols);
-            for (int c = half; c < chunks && !(p.dbg & 4); c += 2) {
+            for (int c = half; c < chunks && !TB_DBG(p.dbg, 4); c += 2) {
                 uint32_t r[16], rc[16];
                 __syncwarp();
                 tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), r);

@@ -142,7 +142,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
             const int z0 = zg * p.zt;
             const int n_planes = min(p.zt, p.Do - z0) + p.kd - 1;
             mbar_wait(&empty_bar[s], ph ^ 1u);
-            if (leader && (p.dbg & 1)) {
+            if (leader && TB_DBG(p.dbg, 1)) {
                 mbar_arrive(&full_bar[s]);
             } else if (leader) {
                 mbar_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(n_planes) * p.span_bytes);
@@ -180,7 +180,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
             mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
-            if (leader && !(p.dbg & 2)) {
+            if (leader && !TB_DBG(p.dbg, 2)) {
                 const uint32_t d_tile = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
                 uint32_t a_plane = stage0_16 + static_cast<uint32_t>(s) * (stage_bytes >> 4);
                 for (int i = 0; i < n_planes; ++i, a_plane += ss16) {
@@ -251,11 +251,11 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
             const int u = u0 + quad * 32 + lane;
             const int prow = u / p.Wp;
             const int q = u - prow * p.Wp;
-            const bool row_ok = u < plane_positions && q < p.Wo && !(p.dbg & 8);   // dbg 8: compute, do not store
+            const bool row_ok = u < plane_positions && q < p.Wo && !TB_DBG(p.dbg, 8);   // dbg 8: compute, do not store
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
             if constexpr (POOL == 0) {
-                for (int item = sub; item < zt_eff * chunks && !(p.dbg & 4); item += kThinzSubs) {
+                for (int item = sub; item < zt_eff * chunks && !TB_DBG(p.dbg, 4); item += kThinzSubs) {
                     const int j = item / chunks;
                     const int64_t m = ((static_cast<int64_t>(nf) * p.Do + z0 + j) * p.Ho + prow) * p.Wo + q;
                     const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
@@ -281,7 +281,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                 // max over the z pairs only: halves what this kernel writes and what the (then 1x2x2) pooling pass reads;
                 // no staging, no barrier, no overlapping windows
                 const int n_zp = (zt_eff + 1) >> 1;
-                for (int item = sub; item < n_zp * chunks && !(p.dbg & 4); item += kThinzSubs) {
+                for (int item = sub; item < n_zp * chunks && !TB_DBG(p.dbg, 4); item += kThinzSubs) {
                     const int zp = item / chunks;
                     const int c = item - zp * chunks;
                     const int Z = (z0 >> 1) + zp;
@@ -315,7 +315,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                 const int et = threadIdx.x - 64;                         // index among the epilogue threads
                 const int n_zp = (zt_eff + 1) >> 1;
                 const int row_f4 = p.n_tile >> 2;                        // float4 slots per staged row
-                for (int zp = 0; zp < n_zp && !(p.dbg & 4); ++zp, pool_buf ^= 1) {
+                for (int zp = 0; zp < n_zp && !TB_DBG(p.dbg, 4); ++zp, pool_buf ^= 1) {
                     // two staging buffers: one barrier per z pair is enough (a buffer is rewritten two pairs later)
                     float4* stage4 = reinterpret_cast<float4*>(pool_stage) + pool_buf * 128 * row_f4;
                     const int Z = (z0 >> 1) + zp;
@@ -393,7 +393,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                         }
                     }
                 }
-                if (p.dbg & 4) {
+                if (TB_DBG(p.dbg, 4)) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[acc]);

@@ -107,6 +107,8 @@ def seq_metrics_device(d_seqs, n_seqs: int, n_res: int) -> np.ndarray:
     """d_seqs: CUDA uint8 tensor holding (n_seqs, n_res) ASCII letters -> (n_seqs, 4) float64 host array
     [charge, isoelectric point, molecular weight, molar extinction]."""
     torch = _torch()
+    from . import seq_metrics
+    seq_metrics.warn_unverified()
     tables, lut = _metric_tables(torch)
     out = torch.empty((n_seqs, 4), dtype=torch.float64, device="cuda")
     _lib.check(_lib.load().timed_b200_seq_metrics(_ptr(d_seqs), int(n_seqs), int(n_res), _ptr(lut), _ptr(tables),

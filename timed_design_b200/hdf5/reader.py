@@ -599,6 +599,14 @@ class Dataset(_Object):
             return None
         shuffle = next((cd[0] if cd else typ.size for fid, cd in self._filters if fid == 2), 0)
         table = [(tuple(int(o) for o in offs), caddr + self._f.base_addr, int(csize)) for offs, csize, mask, caddr in chunks]
+        # the native inflater reads file_base + offset without knowing the file length: a truncated / corrupt file must
+        # raise here instead of faulting there
+        flen = len(self._f.buf)
+        for org, off, size in table:
+            if off < 0 or size < 0 or off + size > flen:
+                raise Hdf5FormatError(f"chunk at offset {off} (+{size} bytes) lies outside the file ({flen} bytes)")
+            if any(o < 0 or o >= s for o, s in zip(org, self._shape)):
+                raise Hdf5FormatError(f"chunk origin {org} lies outside the dataset shape {tuple(self._shape)}")
         return tuple(int(c) for c in cdims[:rank]), table, 1 in fids, int(shuffle), dtype
 
     def _read(self):

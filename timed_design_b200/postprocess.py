@@ -245,6 +245,14 @@ def savetxt_fp16(f, arr16: np.ndarray) -> None:
     f.write(data.decode("ascii") if isinstance(f, io.TextIOBase) else data)
 
 
+def _warn_fallback(native: str, fallback: str, err: Exception) -> None:
+    """The host-side text helpers have a numpy equivalent (same bytes / values, an order of magnitude slower); falling
+    back silently would hide a broken or missing libtimed_b200 symbol."""
+    import warnings
+    warnings.warn(f"{native} unavailable ({type(err).__name__}: {err}); using {fallback} (identical output, much slower)",
+                  RuntimeWarning, stacklevel=3)
+
+
 def savetxt_e18(f, arr) -> None:
     """Byte-identical to ``np.savetxt(f, arr, delimiter=",")`` for a 2-D float32/float64 array (the raw 338-wide rotamer
     dump, predict.py:145-146), formatted by libtimed_b200's host-side writer on all cores; any other input goes through
@@ -258,7 +266,8 @@ def savetxt_e18(f, arr) -> None:
     try:
         from . import _lib
         lib = _lib.load()
-    except Exception:
+    except Exception as e:                                 # library missing: correct but ~13x slower -- say so
+        _warn_fallback("timed_b200_format_csv_e18", "np.savetxt", e)
         np.savetxt(f, a, delimiter=",")
         return
     a = np.ascontiguousarray(a)
@@ -294,7 +303,8 @@ def load_matrix_csv(path) -> np.ndarray:
             del view
             mm.close()
         return out[0] if out.shape[0] == 1 else out              # genfromtxt returns 1-D for a single row
-    except Exception:
+    except Exception as e:                                 # not a rectangular numeric matrix, or the library is missing
+        _warn_fallback("timed_b200_parse_csv", "np.genfromtxt", e)
         return np.genfromtxt(path, delimiter=",", dtype=np.float64)
 
 

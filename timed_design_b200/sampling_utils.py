@@ -180,6 +180,17 @@ def sample_chains(prob_list: t.Sequence[np.ndarray], sample_n: int, rotamer_cate
 
 
 _draw_counter = {"n": 0}
+# Philox stream reserved for random_choice_prob_index: its draws never coincide with a chain's (chains are keyed by
+# their index in sample_with_multiprocessing, or by a hash of their name in sample_from_sequences)
+_RCPI_STREAM = (1 << 63) + 0x52435049
+
+
+def _chain_stream_id(pdb: str) -> int:
+    """Stable 63-bit stream id of a chain key (independent of PYTHONHASHSEED): a caller that loops
+    ``sample_from_sequences`` over chains -- what the reference's starmap does -- gets an independent uniform block per
+    chain instead of the same one for every chain."""
+    import hashlib
+    return int.from_bytes(hashlib.blake2b(str(pdb).encode(), digest_size=8).digest(), "little") >> 1
 
 
 def random_choice_prob_index(probs: np.ndarray, axis: int = 1, return_seq: bool = True,
@@ -199,7 +210,8 @@ def random_choice_prob_index(probs: np.ndarray, axis: int = 1, return_seq: bool 
     _draw_counter["n"] += 1
     if not return_seq and p.shape[1] != 20:
         cats = ["A"] * p.shape[1]            # letters unused: indices requested
-    seqs, idx = sample_block(p, 1, cats, uniforms=u, first_sample=n, return_idx=not return_seq)
+    seqs, idx = sample_block(p, 1, cats, uniforms=u, first_sample=n, return_idx=not return_seq,
+                             stream_id=_RCPI_STREAM)
     if return_seq:
         return np.array(list(seqs[0].tobytes().decode("ascii")))
     return idx[0].astype(np.int64)
@@ -214,9 +226,13 @@ def _rows_to_tuples(seqs_u8: np.ndarray, metrics: t.Optional[np.ndarray] = None)
 
 
 def sample_from_sequences(pdb: str, sample_n: int, pdb_to_probability: dict,
-                          rotamer_categories: t.Optional[t.Sequence[str]], *, stream_id: int = 0) -> dict:
-    """sampling_utils.py:93-136: ``{pdb: [(sequence, charge, pI, mw, ext280)] * sample_n}``."""
+                          rotamer_categories: t.Optional[t.Sequence[str]], *,
+                          stream_id: t.Optional[int] = None) -> dict:
+    """sampling_utils.py:93-136: ``{pdb: [(sequence, charge, pI, mw, ext280)] * sample_n}``.  Without an explicit
+    ``stream_id`` the chain draws from the Philox stream keyed by a stable hash of ``pdb``."""
     probs = np.array(pdb_to_probability[pdb], dtype=np.float64)
+    if stream_id is None:
+        stream_id = _chain_stream_id(pdb)
     seqs, _, metrics = sample_block(probs, int(sample_n), rotamer_categories, stream_id=stream_id, return_metrics=True)
     return {pdb: _rows_to_tuples(seqs, metrics)}
 

@@ -63,6 +63,20 @@ def charge_at(counts: np.ndarray, ph) -> np.ndarray:
     return total
 
 
+_warned = {"done": False}
+
+
+def warn_unverified() -> None:
+    """One RuntimeWarning per process the first time metric values are produced: the residue tables are unverified
+    against ampal 1.5.1 (absent offline), so charge / pI / MW / ext280 must not be taken as drop-in values."""
+    if not _warned["done"]:
+        _warned["done"] = True
+        import warnings
+        warnings.warn("sequence metrics (charge, isoelectric point, molecular weight, extinction) use residue tables that "
+                      "are UNVERIFIED against ampal 1.5.1 (not installable offline); file formats match the reference, "
+                      "metric values may differ", RuntimeWarning, stacklevel=3)
+
+
 def metrics_from_composition(counts: np.ndarray):
     """(charge at pH 7.4, isoelectric point on the 1.0..12.9 step-0.1 grid, molecular weight,
     molar extinction at 280 nm), one row per sequence."""
@@ -77,6 +91,7 @@ def metrics_from_composition(counts: np.ndarray):
 
 def calculate_seq_metrics(seq: str):
     """Drop-in signature of analyse_utils.calculate_seq_metrics for one sequence."""
+    warn_unverified()
     c, p, m, e = metrics_from_composition(composition(np.frombuffer(seq.encode(), dtype=np.uint8)[None, :]))
     return float(c[0]), float(p[0]), float(m[0]), float(e[0])
 
