@@ -5,6 +5,7 @@
 #include "../../include/timed_b200.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -296,7 +297,7 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
     if (!sep_corr && 2 * acc_cols <= 512 && static_cast<int64_t>(ceil_div(m_tiles, 2)) * p.n_tiles >= 2 * 148)
         mts.push_back(2);
     mts.push_back(1);
-    int best_score = -1;
+    int best_score = INT_MIN;
     for (int mt : mts) {
         for (int kc : kcs) {
             const size_t a_sub = 128u * kc * 2u, w_sub = static_cast<size_t>(p.n_tile) * kc * 2u;
@@ -331,7 +332,7 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
             }
         }
     }
-    TB_REQUIRE(best_score >= 0, "conv: no tile configuration fits shared memory");
+    TB_REQUIRE(best_score != INT_MIN, "conv: no tile configuration fits shared memory");
     return 0;
 }
 
