@@ -90,7 +90,6 @@ def test_truncated_file_raises_format_error(tmp_path):
     raw = (G / "spec_earliest.h5").read_bytes()
     p = tmp_path / "cut.h5"
     p.write_bytes(raw[:len(raw) - 3000])
-    with pytest.raises((Hdf5FormatError, KeyError, ValueError, IndexError, Exception)) as ei:
+    with pytest.raises(Hdf5FormatError):
         flat, _ = frames.create_flat_dataset_map(p)
         frames.load_batch(p, flat)
-    assert not isinstance(ei.value, (SystemExit, KeyboardInterrupt))

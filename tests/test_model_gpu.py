@@ -174,3 +174,24 @@ def test_fused_pool_into_cpv_matches_unfused(monkeypatch):
     assert "slab" in m.op_kernel(3, 5)
     assert np.abs(fused - base).max() <= 2e-6
     assert np.abs(fused - ko.forward_torch(cfg, w, X)).max() <= PROB_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("classes", [20, 338])
+def test_fused_head_matches_unfused_bit_for_bit(classes, monkeypatch):
+    """Network head in one launch: col2im gather + bias/ELU/BN + GlobalAveragePooling + Softmax after the head GEMM
+    (20 classes, tap-to-N), or pooling + softmax (338 classes, direct conv).  Same summation orders as the separate
+    col2im / gpool / softmax kernels => identical bits, two (20) / one (338) launches fewer per forward."""
+    from timed_design_b200.model import Model
+    cfg, w = standins.timed_standin(classes, seed=7 if classes == 20 else 8)
+    X = standins.synthetic_frames(9, seed=41)
+    m = Model(cfg, w)
+    fused = m.predict(X)
+    names = [m.op_kernel(i, 9) for i in range(len(m.graph.ops))]
+    assert any("head_" in n for n in names), names
+    monkeypatch.setenv("TIMED_B200_NO_HEADFUSE", "1")
+    m2 = Model(cfg, w)
+    unfused = m2.predict(X)
+    assert m2.launches_per_forward == m.launches_per_forward + (2 if classes == 20 else 1)
+    np.testing.assert_array_equal(fused, unfused)
+    assert np.abs(fused - ko.forward_torch(cfg, w, X)).max() <= PROB_TOL

@@ -173,6 +173,10 @@ struct ConvPlan {
     // im2col along W only.  Same MMA count and activation traffic as folding all taps into N (three N tiles there, three
     // K taps here) but a Z matrix kw times smaller to write and to gather from.
     bool t2n_kw = false;
+    // network head: this tap-to-N conv is read only by GlobalPooling -> Softmax (the graph output): the col2im gather, the
+    // pooling and the softmax run as ONE launch after the GEMM (head_col2im_pool_softmax_kernel) straight into `probs`
+    bool fuse_head = false;
+    int head_is_avg = 1;
     int taps_eff() const { return tap2n ? (t2n_kw ? kw : 1) : (wfold ? kd * kh : kd * kh * kw); }
     // geometry of the GEMM rows (output pixels, or input pixels for tap-to-N)
     int Mo_d() const { return tap2n ? Di : Do; }
@@ -215,9 +219,31 @@ static void free_conv_plan(ConvPlan& p) {
     p.d_c2i_bias = p.d_c2i_scale = p.d_c2i_shift = nullptr;
 }
 
+// Accumulator-truncation compensation factor for a main accumulator that receives `n_nominal` MMAs per output of which
+// the fraction `valid` has non-zero operands (zero 'same' padding adds exact zeros: no truncation).  Measured on the
+// B200 (tools/accum_error.py, profiles/r2_accum_error.jsonl): operands exactly representable in bf16, fp64 reference,
+// relative shrink of the result = c(n)*n with c rising slowly from 1.27e-8 (n = 32) to 1.71e-8 (n = 864) per
+// EFFECTIVE MMA, identical for positive and negative results (truncation toward zero).
+static float accum_comp(double n_nominal, double valid) {
+    if (getenv("TIMED_B200_NO_ACC_COMP")) return 1.0f;
+    const double n = n_nominal * valid;
+    if (n < 1.0) return 1.0f;
+    const double c = 1.30e-8 + 0.09e-8 * std::log2(std::max(n, 32.0) / 32.0);
+    return static_cast<float>(1.0 + c * n);
+}
+
+// mean over the output positions of one axis of (taps that fall inside the input) / (taps)
+static double valid_tap_fraction(int in, int out, int k, int pad0) {
+    double s = 0.0;
+    for (int o = 0; o < out; ++o)
+        for (int t = 0; t < k; ++t) s += (o + t - pad0 >= 0 && o + t - pad0 < in) ? 1.0 : 0.0;
+    return s / (static_cast<double>(out) * k);
+}
+
 // 227 KB per CTA is the limit for static + dynamic shared memory; the kernel keeps ~6.3 KB static
 // (barriers + staged epilogue vectors), and 1 KB of the dynamic part is alignment slack.
 static constexpr size_t kSmemDynamicMax = 220 * 1024;
+static constexpr size_t kHeadSmemMax = 96 * 1024;      // fused head: one frame's (pixels, classes) activation in shared memory
 static constexpr size_t kSmemBudget = kSmemDynamicMax - 1024;
 
 // Pick (kc, mt, kg, stages) for a conv given the number of output rows.
@@ -656,6 +682,9 @@ static int slab_launch(ConvPlan& p, void* in_base, int64_t n_frames, const TView
     e.ldc = out.ld;
     e.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
     k.dbg = debug_mask();
+    e.acc_comp = accum_comp(static_cast<double>(p.kd) * p.kh * p.kw * ceil_div(p.cin, 16),
+                            valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]) *
+                                valid_tap_fraction(p.Wi, p.Wo, p.kw, p.pad0[2]));
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "slab conv: split output channel padding mismatch");
     const size_t w_stage = (static_cast<size_t>(k.w_group) * k.w_tap_bytes + 127) & ~static_cast<size_t>(127);
@@ -828,6 +857,7 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
     e.out_f32 = out.f32; e.out_hi = out.hi; e.out_lo = out.lo;
     e.ldc = out.ld;
     e.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    e.acc_comp = 1.0f;                     // <= 42 MMAs per accumulator: the shrink is below 1e-6
     k.dbg = debug_mask();
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "thinz conv: split output channel padding mismatch");
@@ -1167,6 +1197,22 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.ldc = out.ld;
     k.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
     k.dbg = debug_mask();
+    {
+        // MMAs with real channels per tap (zero-padded K=16 blocks add exact zeros) x taps, x the fraction of taps that
+        // fall inside the volume; three times as many when the corrections share the main accumulator
+        const double per_tap = p.wfold ? p.kwin * 8 / 16.0 : ceil_div(p.cin, 16);
+        double valid = 1.0;
+        if (!p.tap2n && !p.wfold) {
+            valid = valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]) *
+                    valid_tap_fraction(p.Wi, p.Wo, p.kw, p.pad0[2]);
+        } else if (p.wfold) {
+            valid = valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]);
+        } else if (p.t2n_kw) {
+            valid = valid_tap_fraction(p.Wi, p.Wo, p.kw, p.pad0[2]);
+        }
+        const bool shared_acc = !cfg.nfold && !cfg.corr_off;
+        k.acc_comp = accum_comp(per_tap * k.n_taps * (shared_acc ? 3.0 : 1.0), valid);
+    }
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "conv: split output channel padding mismatch");
 
@@ -1208,6 +1254,20 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
         cp.cout = p.cout;
         cp.z_ld = p.z_ld;
         cp.act1 = p.act1; cp.act2 = p.act2; cp.alpha1 = p.alpha1; cp.alpha2 = p.alpha2;
+        if (p.fuse_head) {
+            // final_out is the (frames, classes) probability matrix
+            const size_t smem = (static_cast<size_t>(p.Do) * p.Ho * p.Wo * p.cout + p.cout) * sizeof(float);
+            static bool attr_set = false;
+            if (!attr_set) {
+                TB_CHECK_CUDA(cudaFuncSetAttribute(head_col2im_pool_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(kHeadSmemMax)));
+                attr_set = true;
+            }
+            head_col2im_pool_softmax_kernel<<<static_cast<unsigned>(n_frames), 256, smem, stream>>>(
+                static_cast<const float*>(scratch), cp, p.d_c2i_bias, p.d_c2i_scale, p.d_c2i_shift, p.head_is_avg, final_out.f32);
+            TB_CHECK_CUDA(cudaGetLastError());
+            return 0;
+        }
         const int cw = final_out.fmt == FMT_SPLIT ? final_out.c_pad : final_out.c;
         const int64_t work = n_frames * p.Do * p.Ho * p.Wo * cw;
         if (final_out.fmt == FMT_F32 && p.cout % 4 == 0 && p.z_ld % 4 == 0 && final_out.ld % 4 == 0 &&
@@ -1227,6 +1287,8 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
 // ----------------------------------------------------------------------------- graph
 struct OpNode {
     int alias_of = -1;          // pooling op fused into the conv that feeds it: shares that op's output tensor
+    bool skip = false;          // runs inside another op's launch (fused network head)
+    bool pool_softmax = false;  // GPOOL whose only reader is the final SOFTMAX: one launch writes the probabilities
     tb_op_desc d;
     ConvPlan conv;
     float* d_scale = nullptr;   // AFFINE
@@ -1540,7 +1602,9 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                             if (ops[k].inputs[q] == i) { ++n_readers; j = k; }
                     bool ok = n_readers == 1 && ops[j].op == TB_OP_POOL3D && ops[j].pool_kind == 0 && ops[j].n_inputs == 1 &&
                               ops[j].kernel[0] == 2 && (ops[j].stride[0] == 2 || ops[j].stride[0] <= 0) &&
-                              node.conv.thinz_params.zt % 2 == 0;
+                              node.conv.thinz_params.zt % 2 == 0 &&
+                              // the epilogue pools the RAW sums: its map must be monotone (ELU with a negative alpha is not)
+                              (d.act1 != TB_ACT_ELU || d.alpha1 >= 0.f) && (d.act2 != TB_ACT_ELU || d.alpha2 >= 0.f);
                     const int zo = ok ? (ops[j].pad_same ? (t.D + 1) / 2 : t.D / 2) : 0;
                     if (ok && zo >= 1) {
                         node.conv.fuse_zpool = true;
@@ -1637,6 +1701,34 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
         // pointers are only valid during graph_create
         node.d.kernel_w = node.d.bias = node.d.scale = node.d.shift = nullptr;
     }
+    // Fused network head: ... -> GlobalPooling (j) -> Softmax (k = graph output), each read once.  The pooling op then
+    // writes the probabilities itself (head_pool_softmax_kernel); when it reads a tap-to-N conv (TIMED's 20-class head)
+    // that conv's col2im launch does gather + epilogue + pooling + softmax and both later ops are skipped.
+    if (n_ops >= 3 && ops[n_ops - 1].op == TB_OP_SOFTMAX && !getenv("TIMED_B200_NO_HEADFUSE")) {
+        const int k = n_ops - 1, j = ops[k].inputs[0];
+        auto readers = [&](int t) {
+            int n = 0;
+            for (int a = 0; a < n_ops; ++a)
+                for (int b = 0; b < ops[a].n_inputs; ++b) n += ops[a].inputs[b] == t;
+            return n;
+        };
+        if (ops[j].op == TB_OP_GPOOL && readers(j) == 1 && g->tensors[j].fmt == FMT_F32) {
+            g->ops[j].pool_softmax = true;
+            g->ops[k].skip = true;
+            g->launches -= 1;
+            const int i = ops[j].inputs[0];
+            ConvPlan& c = g->ops[i].conv;
+            const size_t smem = (static_cast<size_t>(c.Do) * c.Ho * c.Wo * c.cout + c.cout) * sizeof(float);
+            if (ops[i].op == TB_OP_CONV3D && c.tap2n && readers(i) == 1 && c.cout % 4 == 0 && c.z_ld % 4 == 0 &&
+                smem <= kHeadSmemMax && g->tensors[i].fmt == FMT_F32) {
+                c.fuse_head = true;
+                c.head_is_avg = ops[j].pool_kind;
+                g->ops[j].pool_softmax = false;
+                g->ops[j].skip = true;
+                g->launches -= 1;
+            }
+        }
+    }
     // conv inputs need 127 readable pixels past the last valid one (im2col column of 128)
     for (int i = 0; i < n_ops; ++i)
         if (ops[i].op == TB_OP_CONV3D) {
@@ -1703,9 +1795,14 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
         const tb_op_desc& d = node.d;
         const TensorInfo& t = g->tensors[i];
         TView out = make_view(t, base + L.offset[i], n_frames);
-        if (i == n_ops - 1) {   // the graph output goes straight to the caller's buffer
+        if (i == n_ops - 1 || node.pool_softmax || (d.op == TB_OP_CONV3D && node.conv.fuse_head)) {
+            // the graph output (or the op that computes it in a fused head) goes straight to the caller's buffer
             out.f32 = d_probs;
-            out.ld = t.C;
+            out.ld = g->n_classes;
+        }
+        if (node.skip) {
+            if (tset) TB_CHECK_CUDA(cudaEventRecord((*tset)[i + 1], s));
+            continue;
         }
         const int64_t out_pix = n_frames * t.pix_per_frame();
         TView in0{};
@@ -1812,8 +1909,12 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 break;
             }
             case TB_OP_GPOOL:
-                gpool_kernel<<<static_cast<unsigned>(n_frames), 128, 0, s>>>(
-                    in0, out, static_cast<int>(ti0->pix_per_frame()), d.pool_kind);
+                if (node.pool_softmax)
+                    head_pool_softmax_kernel<<<static_cast<unsigned>(n_frames), 128, in0.c * sizeof(float), s>>>(
+                        in0, static_cast<int>(ti0->pix_per_frame()), d.pool_kind, d_probs);
+                else
+                    gpool_kernel<<<static_cast<unsigned>(n_frames), 128, 0, s>>>(
+                        in0, out, static_cast<int>(ti0->pix_per_frame()), d.pool_kind);
                 break;
             case TB_OP_SOFTMAX:
                 softmax_kernel<<<static_cast<unsigned>((n_frames * 32 + 255) / 256), 256, 0, s>>>(in0, out, n_frames);
@@ -1972,15 +2073,15 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
                 const int rc = choose_config(c, n_frames * c.Mo_d() * c.Mo_h() * c.Mo_w(), &cfg);
                 if (rc) return rc;
                 name = cfg.pair ? "conv_pair_kernel" : (cfg.cluster2 ? "conv_umma_kernel(cluster2)" : "conv_umma_kernel");
-                if (c.tap2n) name += "+col2im_kernel";
+                if (c.tap2n) name += c.fuse_head ? "+head_col2im_pool_softmax_kernel" : "+col2im_kernel";
             }
             break;
         }
         case TB_OP_INPUT: name = g->tensors[op].cpv ? "input_convert_cpv_kernel" : g->tensors[op].padvol ? "input_convert_padvol_kernel" : "input_convert_kernel"; break;
         case TB_OP_POOL3D: name = node.alias_of >= 0 ? "(fused into the producing conv)" : g->tensors[op].cpv ? "pool3d_cpv_kernel" : "pool3d_vec8_kernel"; break;
         case TB_OP_AFFINE: name = "affine_act_kernel"; break;
-        case TB_OP_GPOOL: name = "gpool_kernel"; break;
-        case TB_OP_SOFTMAX: name = "softmax_kernel"; break;
+        case TB_OP_GPOOL: name = node.skip ? "(fused into the head conv's launch)" : node.pool_softmax ? "head_pool_softmax_kernel" : "gpool_kernel"; break;
+        case TB_OP_SOFTMAX: name = node.skip ? "(fused into the pooling launch)" : "softmax_kernel"; break;
         case TB_OP_CONCAT: name = "copy_channels_kernel"; break;
         case TB_OP_ADD: name = "add_kernel"; break;
         default: name = "?";

@@ -299,6 +299,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                 __syncwarp();                      // tcgen05.ld is .sync.aligned
                 tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(c * 16), r);
                 tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * p.acc_comp);
                 const int n0 = n_idx * p.n_tile + c * 16;
                 if (n0 >= p.c_store) continue;     // warp-uniform
                 epilogue_chunk<ACT1, ACT2, FMT>(p, r, n0, m, row_ok, bias_v, scale_v, shift_v);

@@ -83,6 +83,11 @@ struct ConvKernelParams {
     __nv_bfloat16* out_lo;
     int64_t ldc;           // row pitch of the output in elements
     int32_t c_store;       // columns < c_store are stored (FMT_SPLIT: multiple of 16)
+    // Accumulator-truncation compensation: the tensor core adds every MMA's partial sums into the
+    // fp32 TMEM accumulator with truncation toward zero, a relative shrink of ~1.2e-8 per accumulated MMA that is
+    // COHERENT across the outputs of a layer (tools/accum_error.py).  The epilogue multiplies the main accumulator by
+    // acc_comp = 1 + c(n)*n, n = MMAs with non-zero operands per output (host: accum_comp()).  1.0f switches it off.
+    float acc_comp;
     // ---- bring-up / tuning only (env TIMED_B200_DBG): 1 = skip TMA loads, 2 = skip MMA issue,
     // 4 = skip epilogue math+stores.  Results are garbage; used to time each role in isolation.
     int32_t dbg;
@@ -239,12 +244,12 @@ __device__ __forceinline__ void epilogue_drained(const ConvKernelParams& p, uint
         if (c0 < chunks) {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
-                acc[i][e] = __float_as_uint(__uint_as_float(acc[i][e]) + __uint_as_float(rc0[e]));
+                acc[i][e] = __float_as_uint(fmaf(__uint_as_float(acc[i][e]), p.acc_comp, __uint_as_float(rc0[e])));
         }
         if (c1 < chunks) {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
-                acc[i + 1][e] = __float_as_uint(__uint_as_float(acc[i + 1][e]) + __uint_as_float(rc1[e]));
+                acc[i + 1][e] = __float_as_uint(fmaf(__uint_as_float(acc[i + 1][e]), p.acc_comp, __uint_as_float(rc1[e])));
         }
     }
     tc_fence_before();
@@ -508,9 +513,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rc[i]));
+                            r[i] = __float_as_uint(fmaf(__uint_as_float(r[i]), p.acc_comp, __uint_as_float(rc[i])));
                     } else {
                         tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * p.acc_comp);
                     }
                     const int n0 = n_idx * p.n_tile + c * 16;
                     if (n0 >= p.c_store) continue;     // warp-uniform

@@ -574,6 +574,110 @@ __global__ void gpool_kernel(TView in, TView out, int pix_per_frame, int is_avg)
     }
 }
 
+// ------------------------------------------------------------------ fused network head
+// GlobalAveragePooling3D -> Softmax of one frame by one block, optionally preceded by the col2im gather of a tap-to-N
+// head conv (+ bias / activation / BatchNorm): the TIMED head is then GEMM + ONE launch instead of GEMM + col2im + pool +
+// softmax, and the (frames, pixels, classes) activation never goes to HBM.  Every sum runs in the order of the unfused
+// kernels (col2im_vec4_kernel's tap order, gpool_kernel's pixel order, softmax_kernel's warp tree), so the fused and
+// unfused paths agree bit for bit.  Dynamic shared memory: pix_per_frame * classes floats + classes floats.
+__device__ __forceinline__ void head_pool_softmax(const float* act, float* logits, int n_pix, int c, int is_avg,
+                                                  float* __restrict__ probs_row) {
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float acc = is_avg ? 0.0f : -INFINITY;
+        for (int px = 0; px < n_pix; ++px) {
+            const float v = act[px * c + ch];
+            acc = is_avg ? acc + v : fmaxf(acc, v);
+        }
+        logits[ch] = is_avg ? acc / static_cast<float>(n_pix) : acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float mx = -INFINITY;
+        for (int ch = lane; ch < c; ch += 32) mx = fmaxf(mx, logits[ch]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.0f;
+        for (int ch = lane; ch < c; ch += 32) sum += expf(logits[ch] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int ch = lane; ch < c; ch += 32) probs_row[ch] = expf(logits[ch] - mx) / sum;
+    }
+}
+
+// col2im (+ epilogue) -> global pool -> softmax; requires cout % 4 == 0 and z_ld % 4 == 0 (the float4 gather)
+__global__ void head_col2im_pool_softmax_kernel(const float* __restrict__ Z, Col2imParams cp, const float* __restrict__ bias,
+                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                int is_avg, float* __restrict__ probs) {
+    extern __shared__ float s_head[];
+    const int n_pix = cp.Do * cp.Ho * cp.Wo;
+    float* act = s_head;
+    float* logits = s_head + n_pix * cp.cout;
+    const int64_t nf = blockIdx.x;
+    const int groups = cp.cout / 4;
+    for (int i = threadIdx.x; i < n_pix * groups; i += blockDim.x) {
+        const int co = (i % groups) * 4;
+        int t = i / groups;
+        const int q = t % cp.Wo; t /= cp.Wo;
+        const int pr = t % cp.Ho;
+        const int z = t / cp.Ho;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int tap = 0;
+        for (int a = 0; a < cp.kd; ++a) {
+            const int d = z + a - cp.pd;
+            for (int b = 0; b < cp.kh; ++b) {
+                const int h = pr + b - cp.ph;
+                for (int c = 0; c < cp.kw; ++c, ++tap) {
+                    const int w = q + c - cp.pw;
+                    if (d < 0 || d >= cp.Di || h < 0 || h >= cp.Hi || w < 0 || w >= cp.Wi) continue;
+                    const int64_t ip = ((nf * cp.Di + d) * cp.Hi + h) * cp.Wi + w;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(Z + ip * cp.z_ld + tap * cp.cout + co));
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            }
+        }
+        float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v = apply_act(r[e] + bias[co + e], cp.act1, cp.alpha1);
+            v = fmaf(v, scale[co + e], shift[co + e]);
+            r[e] = apply_act(v, cp.act2, cp.alpha2);
+        }
+        *reinterpret_cast<float4*>(act + ((z * cp.Ho + pr) * cp.Wo + q) * cp.cout + co) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    __syncthreads();
+    head_pool_softmax(act, logits, n_pix, cp.cout, is_avg, probs + nf * cp.cout);
+}
+
+// global pool -> softmax of an fp32 (frames, pixels, classes) tensor: the pool sums straight from global memory
+__global__ void head_pool_softmax_kernel(TView in, int n_pix, int is_avg, float* __restrict__ probs) {
+    extern __shared__ float s_head[];
+    float* logits = s_head;
+    const int64_t nf = blockIdx.x;
+    const int c = in.c;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float acc = is_avg ? 0.0f : -INFINITY;
+        for (int px = 0; px < n_pix; ++px) {
+            const float v = tv_load(in, nf * n_pix + px, ch);
+            acc = is_avg ? acc + v : fmaxf(acc, v);
+        }
+        logits[ch] = is_avg ? acc / static_cast<float>(n_pix) : acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float mx = -INFINITY;
+        for (int ch = lane; ch < c; ch += 32) mx = fmaxf(mx, logits[ch]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.0f;
+        for (int ch = lane; ch < c; ch += 32) sum += expf(logits[ch] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int ch = lane; ch < c; ch += 32) probs[nf * c + ch] = expf(logits[ch] - mx) / sum;
+    }
+}
+
 // ------------------------------------------------------------------ softmax over channels
 // one warp per row; max-subtracted, fp32 (Keras Softmax / activation='softmax').
 __global__ void softmax_kernel(TView in, TView out, int64_t n_rows) {

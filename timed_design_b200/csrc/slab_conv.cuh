@@ -258,7 +258,7 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
                     tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.n_tile + c * 16), rc);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rc[i]));
+                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(fmaf(__uint_as_float(r[i]), p.epi.acc_comp, __uint_as_float(rc[i])));
                     const int n0 = c * 16;
                     if (n0 >= p.epi.c_store) continue;
                     epilogue_chunk<ACT1, ACT2, FMT>(p.epi, r, n0, m, row_ok, s_epi[0], s_epi[1], s_epi[2]);

@@ -89,6 +89,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
     __shared__ __align__(8) uint64_t w_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_epi[3][128];
+    __shared__ __align__(16) float s_sign[128];      // POOL: +1 where the epilogue map is increasing in the accumulator, -1 where decreasing
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -110,6 +111,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         s_epi[0][i] = p.epi.bias[i];
         s_epi[1][i] = p.epi.scale[i];
         s_epi[2][i] = p.epi.shift[i];
+        s_sign[i] = p.epi.scale[i] >= 0.f ? 1.f : -1.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -279,7 +281,10 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             } else if constexpr (POOL == 2) {
                 // max over the z pairs only: halves what this kernel writes and what the (then 1x2x2) pooling pass reads;
-                // no staging, no barrier, no overlapping windows
+                // no staging, no barrier, no overlapping windows.  bias -> activation -> BatchNorm -> activation is a
+                // monotone map of the accumulator (increasing where the folded BN scale is >= 0, decreasing where it is
+                // negative), so the max over the pair is taken on the RAW sums -- max, or min for a negative scale -- and
+                // the epilogue math runs once per pooled value instead of once per plane (the epilogue is ALU-bound).
                 const int n_zp = (zt_eff + 1) >> 1;
                 for (int item = sub; item < n_zp * chunks && !TB_DBG(p.dbg, 4); item += kThinzSubs) {
                     const int zp = item / chunks;
@@ -287,7 +292,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                     const int Z = (z0 >> 1) + zp;
                     const bool two = 2 * zp + 1 < zt_eff;
                     const bool ok = row_ok && Z < p.Zo && (two || p.pool_same);
-                    float v[16];
+                    uint32_t raw[16];
 #pragma unroll
                     for (int pl = 0; pl < 2; ++pl) {
                         if (pl == 1 && !two) break;
@@ -299,12 +304,16 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                         tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(p.n_tile + c * 16), rc);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) rv[i] = __float_as_uint(__uint_as_float(rv[i]) + __uint_as_float(rc[i]));
-                        float x[16];
-                        epilogue_math16<ACT1, ACT2>(p.epi, rv, c * 16, s_epi[0], s_epi[1], s_epi[2], x);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = pl == 0 ? x[i] : fmaxf(v[i], x[i]);
+                        for (int i = 0; i < 16; ++i) {
+                            const float x = __uint_as_float(rv[i]) + __uint_as_float(rc[i]);
+                            const float prev = __uint_as_float(raw[i]);
+                            // s_sign[ch] > 0: increasing map -> keep the larger raw sum; < 0: the smaller one
+                            const float pick = s_sign[c * 16 + i] >= 0.f ? fmaxf(prev, x) : fminf(prev, x);
+                            raw[i] = __float_as_uint(pl == 0 ? x : pick);
+                        }
                     }
+                    float v[16];
+                    epilogue_math16<ACT1, ACT2>(p.epi, raw, c * 16, s_epi[0], s_epi[1], s_epi[2], v);
                     const int64_t m = ((static_cast<int64_t>(nf) * p.Zo + Z) * p.Ho + prow) * p.Wo + q;
                     if (c * 16 < p.epi.c_store) epilogue_store16<FMT>(p.epi, v, c * 16, m, ok);
                 }

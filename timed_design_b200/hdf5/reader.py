@@ -385,7 +385,10 @@ class _Attrs:
 class _Object:
     def __init__(self, f: File, addr: int, name: str):
         self._f, self._addr, self.name = f, addr, name
-        self._msgs = f._messages(addr)
+        try:
+            self._msgs = f._messages(addr)
+        except (IndexError, struct.error) as e:        # reads past the end of the map
+            raise Hdf5FormatError(f"{f.path}: truncated or corrupt file (object header of '{name}' at {addr})") from e
         self._attrs = None
 
     @property
