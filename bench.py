@@ -520,6 +520,23 @@ def main():
         e2e = {"value": world * B * e2e_steps / float(tt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(out.nbytes),
                "steps": e2e_steps, "chunk_frames": args.e2e_chunk, "host_dtype": "float32 (pinned)"}
+        # the float32 host path is PCIe-bound (222 KB per frame); the same call with the frame dtypes that carry fewer bytes:
+        # float16 (a caller whose frames are exact in half) and uint8 (boolean voxels, voxels_as_gaussian = False datasets)
+        alt = {}
+        for name, conv in (("float16", lambda t: t.to(torch.float16)), ("uint8", lambda t: (t > 0.2).to(torch.uint8))):
+            hx = conv(h_frames).contiguous().pin_memory().numpy()
+            model.predict(hx)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                model.predict(hx)
+            ta = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+            alt[name] = {"value": world * B * e2e_steps / float(ta.item()), "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes)}
+        e2e["by_host_dtype"] = alt
 
     if rank != 0:
         if world > 1:

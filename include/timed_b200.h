@@ -38,6 +38,8 @@ extern "C" {
 #define TB_DTYPE_F32 0
 #define TB_DTYPE_F64 1
 #define TB_DTYPE_U8 2 /* numpy bool / uint8 voxels (voxels_as_gaussian == False) */
+#define TB_DTYPE_F16 3 /* IEEE half frames: halves the host->device bytes of predict_host (the e2e path is PCIe-bound at
+                        * 222 KB of float32 per frame); the caller decides whether its frames are exact in half */
 
 /* activation codes */
 #define TB_ACT_NONE 0

@@ -145,12 +145,11 @@ def test_fused_conv_maxpool_epilogue(side, c1, pool_pad, relu, monkeypatch):
     X = standins.synthetic_frames(7, side=side, seed=4)
     cfg, w = _pool_graph(side, c1, pool_pad, relu)
     ref = ko.forward_torch(cfg, w, X)
-    monkeypatch.setenv("TIMED_B200_POOLFUSE", "1")         # opt-in: no faster than the separate pass on TIMED
-    m = Model(cfg, w)
+    m = Model(cfg, w)                                       # default: the whole max-pool runs in the conv epilogue
     fused = m.predict(X)
-    assert any("thinz" in m.op_kernel(i, 7) for i in range(len(m.graph.ops)))
-    monkeypatch.delenv("TIMED_B200_POOLFUSE")
-    m2 = Model(cfg, w)                                      # default: only the z direction is pooled in the epilogue
+    assert any("thinz_conv_kernel(+maxpool)" in m.op_kernel(i, 7) for i in range(len(m.graph.ops)))
+    monkeypatch.setenv("TIMED_B200_NO_POOLFUSE", "1")
+    m2 = Model(cfg, w)                                      # only the z direction is pooled in the epilogue
     zfused = m2.predict(X)
     assert m2.launches_per_forward == m.launches_per_forward + 1
     monkeypatch.setenv("TIMED_B200_NO_ZPOOL", "1")
@@ -167,11 +166,11 @@ def test_fused_pool_into_cpv_matches_unfused(monkeypatch):
     from timed_design_b200.model import Model
     cfg, w = standins.timed_standin(20)
     X = standins.synthetic_frames(5, seed=12)
-    base = Model(cfg, w).predict(X)
-    monkeypatch.setenv("TIMED_B200_POOLFUSE", "1")
     m = Model(cfg, w)
     fused = m.predict(X)
-    assert "slab" in m.op_kernel(3, 5)
+    assert "maxpool" in m.op_kernel(1, 5) and "slab" in m.op_kernel(3, 5)
+    monkeypatch.setenv("TIMED_B200_NO_POOLFUSE", "1")
+    base = Model(cfg, w).predict(X)
     assert np.abs(fused - base).max() <= 2e-6
     assert np.abs(fused - ko.forward_torch(cfg, w, X)).max() <= PROB_TOL
 

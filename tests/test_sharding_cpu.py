@@ -96,14 +96,45 @@ def _write_dataset(path, n=37):
     write_frame_dataset(path, {"1abc": chains}, (7, 7, 7, 6))
 
 
-def _predict_worker(rank, world, port, data, out_dir):
+def _predict_worker(rank, world, port, data, out_dir, start_batch=0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
                       WORLD_SIZE=str(world), TIMED_B200_DIST_BACKEND="gloo")
     from timed_design_b200 import predict
     predict.load_model = lambda path, device=0, **kw: _FakeModel()
-    predict.load_dataset_and_predict([__import__("pathlib").Path("TIMED.h5")], data, batch_size=8,
+    predict.load_dataset_and_predict([__import__("pathlib").Path("TIMED.h5")], data, batch_size=8, start_batch=start_batch,
                                      dataset_map_path=os.path.join(out_dir, "datasetmap.txt"), path_to_output=out_dir)
     dist.destroy_process_group()
+
+
+def test_predict_driver_world2_resumes_from_start_batch(tmp_path, monkeypatch):
+    """start_batch under sharding (predict.py:32,54-57,126): a run that stopped after three batches is resumed by two
+    ranks; the appended files equal those of an uninterrupted single-process run byte for byte."""
+    from pathlib import Path
+    from timed_design_b200 import predict
+    data = tmp_path / "d.hdf5"
+    _write_dataset(data)
+    monkeypatch.setattr(predict, "load_model", lambda path, device=0, **kw: _FakeModel())
+    monkeypatch.chdir(tmp_path)
+    full = tmp_path / "full"
+    full.mkdir()
+    predict.load_dataset_and_predict([Path("TIMED.h5")], data, batch_size=8, dataset_map_path=full / "datasetmap.txt",
+                                     path_to_output=full)
+    # the interrupted run: keep what the first three batches appended (24 rows of each per-frame file + the map)
+    part = tmp_path / "part"
+    part.mkdir()
+    for name in ("TIMED.csv", "encoded_labels.csv"):
+        (part / name).write_text("".join((full / name).read_text().splitlines(keepends=True)[:24]))
+    (part / "datasetmap.txt").write_bytes((full / "datasetmap.txt").read_bytes())
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_predict_worker, args=(r, 2, port, str(data), str(part), 3)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    for name in sorted(f.name for f in full.iterdir()):
+        assert (full / name).read_bytes() == (part / name).read_bytes(), name
 
 
 def test_predict_driver_world2_writes_the_single_process_files(tmp_path, monkeypatch):

@@ -16,7 +16,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libtimed_b200.so"
 
 TB_MAX_INPUTS = 8
-DTYPE_F32, DTYPE_F64, DTYPE_U8 = 0, 1, 2
+DTYPE_F32, DTYPE_F64, DTYPE_U8, DTYPE_F16 = 0, 1, 2, 3
 ABI_VERSION = 3
 
 
@@ -137,7 +137,9 @@ def np_dtype_code(arr: np.ndarray) -> int:
         return DTYPE_F64
     if arr.dtype in (np.bool_, np.uint8):
         return DTYPE_U8
-    raise TypeError(f"frames dtype {arr.dtype} not supported (float32, float64, bool, uint8)")
+    if arr.dtype == np.float16:
+        return DTYPE_F16
+    raise TypeError(f"frames dtype {arr.dtype} not supported (float32, float64, float16, bool, uint8)")
 
 
 def fptr(arr):

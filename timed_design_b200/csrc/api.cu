@@ -732,9 +732,11 @@ static bool thinz_geometry(int kd, int kh, int kw, int cout, int Wp, ThinZGeom* 
     g.span_stride = g.span_bytes;
     const size_t w_smem = (g.w_bytes + 127) & ~static_cast<size_t>(127);
     const size_t stage = 2u * (g.zt + kd - 1) * g.span_stride;
-    const size_t pool_buf = pool ? 2u * 128u * n_tile * sizeof(float) : 0;     // fused max-pool: two staged output tiles
+    // fused max-pool: per z pair of a tile a ring of two windows (256 positions) of raw fp32 sums
+    const size_t pool_buf = pool ? static_cast<size_t>(std::max(1, g.zt / 2)) * 256u * n_tile * sizeof(float) : 0;
     if (w_smem + 2 * stage + pool_buf + 128 > kSmemDynamicMax) return false;
     if (pool && (g.zt & 1)) return false;                                   // z pairs must not straddle tiles
+    if (pool && Wp + 2 > 128) return false;                                 // a 2x2 partner lies at most one window ahead
     g.stages = static_cast<int>(std::min<size_t>(kConvMaxStages, (kSmemDynamicMax - 128 - w_smem - pool_buf) / stage));
     *out = g;
     return true;
@@ -830,9 +832,6 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
         ThinZGeom zg;
         TB_REQUIRE(thinz_geometry(k.kd, k.kh, k.kw, p.cout, k.Wp, &zg, true), "internal: fused pool does not fit");
         k.stages = zg.stages;
-        k.win_stride = 128 - k.Wp - 1;
-        const int max_anchor = 2 * (p.pool_Po - 1) * k.Wp + 2 * (p.pool_Qo - 1);
-        k.windows = max_anchor / k.win_stride + 1;
         k.pool_same = p.pool_same;
         k.Zo = p.pool_Zo; k.Po = p.pool_Po; k.Qo = p.pool_Qo;
         k.pool_cpv = out_info->cpv ? 1 : 0;
@@ -863,7 +862,7 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
                "thinz conv: split output channel padding mismatch");
     const size_t w_smem = (static_cast<size_t>(k.w_bytes) + 127) & ~static_cast<size_t>(127);
     const size_t smem_bytes = 128 + w_smem + static_cast<size_t>(k.stages) * 2u * (k.zt + k.kd - 1) * k.span_stride +
-                              (p.fuse_pool ? 2u * 128u * k.n_tile * sizeof(float) : 0);
+                              (p.fuse_pool ? static_cast<size_t>(std::max(1, k.zt / 2)) * 256u * k.n_tile * sizeof(float) : 0);
     const int grid = static_cast<int>(std::min<int64_t>(tiles, 148));
     int rc = 0;
     bool launched = false;
@@ -1560,9 +1559,10 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 g->launches += node.conv.tap2n ? 2 : 1;
                 // thinz conv read only by a MaxPool(2,2,2; stride 2): the pooling runs in the conv epilogue and this
                 // op's tensor IS the pooled tensor (the pooling op becomes an alias of it)
-                // Opt-in (TIMED_B200_POOLFUSE=1): measured on TIMED block 1 the fused epilogue costs what the separate pooling
-                // pass saves (5.0 vs 3.6 + 1.26 ms; the overlapping windows add 25 % MMA work) -- profiles/r1_summary.md.
-                if (node.conv.thinz && getenv("TIMED_B200_POOLFUSE")) {
+                // Round 1 staged ACTIVATED outputs over overlapping windows (+25 % MMA work) and measured neutral; round 2 pools
+                // the raw sums (monotone epilogue) over a rolling two-window ring: no extra MMA work, 8x less epilogue math.
+                if (node.conv.thinz && !getenv("TIMED_B200_NO_POOLFUSE") &&
+                    (d.act1 != TB_ACT_ELU || d.alpha1 >= 0.f) && (d.act2 != TB_ACT_ELU || d.alpha2 >= 0.f)) {
                     int j = -1, n_readers = 0;
                     for (int k = i + 1; k < n_ops; ++k)
                         for (int q = 0; q < ops[k].n_inputs; ++q)
@@ -1822,6 +1822,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                     if (dtype == TB_DTYPE_F32) input_convert_cpv_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(d_frames), n_frames, cg, oh, ol);
                     else if (dtype == TB_DTYPE_F64) input_convert_cpv_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(d_frames), n_frames, cg, oh, ol);
                     else if (dtype == TB_DTYPE_U8) input_convert_cpv_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(d_frames), n_frames, cg, oh, ol);
+                    else if (dtype == TB_DTYPE_F16) input_convert_cpv_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(d_frames), n_frames, cg, oh, ol);
                     else TB_REQUIRE(false, "unknown frames dtype");
                     break;
                 }
@@ -1829,6 +1830,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                     if (dtype == TB_DTYPE_F32) launch_input_convert_padvol<float>(d_frames, t, n_frames, out, s);
                     else if (dtype == TB_DTYPE_F64) launch_input_convert_padvol<double>(d_frames, t, n_frames, out, s);
                     else if (dtype == TB_DTYPE_U8) launch_input_convert_padvol<uint8_t>(d_frames, t, n_frames, out, s);
+                    else if (dtype == TB_DTYPE_F16) launch_input_convert_padvol<__half>(d_frames, t, n_frames, out, s);
                     else TB_REQUIRE(false, "unknown frames dtype");
                     break;
                 }
@@ -1836,12 +1838,14 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                     if (dtype == TB_DTYPE_F32) launch_input_convert_wfold<float>(d_frames, t, n_frames, out, s);
                     else if (dtype == TB_DTYPE_F64) launch_input_convert_wfold<double>(d_frames, t, n_frames, out, s);
                     else if (dtype == TB_DTYPE_U8) launch_input_convert_wfold<uint8_t>(d_frames, t, n_frames, out, s);
+                    else if (dtype == TB_DTYPE_F16) launch_input_convert_wfold<__half>(d_frames, t, n_frames, out, s);
                     else TB_REQUIRE(false, "unknown frames dtype");
                     break;
                 }
                 if (dtype == TB_DTYPE_F32) launch_input_convert<float>(d_frames, out_pix, out, s);
                 else if (dtype == TB_DTYPE_F64) launch_input_convert<double>(d_frames, out_pix, out, s);
                 else if (dtype == TB_DTYPE_U8) launch_input_convert<uint8_t>(d_frames, out_pix, out, s);
+                else if (dtype == TB_DTYPE_F16) launch_input_convert<__half>(d_frames, out_pix, out, s);
                 else TB_REQUIRE(false, "unknown frames dtype");
                 break;
             case TB_OP_CONV3D: {
@@ -1958,7 +1962,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
 }
 
 static size_t dtype_size(int dtype) {
-    return dtype == TB_DTYPE_F64 ? 8 : (dtype == TB_DTYPE_F32 ? 4 : 1);
+    return dtype == TB_DTYPE_F64 ? 8 : (dtype == TB_DTYPE_F32 ? 4 : (dtype == TB_DTYPE_F16 ? 2 : 1));
 }
 
 // Largest frame count one pass may take: every tensor's pixel count must stay below 2^31 (the

@@ -56,11 +56,9 @@ struct ThinZParams {
     int32_t stages;
     ConvKernelParams epi;     // epilogue fields
     int32_t dbg;
-    int32_t win_stride;       // in-plane positions between consecutive windows (128, or 128 - Wp - 1 when pooling)
-    // ---- fused MaxPool(2,2,2; stride 2) of the conv output (POOL instantiation).  A window owns the pooled pixels
-    // whose anchor position u = 2P*Wp + 2Q lies in its first win_stride positions (all four in-plane partners are then
-    // inside the window); z pairs are the accumulators (2zp, 2zp+1) of the tile.  The epilogue stages the z-maxed,
-    // activated tile in shared memory and writes the pooled pixels in the consumer's layout.
+    int32_t win_stride;       // in-plane positions between consecutive windows (128)
+    // ---- fused MaxPool(2,2,2; stride 2) of the conv output (POOL = 1): see the epilogue.  Pooled pixels are written in the
+    // consumer's layout (chunk-plane padded volume, or a plain NDHWC view).
     int32_t pool_same;        // TF 'same' (partial windows at the far edge are kept) or 'valid'
     int32_t Zo, Po, Qo;       // pooled extents
     int32_t pool_cpv;         // 1: chunk-plane padded volume (out_hi4/out_lo4 + geometry below), 0: plain NDHWC view
@@ -72,6 +70,15 @@ struct ThinZParams {
 };
 
 #if defined(__CUDACC__)
+
+// Tile walked by this CTA at iteration `it`: CTAs take whole (frame, z group) units round-robin and walk a unit's
+// windows consecutively (tile = unit * windows + window), which the fused max-pool needs -- a pooled pixel's 2x2 in-plane
+// partners may lie in the NEXT window -- and which keeps a unit's input planes hot in L2.  -1 when the CTA is done.
+__device__ __forceinline__ int thinz_tile(int it, int windows, int n_tiles_total) {
+    const int unit = static_cast<int>(blockIdx.x) + (it / windows) * static_cast<int>(gridDim.x);
+    const int tile = unit * windows + it % windows;
+    return tile < n_tiles_total ? tile : -1;
+}
 
 // FMT: format of the conv output (POOL = 0, 2) or of the plain pooled output (POOL = 1, ignored for CPV).
 // POOL: 0 none, 1 whole MaxPool(2,2,2;2) in the epilogue, 2 its z direction only.
@@ -124,7 +131,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
     const uint32_t plane_region = static_cast<uint32_t>(max_planes) * p.span_stride;   // hi spans, then lo spans
     const uint32_t stage_bytes = 2u * plane_region;
     const int tiles_per_frame = p.z_groups * p.windows;
-    float* pool_stage = reinterpret_cast<float*>(stage0 + static_cast<size_t>(p.stages) * stage_bytes);   // POOL: 2 x [128][n_tile]
+    float* pool_stage = reinterpret_cast<float*>(stage0 + static_cast<size_t>(p.stages) * stage_bytes);   // POOL 1: zt/2 rings of [256][n_tile] fp32
 
     if (warp == 0) {
         // =============================================================== bulk-copy producer
@@ -136,7 +143,9 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         }
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles_total; tile += gridDim.x) {
+        for (int it = 0;; ++it) {
+            const int tile = thinz_tile(it, p.windows, p.n_tiles_total);
+            if (tile < 0) break;
             const int nf = tile / tiles_per_frame;
             const int r = tile - nf * tiles_per_frame;
             const int zg = r / p.windows;
@@ -174,7 +183,9 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         mbar_wait(&w_bar, 0);
         int s = 0, acc = 0;
         uint32_t ph = 0, acc_ph = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles_total; tile += gridDim.x) {
+        for (int it = 0;; ++it) {
+            const int tile = thinz_tile(it, p.windows, p.n_tiles_total);
+            if (tile < 0) break;
             const int r = tile % tiles_per_frame;
             const int z0 = (r / p.windows) * p.zt;
             const int zt_eff = min(p.zt, p.Do - z0);
@@ -241,8 +252,9 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         const int plane_positions = p.Ho * p.Wp;
         int acc = 0;
         uint32_t acc_ph = 0;
-        int pool_buf = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles_total; tile += gridDim.x) {
+        for (int it = 0;; ++it) {
+            const int tile = thinz_tile(it, p.windows, p.n_tiles_total);
+            if (tile < 0) break;
             const int nf = tile / tiles_per_frame;
             const int r = tile - nf * tiles_per_frame;
             const int zg = r / p.windows;
@@ -321,17 +333,28 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             } else {
+                // Whole MaxPool(2,2,2; stride 2) in the epilogue.  The map accumulator -> output (bias, activation, BatchNorm,
+                // activation) is monotone per channel, so the 2x2x2 maximum is taken on RAW sums (max where the folded BN scale
+                // is >= 0, min where it is negative) and the epilogue math runs once per POOLED value: 8x less ALU work than
+                // activating every conv output (the unfused epilogue is ALU-bound).
+                //   phase 1: z pairs straight from TMEM (planes 2zp, 2zp+1 of the tile), the raw extremum staged in shared
+                //            memory: ring of two windows (256 positions) per z pair, [position][channel] fp32, 16-byte slots
+                //            XOR-swizzled by the position;
+                //   phase 2: in-plane 2x2 of the pooled pixels whose four partners are now staged -- anchors u = 2P*Wp + 2Q in
+                //            [128w - Wp - 1, 128(w+1) - Wp - 1), the tail of the plane with its last window -- then epilogue
+                //            math, split, store in the consumer's layout.  Windows of a unit are consecutive tiles of this CTA
+                //            (thinz_tile), so the ring always holds the previous window.
                 const int et = threadIdx.x - 64;                         // index among the epilogue threads
                 const int n_zp = (zt_eff + 1) >> 1;
-                const int row_f4 = p.n_tile >> 2;                        // float4 slots per staged row
-                for (int zp = 0; zp < n_zp && !TB_DBG(p.dbg, 4); ++zp, pool_buf ^= 1) {
-                    // two staging buffers: one barrier per z pair is enough (a buffer is rewritten two pairs later)
-                    float4* stage4 = reinterpret_cast<float4*>(pool_stage) + pool_buf * 128 * row_f4;
-                    const int Z = (z0 >> 1) + zp;
-                    const bool two = 2 * zp + 1 < zt_eff;                // partner plane exists
-                    const bool z_ok = Z < p.Zo && (two || p.pool_same);  // 'valid' drops a window without its partner
-                    // ---- phase 1: activated conv outputs of the z pair, max over z, into shared memory [row][channel]
-                    for (int unit = sub; unit < (p.n_tile >> 3); unit += kThinzSubs) {       // 8 channels per unit
+                const int row_f4 = p.n_tile >> 2;                        // float4 slots per staged position
+                const int ring_f4 = 256 * row_f4;                        // one z pair's ring
+                float4* ring = reinterpret_cast<float4*>(pool_stage);
+                if (!TB_DBG(p.dbg, 4)) {
+                    // ---- phase 1
+                    for (int item = sub; item < n_zp * (p.n_tile >> 3); item += kThinzSubs) {   // (z pair, 8 channels)
+                        const int zp = item / (p.n_tile >> 3);
+                        const int unit = item - zp * (p.n_tile >> 3);
+                        const bool two = 2 * zp + 1 < zt_eff;
                         float v[8];
 #pragma unroll
                         for (int pl = 0; pl < 2; ++pl) {
@@ -345,68 +368,83 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                float x = (__uint_as_float(rv[i]) + __uint_as_float(rc[i])) + s_epi[0][unit * 8 + i];
-                                x = act_ct<ACT1>(x, p.epi.act1, p.epi.alpha1);
-                                x = fmaf(x, s_epi[1][unit * 8 + i], s_epi[2][unit * 8 + i]);
-                                x = act_ct<ACT2>(x, p.epi.act2, p.epi.alpha2);
-                                v[i] = pl == 0 ? x : fmaxf(v[i], x);
+                                const float x = __uint_as_float(rv[i]) + __uint_as_float(rc[i]);
+                                v[i] = pl == 0 ? x : (s_sign[unit * 8 + i] >= 0.f ? fmaxf(v[i], x) : fminf(v[i], x));
                             }
                         }
-                        // row-major [128][n_tile] fp32 with the 16-byte slot index XORed by the row: a warp's 32 rows would
-                        // otherwise all land on the same four banks
-                        const int srow = quad * 32 + lane;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-                            stage4[srow * row_f4 + ((unit * 2 + i) ^ (srow & 7 & (row_f4 - 1)))] =
-                                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    }
-                    if (zp + 1 == n_zp) {                                // every accumulator of this stage has been read
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kThinzEpiWarps) : "memory");
-                    // ---- phase 2: in-plane 2x2 max of the pooled pixels this window owns, 8 channels per thread
-                    const int groups = p.n_tile >> 3;
-                    for (int w = et; w < p.win_stride * groups && z_ok; w += 32 * kThinzEpiWarps) {
-                        const int g = w % groups;
-                        const int du = w / groups;                       // anchor offset inside the window
-                        const int ua = u0 + du;
-                        const int pa = ua / p.Wp;
-                        const int qa = ua - pa * p.Wp;
-                        if ((pa & 1) || (qa & 1) || pa >= p.Ho || qa >= p.Wo) continue;
-                        const int P = pa >> 1, Q = qa >> 1;
-                        if (P >= p.Po || Q >= p.Qo) continue;
-                        const bool has_q = qa + 1 < p.Wo, has_p = pa + 1 < p.Ho;
-                        if (!p.pool_same && (!has_q || !has_p)) continue;
-                        float m8[8];
-                        auto take = [&](int row, bool first) {
-                            const int sw = row & 7 & (row_f4 - 1);
-                            const float4 a = stage4[row * row_f4 + ((2 * g) ^ sw)];
-                            const float4 b = stage4[row * row_f4 + ((2 * g + 1) ^ sw)];
-                            const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) m8[e] = first ? x[e] : fmaxf(m8[e], x[e]);
-                        };
-                        take(du, true);
-                        if (has_q) take(du + 1, false);
-                        if (has_p) take(du + p.Wp, false);
-                        if (has_q && has_p) take(du + p.Wp + 1, false);
-                        if (p.pool_cpv) {
-                            const int64_t t = p.cpv_lead + ((static_cast<int64_t>(nf) * p.cpv_Dp + Z) * p.cpv_Hp + P) * p.cpv_Wp + Q;
-                            cpv_store(p.out_hi4, p.out_lo4, g * p.cpv_T + t, m8);
-                        } else {
-                            const int64_t pix = ((static_cast<int64_t>(nf) * p.Zo + Z) * p.Po + P) * p.Qo + Q;
-                            if (g * 8 < (FMT == FMT_SPLIT ? p.pool_out.c_pad : p.pool_out.c))
-                                store8<FMT>(p.pool_out, pix * p.pool_out.ld + g * 8, m8);
-                        }
+                        const int srow = (u0 + quad * 32 + lane) & 255;
+                        float4* dst = ring + zp * ring_f4 + srow * row_f4;
+                        const int sw = srow & 7 & (row_f4 - 1);
+                        dst[(unit * 2) ^ sw] = make_float4(v[0], v[1], v[2], v[3]);
+                        dst[(unit * 2 + 1) ^ sw] = make_float4(v[4], v[5], v[6], v[7]);
                     }
                 }
-                if (TB_DBG(p.dbg, 4)) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);            // every accumulator of this stage has been read
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kThinzEpiWarps) : "memory");
+                // ---- phase 2
+                const bool last_win = win + 1 == p.windows;
+                const int a_lo = max(0, u0 - p.Wp - 1);
+                const int a_hi = last_win ? plane_positions : u0 + 128 - p.Wp - 1;
+                // dense enumeration of the pooled pixels anchored in [a_lo, a_hi): even rows pa = 2P, columns Q < Qo; a thread
+                // owns one (channel group, z pair) combination and strides over the pixels (no per-item division cascade, no
+                // lanes idling on odd anchors)
+                const int groups = p.n_tile >> 3;
+                const int combos = groups * n_zp;
+                const int P0 = (a_lo / p.Wp) >> 1;                       // pooled row of the range's first position
+                const int P_hi = min(p.Po - 1, ((a_hi - 1) / p.Wp) >> 1);
+                const int n_cand = a_hi > a_lo ? max(0, P_hi - P0 + 1) * p.Qo : 0;
+                const int my_combo = et % combos;
+                const int g = my_combo % groups;
+                const int zp = my_combo / groups;
+                const int Z = (z0 >> 1) + zp;
+                const bool two = 2 * zp + 1 < zt_eff;
+                const bool z_ok = Z < p.Zo && (two || p.pool_same);
+                const int k_step = (32 * kThinzEpiWarps) / combos;
+                for (int k = et / combos; k < n_cand && z_ok && et < k_step * combos && !TB_DBG(p.dbg, 4); k += k_step) {
+                    const int P = P0 + k / p.Qo;
+                    const int Q = k - (P - P0) * p.Qo;
+                    const int pa = 2 * P, qa = 2 * Q;
+                    const int ua = pa * p.Wp + qa;
+                    if (ua < a_lo || ua >= a_hi || pa >= p.Ho || qa >= p.Wo) continue;
+                    const bool has_q = qa + 1 < p.Wo, has_p = pa + 1 < p.Ho;
+                    if (!p.pool_same && (!has_q || !has_p)) continue;
+                    const float4* zr = ring + zp * ring_f4;
+                    float m8[8];
+                    auto take = [&](int uu, bool first) {
+                        const int row = uu & 255;
+                        const int sw = row & 7 & (row_f4 - 1);
+                        const float4 a = zr[row * row_f4 + ((2 * g) ^ sw)];
+                        const float4 b = zr[row * row_f4 + ((2 * g + 1) ^ sw)];
+                        const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            m8[e] = first ? x[e] : (s_sign[g * 8 + e] >= 0.f ? fmaxf(m8[e], x[e]) : fminf(m8[e], x[e]));
+                    };
+                    take(ua, true);
+                    if (has_q) take(ua + 1, false);
+                    if (has_p) take(ua + p.Wp, false);
+                    if (has_q && has_p) take(ua + p.Wp + 1, false);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float x = m8[e] + s_epi[0][g * 8 + e];
+                        x = act_ct<ACT1>(x, p.epi.act1, p.epi.alpha1);
+                        x = fmaf(x, s_epi[1][g * 8 + e], s_epi[2][g * 8 + e]);
+                        m8[e] = act_ct<ACT2>(x, p.epi.act2, p.epi.alpha2);
+                    }
+                    if (p.pool_cpv) {
+                        const int64_t t = p.cpv_lead + ((static_cast<int64_t>(nf) * p.cpv_Dp + Z) * p.cpv_Hp + P) * p.cpv_Wp + Q;
+                        cpv_store(p.out_hi4, p.out_lo4, g * p.cpv_T + t, m8);
+                    } else {
+                        const int64_t pix = ((static_cast<int64_t>(nf) * p.Zo + Z) * p.Po + P) * p.Qo + Q;
+                        if (g * 8 < (FMT == FMT_SPLIT ? p.pool_out.c_pad : p.pool_out.c))
+                            store8<FMT>(p.pool_out, pix * p.pool_out.ld + g * 8, m8);
+                    }
                 }
+                // the next window's phase 1 overwrites the ring slots of the window before this one: every thread must be
+                // done reading them
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kThinzEpiWarps) : "memory");
             }
             if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
         }

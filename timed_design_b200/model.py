@@ -3,7 +3,7 @@ reference's hot path (``tf.keras.models.load_model`` at predict.py:121 and
 ``frame_model.predict(X_batch)`` at predict.py:142).
 
 Same contract as the reference call sites: ``predict`` is synchronous, takes a host numpy
-array ``(B, D, H, W, C)`` of float64 / float32 / bool and returns a host ``float32``
+array ``(B, D, H, W, C)`` of float64 / float32 / float16 / bool and returns a host ``float32``
 ``(B, n_classes)`` array; exceptions propagate.  All arithmetic runs in libtimed_b200.so on the
 B200 -- there is no CPU path; without the library or a device the calls raise.
 """
@@ -54,7 +54,7 @@ class Model:
         if X.ndim != 5 or tuple(X.shape[1:]) != tuple(self.input_shape):
             raise ValueError(f"expected input of shape (B, {', '.join(map(str, self.input_shape))}), "
                              f"got {X.shape}")
-        if X.dtype not in (np.float32, np.float64, np.bool_, np.uint8):
+        if X.dtype not in (np.float32, np.float64, np.float16, np.bool_, np.uint8):
             X = X.astype(np.float32)
         X = np.ascontiguousarray(X)
         n = X.shape[0]
@@ -86,7 +86,7 @@ class Model:
         ``frames``: (n,D,H,W,C) float32/float64/uint8 CUDA tensor; ``probs``: (n,classes) float32;
         ``workspace``: uint8 CUDA tensor of at least ``workspace_bytes(n)`` bytes."""
         import torch
-        code = {torch.float32: _lib.DTYPE_F32, torch.float64: _lib.DTYPE_F64,
+        code = {torch.float32: _lib.DTYPE_F32, torch.float64: _lib.DTYPE_F64, torch.float16: _lib.DTYPE_F16,
                 torch.uint8: _lib.DTYPE_U8, torch.bool: _lib.DTYPE_U8}[frames.dtype]
         n = frames.shape[0]
         assert frames.is_contiguous() and probs.is_contiguous() and probs.dtype == torch.float32

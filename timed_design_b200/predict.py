@@ -92,8 +92,6 @@ def load_dataset_and_predict(
     cls_to_res = rotamer_class_to_residue() if predict_rotamers else None
     n_batches = ceil(len(flat_dataset_map) / batch_size)
     rank, world, local_rank = _dist_context()
-    if world > 1 and start_batch != 0:
-        raise ValueError("start_batch is not supported when frames are sharded over several GPUs")
     out = None
     for i, m in enumerate(models):
         model_name = (m.stem if isinstance(m, Path) else str(m)) + model_name_suffix
@@ -110,8 +108,12 @@ def load_dataset_and_predict(
             # frames shard by flat index into contiguous per-rank ranges (each chain's rows stay adjacent); every rank
             # predicts its range, ONE all-gather reassembles probabilities and labels, rank 0 writes the reference's files
             from .dist import shard_range
-            n_total = len(flat_dataset_map)
+            # resume (predict.py:32,54-57,126): only the frames from batch `start_batch` on are predicted; they are the
+            # range that is sharded, and the gathered rows are indexed relative to its first frame
+            first = min(start_batch * batch_size, len(flat_dataset_map))
+            n_total = len(flat_dataset_map) - first
             lo, hi = shard_range(n_total, rank, world)
+            lo, hi = lo + first, hi + first
             preds, labels = [], []
             for b0 in range(lo, hi, batch_size):
                 X_batch, y_true_batch = load_batch(dataset_path, flat_dataset_map[b0:min(b0 + batch_size, hi)])
@@ -123,8 +125,9 @@ def load_dataset_and_predict(
         for index in range(start_batch, n_batches):
             current_batch_map = flat_dataset_map[index * batch_size:(index + 1) * batch_size]
             if gathered is not None:
-                y_pred_batch = gathered[0][index * batch_size:(index + 1) * batch_size]
-                y_true_batch = gathered[1][index * batch_size:(index + 1) * batch_size]
+                r0 = (index - start_batch) * batch_size
+                y_pred_batch = gathered[0][r0:r0 + batch_size]
+                y_true_batch = gathered[1][r0:r0 + batch_size]
             else:
                 X_batch, y_true_batch = load_batch(dataset_path, current_batch_map)
                 y_pred_batch = frame_model.predict(X_batch)
@@ -145,9 +148,12 @@ def load_dataset_and_predict(
         # arrays printed with 18 significant digits (already float16-cast in residue mode), so
         # casting them to float16 reproduces the parsed matrix bit for bit without the text round
         # trip -- unless the file already held rows (append mode / start_batch): then honour it.
-        if (rows_before == 0 and start_batch == 0 and raw_rows) or rank != 0:
+        if rows_before == 0 and start_batch == 0 and raw_rows:
             prediction_matrix = np.concatenate(raw_rows).astype(np.float16)
         else:
+            if world > 1:                     # rank 0 has appended the resumed rows: every rank parses the complete file
+                import torch.distributed as dist
+                dist.barrier()
             prediction_matrix = np.genfromtxt(model_out, delimiter=",", dtype=np.float16)
         if prediction_matrix.ndim == 1:
             prediction_matrix = prediction_matrix[None, :]
