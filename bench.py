@@ -554,7 +554,7 @@ def main():
     peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
     step_ms_ops = sum(o["ms"] for o in op_times) / n_steps_timed
     traffic, traffic_source = None, None
-    tp = ROOT / "profiles" / "r1i_dominant_kernel_ncu.json"
+    tp = ROOT / "profiles" / "r2a_dominant_kernel_ncu.json"
     if tp.exists() and args.config == "timed20" and B == 4096:
         traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         traffic_source = f"from profile ({tp.relative_to(ROOT)}: one ncu --set full capture of this kernel at this batch), not measured in this run"
