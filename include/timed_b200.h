@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TIMED_B200_ABI_VERSION 3 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers; 3: predict_stats, float16 frames (both additive) */
+#define TIMED_B200_ABI_VERSION 3 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers; 3: predict_stats, float16 frames, voxelise (all additive) */
 
 /* error codes */
 #define TB_OK 0
@@ -137,6 +137,22 @@ int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t fra
 /* How the last predict_host call was chunked: number of device passes and the largest pass in frames (never above
  * max_chunk_frames: Keras' batch_size bound, /root/reference/predict.py:142 via Model.predict(batch_size=...)). */
 int timed_b200_graph_predict_stats(const tb_graph* g, int64_t* n_passes, int64_t* max_pass_frames);
+
+/* ---- voxeliser: structure -> residue frames (the step BEFORE the path; aposteriori's make-frame-dataset, un-vendored:
+ *      parameters at /root/reference/README.md:84-97,242 and /root/reference/ui.py:63-87, parity unpinned) ------------
+ * Frames of the residues d_res_index[res_first .. res_first + n_res) of one structure (NULL index = identity) into
+ * d_frames (n_res, V, V, V, C).  Atom table:
+ * (n_atoms, 4) float32 x, y, z, gaussian sigma in voxel units; per-atom channel (< 0: not encoded), residue index and
+ * C-beta flag.  d_res_frame: (residues, 12) float32 = origin (C-alpha) then the rows of the rotation into the residue's
+ * local frame.  With encode_cb the centre residue's own C-beta is replaced by the ideal one (x, y, z, sigma in local
+ * coordinates).  property_channel >= 0 adds d_res_property[residue] at C-beta positions to that channel.  d_scratch:
+ * n_res * V^3 * C int32 (fixed-point accumulation: the result is independent of the order atoms are added in). */
+int timed_b200_voxelise(const float* d_atoms_xyzs, const int32_t* d_atom_channel, const int32_t* d_atom_residue,
+                        const int32_t* d_atom_is_cb, int64_t n_atoms, const float* d_res_frame, const float* d_res_property,
+                        const int32_t* d_res_index, int64_t res_first, int64_t n_res, int32_t voxels_per_side, float voxel_edge,
+                        int32_t n_channels,
+                        int32_t as_gaussian, int32_t encode_cb, const float* ideal_cb_xyz_sigma, int32_t cb_channel,
+                        int32_t property_channel, int32_t* d_scratch, void* d_frames, int32_t frames_dtype, void* cuda_stream);
 
 /* ---- single-layer entry for unit/parity tests -------------------------------------------------
  * y = act2(scale*act1(conv3d(x)+bias)+shift) on device buffers.

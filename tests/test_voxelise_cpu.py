@@ -1,0 +1,126 @@
+"""Voxeliser, CPU side: the structure parser, the residue-frame convention and the oracle's
+properties.  tests/golden/1ubq.pdb1.gz is the wwPDB entry 1UBQ (public-domain data), the same file the reference keeps at
+tests/testing_files/ for BASELINE config 1."""
+import itertools
+import json
+from pathlib import Path
+
+import numpy as np
+
+from oracle import voxelise_oracle as vo
+from timed_design_b200 import voxelise as vx
+
+G = Path(__file__).resolve().parent / "golden"
+PDB = G / "1ubq.pdb1.gz"
+
+
+def test_parser_reads_1ubq_chain_a():
+    gold = json.loads((G / "1ubq_chainA.json").read_text())
+    (residues,) = vx.parse_pdb(PDB)
+    assert len(residues) == 76 and {r.chain for r in residues} == {"A"}
+    assert [int(r.res_id) for r in residues] == gold["residue_ids"]
+    assert "".join(vx._THREE_TO_ONE[r.label] for r in residues) == gold["sequence"]
+    tab = vx.build_tables(residues, "CNOCBCA", 1.0)
+    assert len(tab.valid) == 76 and tab.channels == ["C", "N", "O", "CB", "CA"]
+    assert tab.is_cb.sum() == 70                     # six glycines
+
+
+def test_frame_convention_is_pinned_by_the_hard_coded_cbeta():
+    """The reference hard-codes the C-beta of the centre residue (README.md:242: 'the average position of all beta-Carbon
+    in the protein 1QYS after the aforementioned rotations').  Among all assignments of (N, C) to (axis, in-plane axis) the
+    one used here -- N on +y, C in the xy plane at x > 0 -- puts 1ubq's mean C-beta 0.03 A from that constant; every other
+    assignment is at least 0.25 A away."""
+    (residues,) = vx.parse_pdb(PDB)
+    target = np.array(vx.IDEAL_CB)
+    full = [r for r in residues if all(k in r.atoms for k in ("N", "CA", "C", "CB"))]
+    ours = []
+    for r in full:
+        f = vx.residue_frame(r.atoms["N"], r.atoms["CA"], r.atoms["C"]).astype(np.float64)
+        ours.append(f[3:].reshape(3, 3) @ (np.array(r.atoms["CB"]) - f[:3]))
+    d_ours = np.linalg.norm(np.mean(ours, axis=0) - target)
+    assert d_ours < 0.05
+    axes = [np.eye(3)[i] * s for i in range(3) for s in (1, -1)]
+    others = []
+    for first, second in (("N", "C"), ("C", "N")):
+        for a1, a2 in itertools.product(axes, axes):
+            if abs(a1 @ a2) > 0:
+                continue
+            a3 = np.cross(a1, a2)
+            loc = []
+            for r in full:
+                ca = np.array(r.atoms["CA"])
+                e1 = np.array(r.atoms[first]) - ca
+                e1 /= np.linalg.norm(e1)
+                v = np.array(r.atoms[second]) - ca
+                e2 = v - e1 * (v @ e1)
+                e2 /= np.linalg.norm(e2)
+                e3 = np.cross(e1, e2)
+                cb = np.array(r.atoms["CB"]) - ca
+                loc.append((e1 @ cb) * a1 + (e2 @ cb) * a2 + (e3 @ cb) * a3)
+            others.append(np.linalg.norm(np.mean(loc, axis=0) - target))
+    others.sort()
+    assert abs(others[0] - d_ours) < 1e-6 and others[1] > 0.25
+
+
+def _oracle_frames(residues, idx, gaussian=True, codec="CNOCBCA", encode_cb=True):
+    tab = vx.build_tables(residues, codec, 1.0)
+    cb = (*vx.IDEAL_CB, vx.VDW["C"] / 2.3548)
+    prop_ch = len(tab.channels) - 1 if tab.prop is not None else -1
+    return tab, vo.voxelise(tab.atoms, tab.channel, tab.residue, tab.is_cb, tab.frames, tab.prop, list(idx), 21, 1.0,
+                            len(tab.channels), gaussian, encode_cb, cb, tab.channels.index("CB"), prop_ch)
+
+
+def test_oracle_properties_on_1ubq():
+    (residues,) = vx.parse_pdb(PDB)
+    tab, fr = _oracle_frames(residues, [10, 40])
+    ca, c, n, cbc = (tab.channels.index(k) for k in ("CA", "C", "N", "CB"))
+    for k in range(2):
+        f = fr[k]
+        # the centre residue's C-alpha is the maximum of the CA channel's centre voxel, its N sits on +y, its C at +x
+        assert f[10, 10, 10, ca] == f[..., ca].max() > 0.15
+        assert f[10, 11, 10, n] > 0.1 or f[10, 12, 10, n] > 0.1            # N at (0, 1.46, 0)
+        assert f[11, 9, 10, c] > 0.02 or f[11, 10, 10, c] > 0.02           # C at (1.42, -0.55, 0)
+        assert f[9, 9, 9, cbc] > 0.02                                      # ideal C-beta at (-0.74, -0.54, -1.22)
+        # unit-mass stamps: a channel's total lies between the number of its atoms in interior voxels (whole stamp inside
+        # the grid) and the number in any voxel of the grid (border stamps are clipped)
+        r = [10, 40][k]
+        fr12 = tab.frames[r].astype(np.float64)
+        local = (tab.atoms[:, :3].astype(np.float64) - fr12[:3]) @ fr12[3:].reshape(3, 3).T
+        idx = np.rint(local).astype(int) + 10
+        keep = ~((tab.residue == r) & (tab.is_cb == 1))                    # the centre's own C-beta is replaced
+        inside = ((idx >= 0) & (idx <= 20)).all(axis=1) & keep
+        interior = ((idx >= 1) & (idx <= 19)).all(axis=1) & keep
+        for ch in range(5):
+            extra = 1 if ch == cbc else 0                                  # the ideal C-beta
+            tot = float(f[..., ch].sum())
+            lo, hi = interior[tab.channel == ch].sum() + extra, inside[tab.channel == ch].sum() + extra
+            assert lo - 1e-4 <= tot <= hi + 1e-4 and lo >= 3, (ch, lo, tot, hi)
+    # boolean frames: one voxel per atom, the gaussian frame's support contains it
+    _, fb = _oracle_frames(residues, [10], gaussian=False)
+    assert fb.dtype == np.uint8 and set(np.unique(fb)) == {0, 1}
+    assert (fr[0][fb[0] == 1] > 0).all()
+
+
+def test_oracle_is_invariant_under_rigid_motion():
+    """Frames are defined in the residue's own coordinate system: rotating / translating the whole structure must not
+    change them (up to the float32 coordinates of the moved atoms)."""
+    (residues,) = vx.parse_pdb(PDB)
+    rng = np.random.default_rng(3)
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    q *= np.sign(np.linalg.det(q))
+    shift = rng.uniform(-30, 30, 3)
+    moved = [vx.Residue(r.chain, r.res_id, r.label, {k: tuple(q @ np.array(v) + shift) for k, v in r.atoms.items()})
+             for r in residues]
+    _, a = _oracle_frames(residues, [5, 33, 70])
+    _, b = _oracle_frames(moved, [5, 33, 70])
+    assert np.abs(a - b).max() < 2e-4 and np.abs(a - b).mean() < 1e-7
+
+
+def test_property_channels():
+    (residues,) = vx.parse_pdb(PDB)
+    tab, fq = _oracle_frames(residues, [26], codec="CNOCBCAQ")              # K27: a lysine at the centre
+    assert fq.shape[-1] == 6 and residues[26].label == "LYS"
+    assert fq[0, 9, 9, 9, 5] > 0.02                                         # +1 at the ideal C-beta
+    assert fq[0, ..., 5].min() < -0.02                                      # an acidic neighbour's C-beta is negative
+    _, fp = _oracle_frames(residues, [26], codec="CNOCBCAP")
+    assert fp[0, ..., 5].min() >= 0 and fp[0, 9, 9, 9, 5] > 0.02

@@ -24,6 +24,7 @@
 #include "thin_conv.cuh"
 #include "slab_conv.cuh"
 #include "thinz_conv.cuh"
+#include "voxelise.cuh"
 
 namespace tb {
 
@@ -2417,6 +2418,47 @@ int timed_b200_seq_metrics(const uint8_t* d_seqs, int64_t n_seqs, int64_t n_res,
     TB_REQUIRE(n_table_doubles >= 63, "metric table too short");
     seq_metrics_kernel<<<static_cast<unsigned>((n_seqs + 7) / 8), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
         d_seqs, n_seqs, n_res, d_letter_lut, d_tables, d_out);
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+// ---------------------------------------------------------------------------------- voxeliser (8(f)-1)
+int timed_b200_voxelise(const float* d_atoms_xyzs, const int32_t* d_atom_channel, const int32_t* d_atom_residue,
+                        const int32_t* d_atom_is_cb, int64_t n_atoms, const float* d_res_frame, const float* d_res_property,
+                        const int32_t* d_res_index, int64_t res_first, int64_t n_res, int32_t voxels_per_side, float voxel_edge,
+                        int32_t n_channels,
+                        int32_t as_gaussian, int32_t encode_cb, const float* ideal_cb_xyz_sigma, int32_t cb_channel,
+                        int32_t property_channel, int32_t* d_scratch, void* d_frames, int32_t frames_dtype, void* cuda_stream) {
+    TB_REQUIRE(d_atoms_xyzs && d_atom_channel && d_atom_residue && d_atom_is_cb && d_res_frame && d_scratch && d_frames,
+               "null argument");
+    TB_REQUIRE(n_atoms > 0 && n_res > 0 && res_first >= 0, "nothing to voxelise");
+    TB_REQUIRE(voxels_per_side > 0 && (voxels_per_side & 1) && voxel_edge > 0.f, "voxels per side must be odd, edge positive");
+    TB_REQUIRE(n_channels > 0 && cb_channel < n_channels && property_channel < n_channels, "channel index out of range");
+    TB_REQUIRE(!encode_cb || (ideal_cb_xyz_sigma && cb_channel >= 0), "encode_cb needs the ideal C-beta and its channel");
+    TB_REQUIRE(frames_dtype == TB_DTYPE_F32 || frames_dtype == TB_DTYPE_F16 || (frames_dtype == TB_DTYPE_U8 && !as_gaussian),
+               "frames must be float32 / float16 (or uint8 for boolean voxels)");
+    TB_REQUIRE((reinterpret_cast<uintptr_t>(d_atoms_xyzs) & 15) == 0, "atom table must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const int64_t per_frame = static_cast<int64_t>(voxels_per_side) * voxels_per_side * voxels_per_side * n_channels;
+    const int64_t n = n_res * per_frame;
+    TB_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, static_cast<size_t>(n) * sizeof(int32_t), s));
+    VoxeliseParams p;
+    p.atoms = reinterpret_cast<const float4*>(d_atoms_xyzs);
+    p.atom_channel = d_atom_channel; p.atom_residue = d_atom_residue; p.atom_is_cb = d_atom_is_cb;
+    p.n_atoms = n_atoms;
+    p.res_frame = d_res_frame; p.res_property = d_res_property; p.res_index = d_res_index; p.res_first = res_first;
+    p.V = voxels_per_side; p.inv_edge = 1.0f / voxel_edge; p.C = n_channels;
+    p.gaussian = as_gaussian; p.encode_cb = encode_cb;
+    p.cb_x = encode_cb ? ideal_cb_xyz_sigma[0] : 0.f; p.cb_y = encode_cb ? ideal_cb_xyz_sigma[1] : 0.f;
+    p.cb_z = encode_cb ? ideal_cb_xyz_sigma[2] : 0.f; p.cb_sigma = encode_cb ? ideal_cb_xyz_sigma[3] : 1.f;
+    p.cb_channel = cb_channel; p.property_channel = property_channel;
+    p.scratch = d_scratch;
+    voxelise_kernel<<<static_cast<unsigned>(n_res), 256, 0, s>>>(p);
+    TB_CHECK_CUDA(cudaGetLastError());
+    const int grid = grid_for(n, 256);
+    if (frames_dtype == TB_DTYPE_F32) voxelise_finalize_kernel<float><<<grid, 256, 0, s>>>(d_scratch, n, !as_gaussian, static_cast<float*>(d_frames));
+    else if (frames_dtype == TB_DTYPE_F16) voxelise_finalize_kernel<__half><<<grid, 256, 0, s>>>(d_scratch, n, !as_gaussian, static_cast<__half*>(d_frames));
+    else voxelise_finalize_kernel<uint8_t><<<grid, 256, 0, s>>>(d_scratch, n, 1, static_cast<uint8_t*>(d_frames));
     TB_CHECK_CUDA(cudaGetLastError());
     return TB_OK;
 }
