@@ -227,3 +227,29 @@ def test_tap_to_n_variants_agree(monkeypatch):
     for y in (y_kw, y_full, y_direct):
         assert np.abs(y[:2] - ref).max() <= 1e-4 * np.abs(ref).max()
     assert np.abs(y_kw - y_full).max() <= 5e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("shape", [(3, 9, 128, 32, 3, "same"), (2, 7, 64, 24, 3, "valid"), (2, 6, 512, 20, 3, "same"),
+                                   (2, 8, 128, 32, 5, "same")], ids=lambda s: f"s{s[1]}_c{s[2]}_n{s[3]}_k{s[4]}_{s[5]}")
+def test_tap_to_n_kw_in_n_variant(shape, monkeypatch):
+    """Third tap-to-N formulation: the kw taps in the GEMM's N dimension, the (kd,kh) taps in K (im2col over D and H only),
+    col2im summing the kw shifted copies along W -- what DenseCPD's 128 -> 32 growth convs run on.  Against the oracle and
+    the direct conv, 'same' (W margins dropped by the gather) and 'valid' (narrower output) alike."""
+    n, side, ci, co, k, padding = shape
+    rng = np.random.default_rng(side * ci)
+    x = rng.standard_normal((n, side, side, side, ci)).astype(np.float32)
+    w = (rng.standard_normal((k, k, k, ci, co)) * np.sqrt(2.0 / (k ** 3 * ci))).astype(np.float32)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, co).astype(np.float32)
+    sh = (rng.standard_normal(co) * 0.2).astype(np.float32)
+    monkeypatch.setenv("TIMED_B200_TAP2N_W", "1")
+    monkeypatch.setenv("TIMED_B200_TAP2N_MARGIN", "100")         # take the variant whatever the cost model says
+    y_w = run_conv_gpu(x, w, bias=b, scale=sc, shift=sh, padding=padding, act1="relu")
+    monkeypatch.delenv("TIMED_B200_TAP2N_W")
+    monkeypatch.setenv("TIMED_B200_NO_TAP2N", "1")
+    y_direct = run_conv_gpu(x, w, bias=b, scale=sc, shift=sh, padding=padding, act1="relu")
+    ref = ko.np_activation(ko.np_conv3d(x[:1].astype(np.float64), w.astype(np.float64), b.astype(np.float64), padding), "relu")
+    ref = ref * sc + sh
+    assert y_w.shape == y_direct.shape
+    assert np.abs(y_w[:1] - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.abs(y_w - y_direct).max() <= 5e-5 * np.abs(ref).max()

@@ -100,6 +100,11 @@ struct TensorInfo {
     int fmt = FMT_F32;
     int slack_pix = 0;    // extra readable pixels past the end required by im2col consumers
     int last_use = -1;    // index of the last op reading this tensor
+    // Zero-copy Concatenate: an fp32 tensor that is only ever read as a channel slice of a later Concatenate's output is a
+    // VIEW of that output's buffer (producers write their slice with the buffer's row pitch; the Concatenate copies nothing).
+    // Views nest (DenseNet blocks: concat_k is the first slice of concat_{k+1}); view_root / view_c0 are resolved.
+    int view_of = -1, view_off = 0;
+    int view_root = -1, view_c0 = 0;
     // "W-folded" layout of a thin (C <= 8) graph input: 8 stored channels per pixel and W-rows of
     // wf_pitch pixels (wf_lm zero pixels, the W real ones, zero pixels up to the pitch).  A conv
     // then reads kwin consecutive pixels (kwin*8 contiguous elements) as ONE im2col "pixel", so the
@@ -174,14 +179,19 @@ struct ConvPlan {
     // im2col along W only.  Same MMA count and activation traffic as folding all taps into N (three N tiles there, three
     // K taps here) but a Z matrix kw times smaller to write and to gather from.
     bool t2n_kw = false;
+    // tap-to-N with the kw taps in N and the (kd,kh) taps in K ("t2n_w"): Z[(d,h) output row, w input column, kw, co] =
+    // sum_{kd,kh,c} X * W, an im2col over D and H only; col2im then sums the kw shifted copies along W.  N = kw*cout columns
+    // (96 for DenseCPD's 128 -> 32 growth convs: two N-folded MMAs of N = 192 / 96 per K step instead of N = 64 / 32 -- the
+    // thin-N MMAs cost the same ~72 cycles -- for a Z matrix of only 384 bytes per pixel).
+    bool t2n_w = false;
     // network head: this tap-to-N conv is read only by GlobalPooling -> Softmax (the graph output): the col2im gather, the
     // pooling and the softmax run as ONE launch after the GEMM (head_col2im_pool_softmax_kernel) straight into `probs`
     bool fuse_head = false;
     int head_is_avg = 1;
-    int taps_eff() const { return tap2n ? (t2n_kw ? kw : 1) : (wfold ? kd * kh : kd * kh * kw); }
+    int taps_eff() const { return tap2n ? (t2n_kw ? kw : t2n_w ? kd * kh : 1) : (wfold ? kd * kh : kd * kh * kw); }
     // geometry of the GEMM rows (output pixels, or input pixels for tap-to-N)
-    int Mo_d() const { return tap2n ? Di : Do; }
-    int Mo_h() const { return tap2n ? Hi : Ho; }
+    int Mo_d() const { return tap2n && !t2n_w ? Di : Do; }
+    int Mo_h() const { return tap2n && !t2n_w ? Hi : Ho; }
     int Mo_w() const { return tap2n ? (t2n_kw ? Wo : Wi) : Wo; }
     int gemm_n() const { return tap2n ? z_cols : cout; }
     __nv_bfloat16* d_w = nullptr;   // [2][n_alloc][k_total]
@@ -396,8 +406,8 @@ static int encode_a_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* ba
     cuuint64_t strides[4] = {px, px * p.Wi, px * p.Wi * p.Hi, px * p.Wi * p.Hi * p.Di};
     int lower[3] = {-p.pad0[2], -p.pad0[1], -p.pad0[0]};
     int upper[3] = {p.pad1[2] - (p.kw - 1), p.pad1[1] - (p.kh - 1), p.pad1[0] - (p.kd - 1)};
-    if (p.tap2n) {
-        for (int i = p.t2n_kw ? 1 : 0; i < 3; ++i) lower[i] = upper[i] = 0;   // t2n_kw keeps the W window
+    if (p.tap2n) {      // index 0 = W, 1 = H, 2 = D: t2n_kw keeps the W window, t2n_w the D and H windows
+        for (int i = p.t2n_kw ? 1 : 0; i < (p.t2n_w ? 1 : 3); ++i) lower[i] = upper[i] = 0;
     }
     if (p.wfold) {
         // "pixel" = kwin consecutive stored pixels starting pad_w0 to the left of the output
@@ -991,19 +1001,38 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
         // cycles whatever N is, a wide one ~110; the Z matrix is written and read once through HBM at
         // ~23 B/cycle/SM.  Take tap-to-N only when it wins clearly (TIMED's head: 68k vs 168k cycles;
         // DenseCPD's 128->32 growth convs: 68k vs 42k, so they stay on the direct path).
+        // cost model, cycles per 128-row tile (tools/mma_probe.cu: an M = 128 MMA costs ~72 cycles up to N = 64, 135 at
+        // N = 256; N-folded issue = MMAs of 2N and N per K step for N <= 128, three of N otherwise; the Z matrix is written
+        // and read once through HBM at ~23 B/cycle/SM).  TIMED's 512 -> 20 head: direct 124k, (kd,kh)-in-N 45k, kw-in-N 52k;
+        // DenseCPD's 128 -> 32 growth convs: direct 31k, (kd,kh)-in-N 33k, kw-in-N 20k.
         const double k16 = cin_pad / 16.0;
-        const double direct_cost = taps_all * k16 * 3 * 65.0 * ceil_div(round_up(p.cout, 16), 256);
-        // (kd,kh) taps in N, kw taps in K (the default variant): kw K-taps, Z of kd*kh*cout columns
-        const bool kw_in_k = p.kw > 1 && !getenv("TIMED_B200_TAP2N_FULL");
-        const double z_cols = static_cast<double>(kw_in_k ? p.kd * p.kh : taps_all) * p.cout;
-        const double t2n_cost = k16 * (kw_in_k ? p.kw : 1) * 3 * std::ceil(z_cols / 256.0) * 110.0 +
-                                8.0 * z_cols * 128 / 23.0 * 1.5;
+        auto mma = [](double n) { return n <= 64 ? 72.0 : 72.0 + (n - 64.0) * (135.0 - 72.0) / 192.0; };
+        auto gemm = [&](double cols, double k16_total) {
+            const int tiles = ceil_div(round_up(static_cast<int>(cols), 16), 256);
+            const double nt = round_up(ceil_div(round_up(static_cast<int>(cols), 16), tiles), 16);
+            return k16_total * tiles * (nt <= 128 ? mma(2 * nt) + mma(nt) : 3 * mma(nt));
+        };
+        auto zcost = [](double cols) { return 8.0 * cols * 128 / 23.0 * 1.5; };
+        const double direct_cost = gemm(p.cout, taps_all * k16);
+        const double full_cost = gemm(static_cast<double>(taps_all) * p.cout, k16) + zcost(static_cast<double>(taps_all) * p.cout);
+        const double kwk_cost = p.kw > 1 ? gemm(static_cast<double>(p.kd) * p.kh * p.cout, p.kw * k16) + zcost(static_cast<double>(p.kd) * p.kh * p.cout) : 1e30;
+        const double wn_cost = (p.kd * p.kh > 1 && p.kw > 1) ? gemm(static_cast<double>(p.kw) * p.cout, p.kd * p.kh * k16) + zcost(static_cast<double>(p.kw) * p.cout) : 1e30;
+        int variant = 0;                                     // 0 all taps in N, 1 kw in K, 2 kw in N
+        double t2n_cost = full_cost;
+        if (getenv("TIMED_B200_TAP2N_FULL")) variant = 0;
+        else if (getenv("TIMED_B200_TAP2N_W") && wn_cost < 1e29) { variant = 2; t2n_cost = wn_cost; }
+        else {
+            if (kwk_cost < t2n_cost) { variant = 1; t2n_cost = kwk_cost; }
+            if (wn_cost < t2n_cost && !getenv("TIMED_B200_NO_TAP2N_W")) { variant = 2; t2n_cost = wn_cost; }
+        }
         const double margin = getenv("TIMED_B200_TAP2N_MARGIN") ? atof(getenv("TIMED_B200_TAP2N_MARGIN")) : 0.7;
-        p.tap2n = !p.wfold && taps_all > 1 && p.cout <= 64 && taps_all * p.cout <= 1024 && cin_pad >= 64 &&
+        const int zc = (variant == 1 ? p.kd * p.kh : variant == 2 ? p.kw : taps_all) * p.cout;
+        p.tap2n = !p.wfold && taps_all > 1 && p.cout <= 64 && zc <= 1024 && cin_pad >= 64 &&
                   t2n_cost < margin * direct_cost && !getenv("TIMED_B200_NO_TAP2N");
         if (p.tap2n) {
-            p.t2n_kw = p.kw > 1 && !getenv("TIMED_B200_TAP2N_FULL");
-            p.z_cols = (p.t2n_kw ? p.kd * p.kh : taps_all) * p.cout;
+            p.t2n_kw = variant == 1;
+            p.t2n_w = variant == 2;
+            p.z_cols = zc;
             p.z_ld = round_up(p.z_cols, 4);
         }
     }
@@ -1026,11 +1055,13 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
                 const __nv_bfloat16 hi = __float2bfloat16_rn(v);
                 const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
                 // K index: dense = tap*cin_pad + c; W-folded = (kd,kh)-tap * (kwin*8) + kw*8 + c
-                const size_t kidx = p.tap2n ? (p.t2n_kw ? static_cast<size_t>(t % p.kw) * cin_pad + c : static_cast<size_t>(c))
+                const size_t kidx = p.tap2n ? (p.t2n_kw ? static_cast<size_t>(t % p.kw) * cin_pad + c
+                                               : p.t2n_w ? static_cast<size_t>(t / p.kw) * cin_pad + c : static_cast<size_t>(c))
                                   : p.wfold ? static_cast<size_t>(t / p.kw) * cin_pad + static_cast<size_t>(t % p.kw) * 8 + c
                                             : static_cast<size_t>(t) * cin_pad + c;
                 // GEMM column: the output channel, or (tap, channel) for tap-to-N
-                const size_t ncol = p.tap2n ? static_cast<size_t>(p.t2n_kw ? t / p.kw : t) * p.cout + n : static_cast<size_t>(n);
+                const size_t ncol = p.tap2n ? static_cast<size_t>(p.t2n_kw ? t / p.kw : p.t2n_w ? t % p.kw : t) * p.cout + n
+                                            : static_cast<size_t>(n);
                 const size_t o = ncol * p.k_total + kidx;
                 w[o] = hi;
                 w[plane + o] = lo;
@@ -1171,7 +1202,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.acc_cols = cfg.acc_cols;
     k.acc_stages = cfg.acc_stages;
     k.nfold = cfg.nfold;
-    k.kh = p.tap2n ? 1 : p.kh; k.kw = (p.wfold || (p.tap2n && !p.t2n_kw)) ? 1 : p.kw;
+    k.kh = (p.tap2n && !p.t2n_w) ? 1 : p.kh; k.kw = (p.wfold || (p.tap2n && !p.t2n_kw)) ? 1 : p.kw;
     k.n_taps = p.taps_eff();
     k.cin_pad = p.cin_pad;
     k.kc = cfg.kc;
@@ -1180,8 +1211,8 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.n_kblocks = k.n_taps * k.cin_blocks;
     k.stages = cfg.stages;
     k.Do = p.Mo_d(); k.Ho = p.Mo_h(); k.Wo = p.Mo_w();
-    k.lc_d = p.tap2n ? 0 : -p.pad0[0];
-    k.lc_h = p.tap2n ? 0 : -p.pad0[1];
+    k.lc_d = (p.tap2n && !p.t2n_w) ? 0 : -p.pad0[0];
+    k.lc_h = (p.tap2n && !p.t2n_w) ? 0 : -p.pad0[1];
     k.lc_w = (p.wfold || (p.tap2n && !p.t2n_kw)) ? 0 : -p.pad0[2];
     k.lo_plane_frames = static_cast<int32_t>(in_frames_alloc);
     k.w_lo_rows = p.n_alloc;
@@ -1209,6 +1240,8 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
             valid = valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]);
         } else if (p.t2n_kw) {
             valid = valid_tap_fraction(p.Wi, p.Wo, p.kw, p.pad0[2]);
+        } else if (p.t2n_w) {
+            valid = valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]);
         }
         const bool shared_acc = !cfg.nfold && !cfg.corr_off;
         k.acc_comp = accum_comp(per_tap * k.n_taps * (shared_acc ? 3.0 : 1.0), valid);
@@ -1248,9 +1281,10 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     TB_CHECK_CUDA(cudaGetLastError());
     if (p.tap2n) {
         Col2imParams cp;
-        cp.Di = p.Di; cp.Hi = p.Hi; cp.Wi = p.Mo_w(); cp.Do = p.Do; cp.Ho = p.Ho; cp.Wo = p.Wo;
-        cp.kd = p.kd; cp.kh = p.kh; cp.kw = p.t2n_kw ? 1 : p.kw;             // t2n_kw: the GEMM already summed over kw
-        cp.pd = p.pad0[0]; cp.ph = p.pad0[1]; cp.pw = p.t2n_kw ? 0 : p.pad0[2];
+        cp.Di = p.Mo_d(); cp.Hi = p.Mo_h(); cp.Wi = p.Mo_w(); cp.Do = p.Do; cp.Ho = p.Ho; cp.Wo = p.Wo;
+        cp.kd = p.t2n_w ? 1 : p.kd; cp.kh = p.t2n_w ? 1 : p.kh;              // t2n_w: the GEMM already summed over (kd,kh)
+        cp.kw = p.t2n_kw ? 1 : p.kw;                                         // t2n_kw: ... over kw
+        cp.pd = p.t2n_w ? 0 : p.pad0[0]; cp.ph = p.t2n_w ? 0 : p.pad0[1]; cp.pw = p.t2n_kw ? 0 : p.pad0[2];
         cp.cout = p.cout;
         cp.z_ld = p.z_ld;
         cp.act1 = p.act1; cp.act2 = p.act2; cp.alpha1 = p.alpha1; cp.alpha2 = p.alpha2;
@@ -1340,13 +1374,24 @@ static TView make_view(const TensorInfo& t, uint8_t* base, int64_t n_frames) {
     v.f32 = nullptr;
     v.hi = v.lo = nullptr;
     if (t.fmt == FMT_F32) {
-        v.f32 = reinterpret_cast<float*>(base);
+        v.f32 = reinterpret_cast<float*>(base);      // (for a view the caller passes the root's base and fixes ld / offset)
     } else if (t.cpv) {
         v.hi = reinterpret_cast<__nv_bfloat16*>(base);
         v.lo = v.hi + (t.c_pad / 8) * t.cpv_T(n_frames) * 8;
     } else {
         v.hi = reinterpret_cast<__nv_bfloat16*>(base);
         v.lo = v.hi + t.frames_alloc(n_frames) * t.stored_pix_per_frame() * t.c_pad;
+    }
+    return v;
+}
+
+// view of tensor `idx` inside the workspace: a zero-copy Concatenate slice points into its root's buffer
+static TView tensor_view(const tb_graph* g, const Layout& L, int idx, uint8_t* base, int64_t n_frames) {
+    const TensorInfo& t = g->tensors[idx];
+    TView v = make_view(t, base + L.offset[idx], n_frames);
+    if (t.view_root >= 0) {
+        v.f32 += t.view_c0;
+        v.ld = g->tensors[t.view_root].C;
     }
     return v;
 }
@@ -1374,6 +1419,7 @@ static const Layout& get_layout(tb_graph* g, int64_t n_frames) {
     std::vector<Block> free_list;
     size_t top = 0;
     std::vector<std::pair<size_t, size_t>> live(n, {0, 0});
+    std::vector<bool> placed_flag(n, false);
     for (int i = 0; i < n; ++i) {
         // release tensors whose last reader ran before op i
         for (int j = 0; j < i; ++j)
@@ -1396,11 +1442,19 @@ static const Layout& get_layout(tb_graph* g, int64_t n_frames) {
             live[i] = {L.offset[i], 0};
             continue;
         }
-        const size_t need = g->tensors[i].bytes(n_frames);
+        // zero-copy Concatenate: the first view to be produced places the root buffer; views themselves take no storage
+        int place = i;
+        if (g->tensors[i].view_root >= 0) place = g->tensors[i].view_root;
+        if (placed_flag[place]) {
+            if (place != i) { L.offset[i] = L.offset[place]; live[i] = {L.offset[i], 0}; }
+            continue;
+        }
+        placed_flag[place] = true;
+        const size_t need = g->tensors[place].bytes(n_frames);
         bool placed = false;
         for (size_t k = 0; k < free_list.size(); ++k)
             if (free_list[k].size >= need) {
-                L.offset[i] = free_list[k].off;
+                L.offset[place] = free_list[k].off;
                 free_list[k].off += need;
                 free_list[k].size -= need;
                 if (!free_list[k].size) free_list.erase(free_list.begin() + k);
@@ -1410,15 +1464,16 @@ static const Layout& get_layout(tb_graph* g, int64_t n_frames) {
         if (!placed) {
             // grow from the top; merge with a trailing free block if there is one
             if (!free_list.empty() && free_list.back().off + free_list.back().size == top) {
-                L.offset[i] = free_list.back().off;
+                L.offset[place] = free_list.back().off;
                 top = free_list.back().off + need;
                 free_list.pop_back();
             } else {
-                L.offset[i] = top;
+                L.offset[place] = top;
                 top += need;
             }
         }
-        live[i] = {L.offset[i], need};
+        live[place] = {L.offset[place], need};
+        if (place != i) { L.offset[i] = L.offset[place]; live[i] = {L.offset[i], 0}; }
     }
     L.scratch_off = static_cast<size_t>(round_up64(static_cast<int64_t>(top), 1024));
     for (const auto& op : g->ops)
@@ -1702,6 +1757,50 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
         // pointers are only valid during graph_create
         node.d.kernel_w = node.d.bias = node.d.scale = node.d.shift = nullptr;
     }
+    // Zero-copy Concatenate: fp32 inputs of a Concatenate become channel-slice views of its output buffer
+    if (!getenv("TIMED_B200_NO_ZEROCOPY_CONCAT")) {
+        auto readers_ok = [&](int tix) {
+            for (int a = 0; a < n_ops; ++a)
+                for (int b = 0; b < ops[a].n_inputs; ++b)
+                    if (ops[a].inputs[b] == tix && ops[a].op == TB_OP_CONV3D) return false;
+            return true;
+        };
+        for (int k = 1; k < n_ops; ++k) {
+            if (ops[k].op != TB_OP_CONCAT || g->tensors[k].fmt != FMT_F32 || g->tensors[k].C % 8 != 0) continue;
+            int off = 0;
+            for (int b = 0; b < ops[k].n_inputs; ++b) {
+                const int a = ops[k].inputs[b];
+                TensorInfo& ta = g->tensors[a];
+                const int kind = ops[a].op;
+                const bool producer_ok = kind == TB_OP_CONV3D || kind == TB_OP_POOL3D || kind == TB_OP_AFFINE ||
+                                         kind == TB_OP_CONCAT || kind == TB_OP_ADD;
+                bool dup = false;                                  // the same tensor listed twice cannot live at two offsets
+                for (int b2 = 0; b2 < b; ++b2) dup = dup || ops[k].inputs[b2] == a;
+                if (producer_ok && !dup && ta.fmt == FMT_F32 && ta.view_of < 0 && !ta.cpv && !ta.padvol && !ta.wfold &&
+                    g->ops[a].alias_of < 0 && off % 8 == 0 && ta.C % 8 == 0 && readers_ok(a) &&
+                    !(kind == TB_OP_CONV3D && (g->ops[a].conv.fuse_pool || g->ops[a].conv.fuse_zpool))) {
+                    ta.view_of = k;
+                    ta.view_off = off;
+                }
+                off += ta.C;
+            }
+        }
+        for (int i = 0; i < n_ops; ++i) {
+            TensorInfo& t = g->tensors[i];
+            if (t.view_of < 0) continue;
+            int root = i, c0 = 0;
+            while (g->tensors[root].view_of >= 0) { c0 += g->tensors[root].view_off; root = g->tensors[root].view_of; }
+            t.view_root = root;
+            t.view_c0 = c0;
+            g->tensors[root].last_use = std::max(g->tensors[root].last_use, t.last_use);
+        }
+        for (int k = 1; k < n_ops; ++k) {                       // launches saved: one copy per in-place slice
+            if (ops[k].op != TB_OP_CONCAT) continue;
+            for (int b = 0; b < ops[k].n_inputs; ++b)
+                if (g->tensors[ops[k].inputs[b]].view_of == k) g->launches -= 1;
+            if (g->tensors[k].fmt != FMT_SPLIT) g->launches -= 1;   // (the +1 counted the channel-pad zeroing of split outputs)
+        }
+    }
     // Fused network head: ... -> GlobalPooling (j) -> Softmax (k = graph output), each read once.  The pooling op then
     // writes the probabilities itself (head_pool_softmax_kernel); when it reads a tap-to-N conv (TIMED's 20-class head)
     // that conv's col2im launch does gather + epilogue + pooling + softmax and both later ops are skipped.
@@ -1795,7 +1894,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
         OpNode& node = g->ops[i];
         const tb_op_desc& d = node.d;
         const TensorInfo& t = g->tensors[i];
-        TView out = make_view(t, base + L.offset[i], n_frames);
+        TView out = tensor_view(g, L, i, base, n_frames);
         if (i == n_ops - 1 || node.pool_softmax || (d.op == TB_OP_CONV3D && node.conv.fuse_head)) {
             // the graph output (or the op that computes it in a fused head) goes straight to the caller's buffer
             out.f32 = d_probs;
@@ -1810,7 +1909,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
         const TensorInfo* ti0 = nullptr;
         if (d.n_inputs > 0) {
             ti0 = &g->tensors[d.inputs[0]];
-            in0 = make_view(*ti0, base + L.offset[d.inputs[0]], n_frames);
+            in0 = tensor_view(g, L, d.inputs[0], base, n_frames);
         }
         const int cw = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
         switch (d.op) {
@@ -1928,7 +2027,11 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 int c_off = 0;
                 for (int k = 0; k < d.n_inputs; ++k) {
                     const TensorInfo& ts = g->tensors[d.inputs[k]];
-                    TView src = make_view(ts, base + L.offset[d.inputs[k]], n_frames);
+                    if (ts.view_of == i) {                     // zero-copy: the producer wrote this slice in place
+                        c_off += ts.C;
+                        continue;
+                    }
+                    TView src = tensor_view(g, L, d.inputs[k], base, n_frames);
                     if (src.c % 8 == 0 && c_off % 8 == 0 && src.ld % 8 == 0 && out.ld % 8 == 0) {
                         const int grid = grid_for(out_pix * (src.c / 8), 256);
                         if (src.fmt == FMT_SPLIT && out.fmt == FMT_SPLIT)
@@ -1949,7 +2052,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 break;
             }
             case TB_OP_ADD: {
-                TView in1 = make_view(g->tensors[d.inputs[1]], base + L.offset[d.inputs[1]], n_frames);
+                TView in1 = tensor_view(g, L, d.inputs[1], base, n_frames);
                 add_kernel<<<grid_for(out_pix * cw, 256), 256, 0, s>>>(in0, in1, out, out_pix);
                 break;
             }
@@ -2087,7 +2190,12 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
         case TB_OP_AFFINE: name = "affine_act_kernel"; break;
         case TB_OP_GPOOL: name = node.skip ? "(fused into the head conv's launch)" : node.pool_softmax ? "head_pool_softmax_kernel" : "gpool_kernel"; break;
         case TB_OP_SOFTMAX: name = node.skip ? "(fused into the pooling launch)" : "softmax_kernel"; break;
-        case TB_OP_CONCAT: name = "copy_channels_kernel"; break;
+        case TB_OP_CONCAT: {
+            bool all_views = true;
+            for (int b = 0; b < node.d.n_inputs; ++b) all_views = all_views && g->tensors[node.d.inputs[b]].view_of == op;
+            name = all_views ? "(zero-copy: producers write the channel slices)" : "copy_channels_kernel";
+            break;
+        }
         case TB_OP_ADD: name = "add_kernel"; break;
         default: name = "?";
     }
