@@ -72,8 +72,9 @@ def philox_uniform(sample: int, res: int, seed: int, stream_id: int) -> float:
     """Same construction as kernels.cuh::philox_uniform (53-bit double in [0,1))."""
     mix = (stream_id * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
     key = ((seed & _MASK) ^ (mix >> 32), ((seed >> 32) & _MASK) ^ (mix & _MASK))
-    c = philox4x32_10([sample & _MASK, (sample >> 32) & _MASK, res & _MASK, (res >> 32) & _MASK], key)
-    a, b = c[0] >> 5, c[1] >> 6
+    pair = res >> 1                       # one Philox block serves two residues: words 0-1 the even one, 2-3 the odd one
+    c = philox4x32_10([sample & _MASK, (sample >> 32) & _MASK, pair & _MASK, (pair >> 32) & _MASK], key)
+    a, b = (c[2] >> 5, c[3] >> 6) if res & 1 else (c[0] >> 5, c[1] >> 6)
     return (a * 67108864.0 + b) / 9007199254740992.0
 
 

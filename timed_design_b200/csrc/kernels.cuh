@@ -396,26 +396,44 @@ __global__ void affine_act_vec8_kernel(TView in, TView out, int64_t n_pix, const
                                        float alpha2) {
     const int groups = (OUT_FMT == FMT_SPLIT ? out.c_pad : out.c) / 8;
     const int64_t total = n_pix * groups;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t pix = i / groups;
-        const int g = static_cast<int>(i - pix * groups);
+    // (pixel, channel group) of this thread's items advance by a constant stride: one 64-bit division up front instead of
+    // one per item (the DenseNet pre-activation passes run ~10^9 items per launch and were division-bound)
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t i0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    int64_t pix = i0 / groups;
+    int g = static_cast<int>(i0 - pix * groups);
+    const int64_t d_pix = stride / groups;
+    const int d_g = static_cast<int>(stride - d_pix * groups);
+    const bool plain_relu = act1 == ACT_NONE && act2 == ACT_RELU;        // BatchNorm -> ReLU, the DenseNet / ResNet case
+    for (int64_t i = i0; i < total; i += stride) {
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (g * 8 < out.c) {
             load8<IN_FMT>(in, pix * in.ld + g * 8, v);
+            if (plain_relu && g * 8 + 8 <= out.c) {
+                const float4 s0 = *reinterpret_cast<const float4*>(scale + g * 8), s1 = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
+                const float4 h0 = *reinterpret_cast<const float4*>(shift + g * 8), h1 = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int ch = g * 8 + e;
-                if (ch < out.c) {
-                    float x = apply_act(v[e], act1, alpha1);
-                    x = fmaf(x, scale[ch], shift[ch]);
-                    v[e] = apply_act(x, act2, alpha2);
-                } else {
-                    v[e] = 0.0f;
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], sc[e], sh[e]), 0.0f);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int ch = g * 8 + e;
+                    if (ch < out.c) {
+                        float x = apply_act(v[e], act1, alpha1);
+                        x = fmaf(x, scale[ch], shift[ch]);
+                        v[e] = apply_act(x, act2, alpha2);
+                    } else {
+                        v[e] = 0.0f;
+                    }
                 }
             }
         }
         store8<OUT_FMT>(out, pix * out.ld + g * 8, v);
+        pix += d_pix;
+        g += d_g;
+        if (g >= groups) { g -= groups; ++pix; }
     }
 }
 
@@ -839,15 +857,25 @@ __device__ __host__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
 }
 // 53-bit uniform in [0,1) from two 32-bit words, the same construction numpy's legacy
 // random_sample uses: (a>>5, b>>6) -> (a*2^26 + b) / 2^53.
-__device__ __host__ __forceinline__ double philox_uniform(uint64_t sample, uint64_t res,
-                                                          uint64_t seed, uint64_t stream_id) {
+// One Philox block serves TWO residues: counter = (sample, residue >> 1); the even residue takes words 0-1, the odd one
+// words 2-3 (round 1 threw half of every block away).
+__device__ __host__ __forceinline__ void philox_block(uint64_t sample, uint64_t res_pair, uint64_t seed, uint64_t stream_id,
+                                                      uint32_t (&c)[4]) {
     const uint64_t mix = stream_id * 0x9E3779B97F4A7C15ull;
-    uint32_t c[4] = {static_cast<uint32_t>(sample), static_cast<uint32_t>(sample >> 32),
-                     static_cast<uint32_t>(res), static_cast<uint32_t>(res >> 32)};
+    c[0] = static_cast<uint32_t>(sample); c[1] = static_cast<uint32_t>(sample >> 32);
+    c[2] = static_cast<uint32_t>(res_pair); c[3] = static_cast<uint32_t>(res_pair >> 32);
     philox4x32_10(c, static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(mix >> 32),
                   static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(mix));
-    const uint32_t a = c[0] >> 5, b = c[1] >> 6;
-    return (static_cast<double>(a) * 67108864.0 + static_cast<double>(b)) / 9007199254740992.0;
+}
+__device__ __host__ __forceinline__ double philox_words_to_uniform(uint32_t w0, uint32_t w1) {
+    const uint32_t a = w0 >> 5, b = w1 >> 6;
+    return (static_cast<double>(a) * 67108864.0 + static_cast<double>(b)) * (1.0 / 9007199254740992.0);
+}
+__device__ __host__ __forceinline__ double philox_uniform(uint64_t sample, uint64_t res,
+                                                          uint64_t seed, uint64_t stream_id) {
+    uint32_t c[4];
+    philox_block(sample, res >> 1, seed, stream_id, c);
+    return (res & 1) ? philox_words_to_uniform(c[2], c[3]) : philox_words_to_uniform(c[0], c[1]);
 }
 
 __global__ void sample_uniforms_kernel(int64_t n_res, int64_t n_samples, int64_t first_sample,
@@ -946,18 +974,31 @@ __device__ __forceinline__ void sample_word(const double* __restrict__ cdf, int6
                                             uint8_t* __restrict__ seqs, int32_t* __restrict__ idx_out, int64_t wi) {
     uint32_t packed = 0;
     int32_t id4[4] = {0, 0, 0, 0};
+    // one division per word; (sample, residue) then advance incrementally.  A Philox block is reused by the two residues
+    // of a pair when both fall into this word (they do unless the pair straddles the word or a row end).
+    int64_t s = (wi * 4) / n_res;
+    int64_t res = wi * 4 - s * n_res;
+    uint32_t c[4];
+    int64_t have_s = -1, have_pair = -1;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int64_t flat = wi * 4 + e;
         if (flat >= total) break;
-        const int64_t s = flat / n_res;
-        const int64_t res = flat - s * n_res;
-        const double r = uniforms ? uniforms[flat]
-                                  : philox_uniform(static_cast<uint64_t>(first_sample + s),
-                                                   static_cast<uint64_t>(res), seed, stream_id);
+        double r;
+        if (uniforms) {
+            r = uniforms[flat];
+        } else {
+            if (s != have_s || (res >> 1) != have_pair) {
+                philox_block(static_cast<uint64_t>(first_sample + s), static_cast<uint64_t>(res >> 1), seed, stream_id, c);
+                have_s = s;
+                have_pair = res >> 1;
+            }
+            r = (res & 1) ? philox_words_to_uniform(c[2], c[3]) : philox_words_to_uniform(c[0], c[1]);
+        }
         const int j = sample_index(cdf + res * n_cls, n_cls, r);
         id4[e] = j;
         packed |= static_cast<uint32_t>(s_letters[j]) << (8 * e);
+        if (++res == n_res) { res = 0; ++s; }
     }
     if (wi * 4 + 3 < total) {
         reinterpret_cast<uint32_t*>(seqs)[wi] = packed;
