@@ -2439,6 +2439,14 @@ int timed_b200_apply_temperature(const double* d_probs_in, int64_t n_rows, int32
     TB_REQUIRE(n_rows > 0 && n_cls > 0, "empty probability matrix");
     TB_REQUIRE(t != 0.0, "temperature must be non-zero");
     const double inv_t = 1.0 / t;
+    if (n_cls > 32 && n_cls <= 1024) {       // wide rows: a warp per row (kernels.cuh)
+        const int wpb = 4;
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n_rows + wpb - 1) / wpb, 148 * 16));
+        temperature_wide_kernel<<<grid, 32 * wpb, static_cast<size_t>(wpb) * n_cls * sizeof(double),
+                                  static_cast<cudaStream_t>(cuda_stream)>>>(d_probs_in, n_rows, n_cls, inv_t, d_probs_out);
+        TB_CHECK_CUDA(cudaGetLastError());
+        return TB_OK;
+    }
     temperature_kernel<<<static_cast<unsigned>((n_rows + 127) / 128), 128, 0,
                          static_cast<cudaStream_t>(cuda_stream)>>>(d_probs_in, n_rows, n_cls, inv_t, d_probs_out);
     TB_CHECK_CUDA(cudaGetLastError());
@@ -2449,6 +2457,14 @@ int timed_b200_cumsum_rows(const double* d_probs, int64_t n_rows, int32_t n_cls,
                            void* cuda_stream) {
     TB_REQUIRE(d_probs && d_cdf, "null argument");
     TB_REQUIRE(n_rows > 0 && n_cls > 0, "empty probability matrix");
+    if (n_cls > 32 && n_cls <= 1024) {
+        const int wpb = 4;
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n_rows + wpb - 1) / wpb, 148 * 16));
+        cumsum_rows_wide_kernel<<<grid, 32 * wpb, static_cast<size_t>(wpb) * n_cls * sizeof(double),
+                                  static_cast<cudaStream_t>(cuda_stream)>>>(d_probs, n_rows, n_cls, d_cdf);
+        TB_CHECK_CUDA(cudaGetLastError());
+        return TB_OK;
+    }
     cumsum_rows_kernel<<<static_cast<unsigned>((n_rows + 127) / 128), 128, 0,
                          static_cast<cudaStream_t>(cuda_stream)>>>(d_probs, n_rows, n_cls, d_cdf);
     TB_CHECK_CUDA(cudaGetLastError());
@@ -2479,7 +2495,35 @@ int timed_b200_sample_chains(const double* d_cdf, const int64_t* d_row_off, cons
     TB_REQUIRE(n_cls > 0 && n_cls <= 512, "n_cls must be in [1,512]");
     TB_REQUIRE((reinterpret_cast<uintptr_t>(d_seqs) & 3) == 0 && (total_seq_bytes & 3) == 0,
                "d_seqs and the chain offsets must be 4-byte aligned");
-    sample_chains_kernel<<<grid_for(total_seq_bytes / 4, 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    if (!getenv("TIMED_B200_SAMPLER_GATHER")) {
+        // tiled kernel (kernels.cuh): CDF rows of a residue tile in shared memory, lanes = samples of one residue
+        const int tr = n_cls <= 64 ? 32 : 8;
+        const size_t smem = static_cast<size_t>(tr) * n_cls * sizeof(double) + static_cast<size_t>(kSampTileS) * (tr / 4 + 1) * 4;
+        // rows <= letters / samples; every chain adds at most one partial tile
+        const int64_t row_tiles_ub = total_seq_bytes / n_samples / tr + n_chains + 1;
+        const int64_t s_tiles = (n_samples + kSampTileS - 1) / kSampTileS;
+        TB_REQUIRE(row_tiles_ub < (1ll << 31) && s_tiles < 65536, "too many sampler tiles per launch");
+        int32_t* d_tile_off = nullptr;
+        TB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_tile_off), (static_cast<size_t>(n_chains) + 1) * sizeof(int32_t), s));
+        sample_tile_prefix_kernel<<<1, 32, 0, s>>>(d_row_off, n_chains, tr, d_tile_off);
+        const dim3 grid(static_cast<unsigned>(row_tiles_ub), static_cast<unsigned>(s_tiles));
+        if (tr == 32) {
+            static bool attr = false;
+            if (!attr) { TB_CHECK_CUDA(cudaFuncSetAttribute(sample_tiled_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+            sample_tiled_kernel<32><<<grid, kSampTileS, smem, s>>>(d_cdf, d_row_off, d_seq_off, d_tile_off, n_chains, n_cls, n_samples,
+                                                                   first_sample, seed, stream_id0, d_cls_to_letter, d_seqs);
+        } else {
+            static bool attr = false;
+            if (!attr) { TB_CHECK_CUDA(cudaFuncSetAttribute(sample_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+            sample_tiled_kernel<8><<<grid, kSampTileS, smem, s>>>(d_cdf, d_row_off, d_seq_off, d_tile_off, n_chains, n_cls, n_samples,
+                                                                  first_sample, seed, stream_id0, d_cls_to_letter, d_seqs);
+        }
+        TB_CHECK_CUDA(cudaGetLastError());
+        TB_CHECK_CUDA(cudaFreeAsync(d_tile_off, s));
+        return TB_OK;
+    }
+    sample_chains_kernel<<<grid_for(total_seq_bytes / 4, 256), 256, 0, s>>>(
         d_cdf, d_row_off, d_seq_off, n_chains, n_cls, n_samples, first_sample, seed, stream_id0, d_cls_to_letter,
         d_seqs);
     TB_CHECK_CUDA(cudaGetLastError());

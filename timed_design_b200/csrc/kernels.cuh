@@ -926,6 +926,46 @@ __global__ void temperature_kernel(const double* in, int64_t n_rows, int n_cls, 
     for (int j = 0; j < n_cls; ++j) dst[j] = dst[j] / s;
 }
 
+// Wide rows (338 rotamer categories): one WARP per row.  The thread-per-row kernels walk rows 2.7 KB apart (uncoalesced) with
+// 13 k threads in flight; here the lanes load / pow / store a row together through shared memory and lane 0 alone does the
+// order-sensitive part (numpy's pairwise sum, the sequential cumsum) on the staged row: same operations per element and the
+// same summation order => bit-identical results.  Dynamic shared memory: warps_per_block * n_cls doubles.
+__global__ void temperature_wide_kernel(const double* in, int64_t n_rows, int n_cls, double inv_t, double* out) {
+    extern __shared__ double s_rows[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    double* buf = s_rows + static_cast<size_t>(warp) * n_cls;
+    for (int64_t row = blockIdx.x * static_cast<int64_t>(wpb) + warp; row < n_rows; row += static_cast<int64_t>(gridDim.x) * wpb) {
+        const double* src = in + row * n_cls;
+        for (int j = lane; j < n_cls; j += 32) buf[j] = pow(src[j], inv_t);
+        __syncwarp();
+        double ssum = 0.0;
+        if (lane == 0) ssum = np_pairwise_sum(buf, n_cls);
+        ssum = __shfl_sync(0xffffffffu, ssum, 0);
+        double* dst = out + row * n_cls;
+        for (int j = lane; j < n_cls; j += 32) dst[j] = buf[j] / ssum;
+        __syncwarp();
+    }
+}
+__global__ void cumsum_rows_wide_kernel(const double* __restrict__ in, int64_t n_rows, int n_cls, double* __restrict__ out) {
+    extern __shared__ double s_rows[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    double* buf = s_rows + static_cast<size_t>(warp) * n_cls;
+    for (int64_t row = blockIdx.x * static_cast<int64_t>(wpb) + warp; row < n_rows; row += static_cast<int64_t>(gridDim.x) * wpb) {
+        for (int j = lane; j < n_cls; j += 32) buf[j] = in[row * n_cls + j];
+        __syncwarp();
+        if (lane == 0) {
+            double acc = buf[0];
+            for (int j = 1; j < n_cls; ++j) {
+                acc = __dadd_rn(acc, buf[j]);
+                buf[j] = acc;
+            }
+        }
+        __syncwarp();
+        for (int j = lane; j < n_cls; j += 32) out[row * n_cls + j] = buf[j];
+        __syncwarp();
+    }
+}
+
 // probs.cumsum(axis=1): strictly sequential fp64 adds, one thread per row (bit-identical to numpy).
 __global__ void cumsum_rows_kernel(const double* __restrict__ in, int64_t n_rows, int n_cls,
                                    double* __restrict__ out) {
@@ -1051,6 +1091,104 @@ __global__ void sample_chains_kernel(const double* __restrict__ cdf, const int64
         if (wl * 4 >= total) continue;               // alignment padding after the chain's block
         sample_word(cdf + row_off[lo] * n_cls, n_res, n_cls, total, first_sample, seed, stream_id0 + lo, nullptr,
                     s_letters, seqs + seq_off[lo], nullptr, wl);
+    }
+}
+
+// ------------------------------------------------------------------ tiled sampler
+// ncu on sample_chains_kernel (profiles/r2c_sampler_ncu.json): l1tex throughput 94 % of peak, 21.5 sectors per load request --
+// every lane of a warp searches a DIFFERENT CDF row, so each of the ~6 loads per residue touches 32 cache lines and the
+// kernel is bound by L1 line throughput, not by bytes or arithmetic.  Here a CTA owns a tile of TR consecutive residues of
+// one chain x 256 consecutive samples: the tile's CDF rows are staged in shared memory once, the lanes of a warp are 32
+// SAMPLES of the same residue (every search reads one shared-memory row), letters are packed through a shared tile and
+// leave as contiguous runs of TR bytes.  Same generator keys and counters as sample_word => byte-identical output.
+constexpr int kSampTileS = 256;
+
+// tiles of chain c start at tile_off[c]: one thread, chains are few (tens to thousands)
+__global__ void sample_tile_prefix_kernel(const int64_t* __restrict__ row_off, int n_chains, int tr, int32_t* __restrict__ tile_off) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int32_t acc = 0;
+        for (int c = 0; c < n_chains; ++c) {
+            tile_off[c] = acc;
+            acc += static_cast<int32_t>((row_off[c + 1] - row_off[c] + tr - 1) / tr);
+        }
+        tile_off[n_chains] = acc;
+    }
+}
+
+template <int TR>
+__global__ void __launch_bounds__(kSampTileS)
+sample_tiled_kernel(const double* __restrict__ cdf, const int64_t* __restrict__ row_off, const int64_t* __restrict__ seq_off,
+                    const int32_t* __restrict__ tile_off, int n_chains, int n_cls, int64_t n_samples, int64_t first_sample,
+                    uint64_t seed, uint64_t stream_id0, const uint8_t* __restrict__ letters, uint8_t* __restrict__ seqs) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    double* s_cdf = reinterpret_cast<double*>(s_raw);                                   // [TR][n_cls]
+    uint32_t* s_out = reinterpret_cast<uint32_t*>(s_cdf + static_cast<size_t>(TR) * n_cls);   // [256][TR/4 + 1]
+    __shared__ uint8_t s_letters[512];
+    constexpr int PITCH = TR / 4 + 1;
+    for (int i = threadIdx.x; i < n_cls && i < 512; i += blockDim.x) s_letters[i] = letters[i];
+    const int rt = blockIdx.x;
+    if (rt >= tile_off[n_chains]) return;
+    int lo = 0, hi = n_chains - 1;                       // chain owning row tile rt
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tile_off[mid] <= rt) lo = mid; else hi = mid - 1;
+    }
+    const int chain = lo;
+    const int64_t n_res = row_off[chain + 1] - row_off[chain];
+    const int64_t r0 = static_cast<int64_t>(rt - tile_off[chain]) * TR;
+    const int nr = static_cast<int>(min(static_cast<int64_t>(TR), n_res - r0));
+    const double* rows = cdf + (row_off[chain] + r0) * n_cls;
+    for (int i = threadIdx.x; i < nr * n_cls; i += blockDim.x) s_cdf[i] = rows[i];
+    __syncthreads();
+    const int64_t s_local = static_cast<int64_t>(blockIdx.y) * kSampTileS + threadIdx.x;
+    const bool active = s_local < n_samples;
+    const uint64_t stream = stream_id0 + static_cast<uint64_t>(chain);
+    if (active) {
+        uint32_t c[4];
+        int64_t have_pair = -1;
+        uint32_t packed = 0;
+        for (int r = 0; r < nr; ++r) {
+            const int64_t res = r0 + r;
+            if ((res >> 1) != have_pair) {
+                philox_block(static_cast<uint64_t>(first_sample + s_local), static_cast<uint64_t>(res >> 1), seed, stream, c);
+                have_pair = res >> 1;
+            }
+            const double u = (res & 1) ? philox_words_to_uniform(c[2], c[3]) : philox_words_to_uniform(c[0], c[1]);
+            const double* row = s_cdf + r * n_cls;
+            const double last = row[n_cls - 1];
+            int j;
+            if (last != last) {                          // NaN row: the literal first-true scan (see sample_index)
+                j = n_cls;
+                for (int k = 0; k < n_cls; ++k)
+                    if (row[k] > u) { j = k; break; }
+            } else {
+                int a = 0, b = n_cls;
+                if (!(last > u)) a = n_cls;
+                while (a < b) {
+                    const int mid = (a + b) >> 1;
+                    if (row[mid] > u) b = mid; else a = mid + 1;
+                }
+                j = a;
+            }
+            if (j >= n_cls) j = 0;
+            packed |= static_cast<uint32_t>(s_letters[j]) << (8 * (r & 3));
+            if ((r & 3) == 3 || r + 1 == nr) {
+                s_out[threadIdx.x * PITCH + (r >> 2)] = packed;
+                packed = 0;
+            }
+        }
+    }
+    __syncthreads();
+    // write-out: a warp stores one sample row of the tile (nr contiguous bytes) per iteration
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* out = seqs + seq_off[chain];
+    const int64_t s_base = static_cast<int64_t>(blockIdx.y) * kSampTileS;
+    const int rows_here = static_cast<int>(min(static_cast<int64_t>(kSampTileS), n_samples - s_base));
+    for (int sr = warp; sr < rows_here; sr += kSampTileS / 32) {
+        for (int b = lane; b < nr; b += 32) {
+            const uint32_t w = s_out[sr * PITCH + (b >> 2)];
+            out[(s_base + sr) * n_res + r0 + b] = static_cast<uint8_t>(w >> (8 * (b & 3)));
+        }
     }
 }
 

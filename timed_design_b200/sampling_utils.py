@@ -173,10 +173,40 @@ def sample_chains(prob_list: t.Sequence[np.ndarray], sample_n: int, rotamer_cate
         from . import device_post
         metrics = [device_post.seq_metrics_device(d_seq[int(seq_off[i]):], int(sample_n), int(n)) if n else
                    np.zeros((sample_n, 4)) for i, n in enumerate(lengths)]
-    host = d_seq.cpu().numpy()
+    host, pin = _pinned_host(torch, total_bytes)      # pinned: the letters are the bulk of the traffic (1 B per residue)
+    (pin[:total_bytes] if pin is not None else torch.from_numpy(host[:total_bytes])).copy_(d_seq, non_blocking=True)
+    del pin
+    torch.cuda.current_stream().synchronize()
     seqs = [host[int(seq_off[i]):int(seq_off[i]) + int(sample_n) * int(n)].reshape(int(sample_n), int(n))
             for i, n in enumerate(lengths)]
     return (seqs, metrics) if return_metrics else seqs
+
+
+_pin_pool: list = []
+
+
+def _pinned_host(torch, n_bytes: int):
+    """A page-locked uint8 host buffer of at least ``n_bytes`` from a small pool.  The arrays handed back to the caller
+    are numpy views of it; a buffer is reused only once no such view is alive any more (its reference count is back to the
+    pool's own), so results of earlier calls are never overwritten.  Page-locking 100+ MB per call would cost more than the
+    copy it speeds up."""
+    import sys
+    for entry in _pin_pool:
+        if entry["host"].size >= n_bytes and sys.getrefcount(entry["host"]) <= entry["base_refs"]:
+            return entry["host"], entry["tensor"]
+    if len(_pin_pool) >= 4:                               # all leased: drop the oldest lease-free entry, or fall back
+        for i, entry in enumerate(_pin_pool):
+            if sys.getrefcount(entry["host"]) <= entry["base_refs"]:
+                del _pin_pool[i]
+                break
+        else:
+            return np.empty(n_bytes, dtype=np.uint8), None      # pageable (slower copy, still correct)
+    t = torch.empty(max(n_bytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+    host = t.numpy()
+    entry = {"tensor": t, "host": host}
+    _pin_pool.append(entry)
+    entry["base_refs"] = sys.getrefcount(host) - 1        # minus this frame's local name
+    return host, t
 
 
 _draw_counter = {"n": 0}
