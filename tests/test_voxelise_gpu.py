@@ -80,3 +80,28 @@ def test_config1_from_the_real_structure(tmp_path, monkeypatch):
     m.forward_device(dfr, probs, ws, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(probs.cpu().numpy(), m.predict(frames))
+
+
+def test_predict_cli_straight_from_structure_files(tmp_path, monkeypatch):
+    """Extension: --path_to_dataset may be a structure file (or a directory of them).  Frames are voxelised on the GPU and
+    fed to the network without touching the host; the outputs equal those of the .hdf5 route byte for byte."""
+    import shutil
+    from timed_design_b200 import predict
+    from timed_design_b200.hdf5 import write_keras_h5
+    cfg, w = standins.timed_standin(20, c_in=5, filters=(8, 16, 16, 24, 32), calib_frames=0)
+    write_keras_h5(tmp_path / "TIMED.h5", cfg, w)
+    pdbs = tmp_path / "pdbs"
+    pdbs.mkdir()
+    shutil.copy(PDB, pdbs / "1ubq.pdb1.gz")
+    monkeypatch.chdir(tmp_path)
+    a, b = tmp_path / "from_pdb", tmp_path / "from_hdf5"
+    predict.cli(["--path_to_dataset", str(pdbs), "--path_to_model", str(tmp_path / "TIMED.h5"), "--path_to_output", str(a),
+                 "--path_to_datasetmap", str(a / "datasetmap.txt"), "--yes", "--batch_size", "500"])
+    with pytest.warns(RuntimeWarning):
+        data = vx.make_frame_dataset([PDB], tmp_path, "data", codec="CNOCBCA")
+    predict.cli(["--path_to_dataset", str(data), "--path_to_model", str(tmp_path / "TIMED.h5"), "--path_to_output", str(b),
+                 "--path_to_datasetmap", str(b / "datasetmap.txt"), "--yes", "--batch_size", "500"])
+    names = sorted(f.name for f in b.iterdir())
+    assert names == sorted(f.name for f in a.iterdir()) and "TIMED.fasta" in names
+    for name in names:
+        assert (a / name).read_bytes() == (b / name).read_bytes(), name

@@ -27,7 +27,8 @@ from .frames import create_flat_dataset_map, load_batch
 from .model import load_model
 from .postprocess import (convert_dataset_map_for_srb, extract_sequence_from_pred_matrix,
                           get_pdb_keys_to_filter, get_rotamer_codec, rotamer_class_to_residue,
-                          save_consensus_probs, save_dict_to_fasta, save_outputs_to_file, savetxt_e18)
+                          save_consensus_probs, save_dict_to_fasta, save_outputs_to_file, savetxt_e18,
+                          standard_amino_acids)
 
 
 def _dist_context():
@@ -62,6 +63,51 @@ def _gather(arr: np.ndarray, n_total: int, local_rank: int) -> np.ndarray:
     return gather_rows(t, n_total).cpu().numpy()
 
 
+def _structure_files(path):
+    """[structure files] when `path` is a PDB file (.pdb / .pdb1 / .ent, optionally .gz) or a directory of them, else None."""
+    path = Path(path)
+    is_pdb = lambda f: any(x in f.name.lower() for x in (".pdb", ".ent")) and f.is_file()
+    if path.is_dir():
+        files = sorted(f for f in path.iterdir() if is_pdb(f))
+        return files or None
+    return [path] if is_pdb(path) and path.suffix.lower() not in (".hdf5", ".h5") else None
+
+
+def _voxelise_structures(files, codec, all_states, device, filter_pdb_list):
+    """-> (frames on the device (n, V, V, V, C), flat map rows [pdb, chain, res_id, label], one-hot labels (n, 20))."""
+    import torch
+    from . import voxelise
+    frames, flat = [], []
+    for f in files:
+        if f.name.split(".pdb")[0][:4] in filter_pdb_list:
+            continue
+        fr, fl = voxelise.voxelise_structure(f, codec or "CNOCBCA", voxelise_all_states=all_states, device=device,
+                                             return_device=True)
+        frames.append(fr)
+        flat.extend(fl)
+    if not frames:
+        raise ValueError("no structure left to voxelise")
+    order = list(standard_amino_acids.values())
+    onehot = np.eye(20, dtype=np.float64)[[order.index(r[3]) for r in flat]]
+    return (torch.cat(frames) if len(frames) > 1 else frames[0]), np.array(flat, dtype=str), onehot
+
+
+def _forward_device_rows(model, d_frames):
+    """Probabilities of device-resident frames through Model.forward_device (no host round trip of the frames)."""
+    import torch
+    n = d_frames.shape[0]
+    if tuple(d_frames.shape[1:]) != tuple(model.input_shape):
+        raise ValueError(f"voxelised frames have shape {tuple(d_frames.shape[1:])} but the model expects "
+                         f"{tuple(model.input_shape)} (choose the codec with --codec)")
+    out = torch.empty((n, model.n_classes), dtype=torch.float32, device=d_frames.device)
+    chunk = max(1, min(n, model.max_chunk_frames))
+    ws = torch.empty(model.workspace_bytes(chunk), dtype=torch.uint8, device=d_frames.device)
+    stream = torch.cuda.current_stream(d_frames.device).cuda_stream
+    for a in range(0, n, chunk):
+        model.forward_device(d_frames[a:a + chunk].contiguous(), out[a:a + chunk], ws, stream)
+    return out.cpu().numpy()
+
+
 def load_dataset_and_predict(
     models: list,
     dataset_path: Path,
@@ -74,6 +120,7 @@ def load_dataset_and_predict(
     is_consensus: bool = False,
     path_to_output: Path = Path.cwd(),
     binary_outputs: bool = False,
+    codec: str = None,
 ):
     """predict.py:28-194.  Returns (flat_dataset_map, pdb_to_sequence, pdb_to_probability,
     pdb_to_real_sequence, pdb_to_consensus, pdb_to_consensus_prob) of the LAST model."""
@@ -81,7 +128,15 @@ def load_dataset_and_predict(
     n_classes = 338 if predict_rotamers else 20
     print(f"Running model on {n_classes} classes. Rotamer Mode is {predict_rotamers}")
     filter_pdb_list = get_pdb_keys_to_filter(blacklist) if blacklist else []
-    if Path(dataset_map_path).exists():          # a stale map is reused, as the reference does
+    rank, world, local_rank = _dist_context()
+    # Extension: `dataset_path` may be a structure file or a directory of them instead of an
+    # aposteriori .hdf5 -- the frames are then voxelised on the GPU (voxelise.py) and never touch the disk or the host.
+    structures = _structure_files(dataset_path)
+    dev_frames = dev_labels = None
+    if structures is not None:
+        dev_frames, flat_dataset_map, dev_labels = _voxelise_structures(structures, codec, is_consensus, local_rank,
+                                                                        filter_pdb_list)
+    elif Path(dataset_map_path).exists():          # a stale map is reused, as the reference does
         flat_dataset_map = np.genfromtxt(dataset_map_path, delimiter=",", dtype="str")
         if flat_dataset_map.ndim == 1:
             flat_dataset_map = flat_dataset_map[None, :]
@@ -91,7 +146,6 @@ def load_dataset_and_predict(
     flat_categories = get_rotamer_codec()[1] if predict_rotamers else None
     cls_to_res = rotamer_class_to_residue() if predict_rotamers else None
     n_batches = ceil(len(flat_dataset_map) / batch_size)
-    rank, world, local_rank = _dist_context()
     out = None
     for i, m in enumerate(models):
         model_name = (m.stem if isinstance(m, Path) else str(m)) + model_name_suffix
@@ -99,6 +153,13 @@ def load_dataset_and_predict(
         if frame_model.n_classes != n_classes:
             raise ValueError(f"{m}: model has {frame_model.n_classes} outputs but "
                              f"{'--predict_rotamers' if predict_rotamers else 'residue mode'} expects {n_classes}")
+        def predict_rows(a: int, b: int):
+            """(probabilities, one-hot labels) of the frames [a, b) of the flat map."""
+            if dev_frames is not None:
+                return _forward_device_rows(frame_model, dev_frames[a:b]), dev_labels[a:b]
+            X_batch, y_true = load_batch(dataset_path, flat_dataset_map[a:b])
+            return frame_model.predict(X_batch), y_true
+
         rot_out = path_to_output / f"{model_name}_rot.csv"
         model_out = rot_out if predict_rotamers else path_to_output / f"{model_name}.csv"
         rows_before = sum(1 for _ in open(model_out)) if model_out.exists() else 0
@@ -116,9 +177,9 @@ def load_dataset_and_predict(
             lo, hi = lo + first, hi + first
             preds, labels = [], []
             for b0 in range(lo, hi, batch_size):
-                X_batch, y_true_batch = load_batch(dataset_path, flat_dataset_map[b0:min(b0 + batch_size, hi)])
-                preds.append(frame_model.predict(X_batch))
-                labels.append(np.asarray(y_true_batch, dtype=np.float64))
+                y_pred_b, y_true_b = predict_rows(b0, min(b0 + batch_size, hi))
+                preds.append(y_pred_b)
+                labels.append(np.asarray(y_true_b, dtype=np.float64))
             local_p = np.concatenate(preds) if preds else np.zeros((0, n_classes), np.float32)
             local_y = np.concatenate(labels) if labels else np.zeros((0, 20), np.float64)
             gathered = (_gather(local_p.astype(np.float32), n_total, local_rank), _gather(local_y, n_total, local_rank))
@@ -129,8 +190,7 @@ def load_dataset_and_predict(
                 y_pred_batch = gathered[0][r0:r0 + batch_size]
                 y_true_batch = gathered[1][r0:r0 + batch_size]
             else:
-                X_batch, y_true_batch = load_batch(dataset_path, current_batch_map)
-                y_pred_batch = frame_model.predict(X_batch)
+                y_pred_batch, y_true_batch = predict_rows(index * batch_size, min((index + 1) * batch_size, len(flat_dataset_map)))
             raw_rows.append(y_pred_batch)
             if rank != 0:
                 continue                               # only rank 0 touches the output directory
@@ -205,6 +265,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--is_structure_nmr", nargs="?", const=True, default=False, type=_flag,
                    help="NMR ensemble: also build a consensus over the states")
     p.add_argument("--yes", action="store_true", help="Create a missing output directory without asking")
+    p.add_argument("--codec", type=str, default=None,
+                   help="Atom codec when --path_to_dataset is a structure file / directory voxelised on the GPU "
+                        "(CNOCBCA, CNOCBCAQ, CNOCBCAP, ...; default CNOCBCA)")
     p.add_argument("--binary_outputs", action="store_true",
                    help="Also write {model}.npy (the float16 matrix of {model}.csv; sample.py reads it directly)")
     return p
@@ -233,7 +296,8 @@ def main(args) -> None:
         [args.path_to_model], args.path_to_dataset, batch_size=args.batch_size, start_batch=0,
         blacklist=args.path_to_blacklist, dataset_map_path=args.path_to_datasetmap,
         predict_rotamers=args.predict_rotamers, is_consensus=args.is_structure_nmr,
-        path_to_output=args.path_to_output, binary_outputs=getattr(args, "binary_outputs", False))
+        path_to_output=args.path_to_output, binary_outputs=getattr(args, "binary_outputs", False),
+        codec=getattr(args, "codec", None))
 
 
 def cli(argv=None) -> None:

@@ -1,0 +1,53 @@
+"""End-to-end frames/s of the two real-input routes of predict.py on one GPU (run under gpurun):
+  (a) structure files -> GPU voxeliser -> network (no dataset file, frames never leave the device);
+  (b) gzip .hdf5 frame dataset -> load_batch (native inflater on the host threads) -> Model.predict.
+    python tools/bench_structures.py [n_structures]"""
+import json
+import shutil
+import sys
+import tempfile
+import time
+import warnings
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from timed_design_b200 import frames, predict, standins, voxelise  # noqa: E402
+from timed_design_b200.model import Model  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+src = Path(__file__).resolve().parents[1] / "tests" / "golden" / "1ubq.pdb1.gz"
+tmp = Path(tempfile.mkdtemp())
+files = []
+for i in range(n):
+    f = tmp / f"s{i:04d}.pdb1.gz"
+    shutil.copy(src, f)
+    files.append(f)
+cfg, w = standins.timed_standin(20, c_in=5)
+m = Model(cfg, w, max_chunk_frames=4096)
+warnings.simplefilter("ignore")
+# warm-up
+fr, flat, onehot = predict._voxelise_structures(files[:2], "CNOCBCA", False, 0, [])
+predict._forward_device_rows(m, fr)
+t0 = time.perf_counter()
+fr, flat, onehot = predict._voxelise_structures(files, "CNOCBCA", False, 0, [])
+t1 = time.perf_counter()
+p = predict._forward_device_rows(m, fr)
+t2 = time.perf_counter()
+out = {"structures": n, "frames": int(fr.shape[0]),
+       "structure_route": {"voxelise_s": t1 - t0, "network_s": t2 - t1, "frames_per_s": fr.shape[0] / (t2 - t0),
+                           "note": "PDB parsing in Python + timed_b200_voxelise + graph_forward, frames stay on the device"}}
+# (b) the dataset route on the same frames
+data = voxelise.make_frame_dataset(files, tmp, "data", codec="CNOCBCA")
+flat2, _ = frames.create_flat_dataset_map(data)
+t0 = time.perf_counter()
+X, y = frames.load_batch(data, flat2)
+t1 = time.perf_counter()
+p2 = m.predict(X, batch_size=4096)
+t2 = time.perf_counter()
+out["hdf5_route"] = {"load_batch_s": t1 - t0, "predict_s": t2 - t1, "frames_per_s": len(flat2) / (t2 - t0),
+                     "file_MB": data.stat().st_size / 1e6, "note": "gzip float32 frames, native inflater on the host threads"}
+out["max_abs_diff_between_routes"] = float(np.abs(p - p2).max())
+print(json.dumps(out))
+shutil.rmtree(tmp)
