@@ -194,7 +194,8 @@ def _cpu_sampler_task(a):
     if t != 1:
         probs = so.apply_temp_to_probs(probs, t)
     np.random.seed()                      # forked workers would otherwise share the parent's generator state
-    return sum(len(x) for x in so.sample_loop_numpy(probs, n))
+    cats = None if probs.shape[1] == 20 else ["A"] * probs.shape[1]
+    return sum(len(x) for x in so.sample_loop_numpy(probs, n, cats))
 
 
 def cpu_sampler_residues_per_s(chains, samples_per_chain: int, workers: int, temperature: float = 0.5):
