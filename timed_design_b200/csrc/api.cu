@@ -2310,11 +2310,13 @@ int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t fra
     // double-buffered: H2D of chunk i+1 overlaps the forward of chunk i
     const uint8_t* src = static_cast<const uint8_t*>(h_frames);
     int it = 0;
-    // chunk sizes ramp up (chunk/8, chunk/4, chunk/2, chunk, ...): only the first, small copy is not hidden
+    // chunk sizes ramp up by 1.5x (chunk/8, 3/16, 9/32, ... chunk): only the first, small copy is not hidden.  Doubling
+    // stalled the pipeline -- a float32 frame takes 0.69x as long to copy (55 GB/s) as to compute, so the copy of a chunk
+    // twice the size of the running one finishes 38 % late (2 ms per 4096 frames, profiles/r2f e2e by host dtype)
     // behind a forward.  The ramp never exceeds `chunk`: the staging buffers and the workspace are sized for it, and the
     // caller's batch_size bound holds for every pass.
     int64_t cur = n_frames > chunk ? std::min<int64_t>(chunk, std::max<int64_t>(64, chunk / 8)) : chunk;
-    for (int64_t f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++it, cur = std::min(chunk, cur * 2)) {
+    for (int64_t f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++it, cur = std::min(chunk, cur + cur / 2)) {
         const int b = it & 1;
         nf = std::min(cur, n_frames - f0);
         TB_REQUIRE(nf > 0 && nf <= chunk, "internal: predict_host chunk exceeds the staged size");
