@@ -145,12 +145,13 @@ int timed_b200_graph_predict_stats(const tb_graph* g, int64_t* n_passes, int64_t
  * (n_atoms, 4) float32 x, y, z, gaussian sigma in voxel units; per-atom channel (< 0: not encoded), residue index and
  * C-beta flag.  d_res_frame: (residues, 12) float32 = origin (C-alpha) then the rows of the rotation into the residue's
  * local frame.  With encode_cb the centre residue's own C-beta is replaced by the ideal one (x, y, z, sigma in local
- * coordinates).  property_channel >= 0 adds d_res_property[residue] at C-beta positions to that channel.  d_scratch:
+ * coordinates).  d_res_atom_range (residues, 2), optional: [first, end) of the atoms a residue's frame looks at, so that
+ * several structures can share one atom table and one launch.  property_channel >= 0 adds d_res_property[residue] at C-beta positions to that channel.  d_scratch:
  * n_res * V^3 * C int32 (fixed-point accumulation: the result is independent of the order atoms are added in). */
 int timed_b200_voxelise(const float* d_atoms_xyzs, const int32_t* d_atom_channel, const int32_t* d_atom_residue,
                         const int32_t* d_atom_is_cb, int64_t n_atoms, const float* d_res_frame, const float* d_res_property,
-                        const int32_t* d_res_index, int64_t res_first, int64_t n_res, int32_t voxels_per_side, float voxel_edge,
-                        int32_t n_channels,
+                        const int32_t* d_res_index, const int32_t* d_res_atom_range, int64_t res_first, int64_t n_res,
+                        int32_t voxels_per_side, float voxel_edge, int32_t n_channels,
                         int32_t as_gaussian, int32_t encode_cb, const float* ideal_cb_xyz_sigma, int32_t cb_channel,
                         int32_t property_channel, int32_t* d_scratch, void* d_frames, int32_t frames_dtype, void* cuda_stream);
 

@@ -124,3 +124,20 @@ def test_property_channels():
     assert fq[0, ..., 5].min() < -0.02                                      # an acidic neighbour's C-beta is negative
     _, fp = _oracle_frames(residues, [26], codec="CNOCBCAP")
     assert fp[0, ..., 5].min() >= 0 and fp[0, 9, 9, 9, 5] > 0.02
+
+
+def test_vectorised_parser_equals_the_reference_parser():
+    """fast_tables (what predict.py uses) builds exactly the tables of build_tables(parse_pdb(...)), for every codec."""
+    (residues,) = vx.parse_pdb(PDB)
+    for codec in ("CNOCBCA", "CNOCACB", "CNOCBCAQ", "CNOCBCAP"):
+        slow = vx.build_tables(residues, codec, 1.0)
+        ((fast, info),) = vx.fast_tables(PDB, codec, 1.0)
+        for field in ("atoms", "channel", "residue", "is_cb", "frames", "valid"):
+            np.testing.assert_array_equal(getattr(slow, field), getattr(fast, field), err_msg=f"{codec}.{field}")
+        if slow.prop is None:
+            assert fast.prop is None
+        else:
+            np.testing.assert_array_equal(slow.prop, fast.prop)
+        assert list(info.label) == [r.label for r in residues] and list(info.res_id) == [r.res_id for r in residues]
+    states = vx.load_states([PDB, PDB])
+    assert len(states) == 2 and len(vx.flat_map_of(states)) == 152

@@ -68,7 +68,7 @@ SYMBOLS = {
                                                 C.c_void_p, C.c_int64]),
     "timed_b200_graph_predict_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "timed_b200_voxelise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_void_p]),
     "timed_b200_conv3d_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

@@ -2579,8 +2579,8 @@ int timed_b200_seq_metrics(const uint8_t* d_seqs, int64_t n_seqs, int64_t n_res,
 // ---------------------------------------------------------------------------------- voxeliser (8(f)-1)
 int timed_b200_voxelise(const float* d_atoms_xyzs, const int32_t* d_atom_channel, const int32_t* d_atom_residue,
                         const int32_t* d_atom_is_cb, int64_t n_atoms, const float* d_res_frame, const float* d_res_property,
-                        const int32_t* d_res_index, int64_t res_first, int64_t n_res, int32_t voxels_per_side, float voxel_edge,
-                        int32_t n_channels,
+                        const int32_t* d_res_index, const int32_t* d_res_atom_range, int64_t res_first, int64_t n_res,
+                        int32_t voxels_per_side, float voxel_edge, int32_t n_channels,
                         int32_t as_gaussian, int32_t encode_cb, const float* ideal_cb_xyz_sigma, int32_t cb_channel,
                         int32_t property_channel, int32_t* d_scratch, void* d_frames, int32_t frames_dtype, void* cuda_stream) {
     TB_REQUIRE(d_atoms_xyzs && d_atom_channel && d_atom_residue && d_atom_is_cb && d_res_frame && d_scratch && d_frames,
@@ -2601,6 +2601,7 @@ int timed_b200_voxelise(const float* d_atoms_xyzs, const int32_t* d_atom_channel
     p.atom_channel = d_atom_channel; p.atom_residue = d_atom_residue; p.atom_is_cb = d_atom_is_cb;
     p.n_atoms = n_atoms;
     p.res_frame = d_res_frame; p.res_property = d_res_property; p.res_index = d_res_index; p.res_first = res_first;
+    p.res_atom_range = d_res_atom_range;
     p.V = voxels_per_side; p.inv_edge = 1.0f / voxel_edge; p.C = n_channels;
     p.gaussian = as_gaussian; p.encode_cb = encode_cb;
     p.cb_x = encode_cb ? ideal_cb_xyz_sigma[0] : 0.f; p.cb_y = encode_cb ? ideal_cb_xyz_sigma[1] : 0.f;

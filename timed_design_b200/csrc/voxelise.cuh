@@ -25,6 +25,8 @@ struct VoxeliseParams {
     const float* res_frame;       // (n_res_total, 12): origin (3), then the rows x, y, z of the rotation
     const float* res_property;    // (n_res_total) value written to the property channel at C-beta positions, or NULL
     const int32_t* res_index;     // (>= res_first + n_res) residues to voxelise, in output order; NULL = identity
+    const int32_t* res_atom_range;// (n_res_total, 2) [first, end) of the atoms a residue's frame has to look at (its own
+                                  // structure, when several structures share one atom table); NULL = all atoms
     int64_t res_first;
     int32_t V;                    // voxels per side (odd)
     float inv_edge;               // 1 / voxel edge length
@@ -85,7 +87,9 @@ __global__ void voxelise_kernel(const VoxeliseParams p) {
     const float ox = f[0], oy = f[1], oz = f[2];
     int32_t* frame = p.scratch + static_cast<int64_t>(blockIdx.x) * p.V * p.V * p.V * p.C;
     const float prop_self = p.res_property ? p.res_property[r] : 0.f;
-    for (int64_t a = threadIdx.x; a < p.n_atoms; a += blockDim.x) {
+    const int64_t a_first = p.res_atom_range ? p.res_atom_range[2 * r] : 0;
+    const int64_t a_end = p.res_atom_range ? p.res_atom_range[2 * r + 1] : p.n_atoms;
+    for (int64_t a = a_first + threadIdx.x; a < a_end; a += blockDim.x) {
         const int ch = p.atom_channel[a];
         if (ch < 0) continue;
         const bool is_cb = p.atom_is_cb[a] != 0;

@@ -73,23 +73,41 @@ def _structure_files(path):
     return [path] if is_pdb(path) and path.suffix.lower() not in (".hdf5", ".h5") else None
 
 
-def _voxelise_structures(files, codec, all_states, device, filter_pdb_list):
-    """-> (frames on the device (n, V, V, V, C), flat map rows [pdb, chain, res_id, label], one-hot labels (n, 20))."""
-    import torch
-    from . import voxelise
-    frames, flat = [], []
-    for f in files:
-        if f.name.split(".pdb")[0][:4] in filter_pdb_list:
-            continue
-        fr, fl = voxelise.voxelise_structure(f, codec or "CNOCBCA", voxelise_all_states=all_states, device=device,
-                                             return_device=True)
-        frames.append(fr)
-        flat.extend(fl)
-    if not frames:
-        raise ValueError("no structure left to voxelise")
-    order = list(standard_amino_acids.values())
-    onehot = np.eye(20, dtype=np.float64)[[order.index(r[3]) for r in flat]]
-    return (torch.cat(frames) if len(frames) > 1 else frames[0]), np.array(flat, dtype=str), onehot
+class _StructureSource:
+    """Frames of a set of structure files, voxelised on the GPU on demand in blocks of ~`block_frames` frames (a directory of
+    thousands of structures must not sit in HBM as float32 frames all at once); rows() hands out device-resident slices."""
+
+    def __init__(self, files, codec, all_states, device, filter_pdb_list, block_frames: int = 16384):
+        from . import voxelise
+        files = [f for f in files if f.name.split(".pdb")[0][:4] not in filter_pdb_list]
+        if not files:
+            raise ValueError("no structure left to voxelise")
+        self._vx = voxelise
+        self.device = device
+        self.states = voxelise.load_states(files, codec or "CNOCBCA", voxelise_all_states=all_states)
+        self.flat = np.array(voxelise.flat_map_of(self.states), dtype=str)
+        counts = np.array([len(st.order) for st in self.states], dtype=np.int64)
+        self.first = np.concatenate([[0], np.cumsum(counts)])          # first flat row of every state
+        order = list(standard_amino_acids.values())
+        self.labels = np.eye(20, dtype=np.float64)[[order.index(r[3]) for r in self.flat]]
+        self.block_frames = block_frames
+        self._lo = self._hi = 0
+        self._frames = None
+
+    def _load(self, a: int, b: int):
+        s0 = int(np.searchsorted(self.first, a, side="right") - 1)
+        s1 = s0
+        while s1 < len(self.states) and (self.first[s1 + 1] < b or self.first[s1 + 1] - self.first[s0] < self.block_frames):
+            s1 += 1
+        s1 = min(s1 + 1, len(self.states))
+        self._frames = None                                            # release the previous block first
+        self._frames = self._vx.voxelise_states(self.states[s0:s1], device=self.device, return_device=True)
+        self._lo, self._hi = int(self.first[s0]), int(self.first[s1])
+
+    def rows(self, a: int, b: int):
+        if self._frames is None or a < self._lo or b > self._hi:
+            self._load(a, b)
+        return self._frames[a - self._lo:b - self._lo]
 
 
 def _forward_device_rows(model, d_frames):
@@ -132,10 +150,10 @@ def load_dataset_and_predict(
     # Extension: `dataset_path` may be a structure file or a directory of them instead of an
     # aposteriori .hdf5 -- the frames are then voxelised on the GPU (voxelise.py) and never touch the disk or the host.
     structures = _structure_files(dataset_path)
-    dev_frames = dev_labels = None
+    source = None
     if structures is not None:
-        dev_frames, flat_dataset_map, dev_labels = _voxelise_structures(structures, codec, is_consensus, local_rank,
-                                                                        filter_pdb_list)
+        source = _StructureSource(structures, codec, is_consensus, local_rank, filter_pdb_list)
+        flat_dataset_map = source.flat
     elif Path(dataset_map_path).exists():          # a stale map is reused, as the reference does
         flat_dataset_map = np.genfromtxt(dataset_map_path, delimiter=",", dtype="str")
         if flat_dataset_map.ndim == 1:
@@ -155,8 +173,8 @@ def load_dataset_and_predict(
                              f"{'--predict_rotamers' if predict_rotamers else 'residue mode'} expects {n_classes}")
         def predict_rows(a: int, b: int):
             """(probabilities, one-hot labels) of the frames [a, b) of the flat map."""
-            if dev_frames is not None:
-                return _forward_device_rows(frame_model, dev_frames[a:b]), dev_labels[a:b]
+            if source is not None:
+                return _forward_device_rows(frame_model, source.rows(a, b)), source.labels[a:b]
             X_batch, y_true = load_batch(dataset_path, flat_dataset_map[a:b])
             return frame_model.predict(X_batch), y_true
 

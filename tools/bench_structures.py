@@ -28,10 +28,10 @@ cfg, w = standins.timed_standin(20, c_in=5)
 m = Model(cfg, w, max_chunk_frames=4096)
 warnings.simplefilter("ignore")
 # warm-up
-fr, flat, onehot = predict._voxelise_structures(files[:2], "CNOCBCA", False, 0, [])
+fr, flat = voxelise.voxelise_structures(files[:2], "CNOCBCA", return_device=True)
 predict._forward_device_rows(m, fr)
 t0 = time.perf_counter()
-fr, flat, onehot = predict._voxelise_structures(files, "CNOCBCA", False, 0, [])
+fr, flat = voxelise.voxelise_structures(files, "CNOCBCA", return_device=True)
 t1 = time.perf_counter()
 p = predict._forward_device_rows(m, fr)
 t2 = time.perf_counter()
