@@ -115,3 +115,36 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_bench_reference_arm_of_the_sampler_config_and_rank_gating():
+    """`--config sampler --impl reference` times the reference's numpy loop verbatim under a process pool; under a
+    multi-rank launch only rank 0 prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    cmd = [sys.executable, str(root / "bench.py"), "--impl", "reference", "--config", "sampler", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "residues/s" and line["value"] > 1e5
+    assert line["cpu_baseline"]["kind"] == "reference" and "sampled residues/sec" in line["metric"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_configs_name_the_baseline_workloads():
+    import importlib.util
+    root = Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("bench_mod", root / "bench.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert set(mod.CONFIGS) == {"timed20", "timed338", "densecpd", "sampler"}
+    assert "20 classes" in mod.CONFIGS["timed20"]["metric"] and "338" in mod.CONFIGS["timed338"]["metric"]
+    assert "DenseCPD" in mod.CONFIGS["densecpd"]["metric"] and [c["baseline_config"] for c in mod.CONFIGS.values()].count(1) == 1
+    chains = mod.sampler_chains(20)
+    assert len(chains) == 59 and all(60 <= len(c) <= 400 and c.shape[1] == 20 for c in chains)
+    assert len(mod.SAMPLER_TEMPS) == 20 and mod.SAMPLER_TEMPS[0] == 0.1 and mod.SAMPLER_TEMPS[-1] == 2.0
