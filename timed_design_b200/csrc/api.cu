@@ -587,6 +587,7 @@ static bool slab_geometry(int D, int H, int W, int cin, const tb_op_desc& c, Sla
     const size_t w_stage = (w_tap + 127) & ~static_cast<size_t>(127);
     for (int mt : {2, 1}) {
         if (mt * g.acc_cols > 512) continue;
+        if (mt == 2 && getenv("TIMED_B200_SLAB_MT1")) continue;
         g.mt = mt;
         g.acc_stages = std::min(2, 512 / (mt * g.acc_cols));
         g.slab_pix = 128 * mt + g.neg + g.pos;
@@ -669,7 +670,7 @@ static int launch_slab_instance(const SlabConvParams& k, int grid, size_t smem_b
                                            static_cast<int>(kSmemDynamicMax)));
         attr_set = true;
     }
-    slab_conv_kernel<A1, A2, F><<<grid, kConvThreads, smem_bytes, stream>>>(k);
+    slab_conv_kernel<A1, A2, F><<<grid, kSlabThreads, smem_bytes, stream>>>(k);
     return 0;
 }
 
@@ -1112,7 +1113,7 @@ static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map
     if (k.cluster2) {
         cudaLaunchConfig_t lc{};
         lc.gridDim = dim3(grid);
-        lc.blockDim = dim3(kConvThreads);
+        lc.blockDim = dim3(kUmmaThreads);
         lc.dynamicSmemBytes = smem_bytes;
         lc.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -1125,7 +1126,7 @@ static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map
         TB_CHECK_CUDA(cudaLaunchKernelEx(&lc, conv_umma_kernel<A1, A2, F>, map_a, map_w, k));
         return 0;
     }
-    conv_umma_kernel<A1, A2, F><<<grid, kConvThreads, smem_bytes, stream>>>(map_a, map_w, k);
+    conv_umma_kernel<A1, A2, F><<<grid, kUmmaThreads, smem_bytes, stream>>>(map_a, map_w, k);
     return 0;
 }
 

@@ -28,6 +28,7 @@ namespace tb {
 constexpr int kConvMaxStages = 8;
 constexpr int kConvEpilogueWarps = 8;                       // two per TMEM lane quadrant
 constexpr int kConvThreads = 64 + 32 * kConvEpilogueWarps;  // + TMA producer warp + MMA warp
+constexpr int kUmmaThreads = kConvThreads + 32;            // conv_umma_kernel: + a second MMA-issuing warp (warp 10)
 
 enum OutFmt : int { FMT_F32 = 0, FMT_SPLIT = 1 };
 
@@ -265,8 +266,36 @@ __device__ __forceinline__ void epilogue_drained(const ConvKernelParams& p, uint
     }
 }
 
+// One pipeline stage's MMAs for ONE 128-row sub-tile, issued by one thread as a straight run of UTCHMMAs with affine
+// descriptor updates.  MODE 0: separate correction accumulator (d_corr); 1: N-folded (d_corr = d + n_tile);
+// 3: corrections into the main accumulator.
+template <int MODE>
+__device__ __forceinline__ void umma_issue_stage(uint32_t base16, int nkb, uint32_t kb16, int k16_steps, uint32_t w_off16,
+                                                 uint32_t w_sub16, uint32_t a_lo_off16, uint32_t d, uint32_t d_corr,
+                                                 uint32_t desc_hi, uint32_t idesc, uint32_t idesc2, uint32_t accumulate) {
+    for (int j = 0; j < nkb; ++j, base16 += kb16) {
+        for (int kk = 0; kk < k16_steps; ++kk) {
+            const uint32_t a0 = base16 + static_cast<uint32_t>(kk) * 2u;   // +32 B per K=16
+            const uint32_t w_hi = a0 + w_off16;
+            if constexpr (MODE == 0) {
+                umma_bf16_lohi(true, d, a0, w_hi, desc_hi, idesc, accumulate);
+                umma_bf16_lohi(true, d_corr, a0 + a_lo_off16, w_hi, desc_hi, idesc, accumulate);
+                umma_bf16_lohi(true, d_corr, a0, w_hi + w_sub16, desc_hi, idesc, 1u);
+            } else if constexpr (MODE == 1) {
+                umma_bf16_lohi(true, d, a0, w_hi, desc_hi, idesc2, accumulate);
+                umma_bf16_lohi(true, d_corr, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+            } else {
+                umma_bf16_lohi(true, d, a0, w_hi, desc_hi, idesc, accumulate);
+                umma_bf16_lohi(true, d, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
+                umma_bf16_lohi(true, d, a0, w_hi + w_sub16, desc_hi, idesc, 1u);
+            }
+            accumulate = 1u;
+        }
+    }
+}
+
 template <int ACT1, int ACT2, int FMT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_w, const ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -282,14 +311,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int n_iss = (p.mt == 2 && !p.cluster2) ? 2 : 1;      // MMA-issuing threads: one per 128-row sub-tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], p.cluster2 ? 2 : 1);   // cluster mode: both CTAs' MMA warps release a stage
+            // cluster mode: both CTAs' MMA warps release a stage; two sub-tiles: one issuing thread each
+            mbar_init(&empty_bar[s], p.cluster2 ? 2 : n_iss);
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tfull_bar[a], n_iss);
             mbar_init(&tempty_bar[a], kConvEpilogueWarps);
         }
         mbar_fence_init();
@@ -400,9 +431,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 1) {
-        // =============================================================== MMA issuer
+    } else if (warp == 1 || warp == 10) {
+        // =============================================================== MMA issuers (warp 1: sub-tile 0, warp 10: sub-tile 1)
+        // ONE lane of each runs the whole role.  The tensor pipe does not run ahead of an issuing thread by more than
+        // an MMA or two, so issue-side work (address arithmetic, branches, warp reconvergence) is exposed, and even a
+        // bare loop leaves ~8 cycles between two MMAs of one thread; with two sub-tiles a second thread issues the
+        // second one's MMAs (disjoint accumulators: every output's accumulation order stays fixed), which closes the
+        // gap (tools/mma_pattern_probe.cu, profiles/r2i_mma_pattern_probe.txt).
         const bool leader = elect_one();
+        const int q = warp == 1 ? 0 : 1;
         const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.n_tile));
         const uint32_t idesc2 = umma_idesc_bf16_m128(static_cast<uint32_t>(2 * p.n_tile));
         // descriptor = {lo: start address >> 4 | LBO(=1) << 16, hi: SBO >> 4 | version << 14 | swizzle << 29}
@@ -413,74 +450,48 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         const uint32_t a_lo_off16 = static_cast<uint32_t>(p.mt) * a_sub16;       // hi plane -> lo plane
         const uint32_t w_off16 = 2u * static_cast<uint32_t>(p.mt) * a_sub16;     // A block -> W block
         const uint32_t smem_base16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+        const int mode = (p.corr_off && !p.nfold) ? 0 : p.nfold ? 1 : 3;
+        const uint32_t corr_off = mode == 0 ? static_cast<uint32_t>(p.corr_off) : static_cast<uint32_t>(p.n_tile);
+        const bool skip = TB_DBG(p.dbg, 2);
+        const int kg = p.kg, n_kblocks = p.n_kblocks, stages = p.stages, acc_stages = p.acc_stages, mt = p.mt;
+        const bool mcast = p.cluster2 != 0;
         int s = 0;
         uint32_t ph = 0;
         int acc = 0;
         uint32_t acc_ph = 0;
+        if (leader && q < n_iss)
         for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
             mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
             tc_fence_after();
             uint32_t accumulate = 0;
-            const uint32_t d0 = tmem_base + static_cast<uint32_t>((acc * p.mt) * p.acc_cols);
-            const uint32_t d1 = d0 + static_cast<uint32_t>(p.acc_cols);
             for (int g = 0; g < n_groups; ++g) {
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const int nkb = min(p.kg, p.n_kblocks - g * p.kg);
-                uint32_t base16 = (smem_base16 + static_cast<uint32_t>(s) * (stage_bytes >> 4)) | lo_flags;
-                if (leader && !TB_DBG(p.dbg, 2)) {
-                    // one thread issues; the issue pattern is selected outside the K loops so that each loop
-                    // body is a straight run of UTCHMMAs with affine descriptor updates
-                    const int mode = (p.corr_off && !p.nfold) ? 0 : p.nfold ? (p.mt == 2 ? 2 : 1) : (p.mt == 2 ? 4 : 3);
-                    const uint32_t n_t = static_cast<uint32_t>(p.n_tile);
-                    for (int j = 0; j < nkb; ++j, base16 += kb16) {
-#pragma unroll 2
-                        for (int kk = 0; kk < k16_steps; ++kk) {
-                            const uint32_t a0 = base16 + static_cast<uint32_t>(kk) * 2u;   // +32 B per K=16
-                            const uint32_t w_hi = a0 + w_off16;
-                            const uint32_t w_lo = w_hi + w_sub16;
-                            if (mode == 0) {                       // separate correction accumulator
-                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(true, d0 + p.corr_off, a0 + a_lo_off16, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(true, d0 + p.corr_off, a0, w_lo, desc_hi, idesc, 1u);
-                            } else if (mode == 1) {                // N-folded, one sub-tile
-                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc2, accumulate);
-                                umma_bf16_lohi(true, d0 + n_t, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                            } else if (mode == 2) {                // N-folded, two sub-tiles
-                                const uint32_t a1 = a0 + a_sub16;
-                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc2, accumulate);
-                                umma_bf16_lohi(true, d0 + n_t, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                                umma_bf16_lohi(true, d1, a1, w_hi, desc_hi, idesc2, accumulate);
-                                umma_bf16_lohi(true, d1 + n_t, a1 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                            } else if (mode == 4) {                // two sub-tiles sharing every W tile
-                                const uint32_t a1 = a0 + a_sub16;
-                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(true, d1, a1, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(true, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                                umma_bf16_lohi(true, d1, a1 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                                umma_bf16_lohi(true, d0, a0, w_lo, desc_hi, idesc, 1u);
-                                umma_bf16_lohi(true, d1, a1, w_lo, desc_hi, idesc, 1u);
-                            } else {
-                                umma_bf16_lohi(true, d0, a0, w_hi, desc_hi, idesc, accumulate);
-                                umma_bf16_lohi(true, d0, a0 + a_lo_off16, w_hi, desc_hi, idesc, 1u);
-                                umma_bf16_lohi(true, d0, a0, w_lo, desc_hi, idesc, 1u);
-                            }
-                            accumulate = 1u;
-                        }
-                    }
+                const int nkb = min(kg, n_kblocks - g * kg);
+                const uint32_t stage16 = (smem_base16 + static_cast<uint32_t>(s) * (stage_bytes >> 4)) | lo_flags;
+                // this thread's sub-tiles: its own when each has an issuer, otherwise all of them
+                for (int sub = q; sub < mt && !skip; sub += n_iss) {
+                    const uint32_t base16 = stage16 + static_cast<uint32_t>(sub) * a_sub16;
+                    const uint32_t w_rel = w_off16 - static_cast<uint32_t>(sub) * a_sub16;
+                    const uint32_t a_lo_rel = a_lo_off16;
+                    const uint32_t d = tmem_base + static_cast<uint32_t>(acc * mt + sub) * static_cast<uint32_t>(p.acc_cols);
+                    if (mode == 0)
+                        umma_issue_stage<0>(base16, nkb, kb16, k16_steps, w_rel, w_sub16, a_lo_rel, d, d + corr_off, desc_hi, idesc, idesc2, accumulate);
+                    else if (mode == 1)
+                        umma_issue_stage<1>(base16, nkb, kb16, k16_steps, w_rel, w_sub16, a_lo_rel, d, d + corr_off, desc_hi, idesc, idesc2, accumulate);
+                    else
+                        umma_issue_stage<3>(base16, nkb, kb16, k16_steps, w_rel, w_sub16, a_lo_rel, d, d + corr_off, desc_hi, idesc, idesc2, accumulate);
                 }
                 accumulate = 1u;
-                if (leader) {                             // frees the smem stage when the MMAs retire
-                    if (p.cluster2) umma_commit_mcast(&empty_bar[s], 3);
-                    else umma_commit(&empty_bar[s]);
-                }
-                __syncwarp();
-                if (++s == p.stages) { s = 0; ph ^= 1u; }
+                // frees the smem stage when the MMAs retire
+                if (mcast) umma_commit_mcast(&empty_bar[s], 3);
+                else umma_commit(&empty_bar[s]);
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
-            if (leader) umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
-            __syncwarp();
-            if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+            umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
+            if (++acc == acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
+        __syncwarp();
     } else {
         // =============================================================== epilogue (warps 2..9)
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read

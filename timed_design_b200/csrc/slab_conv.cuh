@@ -27,6 +27,8 @@
 namespace tb {
 
 constexpr int kSlabWStages = 8;
+constexpr int kSlabThreads = kConvThreads + 32;   // + a second MMA-issuing warp (warp 10)
+constexpr int kSlabMaxTaps = 343;            // 7 x 7 x 7, the planner's limit
 
 struct SlabConvParams {
     // ---- tiling over the padded linearisation of the input
@@ -61,7 +63,7 @@ struct SlabConvParams {
 #if defined(__CUDACC__)
 
 template <int ACT1, int ACT2, int FMT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kSlabThreads, 1)
 slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -75,24 +77,30 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
     __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_epi[3][128];
+    __shared__ int32_t s_tap_off[kSlabMaxTaps];      // position offset of every filter tap
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
+        // one issuing thread per M tile (p.mt of them): each commits once to the barriers that release operands / publish a tile
         for (int b = 0; b < 2; ++b) {
             mbar_init(&slab_full[b], 1);
-            mbar_init(&slab_empty[b], 1);
-            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&slab_empty[b], p.mt);
+            mbar_init(&tfull_bar[b], p.mt);
             mbar_init(&tempty_bar[b], kConvEpilogueWarps);
         }
         for (int s = 0; s < p.w_stages; ++s) {
             mbar_init(&w_full[s], 1);
-            mbar_init(&w_empty[s], 1);
+            mbar_init(&w_empty[s], p.mt);
         }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc_512(&tmem_base_slot);
+    for (int i = threadIdx.x; i < p.kd * p.kh * p.kw; i += blockDim.x) {
+        const int a = i / (p.kh * p.kw), b = (i / p.kw) % p.kh, c = i % p.kw;
+        s_tap_off[i] = (a - p.pd) * p.Hp * p.Wp + (b - p.ph) * p.Wp + (c - p.pw);
+    }
     for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) {
         s_epi[0][i] = p.epi.bias[i];
         s_epi[1][i] = p.epi.scale[i];
@@ -163,8 +171,8 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
             }
             sb ^= 1;
         }
-    } else if (warp == 1) {
-        // =============================================================== MMA issuer
+    } else if (warp == 1 || warp == 10) {
+        // =============================================================== MMA issuers: warp 1 -> M tile 0, warp 10 -> M tile 1
         const bool leader = elect_one();
         const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.n_tile));
         const uint32_t idesc2 = umma_idesc_bf16_m128(static_cast<uint32_t>(2 * p.n_tile));
@@ -175,58 +183,62 @@ slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
         const uint32_t smem16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
         const uint32_t w_ring16 = (smem_u32(w_ring) & 0x3FFFFu) >> 4;
         const int k_steps = p.n_chunks >> 1;
-        const int hw = p.Hp * p.Wp;
         int sb = 0, ws = 0, acc = 0;
         uint32_t sph[2] = {0, 0}, wph = 0, acc_ph = 0;
+        // ONE lane runs the whole role, and the per-tap work between MMAs is a table load and a few adds: the tensor
+        // pipe does not run ahead of an issuing thread by more than an MMA or two, so every cycle the issue loop spends
+        // on address arithmetic, branches or warp reconvergence is a cycle the pipe idles.  Even a bare issue loop
+        // leaves ~8 cycles between two MMAs of one thread; two threads issuing to DISJOINT accumulators (one M tile
+        // each, so the accumulation order of every output stays fixed) close that gap: tools/mma_pattern_probe.cu
+        // measures 252 -> 224 cycles per K step for this kernel's pattern, which is the shared-memory operand bound.
+        const int q = warp == 1 ? 0 : 1;
+        const uint32_t n_tile = static_cast<uint32_t>(p.n_tile), acc_cols = static_cast<uint32_t>(p.acc_cols);
+        const uint32_t stage16 = w_stage_bytes >> 4;
+        const int w_group = p.w_group, w_stages = p.w_stages, acc_stages = p.acc_stages;
+        const bool skip = TB_DBG(p.dbg, 2);
+        const uint32_t a_step = 2u * stride16, b_step = 2u * w_lbo16;
+        if (leader && q < p.mt)
         for (int tile = blockIdx.x; tile < p.n_tiles_total; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
             mbar_wait(&slab_full[sb], sph[sb]);
             sph[sb] ^= 1u;
             tc_fence_after();
-            const uint32_t d_tile = tmem_base + static_cast<uint32_t>(acc * p.mt * p.acc_cols);
-            // first row of M tile 0 for a tap with position offset 0
-            const uint32_t a_tile16 = smem16 + static_cast<uint32_t>(sb) * (slab_bytes >> 4) + static_cast<uint32_t>(p.neg_halo);
+            const uint32_t d_main = tmem_base + static_cast<uint32_t>(acc * p.mt + q) * acc_cols;
+            const uint32_t d_corr = d_main + n_tile;
+            // first row of this issuer's M tile for a tap with position offset 0
+            const uint32_t a_tile = (smem16 + static_cast<uint32_t>(sb) * (slab_bytes >> 4) + static_cast<uint32_t>(p.neg_halo) +
+                                     static_cast<uint32_t>(q) * 128u) | (stride16 << 16);
             uint32_t accumulate = 0;
-            int tap = 0, in_group = 0;
-            for (int a = 0; a < p.kd; ++a)
-                for (int b = 0; b < p.kh; ++b)
-                    for (int c = 0; c < p.kw; ++c, ++tap) {
-                        if (in_group == 0) {
-                            mbar_wait(&w_full[ws], wph);
-                            tc_fence_after();
-                        }
-                        if (leader && !TB_DBG(p.dbg, 2)) {
-                            const int off = (a - p.pd) * hw + (b - p.ph) * p.Wp + (c - p.pw);
-                            uint32_t a_k = (a_tile16 + static_cast<uint32_t>(off)) | (stride16 << 16);
-                            uint32_t b_k = (w_ring16 + static_cast<uint32_t>(ws) * (w_stage_bytes >> 4) +
-                                            static_cast<uint32_t>(in_group) * (p.w_tap_bytes >> 4)) | (w_lbo16 << 16);
-                            for (int ks = 0; ks < k_steps; ++ks, a_k += 2u * stride16, b_k += 2u * w_lbo16) {
-#pragma unroll 2
-                                for (int mi = 0; mi < p.mt; ++mi) {
-                                    const uint32_t a_hi = a_k + static_cast<uint32_t>(mi) * 128u;
-                                    const uint32_t d_main = d_tile + static_cast<uint32_t>(mi * p.acc_cols);
-                                    umma_bf16_desc(true, d_main, a_hi, desc_hi, b_k, desc_hi, idesc2, accumulate);
-                                    umma_bf16_desc(true, d_main + p.n_tile, a_hi + plane16, desc_hi, b_k, desc_hi, idesc, 1u);
-                                }
-                                accumulate = 1u;
-                            }
-                        }
+            int in_group = 0;
+            uint32_t b_k = 0;
+            for (int tap = 0; tap < n_taps; ++tap) {
+                if (in_group == 0) {
+                    mbar_wait(&w_full[ws], wph);
+                    tc_fence_after();
+                    b_k = (w_ring16 + static_cast<uint32_t>(ws) * stage16) | (w_lbo16 << 16);
+                }
+                uint32_t a_k = a_tile + static_cast<uint32_t>(s_tap_off[tap]);
+                if (!skip) {
+                    for (int ks = 0; ks < k_steps; ++ks, a_k += a_step, b_k += b_step) {
+                        umma_bf16_desc(true, d_main, a_k, desc_hi, b_k, desc_hi, idesc2, accumulate);
+                        umma_bf16_desc(true, d_corr, a_k + plane16, desc_hi, b_k, desc_hi, idesc, 1u);
                         accumulate = 1u;
-                        if (++in_group == p.w_group || tap + 1 == n_taps) {
-                            in_group = 0;
-                            if (leader) umma_commit(&w_empty[ws]);
-                            __syncwarp();
-                            if (++ws == p.w_stages) { ws = 0; wph ^= 1u; }
-                        }
                     }
-            if (leader) {
-                umma_commit(&slab_empty[sb]);
-                umma_commit(&tfull_bar[acc]);
+                } else {
+                    b_k += static_cast<uint32_t>(k_steps) * b_step;
+                }
+                if (++in_group == w_group || tap + 1 == n_taps) {
+                    in_group = 0;
+                    umma_commit(&w_empty[ws]);
+                    if (++ws == w_stages) { ws = 0; wph ^= 1u; }
+                }
             }
-            __syncwarp();
+            umma_commit(&slab_empty[sb]);
+            umma_commit(&tfull_bar[acc]);
             sb ^= 1;
-            if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+            if (++acc == acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
+        __syncwarp();
     } else {
         // =============================================================== epilogue (warps 2..9)
         const int quad = warp & 3;

@@ -1,16 +1,6 @@
 #!/bin/bash
-# GPU parity tests, then A/B bench lines.  usage: tools/gpu_ab.sh tag "label|ENV=1 ENV2=x" "label2|" ...
-tag=$1; shift
-mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests -x -q -m gpu ) > gpurun_out/${tag}_pytest.log 2>&1
-tail -6 gpurun_out/${tag}_pytest.log
-summ() { python -c "
-import sys, json
-try:
-    l=json.loads(sys.stdin.readlines()[-1]); print(round(l['value']), round(l['ms_per_step'],2), l['clocks'].get('sm_mhz'), {k.split(':')[1]: round(v,2) for k,v in l['roofline']['per_op_ms'].items()})
-except Exception as e: print('FAILED', e)"; }
-for v in "$@"; do
-  label=${v%%|*}; envs=${v#*|}
-  echo "== $label [$envs]"
-  env $envs timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline 2>gpurun_out/${tag}_${label}.err | tee gpurun_out/${tag}_${label}.json | summ
-done
+# A/B of two builds of the library on the default bench: tools/gpu_ab.sh [lib_a lib_b]; prints frames/s and per-conv ms.
+A=${1:-libtimed_b200_base.so}; B=${2:-libtimed_b200.so}
+for i in 1 2; do for lib in $A $B; do echo "$lib"; TIMED_B200_LIB=$PWD/timed_design_b200/$lib timeout 300 python bench.py --no-e2e --no-cpu-baseline --steps 20 2>/dev/null | python -c "
+import sys,json
+l=json.loads(sys.stdin.readline()); po=l['roofline']['per_op_ms']; print(round(l['value'],0), {k.split(':')[1]: round(v,2) for k,v in po.items() if 'conv' in k}, l['clocks']['sm_mhz'])"; done; done
