@@ -96,6 +96,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
     __shared__ __align__(8) uint64_t w_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_epi[3][128];
+    __shared__ uint32_t s_step_a[64];                // per K step: A descriptor low word relative to the plane's span
     __shared__ __align__(16) float s_sign[128];      // POOL: +1 where the epilogue map is increasing in the accumulator, -1 where decreasing
 
     const int warp = threadIdx.x >> 5;
@@ -114,6 +115,20 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc_512(&tmem_base_slot);
+    if (threadIdx.x < 64) {
+        // K steps of one input plane: (kh row, kw pair) -- the pair's pixels are adjacent, LBO = 1 -- then the odd kw tap
+        // of two consecutive rows, LBO = Wp (or 1: an aliased, zero-weighted neighbour, for the last odd row)
+        const int st = threadIdx.x, pairs = p.kw >> 1, n_pair_steps = p.kh * pairs;
+        uint32_t v = 0;
+        if (st < n_pair_steps) {
+            v = (static_cast<uint32_t>((st / pairs) * p.Wp + 2 * (st % pairs))) | (1u << 16);
+        } else {
+            const int rr = 2 * (st - n_pair_steps);
+            if (rr < p.kh)
+                v = static_cast<uint32_t>(p.kw - 1 + rr * p.Wp) | ((rr + 1 < p.kh ? static_cast<uint32_t>(p.Wp) : 1u) << 16);
+        }
+        s_step_a[st] = v;
+    }
     for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) {
         s_epi[0][i] = p.epi.bias[i];
         s_epi[1][i] = p.epi.scale[i];
@@ -179,71 +194,72 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         const uint32_t ss16 = static_cast<uint32_t>(p.span_stride) >> 4;
         const uint32_t b1_lbo = static_cast<uint32_t>(p.b1_rows), b2_lbo = static_cast<uint32_t>(p.b2_rows);   // rows*16 B >> 4
         const uint32_t step16 = 2u * (b1_lbo + b2_lbo);
-        const int pairs = p.kw >> 1;
-        mbar_wait(&w_bar, 0);
+        const int n_steps = p.kh * (p.kw >> 1) + ((p.kw & 1) ? (p.kh + 1) / 2 : 0);
+        const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
+        const int zt = p.zt, kd = p.kd, Do = p.Do, windows = p.windows, n_tiles_total = p.n_tiles_total;
+        const int stages = p.stages, acc_stages = p.acc_stages;
+        const uint32_t acc_cols = static_cast<uint32_t>(p.acc_cols), stage16 = stage_bytes >> 4;
+        const bool skip = TB_DBG(p.dbg, 2);
+        const uint32_t idesc_f = umma_idesc_bf16_m128(n2);
+        const uint32_t bf = (w_base16 + static_cast<uint32_t>(kd - 1) * n2) | (b1_lbo << 16);
         int s = 0, acc = 0;
         uint32_t ph = 0, acc_ph = 0;
+        // ONE lane runs the whole role (see slab_conv.cuh: issue-side work is exposed, the tensor pipe does not run ahead),
+        // with per-plane descriptors hoisted and the per-step A offsets in a table
+        if (leader) {
+        mbar_wait(&w_bar, 0);
         for (int it = 0;; ++it) {
-            const int tile = thinz_tile(it, p.windows, p.n_tiles_total);
+            const int tile = thinz_tile(it, windows, n_tiles_total);
             if (tile < 0) break;
             const int r = tile % tiles_per_frame;
-            const int z0 = (r / p.windows) * p.zt;
-            const int zt_eff = min(p.zt, p.Do - z0);
-            const int n_planes = zt_eff + p.kd - 1;
+            const int z0 = (r / windows) * zt;
+            const int zt_eff = min(zt, Do - z0);
+            const int n_planes = zt_eff + kd - 1;
             mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
-            if (leader && !TB_DBG(p.dbg, 2)) {
-                const uint32_t d_tile = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
-                uint32_t a_plane = stage0_16 + static_cast<uint32_t>(s) * (stage_bytes >> 4);
+            if (!skip) {
+                const uint32_t d_tile = tmem_base + static_cast<uint32_t>(acc) * acc_cols;
+                uint32_t a_plane = stage0_16 + static_cast<uint32_t>(s) * stage16;
                 for (int i = 0; i < n_planes; ++i, a_plane += ss16) {
                     // output planes fed by input plane i: j_lo..j_hi through filter slices kd' = i - j
                     const int j_hi = min(zt_eff - 1, i);
-                    const int j_lo = max(0, i - (p.kd - 1));
+                    const int j_lo = max(0, i - (kd - 1));
                     const uint32_t cnt = static_cast<uint32_t>(j_hi - j_lo + 1);
-                    const uint32_t row0 = static_cast<uint32_t>(p.kd - 1 - (i - j_lo)) * n2;     // first B row (both blocks)
+                    const uint32_t row0 = static_cast<uint32_t>(kd - 1 - (i - j_lo)) * n2;     // first B row (both blocks)
                     const uint32_t d_lo = d_tile + static_cast<uint32_t>(j_lo) * n2;
-                    const bool fresh = i < zt_eff;              // output plane i gets its first contribution (kd' = 0)
+                    const uint32_t d_lo2 = d_lo + n_tile;
                     const uint32_t idesc1 = umma_idesc_bf16_m128(cnt * n2);
-                    const uint32_t idesc1b = umma_idesc_bf16_m128(cnt > 1 ? (cnt - 1) * n2 : n2);
-                    const uint32_t idesc_f = umma_idesc_bf16_m128(n2);
-                    const uint32_t idesc2 = umma_idesc_bf16_m128(cnt * n2 - static_cast<uint32_t>(p.n_tile));
-                    uint32_t b = w_base16;
-                    bool first = true;
-                    auto issue = [&](uint32_t a_hi) {
-                        const uint32_t b1 = (b + row0) | (b1_lbo << 16);
-                        const uint32_t b2 = (b + 2u * b1_lbo + row0) | (b2_lbo << 16);
-                        if (first && fresh) {
-                            // the kd' = 0 block initialises output plane i's (main | correction) columns
-                            const uint32_t bf = (b + static_cast<uint32_t>(p.kd - 1) * n2) | (b1_lbo << 16);
-                            umma_bf16_desc(true, d_tile + static_cast<uint32_t>(i) * n2, a_hi, desc_hi, bf, desc_hi, idesc_f, 0u);
-                            if (cnt > 1) umma_bf16_desc(true, d_lo, a_hi, desc_hi, b1, desc_hi, idesc1b, 1u);
-                        } else {
-                            umma_bf16_desc(true, d_lo, a_hi, desc_hi, b1, desc_hi, idesc1, 1u);
-                        }
-                        umma_bf16_desc(true, d_lo + p.n_tile, a_hi + plane16, desc_hi, b2, desc_hi, idesc2, 1u);
-                        first = false;
-                        b += step16;
-                    };
-                    uint32_t a_row = a_plane;
-                    for (int rr = 0; rr < p.kh; ++rr, a_row += static_cast<uint32_t>(p.Wp))
-                        for (int jp = 0; jp < pairs; ++jp)
-                            issue((a_row + 2u * static_cast<uint32_t>(jp)) | (1u << 16));
-                    if (p.kw & 1) {
-                        a_row = a_plane + static_cast<uint32_t>(p.kw - 1);
-                        for (int rr = 0; rr < p.kh; rr += 2, a_row += 2u * static_cast<uint32_t>(p.Wp))
-                            issue(a_row | ((rr + 1 < p.kh ? static_cast<uint32_t>(p.Wp) : 1u) << 16));
+                    const uint32_t idesc2 = umma_idesc_bf16_m128(cnt * n2 - n_tile);
+                    uint32_t b1 = (w_base16 + row0) | (b1_lbo << 16);
+                    uint32_t b2 = (w_base16 + 2u * b1_lbo + row0) | (b2_lbo << 16);
+                    int st = 0;
+                    if (i < zt_eff) {
+                        // output plane i gets its first contribution (kd' = 0): that block initialises the plane's
+                        // (main | correction) columns
+                        const uint32_t a_hi = a_plane + s_step_a[0];
+                        umma_bf16_desc(true, d_tile + static_cast<uint32_t>(i) * n2, a_hi, desc_hi, bf, desc_hi, idesc_f, 0u);
+                        if (cnt > 1)
+                            umma_bf16_desc(true, d_lo, a_hi, desc_hi, b1, desc_hi, umma_idesc_bf16_m128((cnt - 1) * n2), 1u);
+                        umma_bf16_desc(true, d_lo2, a_hi + plane16, desc_hi, b2, desc_hi, idesc2, 1u);
+                        b1 += step16;
+                        b2 += step16;
+                        st = 1;
+                    }
+                    for (; st < n_steps; ++st, b1 += step16, b2 += step16) {
+                        const uint32_t a_hi = a_plane + s_step_a[st];
+                        umma_bf16_desc(true, d_lo, a_hi, desc_hi, b1, desc_hi, idesc1, 1u);
+                        umma_bf16_desc(true, d_lo2, a_hi + plane16, desc_hi, b2, desc_hi, idesc2, 1u);
                     }
                 }
             }
-            if (leader) {
-                umma_commit(&empty_bar[s]);
-                umma_commit(&tfull_bar[acc]);
-            }
-            __syncwarp();
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
-            if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+            umma_commit(&empty_bar[s]);
+            umma_commit(&tfull_bar[acc]);
+            if (++s == stages) { s = 0; ph ^= 1u; }
+            if (++acc == acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
+        }
+        __syncwarp();
     } else {
         // =============================================================== epilogue (warps 2..9)
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
