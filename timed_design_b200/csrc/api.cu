@@ -817,6 +817,7 @@ static int thinz_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo&
     t.acc_cols = g.acc_cols;
     t.acc_stages = g.acc_stages;
     t.stages = g.stages;
+    t.issuers = getenv("TIMED_B200_THINZ_ISSUERS") ? std::max(1, std::min(2, atoi(getenv("TIMED_B200_THINZ_ISSUERS")))) : 2;
     return 0;
 }
 

@@ -21,12 +21,14 @@
 
 namespace tb {
 
-// Epilogue warps: kThinzSubs per TMEM lane quadrant.  Measured (profiles/r1_summary.md): 16 warps are no faster than 8
-// (epilogue-only 1.67 vs 1.70 ms) and cost 0.3 ms in the full kernel -- the epilogue is bound by its strided 16-byte
-// stores, not by issue slots.
+// Epilogue warps: kThinzSubs per TMEM lane quadrant.  Measured: 16 warps are no faster than 8 for the unfused epilogue
+// (profiles/r1_summary.md), nor are 12 for the fused max-pool one (round 2: 2.91 ms either way).  Role timing of the fused
+// epilogue (bring-up build, TIMED_B200_DBG 2/18/34/50): barriers + loads 0.71 ms, phase 1 +0.67 ms (128 KB of TMEM per
+// tile at ~128 B/cycle), phase 2 +0.69 ms (a short dependent chain per pooled pixel between two CTA-wide barriers);
+// neither phase responds to fewer ALU instructions, more warps or wider TMEM loads.
 constexpr int kThinzEpiWarps = 8;
 constexpr int kThinzSubs = kThinzEpiWarps / 4;
-constexpr int kThinzThreads = 64 + 32 * kThinzEpiWarps;
+constexpr int kThinzThreads = 64 + 32 * kThinzEpiWarps + 32;   // producer, MMA issuer, epilogue warps, second MMA issuer (the last warp)
 
 struct ThinZParams {
     // ---- tiling: tile = (frame, z group of zt output planes, window of 128 in-plane positions u = p*Wp + q)
@@ -59,6 +61,7 @@ struct ThinZParams {
     int32_t win_stride;       // in-plane positions between consecutive windows (128)
     // ---- fused MaxPool(2,2,2; stride 2) of the conv output (POOL = 1): see the epilogue.  Pooled pixels are written in the
     // consumer's layout (chunk-plane padded volume, or a plain NDHWC view).
+    int32_t issuers;          // MMA-issuing threads (1 or 2; 2 needs two accumulator stages)
     int32_t pool_same;        // TF 'same' (partial windows at the far edge are kept) or 'valid'
     int32_t Zo, Po, Qo;       // pooled extents
     int32_t pool_cpv;         // 1: chunk-plane padded volume (out_hi4/out_lo4 + geometry below), 0: plain NDHWC view
@@ -183,8 +186,8 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-    } else if (warp == 1) {
-        // =============================================================== MMA issuer
+    } else if (warp == 1 || warp == 2 + kThinzEpiWarps) {
+        // =============================================================== MMA issuers
         const bool leader = elect_one();
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);            // no swizzle, SBO = 128 B
         const uint32_t n2 = static_cast<uint32_t>(2 * p.n_tile);
@@ -202,13 +205,18 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         const bool skip = TB_DBG(p.dbg, 2);
         const uint32_t idesc_f = umma_idesc_bf16_m128(n2);
         const uint32_t bf = (w_base16 + static_cast<uint32_t>(kd - 1) * n2) | (b1_lbo << 16);
-        int s = 0, acc = 0;
-        uint32_t ph = 0, acc_ph = 0;
         // ONE lane runs the whole role (see slab_conv.cuh: issue-side work is exposed, the tensor pipe does not run ahead),
-        // with per-plane descriptors hoisted and the per-step A offsets in a table
-        if (leader) {
+        // with per-plane descriptors hoisted and the per-step A offsets in a table.  With two accumulator stages there
+        // are two issuers: warp 1 takes the even tiles of this CTA's sequence (stage 0), the last warp the odd ones (stage 1),
+        // so the two streams never touch the same accumulator or input stage -- every output keeps a fixed accumulation
+        // order -- and one fills the other's issue gaps (tools/mma_pattern_probe.cu: 193 -> 176 cycles per step pair).
+        const int n_iss = (acc_stages == 2 && p.issuers == 2) ? 2 : 1;
+        const int q = warp == 1 ? 0 : 1;
+        int s = q, acc = q;                                   // stages >= 2
+        uint32_t ph = 0, acc_ph = 0;
+        if (leader && q < n_iss) {
         mbar_wait(&w_bar, 0);
-        for (int it = 0;; ++it) {
+        for (int it = q;; it += n_iss) {
             const int tile = thinz_tile(it, windows, n_tiles_total);
             if (tile < 0) break;
             const int r = tile % tiles_per_frame;
@@ -255,17 +263,44 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
             }
             umma_commit(&empty_bar[s]);
             umma_commit(&tfull_bar[acc]);
-            if (++s == stages) { s = 0; ph ^= 1u; }
-            if (++acc == acc_stages) { acc = 0; acc_ph ^= 1u; }
+            s += n_iss;
+            if (s >= stages) { s -= stages; ph ^= 1u; }
+            if (n_iss == 2) acc_ph ^= 1u;                      // this issuer's stage, used every iteration
+            else if (++acc == acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
         }
         __syncwarp();
     } else {
-        // =============================================================== epilogue (warps 2..9)
+        // =============================================================== epilogue (warps 2 .. 2 + kThinzEpiWarps - 1)
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int sub = (warp - 2) >> 2;              // which of the quadrant's kThinzSubs warps
         const int chunks = p.n_tile / 16;
         const int plane_positions = p.Ho * p.Wp;
+        // POOL 1: the shared-memory pipe is the MMAs' (operand reads take ~86 % of its cycles), so the epilogue keeps its
+        // per-channel constants in registers: a bit mask of the decreasing channels, and -- a thread's channel group in
+        // phase 2 never changes -- that group's bias / scale / shift
+        uint32_t neg_mask[4] = {0u, 0u, 0u, 0u};
+        float e_bias[8], e_scale[8], e_shift[8];
+        uint32_t e_flip[8];
+        const int pool_g = (threadIdx.x - 64) % (p.n_tile >> 3);
+        if constexpr (POOL == 1) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                for (int b = 0; b < 32 && w * 32 + b < p.n_tile; ++b)
+                    if (s_sign[w * 32 + b] < 0.f) neg_mask[w] |= 1u << b;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                e_bias[e] = s_epi[0][pool_g * 8 + e];
+                e_scale[e] = s_epi[1][pool_g * 8 + e];
+                e_shift[e] = s_epi[2][pool_g * 8 + e];
+                e_flip[e] = s_sign[pool_g * 8 + e] < 0.f ? 0x80000000u : 0u;
+            }
+        }
+        auto neg_bits8 = [&](int unit) -> uint32_t {          // the 8 mask bits of channels unit*8 .. unit*8+7
+            const int w = unit >> 2;
+            const uint32_t word = w == 0 ? neg_mask[0] : w == 1 ? neg_mask[1] : w == 2 ? neg_mask[2] : neg_mask[3];
+            return (word >> ((unit & 3) * 8)) & 0xFFu;
+        };
         int acc = 0;
         uint32_t acc_ph = 0;
         for (int it = 0;; ++it) {
@@ -365,12 +400,18 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                 const int row_f4 = p.n_tile >> 2;                        // float4 slots per staged position
                 const int ring_f4 = 256 * row_f4;                        // one z pair's ring
                 float4* ring = reinterpret_cast<float4*>(pool_stage);
-                if (!TB_DBG(p.dbg, 4)) {
+                if (!TB_DBG(p.dbg, 4) && !TB_DBG(p.dbg, 32)) {         // bring-up build: 32 skips phase 1, 16 phase 2
                     // ---- phase 1
                     for (int item = sub; item < n_zp * (p.n_tile >> 3); item += kThinzSubs) {   // (z pair, 8 channels)
                         const int zp = item / (p.n_tile >> 3);
                         const int unit = item - zp * (p.n_tile >> 3);
                         const bool two = 2 * zp + 1 < zt_eff;
+                        // decreasing channels are staged NEGATED (sign-bit flip, exact), so that every later reduction is a
+                        // plain maximum; phase 2 flips them back
+                        const uint32_t neg8 = neg_bits8(unit);
+                        uint32_t xm[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) xm[i] = ((neg8 >> i) & 1u) << 31;
                         float v[8];
 #pragma unroll
                         for (int pl = 0; pl < 2; ++pl) {
@@ -384,8 +425,8 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float x = __uint_as_float(rv[i]) + __uint_as_float(rc[i]);
-                                v[i] = pl == 0 ? x : (s_sign[unit * 8 + i] >= 0.f ? fmaxf(v[i], x) : fminf(v[i], x));
+                                const float x = __uint_as_float(__float_as_uint(__uint_as_float(rv[i]) + __uint_as_float(rc[i])) ^ xm[i]);
+                                v[i] = pl == 0 ? x : fmaxf(v[i], x);
                             }
                         }
                         const int srow = (u0 + quad * 32 + lane) & 255;
@@ -412,15 +453,17 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                 const int P_hi = min(p.Po - 1, ((a_hi - 1) / p.Wp) >> 1);
                 const int n_cand = a_hi > a_lo ? max(0, P_hi - P0 + 1) * p.Qo : 0;
                 const int my_combo = et % combos;
-                const int g = my_combo % groups;
+                const int g = pool_g;                                    // == my_combo % groups
                 const int zp = my_combo / groups;
                 const int Z = (z0 >> 1) + zp;
                 const bool two = 2 * zp + 1 < zt_eff;
                 const bool z_ok = Z < p.Zo && (two || p.pool_same);
                 const int k_step = (32 * kThinzEpiWarps) / combos;
-                for (int k = et / combos; k < n_cand && z_ok && et < k_step * combos && !TB_DBG(p.dbg, 4); k += k_step) {
-                    const int P = P0 + k / p.Qo;
-                    const int Q = k - (P - P0) * p.Qo;
+                const int k0 = et / combos;
+                const int dP = k_step / p.Qo, dQ = k_step - dP * p.Qo;      // pixel stride as (rows, columns): no division per pixel
+                int P = P0 + k0 / p.Qo, Q = k0 % p.Qo;
+                for (int k = k0; k < n_cand && z_ok && et < k_step * combos && !TB_DBG(p.dbg, 4) && !TB_DBG(p.dbg, 16);
+                     k += k_step, P += dP + (Q + dQ >= p.Qo ? 1 : 0), Q = Q + dQ >= p.Qo ? Q + dQ - p.Qo : Q + dQ) {
                     const int pa = 2 * P, qa = 2 * Q;
                     const int ua = pa * p.Wp + qa;
                     if (ua < a_lo || ua >= a_hi || pa >= p.Ho || qa >= p.Wo) continue;
@@ -436,7 +479,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                         const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                         for (int e = 0; e < 8; ++e)
-                            m8[e] = first ? x[e] : (s_sign[g * 8 + e] >= 0.f ? fmaxf(m8[e], x[e]) : fminf(m8[e], x[e]));
+                            m8[e] = first ? x[e] : fmaxf(m8[e], x[e]);
                     };
                     take(ua, true);
                     if (has_q) take(ua + 1, false);
@@ -444,9 +487,9 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                     if (has_q && has_p) take(ua + p.Wp + 1, false);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        float x = m8[e] + s_epi[0][g * 8 + e];
+                        float x = __uint_as_float(__float_as_uint(m8[e]) ^ e_flip[e]) + e_bias[e];
                         x = act_ct<ACT1>(x, p.epi.act1, p.epi.alpha1);
-                        x = fmaf(x, s_epi[1][g * 8 + e], s_epi[2][g * 8 + e]);
+                        x = fmaf(x, e_scale[e], e_shift[e]);
                         m8[e] = act_ct<ACT2>(x, p.epi.act2, p.epi.alpha2);
                     }
                     if (p.pool_cpv) {
