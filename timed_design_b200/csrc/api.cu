@@ -443,6 +443,27 @@ static int encode_a_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* ba
     return 0;
 }
 
+// Tiled map over the same activation tensor for voxel-stationary tiles (conv_pair.cuh): box = kc channels of ONE
+// voxel x 128 consecutive frames.
+static int encode_a_vox_map(const ConvPlan& p, const ConvPlan::Config& cfg, void* base, int64_t frames_alloc,
+                            CUtensorMap* out) {
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(p.cin_pad), static_cast<cuuint64_t>(p.Wi),
+                          static_cast<cuuint64_t>(p.Hi), static_cast<cuuint64_t>(p.Di),
+                          static_cast<cuuint64_t>(2 * frames_alloc)};
+    const cuuint64_t px = static_cast<cuuint64_t>(p.cin_pad) * 2;
+    cuuint64_t strides[4] = {px, px * p.Wi, px * p.Wi * p.Hi, px * p.Wi * p.Hi * p.Di};
+    cuuint32_t box[5] = {static_cast<cuuint32_t>(cfg.kc), 1, 1, 1, 128};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, cfg.tma_swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(activations, voxel-stationary) failed, CUresult=" + std::to_string(r));
+        return TB_ERR_CUDA;
+    }
+    return 0;
+}
+
 // ----------------------------------------------------------------------------- thin-input conv plan
 // Number of K=16 MMA steps thin_conv_kernel needs for a (kd,kh,kw) filter: kw/2 in-row pixel pairs per
 // filter row plus the left-over odd taps paired across consecutive filter rows.
@@ -1132,8 +1153,8 @@ static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map
 }
 
 template <int A1, int A2, int F>
-static int launch_pair_instance(const CUtensorMap& map_a, const CUtensorMap& map_w, const ConvKernelParams& k,
-                                int grid, size_t smem_bytes, cudaStream_t stream) {
+static int launch_pair_instance(const CUtensorMap& map_a, const CUtensorMap& map_w, const CUtensorMap& map_v,
+                                const ConvKernelParams& k, int grid, size_t smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;       // per instantiation
     if (!attr_set) {
         TB_CHECK_CUDA(cudaFuncSetAttribute(conv_pair_kernel<A1, A2, F>,
@@ -1153,7 +1174,7 @@ static int launch_pair_instance(const CUtensorMap& map_a, const CUtensorMap& map
     attr[0].val.clusterDim.z = 1;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    TB_CHECK_CUDA(cudaLaunchKernelEx(&lc, conv_pair_kernel<A1, A2, F>, map_a, map_w, k));
+    TB_CHECK_CUDA(cudaLaunchKernelEx(&lc, conv_pair_kernel<A1, A2, F>, map_a, map_w, map_v, k));
     return 0;
 }
 
@@ -1190,6 +1211,24 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     if (rc) return rc;
     rc = encode_a_map(p, cfg, in_base, in_frames_alloc, p.cin_pad, &map_a);
     if (rc) return rc;
+    // Voxel-stationary tiles for the pair kernel (conv_pair.cuh): worth it when the taps skipped in the zero padding
+    // outweigh the frames a partial last block of 256 wastes
+    CUtensorMap map_v = map_a;
+    bool vox = false;
+    if (cfg.pair && !p.tap2n && !p.wfold && !getenv("TIMED_B200_NO_VOX")) {
+        const double valid = valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]) *
+                             valid_tap_fraction(p.Wi, p.Wo, p.kw, p.pad0[2]);
+        const int64_t fblocks = (n_frames + 255) / 256;
+        const double rows_ratio = static_cast<double>(fblocks * 256) / static_cast<double>(n_frames);
+        const bool centre_ok = p.pad0[0] < p.kd && p.pad0[1] < p.kh && p.pad0[2] < p.kw && p.pad0[0] < p.Di + 0 &&
+                               p.Do <= p.Di && p.Ho <= p.Hi && p.Wo <= p.Wi;
+        vox = centre_ok && (valid * rows_ratio < 0.93 || getenv("TIMED_B200_FORCE_VOX")) &&
+              fblocks * p.Do * p.Ho * p.Wo * p.n_tiles < (1ll << 30);
+        if (vox) {
+            rc = encode_a_vox_map(p, cfg, in_base, in_frames_alloc, &map_v);
+            if (rc) return rc;
+        }
+    }
 
     ConvKernelParams k;
     std::memset(&k, 0, sizeof(k));
@@ -1197,6 +1236,12 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     const int m_tiles = static_cast<int>((m_total64 + 127) / 128);
     k.mt = cfg.mt;
     k.n_ctile_m = ceil_div(m_tiles, (cfg.cluster2 || cfg.pair) ? 2 : cfg.mt);   // cluster / pair mode: tiles are 256-row pair-tiles
+    if (vox) {
+        k.vox = 1;
+        k.vox_frames = static_cast<int32_t>(n_frames);
+        k.Di = p.Di; k.Hi = p.Hi; k.Wi = p.Wi;
+        k.n_ctile_m = static_cast<int32_t>(((n_frames + 255) / 256) * p.Do * p.Ho * p.Wo);
+    }
     k.cluster2 = cfg.cluster2;
     k.corr_off = cfg.corr_off;
     k.n_tiles = p.n_tiles;
@@ -1258,7 +1303,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     bool launched = false;
 #define TB_CONV_CASE(A1, A2, F)                                                                         \
     if (!launched && k.act1 == (A1) && k.act2 == (A2) && k.out_fmt == (F)) {                            \
-        rc = cfg.pair ? launch_pair_instance<A1, A2, F>(map_a, map_w, k, grid, cfg.smem_bytes, stream)  \
+        rc = cfg.pair ? launch_pair_instance<A1, A2, F>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream)  \
                       : launch_conv_instance<A1, A2, F>(map_a, map_w, k, grid, cfg.smem_bytes, stream); \
         launched = true;                                                                                \
     }
@@ -1274,8 +1319,8 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     TB_CONV_CASE(ACT_NONE, ACT_ELU, FMT_F32)
 #undef TB_CONV_CASE
     if (!launched && cfg.pair)
-        rc = k.out_fmt == FMT_SPLIT ? launch_pair_instance<-1, -1, FMT_SPLIT>(map_a, map_w, k, grid, cfg.smem_bytes, stream)
-                                    : launch_pair_instance<-1, -1, FMT_F32>(map_a, map_w, k, grid, cfg.smem_bytes, stream);
+        rc = k.out_fmt == FMT_SPLIT ? launch_pair_instance<-1, -1, FMT_SPLIT>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream)
+                                    : launch_pair_instance<-1, -1, FMT_F32>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream);
     else if (!launched)
         rc = k.out_fmt == FMT_SPLIT ? launch_conv_instance<-1, -1, FMT_SPLIT>(map_a, map_w, k, grid, cfg.smem_bytes, stream)
                                     : launch_conv_instance<-1, -1, FMT_F32>(map_a, map_w, k, grid, cfg.smem_bytes, stream);
@@ -2318,7 +2363,12 @@ int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t fra
     // behind a forward.  The ramp never exceeds `chunk`: the staging buffers and the workspace are sized for it, and the
     // caller's batch_size bound holds for every pass.
     int64_t cur = n_frames > chunk ? std::min<int64_t>(chunk, std::max<int64_t>(64, chunk / 8)) : chunk;
-    for (int64_t f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++it, cur = std::min(chunk, cur + cur / 2)) {
+    // Passes of 512 frames and more are whole multiples of 256: the wide convs tile 256 frames per voxel (conv_pair.cuh)
+    auto next_pass = [&](int64_t c) {
+        c = std::min(chunk, c + c / 2);
+        return c >= 512 && c < chunk ? c & ~static_cast<int64_t>(255) : c;
+    };
+    for (int64_t f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++it, cur = next_pass(cur)) {
         const int b = it & 1;
         nf = std::min(cur, n_frames - f0);
         TB_REQUIRE(nf > 0 && nf <= chunk, "internal: predict_host chunk exceeds the staged size");

@@ -56,6 +56,38 @@ __device__ __forceinline__ void tma_load_im2col_5d_pair(void* smem_dst, const CU
         "r"(d), "r"(n), "h"(ow), "h"(oh), "h"(od)
         : "memory");
 }
+// tiled (not im2col) 5-D box: voxel-stationary tiles fetch {kc channels} x {128 frames} at one input voxel
+__device__ __forceinline__ void tma_load_5d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                                 int32_t c, int32_t w, int32_t h, int32_t d, int32_t n) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h),
+        "r"(d), "r"(n)
+        : "memory");
+}
+// Voxel-stationary tile: m_ct -> (frame block, output voxel) and the range of filter taps that fall inside the input
+struct VoxTile {
+    int fb, vox, z, y, x;
+    int a0, a1, b0, b1, c0, c1;      // valid tap ranges along d, h, w (inclusive)
+    int n_kb;                        // k-blocks of the tile: valid taps x cin_blocks
+};
+__device__ __forceinline__ VoxTile vox_decode(const ConvKernelParams& p, int m_ct) {
+    VoxTile v;
+    const int n_vox = p.Do * p.Ho * p.Wo;
+    v.fb = m_ct / n_vox;
+    v.vox = m_ct - v.fb * n_vox;
+    v.x = v.vox % p.Wo;
+    const int t = v.vox / p.Wo;
+    v.y = t % p.Ho;
+    v.z = t / p.Ho;
+    const int kd = p.n_taps / (p.kh * p.kw);
+    v.a0 = max(0, -(v.z + p.lc_d)); v.a1 = min(kd - 1, p.Di - 1 - (v.z + p.lc_d));
+    v.b0 = max(0, -(v.y + p.lc_h)); v.b1 = min(p.kh - 1, p.Hi - 1 - (v.y + p.lc_h));
+    v.c0 = max(0, -(v.x + p.lc_w)); v.c1 = min(p.kw - 1, p.Wi - 1 - (v.x + p.lc_w));
+    v.n_kb = max(0, v.a1 - v.a0 + 1) * max(0, v.b1 - v.b0 + 1) * max(0, v.c1 - v.c0 + 1) * p.cin_blocks;
+    return v;
+}
 // D[tmem, both CTAs] (+)= A * B, M = 256 over the pair; descriptors as (lo, shared hi) halves
 __device__ __forceinline__ void umma_bf16_pair(bool leader, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
@@ -101,7 +133,8 @@ constexpr int kPairThreads = 32 * (kPairEpilogueWarp0 + kConvEpilogueWarps);
 template <int ACT1, int ACT2, int FMT>
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
-                 const __grid_constant__ CUtensorMap map_w, const ConvKernelParams p) {
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_v,
+                 const ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -132,6 +165,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_v);
     }
     if (warp == 1) tmem_alloc_512_pair(&tmem_base_slot);
     const int n_alloc = p.n_tiles * p.n_tile;
@@ -154,7 +188,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
     const int tile_step = static_cast<int>(gridDim.x >> 1);
     const uint32_t kb_bytes = 2u * p.a_sub_bytes + 2u * p.w_sub_bytes;   // per CTA
     const uint32_t stage_bytes = kb_bytes * static_cast<uint32_t>(p.kg);
-    const int n_groups = (p.n_kblocks + p.kg - 1) / p.kg;
     const int half_rows = p.n_tile >> 1;
 
     if (warp < kPairEpilogueWarp0) {
@@ -167,45 +200,61 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
         for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
             const int m_ct = tile / p.n_tiles;
             const int n_idx = tile - m_ct * p.n_tiles;
-            int m0 = (m_ct * 2 + static_cast<int>(cta_rank)) * 128;
-            if (m0 >= p.m_total) m0 = 0;           // dummy half: rows are discarded by the epilogue
-            const int q = m0 % p.Wo;
-            int t = m0 / p.Wo;
-            const int pp = t % p.Ho;
-            t /= p.Ho;
-            const int z = t % p.Do;
-            const int nf = t / p.Do;
-            const int bw = q + p.lc_w, bh = pp + p.lc_h, bd = z + p.lc_d;
+            // base coordinates of the tile's A boxes, the tap ranges it walks and its k-block count
+            int bw, bh, bd, nf, n_kb = p.n_kblocks;
+            int a0 = 0, b0 = 0, b1 = p.kh - 1, c0 = 0, c1 = p.kw - 1;
+            if (p.vox) {
+                const VoxTile v = vox_decode(p, m_ct);
+                bw = v.x + p.lc_w; bh = v.y + p.lc_h; bd = v.z + p.lc_d;
+                nf = (v.fb * 2 + static_cast<int>(cta_rank)) * 128;
+                a0 = v.a0; b0 = v.b0; b1 = v.b1; c0 = v.c0; c1 = v.c1;
+                n_kb = v.n_kb;
+            } else {
+                int m0 = (m_ct * 2 + static_cast<int>(cta_rank)) * 128;
+                if (m0 >= p.m_total) m0 = 0;           // dummy half: rows are discarded by the epilogue
+                const int q = m0 % p.Wo;
+                int t = m0 / p.Wo;
+                const int pp = t % p.Ho;
+                t /= p.Ho;
+                const int z = t % p.Do;
+                nf = t / p.Do;
+                bw = q + p.lc_w; bh = pp + p.lc_h; bd = z + p.lc_d;
+            }
+            const int n_groups = (n_kb + p.kg - 1) / p.kg;
             const int w_row0 = n_idx * p.n_tile + static_cast<int>(cta_rank) * half_rows;
+            int ta = a0, tb = b0, tc = c0, cb = 0;                 // current tap (d, h, w) and channel block
             for (int g = 0; g < n_groups; ++g) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                const int kb0 = g * p.kg;
-                const int nkb = min(p.kg, p.n_kblocks - kb0);
+                const int nkb = min(p.kg, n_kb - g * p.kg);
                 if (leader) {
                     if (TB_DBG(p.dbg, 1)) {
                         if (leader_cta) mbar_arrive(&full_bar[s]);
                     } else {
                         if (leader_cta) mbar_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(nkb) * kb_bytes);
                         uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-                        int tap = kb0 / p.cin_blocks;
-                        int cb = kb0 - tap * p.cin_blocks;
                         for (int j = 0; j < nkb; ++j) {
-                            const int tkw = tap % p.kw;
-                            const int t2 = tap / p.kw;
-                            const int tkh = t2 % p.kh;
-                            const int tkd = t2 / p.kh;
+                            const int tap = (ta * p.kh + tb) * p.kw + tc;
                             uint8_t* base = st + static_cast<size_t>(j) * kb_bytes;
-                            tma_load_im2col_5d_pair(base, &map_a, &full_bar[s], cb * p.kc, bw, bh, bd, nf,
-                                                    static_cast<uint16_t>(tkw), static_cast<uint16_t>(tkh),
-                                                    static_cast<uint16_t>(tkd));
-                            tma_load_im2col_5d_pair(base + p.a_sub_bytes, &map_a, &full_bar[s], cb * p.kc, bw, bh,
-                                                    bd, nf + p.lo_plane_frames, static_cast<uint16_t>(tkw),
-                                                    static_cast<uint16_t>(tkh), static_cast<uint16_t>(tkd));
+                            if (p.vox) {
+                                tma_load_5d_pair(base, &map_v, &full_bar[s], cb * p.kc, bw + tc, bh + tb, bd + ta, nf);
+                                tma_load_5d_pair(base + p.a_sub_bytes, &map_v, &full_bar[s], cb * p.kc, bw + tc, bh + tb, bd + ta,
+                                                 nf + p.lo_plane_frames);
+                            } else {
+                                tma_load_im2col_5d_pair(base, &map_a, &full_bar[s], cb * p.kc, bw, bh, bd, nf,
+                                                        static_cast<uint16_t>(tc), static_cast<uint16_t>(tb),
+                                                        static_cast<uint16_t>(ta));
+                                tma_load_im2col_5d_pair(base + p.a_sub_bytes, &map_a, &full_bar[s], cb * p.kc, bw, bh,
+                                                        bd, nf + p.lo_plane_frames, static_cast<uint16_t>(tc),
+                                                        static_cast<uint16_t>(tb), static_cast<uint16_t>(ta));
+                            }
                             uint8_t* wb = base + 2 * p.a_sub_bytes;
                             const int kcoord = tap * p.cin_pad + cb * p.kc;
                             tma_load_2d_pair(wb, &map_w, &full_bar[s], kcoord, w_row0);
                             tma_load_2d_pair(wb + p.w_sub_bytes, &map_w, &full_bar[s], kcoord, p.w_lo_rows + w_row0);
-                            if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+                            if (++cb == p.cin_blocks) {
+                                cb = 0;
+                                if (++tc > c1) { tc = c0; if (++tb > b1) { tb = b0; ++ta; } }
+                            }
                         }
                     }
                 }
@@ -228,6 +277,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             int acc = 0;
             uint32_t acc_ph = 0;
             for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+                const int n_kb = p.vox ? vox_decode(p, tile / p.n_tiles).n_kb : p.n_kblocks;
+                const int n_groups = (n_kb + p.kg - 1) / p.kg;
                 mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
                 tc_fence_after();
                 uint32_t accumulate = 0;
@@ -235,7 +286,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                 for (int g = 0; g < n_groups; ++g) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const int nkb = min(p.kg, p.n_kblocks - g * p.kg);
+                    const int nkb = min(p.kg, n_kb - g * p.kg);
                     uint32_t base16 = (smem_base16 + static_cast<uint32_t>(s) * (stage_bytes >> 4)) | lo_flags;
                     if (!TB_DBG(p.dbg, 2)) {
                         for (int j = 0; j < nkb; ++j, base16 += kb16) {
@@ -281,8 +332,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             const int n_idx = tile - m_ct * p.n_tiles;
             mbar_wait_relaxed(&tfull_bar[acc], acc_ph);   // a whole mainloop away: sleep between polls (0.7 % on conv5)
             tc_fence_after();
-            const int64_t m = static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank)) * 128 + row_in_tile;
-            const bool row_ok = m < p.m_total && !TB_DBG(p.dbg, 8);
+            int64_t m = static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank)) * 128 + row_in_tile;
+            bool row_ok = m < p.m_total && !TB_DBG(p.dbg, 8);
+            if (p.vox) {                               // row = frame, at the tile's voxel
+                const int n_vox = p.Do * p.Ho * p.Wo;
+                const int fb = m_ct / n_vox;
+                const int frame = (fb * 2 + static_cast<int>(cta_rank)) * 128 + row_in_tile;
+                m = static_cast<int64_t>(frame) * n_vox + (m_ct - fb * n_vox);
+                row_ok = frame < p.vox_frames && !TB_DBG(p.dbg, 8);
+            }
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>(acc * p.acc_cols);
             if (p.corr_off && !TB_DBG(p.dbg, 4)) {

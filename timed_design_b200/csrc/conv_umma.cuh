@@ -89,6 +89,14 @@ struct ConvKernelParams {
     // COHERENT across the outputs of a layer (tools/accum_error.py).  The epilogue multiplies the main accumulator by
     // acc_comp = 1 + c(n)*n, n = MMAs with non-zero operands per output (host: accum_comp()).  1.0f switches it off.
     float acc_comp;
+    // ---- voxel-stationary tiles (conv_pair_kernel only, stride 1): the 256 rows of a pair-tile are 256 consecutive FRAMES at
+    // ONE output voxel, so a filter tap that falls into the zero 'same' padding is invalid for the whole tile and is
+    // skipped -- at 6^3 with a 3^3 filter that is 30 % of the MMAs (and of the operand traffic).  Skipped taps would have
+    // added exact zeros, and the remaining ones keep their order: results are bit-identical to the im2col tiling.
+    // n_ctile_m = frame blocks x output voxels (tile -> m_ct -> (frame block, voxel)).
+    int32_t vox;
+    int32_t vox_frames;       // frames in this launch
+    int32_t Di, Hi, Wi;       // input extents (validity of a tap: 0 <= out + lc + tap < in)
     // ---- bring-up / tuning only (env TIMED_B200_DBG): 1 = skip TMA loads, 2 = skip MMA issue,
     // 4 = skip epilogue math+stores.  Results are garbage; used to time each role in isolation.
     int32_t dbg;
