@@ -1123,7 +1123,8 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
 }
 
 template <int A1, int A2, int F>
-static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map_w, const ConvKernelParams& k,
+static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map_w, const CUtensorMap& map_v,
+                                const ConvKernelParams& k,
                                 int grid, size_t smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;       // per instantiation
     if (!attr_set) {
@@ -1145,10 +1146,10 @@ static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map
         attr[0].val.clusterDim.z = 1;
         lc.attrs = attr;
         lc.numAttrs = 1;
-        TB_CHECK_CUDA(cudaLaunchKernelEx(&lc, conv_umma_kernel<A1, A2, F>, map_a, map_w, k));
+        TB_CHECK_CUDA(cudaLaunchKernelEx(&lc, conv_umma_kernel<A1, A2, F>, map_a, map_w, map_v, k));
         return 0;
     }
-    conv_umma_kernel<A1, A2, F><<<grid, kUmmaThreads, smem_bytes, stream>>>(map_a, map_w, k);
+    conv_umma_kernel<A1, A2, F><<<grid, kUmmaThreads, smem_bytes, stream>>>(map_a, map_w, map_v, k);
     return 0;
 }
 
@@ -1211,15 +1212,16 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     if (rc) return rc;
     rc = encode_a_map(p, cfg, in_base, in_frames_alloc, p.cin_pad, &map_a);
     if (rc) return rc;
-    // Voxel-stationary tiles for the pair kernel (conv_pair.cuh): worth it when the taps skipped in the zero padding
-    // outweigh the frames a partial last block of 256 wastes
+    // Voxel-stationary tiles (ConvKernelParams::vox): worth it when the taps skipped in the zero padding outweigh the
+    // frames a partial last block of 256 (128 for single-sub-tile configurations) wastes
     CUtensorMap map_v = map_a;
     bool vox = false;
-    if (cfg.pair && !p.tap2n && !p.wfold && !getenv("TIMED_B200_NO_VOX")) {
+    const int vox_rows = cfg.pair ? 256 : 128 * cfg.mt;          // frames per voxel-stationary tile
+    if (!cfg.cluster2 && !p.tap2n && !p.wfold && !getenv("TIMED_B200_NO_VOX")) {
         const double valid = valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]) *
                              valid_tap_fraction(p.Wi, p.Wo, p.kw, p.pad0[2]);
-        const int64_t fblocks = (n_frames + 255) / 256;
-        const double rows_ratio = static_cast<double>(fblocks * 256) / static_cast<double>(n_frames);
+        const int64_t fblocks = (n_frames + vox_rows - 1) / vox_rows;
+        const double rows_ratio = static_cast<double>(fblocks * vox_rows) / static_cast<double>(n_frames);
         const bool centre_ok = p.pad0[0] < p.kd && p.pad0[1] < p.kh && p.pad0[2] < p.kw && p.pad0[0] < p.Di + 0 &&
                                p.Do <= p.Di && p.Ho <= p.Hi && p.Wo <= p.Wi;
         vox = centre_ok && (valid * rows_ratio < 0.93 || getenv("TIMED_B200_FORCE_VOX")) &&
@@ -1240,7 +1242,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
         k.vox = 1;
         k.vox_frames = static_cast<int32_t>(n_frames);
         k.Di = p.Di; k.Hi = p.Hi; k.Wi = p.Wi;
-        k.n_ctile_m = static_cast<int32_t>(((n_frames + 255) / 256) * p.Do * p.Ho * p.Wo);
+        k.n_ctile_m = static_cast<int32_t>(((n_frames + vox_rows - 1) / vox_rows) * p.Do * p.Ho * p.Wo);
     }
     k.cluster2 = cfg.cluster2;
     k.corr_off = cfg.corr_off;
@@ -1304,7 +1306,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
 #define TB_CONV_CASE(A1, A2, F)                                                                         \
     if (!launched && k.act1 == (A1) && k.act2 == (A2) && k.out_fmt == (F)) {                            \
         rc = cfg.pair ? launch_pair_instance<A1, A2, F>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream)  \
-                      : launch_conv_instance<A1, A2, F>(map_a, map_w, k, grid, cfg.smem_bytes, stream); \
+                      : launch_conv_instance<A1, A2, F>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream); \
         launched = true;                                                                                \
     }
     TB_CONV_CASE(ACT_ELU, ACT_NONE, FMT_SPLIT)
@@ -1322,8 +1324,8 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
         rc = k.out_fmt == FMT_SPLIT ? launch_pair_instance<-1, -1, FMT_SPLIT>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream)
                                     : launch_pair_instance<-1, -1, FMT_F32>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream);
     else if (!launched)
-        rc = k.out_fmt == FMT_SPLIT ? launch_conv_instance<-1, -1, FMT_SPLIT>(map_a, map_w, k, grid, cfg.smem_bytes, stream)
-                                    : launch_conv_instance<-1, -1, FMT_F32>(map_a, map_w, k, grid, cfg.smem_bytes, stream);
+        rc = k.out_fmt == FMT_SPLIT ? launch_conv_instance<-1, -1, FMT_SPLIT>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream)
+                                    : launch_conv_instance<-1, -1, FMT_F32>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream);
     if (rc) return rc;
     TB_CHECK_CUDA(cudaGetLastError());
     if (p.tap2n) {

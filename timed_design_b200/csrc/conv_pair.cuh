@@ -66,28 +66,6 @@ __device__ __forceinline__ void tma_load_5d_pair(void* smem_dst, const CUtensorM
         "r"(d), "r"(n)
         : "memory");
 }
-// Voxel-stationary tile: m_ct -> (frame block, output voxel) and the range of filter taps that fall inside the input
-struct VoxTile {
-    int fb, vox, z, y, x;
-    int a0, a1, b0, b1, c0, c1;      // valid tap ranges along d, h, w (inclusive)
-    int n_kb;                        // k-blocks of the tile: valid taps x cin_blocks
-};
-__device__ __forceinline__ VoxTile vox_decode(const ConvKernelParams& p, int m_ct) {
-    VoxTile v;
-    const int n_vox = p.Do * p.Ho * p.Wo;
-    v.fb = m_ct / n_vox;
-    v.vox = m_ct - v.fb * n_vox;
-    v.x = v.vox % p.Wo;
-    const int t = v.vox / p.Wo;
-    v.y = t % p.Ho;
-    v.z = t / p.Ho;
-    const int kd = p.n_taps / (p.kh * p.kw);
-    v.a0 = max(0, -(v.z + p.lc_d)); v.a1 = min(kd - 1, p.Di - 1 - (v.z + p.lc_d));
-    v.b0 = max(0, -(v.y + p.lc_h)); v.b1 = min(p.kh - 1, p.Hi - 1 - (v.y + p.lc_h));
-    v.c0 = max(0, -(v.x + p.lc_w)); v.c1 = min(p.kw - 1, p.Wi - 1 - (v.x + p.lc_w));
-    v.n_kb = max(0, v.a1 - v.a0 + 1) * max(0, v.b1 - v.b0 + 1) * max(0, v.c1 - v.c0 + 1) * p.cin_blocks;
-    return v;
-}
 // D[tmem, both CTAs] (+)= A * B, M = 256 over the pair; descriptors as (lo, shared hi) halves
 __device__ __forceinline__ void umma_bf16_pair(bool leader, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {

@@ -274,6 +274,39 @@ __device__ __forceinline__ void epilogue_drained(const ConvKernelParams& p, uint
     }
 }
 
+// Voxel-stationary tile (ConvKernelParams::vox): m_ct -> (frame block, output voxel) and the range of filter taps that
+// fall inside the input
+struct VoxTile {
+    int fb, vox, z, y, x;
+    int a0, a1, b0, b1, c0, c1;      // valid tap ranges along d, h, w (inclusive)
+    int n_kb;                        // k-blocks of the tile: valid taps x cin_blocks
+};
+__device__ __forceinline__ VoxTile vox_decode(const ConvKernelParams& p, int m_ct) {
+    VoxTile v;
+    const int n_vox = p.Do * p.Ho * p.Wo;
+    v.fb = m_ct / n_vox;
+    v.vox = m_ct - v.fb * n_vox;
+    v.x = v.vox % p.Wo;
+    const int t = v.vox / p.Wo;
+    v.y = t % p.Ho;
+    v.z = t / p.Ho;
+    const int kd = p.n_taps / (p.kh * p.kw);
+    v.a0 = max(0, -(v.z + p.lc_d)); v.a1 = min(kd - 1, p.Di - 1 - (v.z + p.lc_d));
+    v.b0 = max(0, -(v.y + p.lc_h)); v.b1 = min(p.kh - 1, p.Hi - 1 - (v.y + p.lc_h));
+    v.c0 = max(0, -(v.x + p.lc_w)); v.c1 = min(p.kw - 1, p.Wi - 1 - (v.x + p.lc_w));
+    v.n_kb = max(0, v.a1 - v.a0 + 1) * max(0, v.b1 - v.b0 + 1) * max(0, v.c1 - v.c0 + 1) * p.cin_blocks;
+    return v;
+}
+// tiled (not im2col) 5-D box: {kc channels} x {128 frames} at one input voxel
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c, int32_t w,
+                                            int32_t h, int32_t d, int32_t n) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n)
+        : "memory");
+}
+
 // One pipeline stage's MMAs for ONE 128-row sub-tile, issued by one thread as a straight run of UTCHMMAs with affine
 // descriptor updates.  MODE 0: separate correction accumulator (d_corr); 1: N-folded (d_corr = d + n_tile);
 // 3: corrections into the main accumulator.
@@ -305,7 +338,8 @@ __device__ __forceinline__ void umma_issue_stage(uint32_t base16, int nkb, uint3
 template <int ACT1, int ACT2, int FMT>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
-                 const __grid_constant__ CUtensorMap map_w, const ConvKernelParams p) {
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_v,
+                 const ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -336,6 +370,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_v);
     }
     const uint32_t cta_rank = p.cluster2 ? cluster_ctarank() : 0u;
     if (warp == 1) tmem_alloc_512(&tmem_base_slot);
@@ -361,7 +396,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     const int tile_step = p.cluster2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const uint32_t kb_bytes = static_cast<uint32_t>(p.mt) * 2u * p.a_sub_bytes + 2u * p.w_sub_bytes;
     const uint32_t stage_bytes = kb_bytes * static_cast<uint32_t>(p.kg);
-    const int n_groups = (p.n_kblocks + p.kg - 1) / p.kg;
 
     if (warp == 0) {
         // =============================================================== TMA producer
@@ -373,48 +407,63 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             const int m_ct = tile / p.n_tiles;
             const int n_idx = tile - m_ct * p.n_tiles;
             int32_t bw[2], bh[2], bd[2], bn[2];
+            int n_kb = p.n_kblocks;
+            int a0 = 0, b0 = 0, b1 = p.kh - 1, c0 = 0, c1 = p.kw - 1;       // tap ranges the tile walks
+            if (p.vox) {
+                const VoxTile v = vox_decode(p, m_ct);
+                for (int mi = 0; mi < 2; ++mi) {
+                    bw[mi] = v.x + p.lc_w; bh[mi] = v.y + p.lc_h; bd[mi] = v.z + p.lc_d;
+                    bn[mi] = (v.fb * p.mt + mi) * 128;
+                }
+                a0 = v.a0; b0 = v.b0; b1 = v.b1; c0 = v.c0; c1 = v.c1;
+                n_kb = v.n_kb;
+            } else {
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi) {
-                int m0 = p.cluster2 ? (m_ct * 2 + static_cast<int>(cta_rank)) * 128 : (m_ct * p.mt + mi) * 128;
-                if (m0 >= p.m_total) m0 = 0;       // dummy sub-tile: rows are discarded later
-                const int q = m0 % p.Wo;
-                int t = m0 / p.Wo;
-                const int pp = t % p.Ho;
-                t /= p.Ho;
-                const int z = t % p.Do;
-                const int nf = t / p.Do;
-                bw[mi] = q + p.lc_w;
-                bh[mi] = pp + p.lc_h;
-                bd[mi] = z + p.lc_d;
-                bn[mi] = nf;
+                for (int mi = 0; mi < 2; ++mi) {
+                    int m0 = p.cluster2 ? (m_ct * 2 + static_cast<int>(cta_rank)) * 128 : (m_ct * p.mt + mi) * 128;
+                    if (m0 >= p.m_total) m0 = 0;       // dummy sub-tile: rows are discarded later
+                    const int q = m0 % p.Wo;
+                    int t = m0 / p.Wo;
+                    const int pp = t % p.Ho;
+                    t /= p.Ho;
+                    const int z = t % p.Do;
+                    const int nf = t / p.Do;
+                    bw[mi] = q + p.lc_w;
+                    bh[mi] = pp + p.lc_h;
+                    bd[mi] = z + p.lc_d;
+                    bn[mi] = nf;
+                }
             }
+            const int n_groups = (n_kb + p.kg - 1) / p.kg;
+            int ta = a0, tb = b0, tc = c0, cb = 0;                 // current tap (d, h, w) and channel block
             for (int g = 0; g < n_groups; ++g) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                const int kb0 = g * p.kg;
-                const int nkb = min(p.kg, p.n_kblocks - kb0);
+                const int nkb = min(p.kg, n_kb - g * p.kg);
                 if (leader) {
                     if (TB_DBG(p.dbg, 1)) {
                         mbar_arrive(&full_bar[s]);
                     } else {
                         mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * kb_bytes);
                         uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-                        int tap = kb0 / p.cin_blocks;
-                        int cb = kb0 - tap * p.cin_blocks;
                         for (int j = 0; j < nkb; ++j) {
-                            const int tkw = tap % p.kw;
-                            const int t2 = tap / p.kw;
-                            const int tkh = t2 % p.kh;
-                            const int tkd = t2 / p.kh;
+                            const int tap = (ta * p.kh + tb) * p.kw + tc;
                             uint8_t* base = st + static_cast<size_t>(j) * kb_bytes;
                             for (int mi = 0; mi < p.mt; ++mi) {
-                                tma_load_im2col_5d(base + mi * p.a_sub_bytes, &map_a, &full_bar[s],
-                                                   cb * p.kc, bw[mi], bh[mi], bd[mi], bn[mi],
-                                                   static_cast<uint16_t>(tkw), static_cast<uint16_t>(tkh),
-                                                   static_cast<uint16_t>(tkd));
-                                tma_load_im2col_5d(base + (p.mt + mi) * p.a_sub_bytes, &map_a, &full_bar[s],
-                                                   cb * p.kc, bw[mi], bh[mi], bd[mi],
-                                                   bn[mi] + p.lo_plane_frames, static_cast<uint16_t>(tkw),
-                                                   static_cast<uint16_t>(tkh), static_cast<uint16_t>(tkd));
+                                if (p.vox) {
+                                    tma_load_5d(base + mi * p.a_sub_bytes, &map_v, &full_bar[s], cb * p.kc, bw[mi] + tc,
+                                                bh[mi] + tb, bd[mi] + ta, bn[mi]);
+                                    tma_load_5d(base + (p.mt + mi) * p.a_sub_bytes, &map_v, &full_bar[s], cb * p.kc, bw[mi] + tc,
+                                                bh[mi] + tb, bd[mi] + ta, bn[mi] + p.lo_plane_frames);
+                                } else {
+                                    tma_load_im2col_5d(base + mi * p.a_sub_bytes, &map_a, &full_bar[s],
+                                                       cb * p.kc, bw[mi], bh[mi], bd[mi], bn[mi],
+                                                       static_cast<uint16_t>(tc), static_cast<uint16_t>(tb),
+                                                       static_cast<uint16_t>(ta));
+                                    tma_load_im2col_5d(base + (p.mt + mi) * p.a_sub_bytes, &map_a, &full_bar[s],
+                                                       cb * p.kc, bw[mi], bh[mi], bd[mi],
+                                                       bn[mi] + p.lo_plane_frames, static_cast<uint16_t>(tc),
+                                                       static_cast<uint16_t>(tb), static_cast<uint16_t>(ta));
+                                }
                             }
                             uint8_t* wb = base + 2 * p.mt * p.a_sub_bytes;
                             const int kcoord = tap * p.cin_pad + cb * p.kc;
@@ -431,7 +480,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                                 tma_load_2d(wb + p.w_sub_bytes, &map_w, &full_bar[s], kcoord,
                                             p.w_lo_rows + n_idx * p.n_tile);
                             }
-                            if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+                            if (++cb == p.cin_blocks) {
+                                cb = 0;
+                                if (++tc > c1) { tc = c0; if (++tb > b1) { tb = b0; ++ta; } }
+                            }
                         }
                     }
                 }
@@ -469,13 +521,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         uint32_t acc_ph = 0;
         if (leader && q < n_iss)
         for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+            const int n_kb = p.vox ? vox_decode(p, tile / p.n_tiles).n_kb : n_kblocks;
+            const int n_groups = (n_kb + kg - 1) / kg;
             mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
             tc_fence_after();
             uint32_t accumulate = 0;
             for (int g = 0; g < n_groups; ++g) {
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const int nkb = min(kg, n_kblocks - g * kg);
+                const int nkb = min(kg, n_kb - g * kg);
                 const uint32_t stage16 = (smem_base16 + static_cast<uint32_t>(s) * (stage_bytes >> 4)) | lo_flags;
                 // this thread's sub-tiles: its own when each has an issuer, otherwise all of them
                 for (int sub = q; sub < mt && !skip; sub += n_iss) {
@@ -517,9 +571,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
             for (int mi = 0; mi < p.mt && !TB_DBG(p.dbg, 4); ++mi) {
-                const int64_t m = (p.cluster2 ? static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank))
-                                              : static_cast<int64_t>(m_ct * p.mt + mi)) * 128 + row_in_tile;
-                const bool row_ok = m < p.m_total && !TB_DBG(p.dbg, 8);
+                int64_t m = (p.cluster2 ? static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank))
+                                        : static_cast<int64_t>(m_ct * p.mt + mi)) * 128 + row_in_tile;
+                bool row_ok = m < p.m_total && !TB_DBG(p.dbg, 8);
+                if (p.vox) {                           // row = frame, at the tile's voxel
+                    const int n_vox = p.Do * p.Ho * p.Wo;
+                    const int fb = m_ct / n_vox;
+                    const int frame = (fb * p.mt + mi) * 128 + row_in_tile;
+                    m = static_cast<int64_t>(frame) * n_vox + (m_ct - fb * n_vox);
+                    row_ok = frame < p.vox_frames && !TB_DBG(p.dbg, 8);
+                }
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                        static_cast<uint32_t>((acc * p.mt + mi) * p.acc_cols);
                 for (int c = half; c < chunks; c += 2) {
