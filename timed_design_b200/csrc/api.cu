@@ -1179,6 +1179,24 @@ static int launch_pair_instance(const CUtensorMap& map_a, const CUtensorMap& map
     return 0;
 }
 
+// Voxel-stationary tiles (ConvKernelParams::vox) for the im2col kernels: worth it when the taps skipped in the zero
+// padding outweigh the frames a partial last block of 256 (128 for single-sub-tile configurations) wastes.
+// `valid_out`: fraction of the filter taps that fall inside the volume, averaged over the output voxels.
+static bool vox_tiles(const ConvPlan& p, const ConvPlan::Config& cfg, int64_t n_frames, double* valid_out) {
+    if (cfg.cluster2 || p.tap2n || p.wfold || getenv("TIMED_B200_NO_VOX")) return false;
+    const int vox_rows = cfg.pair ? 256 : 128 * cfg.mt;
+    const double valid = valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]) *
+                         valid_tap_fraction(p.Wi, p.Wo, p.kw, p.pad0[2]);
+    if (valid_out) *valid_out = valid;
+    const int64_t fblocks = (n_frames + vox_rows - 1) / vox_rows;
+    const double rows_ratio = static_cast<double>(fblocks * vox_rows) / static_cast<double>(n_frames);
+    // every output voxel keeps at least its centre tap
+    const bool centre_ok = p.pad0[0] < p.kd && p.pad0[1] < p.kh && p.pad0[2] < p.kw && p.Do <= p.Di && p.Ho <= p.Hi &&
+                           p.Wo <= p.Wi;
+    return centre_ok && (valid * rows_ratio < 0.93 || getenv("TIMED_B200_FORCE_VOX")) &&
+           fblocks * p.Do * p.Ho * p.Wo * p.n_tiles < (1ll << 30);
+}
+
 // Launch one conv over `n_frames` frames.  `in_base`: split tensor base (hi plane first);
 // `in_frames_alloc`: frames per plane in that allocation.
 // bytes of fp32 scratch (the Z matrix) a tap-to-N conv needs for n_frames
@@ -1212,24 +1230,12 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     if (rc) return rc;
     rc = encode_a_map(p, cfg, in_base, in_frames_alloc, p.cin_pad, &map_a);
     if (rc) return rc;
-    // Voxel-stationary tiles (ConvKernelParams::vox): worth it when the taps skipped in the zero padding outweigh the
-    // frames a partial last block of 256 (128 for single-sub-tile configurations) wastes
     CUtensorMap map_v = map_a;
-    bool vox = false;
     const int vox_rows = cfg.pair ? 256 : 128 * cfg.mt;          // frames per voxel-stationary tile
-    if (!cfg.cluster2 && !p.tap2n && !p.wfold && !getenv("TIMED_B200_NO_VOX")) {
-        const double valid = valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]) *
-                             valid_tap_fraction(p.Wi, p.Wo, p.kw, p.pad0[2]);
-        const int64_t fblocks = (n_frames + vox_rows - 1) / vox_rows;
-        const double rows_ratio = static_cast<double>(fblocks * vox_rows) / static_cast<double>(n_frames);
-        const bool centre_ok = p.pad0[0] < p.kd && p.pad0[1] < p.kh && p.pad0[2] < p.kw && p.pad0[0] < p.Di + 0 &&
-                               p.Do <= p.Di && p.Ho <= p.Hi && p.Wo <= p.Wi;
-        vox = centre_ok && (valid * rows_ratio < 0.93 || getenv("TIMED_B200_FORCE_VOX")) &&
-              fblocks * p.Do * p.Ho * p.Wo * p.n_tiles < (1ll << 30);
-        if (vox) {
-            rc = encode_a_vox_map(p, cfg, in_base, in_frames_alloc, &map_v);
-            if (rc) return rc;
-        }
+    const bool vox = vox_tiles(p, cfg, n_frames, nullptr);
+    if (vox) {
+        rc = encode_a_vox_map(p, cfg, in_base, in_frames_alloc, &map_v);
+        if (rc) return rc;
     }
 
     ConvKernelParams k;
@@ -2230,6 +2236,12 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
                 const int rc = choose_config(c, n_frames * c.Mo_d() * c.Mo_h() * c.Mo_w(), &cfg);
                 if (rc) return rc;
                 name = cfg.pair ? "conv_pair_kernel" : (cfg.cluster2 ? "conv_umma_kernel(cluster2)" : "conv_umma_kernel");
+                double valid = 1.0;
+                if (vox_tiles(c, cfg, n_frames, &valid)) {
+                    char buf[96];
+                    snprintf(buf, sizeof(buf), "(voxel-stationary tiles, valid taps %.3f)", valid);
+                    name += buf;
+                }
                 if (c.tap2n) name += c.fuse_head ? "+head_col2im_pool_softmax_kernel" : "+col2im_kernel";
             }
             break;

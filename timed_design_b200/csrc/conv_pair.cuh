@@ -58,12 +58,12 @@ __device__ __forceinline__ void tma_load_im2col_5d_pair(void* smem_dst, const CU
 }
 // tiled (not im2col) 5-D box: voxel-stationary tiles fetch {kc channels} x {128 frames} at one input voxel
 __device__ __forceinline__ void tma_load_5d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
-                                                 int32_t c, int32_t w, int32_t h, int32_t d, int32_t n) {
+                                                 int32_t c, int32_t w, int32_t h, int32_t d, int32_t n, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h),
-        "r"(d), "r"(n)
+        "r"(d), "r"(n), "l"(policy)
         : "memory");
 }
 // D[tmem, both CTAs] (+)= A * B, M = 256 over the pair; descriptors as (lo, shared hi) halves
@@ -173,6 +173,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
     if (warp == 0) {
         // =============================================================== TMA producer (both CTAs)
         const bool leader = elect_one();
+        const uint64_t pol_a = l2_policy_evict_last();
         int s = 0;
         uint32_t ph = 0;
         for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
@@ -214,9 +215,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                             const int tap = (ta * p.kh + tb) * p.kw + tc;
                             uint8_t* base = st + static_cast<size_t>(j) * kb_bytes;
                             if (p.vox) {
-                                tma_load_5d_pair(base, &map_v, &full_bar[s], cb * p.kc, bw + tc, bh + tb, bd + ta, nf);
+                                tma_load_5d_pair(base, &map_v, &full_bar[s], cb * p.kc, bw + tc, bh + tb, bd + ta, nf, pol_a);
                                 tma_load_5d_pair(base + p.a_sub_bytes, &map_v, &full_bar[s], cb * p.kc, bw + tc, bh + tb, bd + ta,
-                                                 nf + p.lo_plane_frames);
+                                                 nf + p.lo_plane_frames, pol_a);
                             } else {
                                 tma_load_im2col_5d_pair(base, &map_a, &full_bar[s], cb * p.kc, bw, bh, bd, nf,
                                                         static_cast<uint16_t>(tc), static_cast<uint16_t>(tb),

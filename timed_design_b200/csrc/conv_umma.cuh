@@ -150,7 +150,9 @@ __device__ __forceinline__ void umma_bf16_lohi(bool leader, uint32_t d_tmem, uin
 
 // 256-bit global store (STG.256, sm_100): `dst` must be 32-byte aligned
 __device__ __forceinline__ void st_global_256(void* dst, const uint32_t (&r)[8]) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(r[0]), "r"(r[1]),
+    // evict-first in L2: a conv output is GBs per step and is not read again before it has been evicted anyway, while the
+    // input planes and weights the other tiles still need should stay
+    asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(r[0]), "r"(r[1]),
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
@@ -298,12 +300,18 @@ __device__ __forceinline__ VoxTile vox_decode(const ConvKernelParams& p, int m_c
     return v;
 }
 // tiled (not im2col) 5-D box: {kc channels} x {128 frames} at one input voxel
+// (L2 evict-last: a voxel's frames are re-read by up to 27 taps x the N tiles of neighbouring voxel tiles)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c, int32_t w,
-                                            int32_t h, int32_t d, int32_t n) {
+                                            int32_t h, int32_t d, int32_t n, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n)
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "l"(policy)
         : "memory");
 }
 
@@ -401,6 +409,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         // =============================================================== TMA producer
         // The whole warp walks the loops (uniform control flow); one elected lane issues.
         const bool leader = elect_one();
+        const uint64_t pol_a = l2_policy_evict_last();
         int s = 0;
         uint32_t ph = 0;
         for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
@@ -451,9 +460,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                             for (int mi = 0; mi < p.mt; ++mi) {
                                 if (p.vox) {
                                     tma_load_5d(base + mi * p.a_sub_bytes, &map_v, &full_bar[s], cb * p.kc, bw[mi] + tc,
-                                                bh[mi] + tb, bd[mi] + ta, bn[mi]);
+                                                bh[mi] + tb, bd[mi] + ta, bn[mi], pol_a);
                                     tma_load_5d(base + (p.mt + mi) * p.a_sub_bytes, &map_v, &full_bar[s], cb * p.kc, bw[mi] + tc,
-                                                bh[mi] + tb, bd[mi] + ta, bn[mi] + p.lo_plane_frames);
+                                                bh[mi] + tb, bd[mi] + ta, bn[mi] + p.lo_plane_frames, pol_a);
                                 } else {
                                     tma_load_im2col_5d(base + mi * p.a_sub_bytes, &map_a, &full_bar[s],
                                                        cb * p.kc, bw[mi], bh[mi], bd[mi], bn[mi],
