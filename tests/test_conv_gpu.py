@@ -152,6 +152,35 @@ def test_pair_mode_small_shapes(case, monkeypatch):
         assert np.abs(y - y_single).max() <= 1e-4 * np.abs(ref).max()
 
 
+VOX_CASES = [
+    # name, frames, side, c_in, c_out, k, padding          kernel the planner picks
+    ("vox_pair_c256_n512", 300, 6, 256, 512, 3, "same"),   # conv_pair: 2 blocks of 256 frames, the second 17 % full
+    ("vox_pair_k5_c128_n256", 130, 5, 128, 256, 5, "same"),  # 5^3 filter on 5^3 voxels: 8 .. 125 valid taps per voxel
+    ("vox_umma_c64_n128", 260, 6, 64, 128, 3, "same"),     # conv_umma, N-folded, two sub-tiles of 128 frames
+    ("vox_umma_even_k2", 140, 4, 64, 96, 2, "same"),       # even filter: padding on the far side only
+]
+
+
+@pytest.mark.parametrize("case", VOX_CASES, ids=lambda c: c[0])
+def test_voxel_stationary_tiles_are_bit_identical(case, monkeypatch):
+    """Voxel-stationary tiles (ConvKernelParams::vox: the rows of a tile are frames at ONE output voxel, and filter taps
+    that fall into the zero padding are skipped) must give the same BITS as the im2col tiling -- a skipped tap would have
+    added exact zeros and the others keep their order -- and agree with the fp64 oracle."""
+    name, n, side, ci, co, k, padding = case
+    rng = np.random.default_rng(abs(hash(name)) % 2 ** 31)
+    x = rng.standard_normal((n, side, side, side, ci)).astype(np.float32)
+    w = (rng.standard_normal((k, k, k, ci, co)) * np.sqrt(2.0 / (k ** 3 * ci))).astype(np.float32)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    monkeypatch.setenv("TIMED_B200_NO_VOX", "1")
+    y_im2col = run_conv_gpu(x, w, bias=b, padding=padding, act1="elu")
+    monkeypatch.delenv("TIMED_B200_NO_VOX")
+    monkeypatch.setenv("TIMED_B200_FORCE_VOX", "1")
+    y_vox = run_conv_gpu(x, w, bias=b, padding=padding, act1="elu")
+    np.testing.assert_array_equal(y_vox, y_im2col)
+    ref = ko.np_activation(ko.np_conv3d(x[-2:].astype(np.float64), w.astype(np.float64), b.astype(np.float64), padding), "elu")
+    assert np.abs(y_vox[-2:] - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
 SLAB_CASES = [
     ("slab_c32_n64_11_many", 40, 11, 32, 64, 3, "same"),
     ("slab_c64_n128_13", 3, 13, 64, 128, 3, "same"),

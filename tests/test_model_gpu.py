@@ -194,3 +194,21 @@ def test_fused_head_matches_unfused_bit_for_bit(classes, monkeypatch):
     assert m2.launches_per_forward == m.launches_per_forward + (2 if classes == 20 else 1)
     np.testing.assert_array_equal(fused, unfused)
     assert np.abs(fused - ko.forward_torch(cfg, w, X)).max() <= PROB_TOL
+
+
+@pytest.mark.gpu
+def test_voxel_stationary_tiles_do_not_change_the_probabilities(monkeypatch):
+    """256 frames per pass is where the wide convs switch to voxel-stationary tiles (skip the taps in the zero padding):
+    same bits as the im2col tiling, whatever the pass size."""
+    from timed_design_b200.model import Model
+    cfg, w = standins.timed_standin(20)
+    X = standins.synthetic_frames(600, seed=12)
+    m = Model(cfg, w)
+    a = m.predict(X, batch_size=4096)                     # passes of 512 + 88 frames: the first with voxel-stationary tiles
+    monkeypatch.setenv("TIMED_B200_NO_VOX", "1")
+    b = m.predict(X, batch_size=4096)
+    monkeypatch.delenv("TIMED_B200_NO_VOX")
+    c = m.predict(X, batch_size=100)                      # six passes, none reaches 256 frames
+    m.close()
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a, c)

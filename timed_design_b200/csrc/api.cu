@@ -2371,18 +2371,16 @@ int timed_b200_graph_predict_host(tb_graph* g, const void* h_frames, int32_t fra
     // double-buffered: H2D of chunk i+1 overlaps the forward of chunk i
     const uint8_t* src = static_cast<const uint8_t*>(h_frames);
     int it = 0;
-    // chunk sizes ramp up by 1.5x (chunk/8, 3/16, 9/32, ... chunk): only the first, small copy is not hidden.  Doubling
-    // stalled the pipeline -- a float32 frame takes 0.69x as long to copy (55 GB/s) as to compute, so the copy of a chunk
-    // twice the size of the running one finishes 38 % late (2 ms per 4096 frames, profiles/r2f e2e by host dtype)
-    // behind a forward.  The ramp never exceeds `chunk`: the staging buffers and the workspace are sized for it, and the
-    // caller's batch_size bound holds for every pass.
-    int64_t cur = n_frames > chunk ? std::min<int64_t>(chunk, std::max<int64_t>(64, chunk / 8)) : chunk;
-    // Passes of 512 frames and more are whole multiples of 256: the wide convs tile 256 frames per voxel (conv_pair.cuh)
-    auto next_pass = [&](int64_t c) {
-        c = std::min(chunk, c + c / 2);
-        return c >= 512 && c < chunk ? c & ~static_cast<int64_t>(255) : c;
-    };
-    for (int64_t f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++it, cur = next_pass(cur)) {
+    // Uniform passes of min(chunk, 512) frames.  Exposed are the first pass's copy and the last pass's forward, so passes
+    // should be small; 512 = two 256-frame blocks of the voxel-stationary conv tiles keeps the kernels efficient.  Measured
+    // with TIMED-20 at 214 k frames/s on the device (tools/gpu_e2e_chunks.sh, float32 / float16 / uint8 host frames):
+    // uniform 512: 191.5 / 197.9 / 204.4 k frames/s; uniform 256: 190.0 / 196.1 / 199.1; uniform 1024: 179.6 / 195.0 / 201.8;
+    // the 1.5x ramp this replaces (128 -> 1024, tuned when a forward took 1.45x the copy of its frames): 183.9 / 196.4 / 195.1.
+    // A pass never exceeds `chunk`: the staging buffers and the workspace are sized for it, and the caller's batch_size
+    // bound holds for every pass.
+    int64_t cur = std::min<int64_t>(chunk, 512);
+    if (const char* e = getenv("TIMED_B200_PASS_FRAMES")) cur = std::max<int64_t>(1, std::min<int64_t>(chunk, atoll(e)));   // A/B
+    for (int64_t f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++it) {
         const int b = it & 1;
         nf = std::min(cur, n_frames - f0);
         TB_REQUIRE(nf > 0 && nf <= chunk, "internal: predict_host chunk exceeds the staged size");
