@@ -212,3 +212,32 @@ def test_voxel_stationary_tiles_do_not_change_the_probabilities(monkeypatch):
     m.close()
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(a, c)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("side,k,cin,classes", [(6, 3, 64, 20), (5, 2, 48, 338), (4, 3, 20, 7)])
+def test_linear_head_conv_gap_collapse(side, k, cin, classes, monkeypatch):
+    """A head conv WITHOUT activation followed by GlobalAveragePooling is evaluated as box sums of its input + one dense GEMM
+    (the average commutes with the conv, ConvPlan::gap_collapse): same probabilities as convolving every voxel
+    (TIMED_B200_NO_GAPFOLD) and as the oracle.  TIMED's own head has ELU + BatchNorm before the pooling and keeps the
+    per-voxel path."""
+    from timed_design_b200.model import Model
+    b = standins._Builder(f"linear_head_{side}_{k}_{cin}_{classes}", (side, side, side, 6), 21,
+                          standins.synthetic_frames(4, side, 6, seed=99))
+    x = b.conv3d(b.input_name, cin, 3, "same")
+    x = b.bn(b.elu(x))
+    x = b.conv3d(x, classes, k, "same")                    # linear head
+    x = b.softmax(b.gap(x))
+    cfg, w = b.finish(x)
+    X = standins.synthetic_frames(70, side=side, seed=5)
+    m = Model(cfg, w)
+    p = m.predict(X)
+    kernels = [m.op_kernel(i, 70) for i in range(len(m.graph.ops))]
+    monkeypatch.setenv("TIMED_B200_NO_GAPFOLD", "1")
+    m2 = Model(cfg, w)
+    p2 = m2.predict(X)
+    m.close(); m2.close()
+    ref = ko.forward_torch(cfg, w, X)
+    assert np.abs(p - ref).max() <= PROB_TOL
+    assert np.abs(p - p2).max() <= 2e-5
+    assert any("gap_boxsum_kernel" in kk for kk in kernels), kernels

@@ -188,6 +188,12 @@ struct ConvPlan {
     // pooling and the softmax run as ONE launch after the GEMM (head_col2im_pool_softmax_kernel) straight into `probs`
     bool fuse_head = false;
     int head_is_avg = 1;
+    // network head, linear conv -> GlobalAveragePooling -> (Softmax): the average commutes with the conv, so the launch is a
+    // box sum of the input per filter tap (gap_boxsum_kernel), ONE dense GEMM over K = taps*cin (`dense`, a 1x1x1 plan over
+    // the same DHWIO weights) and the softmax -- D*H*W times fewer MMAs than convolving every voxel
+    bool gap_collapse = false;
+    bool gap_softmax = false;        // the Softmax that follows runs in this launch too (else: pooled logits are the output)
+    ConvPlan* dense = nullptr;       // owned
     int taps_eff() const { return tap2n ? (t2n_kw ? kw : t2n_w ? kd * kh : 1) : (wfold ? kd * kh : kd * kh * kw); }
     // geometry of the GEMM rows (output pixels, or input pixels for tap-to-N)
     int Mo_d() const { return tap2n && !t2n_w ? Di : Do; }
@@ -214,6 +220,11 @@ struct ConvPlan {
 };
 
 static void free_conv_plan(ConvPlan& p) {
+    if (p.dense) {
+        free_conv_plan(*p.dense);
+        delete p.dense;
+        p.dense = nullptr;
+    }
     cudaFree(p.d_w);
     cudaFree(p.d_bias);
     cudaFree(p.d_scale);
@@ -1201,13 +1212,57 @@ static bool vox_tiles(const ConvPlan& p, const ConvPlan::Config& cfg, int64_t n_
 // `in_frames_alloc`: frames per plane in that allocation.
 // bytes of fp32 scratch (the Z matrix) a tap-to-N conv needs for n_frames
 static size_t conv_scratch_bytes(const ConvPlan& p, int64_t n_frames) {
+    if (p.gap_collapse)       // box sums (split planes) + pooled logits
+        return static_cast<size_t>(round_up64(2 * n_frames * p.dense->cin_pad * 2, 1024) +
+                                   round_up64(n_frames * round_up(p.cout, 4) * 4, 1024));
     if (!p.tap2n) return 0;
     return static_cast<size_t>(round_up64(n_frames * p.Mo_d() * p.Mo_h() * p.Mo_w() * static_cast<int64_t>(p.z_ld) * 4, 1024));
 }
 
 static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames,
                        const TView& final_out, cudaStream_t stream, void* scratch = nullptr,
-                       size_t scratch_bytes = 0, const TensorInfo* out_info = nullptr) {
+                       size_t scratch_bytes = 0, const TensorInfo* out_info = nullptr);
+
+// Linear head conv -> GlobalAveragePooling (-> Softmax), collapsed (ConvPlan::gap_collapse).  `in_base`: the conv's input,
+// split NDHWC planes; `final_out`: (frames, classes) fp32 -- probabilities, or pooled logits without the softmax.
+static int gap_head_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames, const TView& final_out,
+                           cudaStream_t stream, void* scratch, size_t scratch_bytes) {
+    TB_REQUIRE(scratch && scratch_bytes >= conv_scratch_bytes(p, n_frames), "head: scratch too small");
+    ConvPlan& d = *p.dense;
+    const int64_t s_plane = n_frames * d.cin_pad;                          // elements per split plane of the box sums
+    __nv_bfloat16* S = static_cast<__nv_bfloat16*>(scratch);
+    float* logits = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + round_up64(2 * s_plane * 2, 1024));
+    const int taps = p.kd * p.kh * p.kw;
+    if (d.cin_pad != taps * p.cin) TB_CHECK_CUDA(cudaMemsetAsync(S, 0, static_cast<size_t>(2 * s_plane) * 2, stream));
+    BoxSumParams b;
+    b.D = p.Di; b.H = p.Hi; b.W = p.Wi; b.c_pad = p.cin_pad; b.cin = p.cin;
+    b.kd = p.kd; b.kh = p.kh; b.kw = p.kw; b.pd = p.pad0[0]; b.ph = p.pad0[1]; b.pw = p.pad0[2];
+    b.Do = p.Do; b.Ho = p.Ho; b.Wo = p.Wo;
+    b.k_pad = d.cin_pad;
+    b.inv_n = 1.0f / static_cast<float>(static_cast<int64_t>(p.Do) * p.Ho * p.Wo);
+    b.in_lo_off = in_frames_alloc * p.Di * p.Hi * p.Wi * static_cast<int64_t>(p.cin_pad);
+    b.out_lo_off = s_plane;
+    const int64_t work = n_frames * ((p.cin + 1) / 2);
+    gap_boxsum_kernel<<<grid_for(work, 128), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(in_base), S, n_frames, b);
+    TB_CHECK_CUDA(cudaGetLastError());
+    TView lv{};
+    lv.fmt = FMT_F32;
+    lv.f32 = p.gap_softmax ? logits : final_out.f32;
+    lv.ld = p.gap_softmax ? round_up(p.cout, 4) : final_out.ld;
+    lv.c = lv.c_pad = p.cout;
+    int rc = conv_launch(d, S, n_frames, n_frames, lv, stream);
+    if (rc) return rc;
+    if (p.gap_softmax) {
+        softmax_kernel<<<static_cast<unsigned>((n_frames * 32 + 255) / 256), 256, 0, stream>>>(lv, final_out, n_frames);
+        TB_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames,
+                       const TView& final_out, cudaStream_t stream, void* scratch,
+                       size_t scratch_bytes, const TensorInfo* out_info) {
+    if (p.gap_collapse) return gap_head_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream, scratch, scratch_bytes);
     if (p.slab) return slab_launch(p, in_base, n_frames, final_out, stream);
     if (p.thinz) return thinz_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream, out_info);
     if (p.thin) return thin_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream);
@@ -1874,6 +1929,34 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
             const int i = ops[j].inputs[0];
             ConvPlan& c = g->ops[i].conv;
             const size_t smem = (static_cast<size_t>(c.Do) * c.Ho * c.Wo * c.cout + c.cout) * sizeof(float);
+            // linear conv -> average pooling: collapse to box sums + one dense GEMM (ConvPlan::gap_collapse)
+            const TensorInfo& hin = g->tensors[ops[i].inputs[0]];
+            if (getenv("TIMED_B200_VERBOSE"))
+                fprintf(stderr, "head: op %d conv=%d readers=%d act=%d/%d pool_kind=%d k=%d,%d,%d slab=%d thin=%d thinz=%d wfold=%d "
+                        "in fmt=%d cpv=%d padvol=%d wfold=%d view_of=%d\n", i, ops[i].op == TB_OP_CONV3D, readers(i), ops[i].act1,
+                        ops[i].act2, ops[j].pool_kind, c.kd, c.kh, c.kw, c.slab, c.thin, c.thinz, c.wfold, hin.fmt, hin.cpv,
+                        hin.padvol, hin.wfold, hin.view_of);
+            if (ops[i].op == TB_OP_CONV3D && readers(i) == 1 && ops[i].act1 == ACT_NONE && ops[i].act2 == ACT_NONE &&
+                ops[j].pool_kind == 1 && c.kd <= 3 && c.kh <= 3 && c.kw <= 3 && c.kd * c.kh * c.kw > 1 && !c.slab && !c.thin &&
+                !c.thinz && !c.wfold && hin.fmt == FMT_SPLIT && !hin.cpv && !hin.padvol && !hin.wfold &&
+                hin.view_of < 0 && !getenv("TIMED_B200_NO_GAPFOLD")) {
+                tb_op_desc d2 = ops[i];
+                d2.kernel[0] = d2.kernel[1] = d2.kernel[2] = 1;
+                d2.pad_same = 0;
+                const int k_dense = c.kd * c.kh * c.kw * c.cin;             // DHWIO read as (taps * cin, cout)
+                ConvPlan* dn = new ConvPlan;
+                dn->precise = c.precise;
+                const int rc = conv_plan_create(*dn, d2, 1, 1, 1, k_dense, round_up(k_dense, 16));
+                if (rc) { delete dn; return rc; }
+                c.dense = dn;
+                c.gap_collapse = c.gap_softmax = true;
+                cudaFree(c.d_w);                                            // the per-voxel conv's packed weights are not used
+                c.d_w = nullptr;
+                g->launches += 3 - (c.tap2n ? 2 : 1);                       // box sums, dense GEMM, softmax
+                g->ops[j].pool_softmax = false;
+                g->ops[j].skip = true;
+                g->launches -= 1;
+            } else
             if (ops[i].op == TB_OP_CONV3D && c.tap2n && readers(i) == 1 && c.cout % 4 == 0 && c.z_ld % 4 == 0 &&
                 smem <= kHeadSmemMax && g->tensors[i].fmt == FMT_F32) {
                 c.fuse_head = true;
@@ -1950,7 +2033,7 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
         const tb_op_desc& d = node.d;
         const TensorInfo& t = g->tensors[i];
         TView out = tensor_view(g, L, i, base, n_frames);
-        if (i == n_ops - 1 || node.pool_softmax || (d.op == TB_OP_CONV3D && node.conv.fuse_head)) {
+        if (i == n_ops - 1 || node.pool_softmax || (d.op == TB_OP_CONV3D && (node.conv.fuse_head || node.conv.gap_collapse))) {
             // the graph output (or the op that computes it in a fused head) goes straight to the caller's buffer
             out.f32 = d_probs;
             out.ld = g->n_classes;
@@ -2228,7 +2311,8 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
     switch (node.d.op) {
         case TB_OP_CONV3D: {
             const ConvPlan& c = node.conv;
-            if (c.slab) name = "slab_conv_kernel";
+            if (c.gap_collapse) name = "gap_boxsum_kernel+conv_umma_kernel(dense over taps*cin)+softmax_kernel";
+            else if (c.slab) name = "slab_conv_kernel";
             else if (c.thinz) name = c.fuse_pool ? "thinz_conv_kernel(+maxpool)" : c.fuse_zpool ? "thinz_conv_kernel(+z-maxpool)" : "thinz_conv_kernel";
             else if (c.thin) name = "thin_conv_kernel";
             else {

@@ -696,6 +696,101 @@ __global__ void head_pool_softmax_kernel(TView in, int n_pix, int is_avg, float*
     }
 }
 
+// ------------------------------------------------------------------ linear head conv + GlobalAveragePooling, collapsed
+// mean_p conv(x)[p] = bias + sum_tap W_tap . S_tap,  S_tap = (1/P) sum_{p : p + tap - pad inside the volume} x[p + tap - pad]:
+// the average over the output voxels commutes with a conv that has no activation, so the head needs one box sum of the
+// input per filter tap (this kernel) and ONE (frames x taps*C_in) x (taps*C_in x classes) GEMM instead of a conv over every
+// voxel -- D*H*W times fewer MMAs.  A thread owns two channels of one frame; the box sums are separable: row sums over x for
+// the kw ranges, folded over y into the (kh, kw) ranges of a plane, folded over z.  Filter extents <= 3.
+// Output: split bf16 planes, row = frame, column = tap * cin + c (the K order of the DHWIO kernel read as a dense layer).
+struct BoxSumParams {
+    int32_t D, H, W, c_pad, cin;
+    int32_t kd, kh, kw, pd, ph, pw;      // filter extents, padding before
+    int32_t Do, Ho, Wo;
+    int32_t k_pad;                       // columns per output row (>= taps * cin, zero padded by the caller)
+    float inv_n;                         // 1 / (Do * Ho * Wo)
+    int64_t in_lo_off, out_lo_off;       // element offset of the lo plane
+};
+__global__ void gap_boxsum_kernel(const __nv_bfloat16* __restrict__ in_hi, __nv_bfloat16* __restrict__ out_hi,
+                                  int64_t n_frames, BoxSumParams p) {
+    const int pairs = (p.cin + 1) >> 1;
+    const int64_t total = n_frames * pairs;
+    // first / last input coordinate each tap touches, per axis
+    int lo_d[3], hi_d[3], lo_h[3], hi_h[3], lo_w[3], hi_w[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        lo_d[t] = max(0, t - p.pd); hi_d[t] = min(p.D - 1, p.Do - 1 + t - p.pd);
+        lo_h[t] = max(0, t - p.ph); hi_h[t] = min(p.H - 1, p.Ho - 1 + t - p.ph);
+        lo_w[t] = max(0, t - p.pw); hi_w[t] = min(p.W - 1, p.Wo - 1 + t - p.pw);
+    }
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t f = idx / pairs;
+        const int c = 2 * static_cast<int>(idx - f * pairs);
+        const bool two = c + 1 < p.cin;
+        float acc[3][3][3][2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int w = 0; w < 3; ++w) acc[a][b][w][0] = acc[a][b][w][1] = 0.f;
+        const __nv_bfloat16* src = in_hi + f * p.D * p.H * p.W * static_cast<int64_t>(p.c_pad) + c;
+        for (int z = 0; z < p.D; ++z) {
+            float py[3][3][2];
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int w = 0; w < 3; ++w) py[b][w][0] = py[b][w][1] = 0.f;
+            for (int y = 0; y < p.H; ++y) {
+                float r[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+                const __nv_bfloat16* row = src + (static_cast<int64_t>(z) * p.H + y) * p.W * p.c_pad;
+                for (int x = 0; x < p.W; ++x, row += p.c_pad) {
+                    // c is even and c_pad a multiple of 16: the pair is 4-byte aligned (the odd tail channel of an odd cin
+                    // reads a zero pad channel)
+                    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(row);
+                    const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(row + p.in_lo_off);
+                    const float v0 = __low2float(h2) + __low2float(l2), v1 = __high2float(h2) + __high2float(l2);
+#pragma unroll
+                    for (int w = 0; w < 3; ++w)
+                        if (w < p.kw && x >= lo_w[w] && x <= hi_w[w]) { r[w][0] += v0; r[w][1] += v1; }
+                }
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+                    if (b < p.kh && y >= lo_h[b] && y <= hi_h[b]) {
+#pragma unroll
+                        for (int w = 0; w < 3; ++w) { py[b][w][0] += r[w][0]; py[b][w][1] += r[w][1]; }
+                    }
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                if (a < p.kd && z >= lo_d[a] && z <= hi_d[a]) {
+#pragma unroll
+                    for (int b = 0; b < 3; ++b)
+#pragma unroll
+                        for (int w = 0; w < 3; ++w) { acc[a][b][w][0] += py[b][w][0]; acc[a][b][w][1] += py[b][w][1]; }
+                }
+        }
+        __nv_bfloat16* dst = out_hi + f * static_cast<int64_t>(p.k_pad) + c;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    if (a >= p.kd || b >= p.kh || w >= p.kw) continue;
+                    const int tap = (a * p.kh + b) * p.kw + w;
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(acc[a][b][w][0] * p.inv_n, h0, l0);
+                    split_bf16(acc[a][b][w][1] * p.inv_n, h1, l1);
+                    __nv_bfloat16* o = dst + static_cast<int64_t>(tap) * p.cin;
+                    o[0] = h0;
+                    o[p.out_lo_off] = l0;
+                    if (two) { o[1] = h1; o[1 + p.out_lo_off] = l1; }
+                }
+    }
+}
+
 // ------------------------------------------------------------------ softmax over channels
 // one warp per row; max-subtracted, fp32 (Keras Softmax / activation='softmax').
 __global__ void softmax_kernel(TView in, TView out, int64_t n_rows) {

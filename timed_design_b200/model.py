@@ -123,8 +123,8 @@ class Model:
 
     def op_kernel(self, op_index: int, n_frames: int) -> str:
         """Name of the CUDA kernel(s) fused op `op_index` launches at this batch size."""
-        buf = C.create_string_buffer(96)
-        _lib.check(_lib.load().timed_b200_graph_op_kernel(self._h, int(op_index), int(n_frames), buf, 96))
+        buf = C.create_string_buffer(160)
+        _lib.check(_lib.load().timed_b200_graph_op_kernel(self._h, int(op_index), int(n_frames), buf, 160))
         return buf.value.decode()
 
     def close(self) -> None:
