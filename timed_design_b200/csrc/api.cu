@@ -194,6 +194,7 @@ struct ConvPlan {
     bool gap_collapse = false;
     bool gap_softmax = false;        // the Softmax that follows runs in this launch too (else: pooled logits are the output)
     ConvPlan* dense = nullptr;       // owned
+    int32_t* d_progress = nullptr;   // completed-tile counter of the voxel-stationary pair kernel (ConvKernelParams::progress)
     int taps_eff() const { return tap2n ? (t2n_kw ? kw : t2n_w ? kd * kh : 1) : (wfold ? kd * kh : kd * kh * kw); }
     // geometry of the GEMM rows (output pixels, or input pixels for tap-to-N)
     int Mo_d() const { return tap2n && !t2n_w ? Di : Do; }
@@ -220,6 +221,8 @@ struct ConvPlan {
 };
 
 static void free_conv_plan(ConvPlan& p) {
+    cudaFree(p.d_progress);
+    p.d_progress = nullptr;
     if (p.dense) {
         free_conv_plan(*p.dense);
         delete p.dense;
@@ -1302,6 +1305,13 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     if (vox) {
         k.vox = 1;
         k.vox_frames = static_cast<int32_t>(n_frames);
+        const int window = getenv("TIMED_B200_TILE_WINDOW") ? atoi(getenv("TIMED_B200_TILE_WINDOW")) : 148;   // two rounds of 74 pairs
+        if (cfg.pair && window > 0) {
+            if (!p.d_progress) TB_CHECK_CUDA(cudaMalloc(&p.d_progress, sizeof(int32_t)));
+            TB_CHECK_CUDA(cudaMemsetAsync(p.d_progress, 0, sizeof(int32_t), stream));
+            k.progress = p.d_progress;
+            k.window = window;
+        }
         k.Di = p.Di; k.Hi = p.Hi; k.Wi = p.Wi;
         k.n_ctile_m = static_cast<int32_t>(((n_frames + vox_rows - 1) / vox_rows) * p.Do * p.Ho * p.Wo);
     }

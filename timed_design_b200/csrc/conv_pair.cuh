@@ -201,6 +201,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             }
             const int n_groups = (n_kb + p.kg - 1) / p.kg;
             const int w_row0 = n_idx * p.n_tile + static_cast<int>(cta_rank) * half_rows;
+            if (p.progress) {                      // do not run more than `window` tiles ahead of the completed count
+                if (leader) {
+                    uint32_t spins = 0;
+                    while (ld_acquire_gpu(p.progress) < tile - p.window) {
+                        __nanosleep(256);
+                        if (++spins > (1u << 24)) { printf("timed_b200: tile throttle timed out (block %d)\n", blockIdx.x); __trap(); }
+                    }
+                }
+                __syncwarp();
+            }
             int ta = a0, tb = b0, tc = c0, cb = 0;                 // current tap (d, h, w) and channel block
             for (int g = 0; g < n_groups; ++g) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -328,6 +338,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                 uint64_t* bar = &tempty_bar[acc];
                 epilogue_drained<ACT1, ACT2, FMT>(p, tbase, half, chunks, n_idx * p.n_tile, m, row_ok, bias_v, scale_v,
                                                   shift_v, [&] { if (lane == 0) mbar_arrive_cluster(bar, 0); });
+                if (p.progress && leader_cta && warp == kPairEpilogueWarp0 && lane == 0) atomicAdd(p.progress, 1);
                 if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
                 continue;
             }
@@ -345,6 +356,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+            if (p.progress && leader_cta && warp == kPairEpilogueWarp0 && lane == 0) atomicAdd(p.progress, 1);
             if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
     }

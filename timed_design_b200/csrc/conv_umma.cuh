@@ -96,6 +96,13 @@ struct ConvKernelParams {
     // n_ctile_m = frame blocks x output voxels (tile -> m_ct -> (frame block, voxel)).
     int32_t vox;
     int32_t vox_frames;       // frames in this launch
+    // Throttle for the static round-robin over tiles of UNEQUAL cost (8 .. 27 taps): no CTA pair starts tile t before
+    // `*progress` >= t - window tiles have been completed (any pair's).  A pair that runs ahead would otherwise idle at the end
+    // of the kernel; idling earlier costs nothing and keeps the tiles in flight within ~3 rounds, i.e. within the input planes
+    // the L2 can hold.  The pair that owns the lowest unfinished tile is never held, so this cannot
+    // deadlock.  nullptr: off.
+    int32_t* progress;
+    int32_t window;
     int32_t Di, Hi, Wi;       // input extents (validity of a tap: 0 <= out + lc + tap < in)
     // ---- bring-up / tuning only (env TIMED_B200_DBG): 1 = skip TMA loads, 2 = skip MMA issue,
     // 4 = skip epilogue math+stores.  Results are garbage; used to time each role in isolation.
