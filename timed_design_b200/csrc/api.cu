@@ -1207,7 +1207,12 @@ static bool vox_tiles(const ConvPlan& p, const ConvPlan::Config& cfg, int64_t n_
     // every output voxel keeps at least its centre tap
     const bool centre_ok = p.pad0[0] < p.kd && p.pad0[1] < p.kh && p.pad0[2] < p.kw && p.Do <= p.Di && p.Ho <= p.Hi &&
                            p.Wo <= p.Wi;
-    return centre_ok && (valid * rows_ratio < 0.93 || getenv("TIMED_B200_FORCE_VOX")) &&
+    // A tile's operand boxes are frame-strided, so their reuse across neighbouring voxels has to come from the L2: the
+    // kd input planes x vox_rows frames a z-plane of tiles touches (hi + lo) must fit (measured up to 57 MB: TIMED-338's
+    // 512-channel head at 6^3); large volumes stay on the im2col tiling, whose rows are contiguous in memory
+    const double live_bytes = static_cast<double>(p.kd) * p.Hi * p.Wi * vox_rows * p.cin_pad * 4.0;
+    const bool l2_ok = live_bytes <= 64e6 || getenv("TIMED_B200_FORCE_VOX");
+    return centre_ok && l2_ok && (valid * rows_ratio < 0.93 || getenv("TIMED_B200_FORCE_VOX")) &&
            fblocks * p.Do * p.Ho * p.Wo * p.n_tiles < (1ll << 30);
 }
 
