@@ -1310,8 +1310,9 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     if (vox) {
         k.vox = 1;
         k.vox_frames = static_cast<int32_t>(n_frames);
-        const int window = getenv("TIMED_B200_TILE_WINDOW") ? atoi(getenv("TIMED_B200_TILE_WINDOW")) : 148;   // two rounds of 74 pairs
-        if (cfg.pair && window > 0) {
+        // two rounds of the persistent grid: 74 CTA pairs, or 148 CTAs
+        const int window = (getenv("TIMED_B200_TILE_WINDOW") ? atoi(getenv("TIMED_B200_TILE_WINDOW")) : 148) * (cfg.pair ? 1 : 2);
+        if (window > 0) {
             if (!p.d_progress) TB_CHECK_CUDA(cudaMalloc(&p.d_progress, sizeof(int32_t)));
             TB_CHECK_CUDA(cudaMemsetAsync(p.d_progress, 0, sizeof(int32_t), stream));
             k.progress = p.d_progress;

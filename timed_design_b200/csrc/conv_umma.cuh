@@ -451,6 +451,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                 }
             }
             const int n_groups = (n_kb + p.kg - 1) / p.kg;
+            if (p.progress) {                      // do not run more than `window` tiles ahead of the completed count
+                if (leader) {
+                    uint32_t spins = 0;
+                    while (ld_acquire_gpu(p.progress) < tile - p.window) {
+                        __nanosleep(256);
+                        if (++spins > (1u << 24)) { printf("timed_b200: tile throttle timed out (block %d)\n", blockIdx.x); __trap(); }
+                    }
+                }
+                __syncwarp();
+            }
             int ta = a0, tb = b0, tc = c0, cb = 0;                 // current tap (d, h, w) and channel block
             for (int g = 0; g < n_groups; ++g) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -623,6 +633,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (p.progress && warp == 2 && lane == 0) atomicAdd(p.progress, 1);
             if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
     }
