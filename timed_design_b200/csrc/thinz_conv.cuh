@@ -413,20 +413,25 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) xm[i] = ((neg8 >> i) & 1u) << 31;
                         float v[8];
-#pragma unroll
-                        for (int pl = 0; pl < 2; ++pl) {
-                            if (pl == 1 && !two) break;
+                        {
+                            // both planes' loads in flight before the one wait (the phase is bound by TMEM round trips)
                             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                                   static_cast<uint32_t>(acc * p.acc_cols + (2 * zp + pl) * 2 * p.n_tile);
-                            uint32_t rv[8], rc[8];
+                                                   static_cast<uint32_t>(acc * p.acc_cols + 2 * zp * 2 * p.n_tile + unit * 8);
+                            uint32_t rv0[8], rc0[8], rv1[8], rc1[8];
                             __syncwarp();
-                            tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(unit * 8), rv);
-                            tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(p.n_tile + unit * 8), rc);
+                            tmem_ld_32x32b_x8(tbase, rv0);
+                            tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(p.n_tile), rc0);
+                            if (two) {
+                                tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(2 * p.n_tile), rv1);
+                                tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(3 * p.n_tile), rc1);
+                            }
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float x = __uint_as_float(__float_as_uint(__uint_as_float(rv[i]) + __uint_as_float(rc[i])) ^ xm[i]);
-                                v[i] = pl == 0 ? x : fmaxf(v[i], x);
+                                const float x0 = __uint_as_float(__float_as_uint(__uint_as_float(rv0[i]) + __uint_as_float(rc0[i])) ^ xm[i]);
+                                v[i] = x0;
+                                if (two)
+                                    v[i] = fmaxf(x0, __uint_as_float(__float_as_uint(__uint_as_float(rv1[i]) + __uint_as_float(rc1[i])) ^ xm[i]));
                             }
                         }
                         const int srow = (u0 + quad * 32 + lane) & 255;
