@@ -156,7 +156,9 @@ def test_fused_conv_maxpool_epilogue(side, c1, pool_pad, relu, monkeypatch):
     unfused = Model(cfg, w).predict(X)
     for got in (fused, zfused, unfused):
         assert np.abs(got - ref).max() <= PROB_TOL
-    assert np.abs(fused - unfused).max() <= 2e-6 and np.abs(zfused - unfused).max() <= 2e-6
+    # (the fused instantiation accumulates the bf16-split corrections in the main TMEM columns, the others in their own:
+    # the same products summed in a different order)
+    assert np.abs(fused - unfused).max() <= 5e-6 and np.abs(zfused - unfused).max() <= 2e-6
 
 
 @pytest.mark.gpu

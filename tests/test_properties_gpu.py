@@ -99,6 +99,26 @@ def test_device_resident_forward_matches_host_path(timed):
         m.forward_device(d, probs, small_ws)
 
 
+@pytest.mark.parametrize("n", [5, 40, 300])
+def test_results_do_not_depend_on_workspace_contents(timed, n):
+    """The caller's workspace is scratch: whatever it holds on entry -- here 0xFF bytes, i.e. NaN patterns in every bf16 /
+    fp32 slot, then zeros -- the probabilities are the same bits.  (Round 2 finding: the thin first-layer kernels multiply
+    one never-written pixel behind the last frame by a zero weight; 0 x NaN poisoned the last frame's row.)"""
+    import torch
+    _, _, m = timed
+    X = standins.synthetic_frames(n, seed=31)
+    host = m.predict(X)
+    d = torch.from_numpy(X).cuda()
+    probs = torch.empty((n, 20), dtype=torch.float32, device="cuda")
+    ws = torch.empty(m.workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    for fill in (255, 0, 127):
+        ws.fill_(fill)
+        probs.fill_(float("nan"))
+        m.forward_device(d, probs, ws, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(probs.cpu().numpy(), host)
+
+
 def test_wfold_and_dense_input_layouts_agree(monkeypatch):
     """The W-folded first-layer path and the generic im2col path are two routes to the same conv."""
     import subprocess

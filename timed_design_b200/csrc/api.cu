@@ -168,6 +168,7 @@ struct ConvPlan {
     int pool_same = 0, pool_Zo = 0, pool_Po = 0, pool_Qo = 0;
     bool thinz = false;              // kd taps folded into N (thinz_conv.cuh)
     ThinZParams thinz_params;
+    size_t thinz_merged_off = 0, thinz_merged_bytes = 0;   // the fused-pool instantiation's weight layout inside d_thin_w
     ThinConvParams thin_params;      // static part, completed per launch
     uint8_t* d_thin_w = nullptr;
     bool tap2n = false;
@@ -773,6 +774,16 @@ static bool thinz_geometry(int kd, int kh, int kw, int cout, int Wp, ThinZGeom* 
     g.n_steps = kh * (kw / 2) + ((kw & 1) ? (kh + 1) / 2 : 0);
     g.b1_rows = kd * 2 * n_tile;
     g.b2_rows = (2 * kd - 1) * n_tile;
+    if (pool) {
+        // fused max-pool instantiation: corrections accumulate in the MAIN columns (three MMAs of N = cnt*n_tile per step
+        // instead of N-folded two; a conv this thin has <= ~45 MMAs per output, so the truncation they add is < 1e-6): the
+        // epilogue -- which paces this kernel -- reads half the TMEM, and the accumulators of a tile take half the columns,
+        // so there are four stages instead of two between the MMA issuers and the epilogue
+        g.acc_cols = round_up(g.zt * n_tile, 32);
+        const int st = 512 / g.acc_cols;
+        g.acc_stages = st >= 4 ? 4 : st >= 2 ? 2 : 1;
+        g.b1_rows = g.b2_rows = kd * n_tile;                      // [W_hi slices] and [W_lo slices]
+    }
     g.w_bytes = static_cast<size_t>(g.n_steps) * 2 * 16 * (g.b1_rows + g.b2_rows);
     const int span_pix = (128 + (kh - 1) * Wp + kw + 1 + 1) & ~1;   // window + filter extent + the aliased next pixel
     g.span_bytes = span_pix * 16;
@@ -830,10 +841,35 @@ static int thinz_plan_create(ConvPlan& p, const tb_op_desc& d, const TensorInfo&
                     }
             }
         }
+    // the fused max-pool instantiation's layout (thinz_geometry(pool)): per step [W_hi: 2 K-chunks][kd*n_tile rows][8] then
+    // [W_lo: the same]; appended to the same allocation, selected at launch
+    const size_t m_rows = static_cast<size_t>(p.kd) * n_tile;
+    const size_t m_step = 2 * 2 * m_rows * 8;
+    const size_t m_off = (w.size() + 63) & ~static_cast<size_t>(63);           // 128-byte aligned
+    w.resize(m_off + m_step * g.n_steps, __float2bfloat16(0.0f));
+    for (int sidx = 0; sidx < g.n_steps; ++sidx)
+        for (int hsel = 0; hsel < 2; ++hsel) {
+            const Half h = hsel ? steps[sidx].second : steps[sidx].first;
+            if (h.row < 0) continue;
+            __nv_bfloat16* bh = w.data() + m_off + sidx * m_step + static_cast<size_t>(hsel) * m_rows * 8;
+            __nv_bfloat16* bl = bh + 2 * m_rows * 8;
+            for (int blk = 0; blk < p.kd; ++blk) {
+                const int tap = ((p.kd - 1 - blk) * p.kh + h.row) * p.kw + h.kwi;
+                for (int c = 0; c < p.cin; ++c)
+                    for (int n = 0; n < p.cout; ++n) {
+                        const float v = d.kernel_w[(static_cast<size_t>(tap) * p.cin + c) * p.cout + n];
+                        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                        bh[(static_cast<size_t>(blk) * n_tile + n) * 8 + c] = hi;
+                        bl[(static_cast<size_t>(blk) * n_tile + n) * 8 + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+                    }
+            }
+        }
     TB_CHECK_CUDA(cudaMalloc(&p.d_thin_w, w.size() * sizeof(__nv_bfloat16)));
     TB_CHECK_CUDA(cudaMemcpy(p.d_thin_w, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     t.w_packed = p.d_thin_w;
-    t.w_bytes = static_cast<uint32_t>(w.size() * 2);
+    t.w_bytes = static_cast<uint32_t>(m_off * 2);
+    p.thinz_merged_off = m_off * 2;
+    p.thinz_merged_bytes = m_step * g.n_steps * 2;
     t.n_steps = g.n_steps;
     t.b1_rows = g.b1_rows; t.b2_rows = g.b2_rows;
     t.zt = g.zt;
@@ -880,6 +916,12 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
         ThinZGeom zg;
         TB_REQUIRE(thinz_geometry(k.kd, k.kh, k.kw, p.cout, k.Wp, &zg, true), "internal: fused pool does not fit");
         k.stages = zg.stages;
+        k.acc_cols = zg.acc_cols;
+        k.acc_stages = zg.acc_stages;
+        k.b1_rows = zg.b1_rows; k.b2_rows = zg.b2_rows;
+        k.w_packed = p.d_thin_w + p.thinz_merged_off;
+        k.w_bytes = static_cast<uint32_t>(p.thinz_merged_bytes);
+        TB_REQUIRE(zg.w_bytes == p.thinz_merged_bytes, "internal: thinz merged weight size");
         k.pool_same = p.pool_same;
         k.Zo = p.pool_Zo; k.Po = p.pool_Po; k.Qo = p.pool_Qo;
         k.pool_cpv = out_info->cpv ? 1 : 0;
@@ -905,6 +947,10 @@ static int thinz_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int
     e.ldc = out.ld;
     e.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
     e.acc_comp = 1.0f;                     // <= 42 MMAs per accumulator: the shrink is below 1e-6
+    if (p.fuse_pool)                       // corrections share the main columns: 3 MMAs per step and filter slice
+        e.acc_comp = accum_comp(3.0 * p.kd * k.n_steps,
+                                valid_tap_fraction(p.Di, p.Do, p.kd, p.pad0[0]) * valid_tap_fraction(p.Hi, p.Ho, p.kh, p.pad0[1]) *
+                                    valid_tap_fraction(p.Wi, p.Wo, p.kw, p.pad0[2]));
     k.dbg = debug_mask();
     TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
                "thinz conv: split output channel padding mismatch");
@@ -2018,6 +2064,13 @@ static void launch_input_convert_padvol(const void* x, const TensorInfo& t, int6
     input_convert_padvol_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
         static_cast<const T*>(x), n_frames, t.D, t.H, t.W, t.C, t.pv_d0, t.pv_h0, t.pv_w0, t.pv_Dp, t.pv_Hp,
         t.pv_Wp, out.hi, out.lo);
+    // The thin kernels pair a partner-less odd filter tap with the NEXT stored pixel under a zero weight: for the last
+    // valid output of the last frame that pixel is the first one of the slack frame behind the volume, which nobody
+    // writes -- and 0 x NaN is NaN, so a workspace that happens to hold NaN bit patterns there would poison one row.
+    // Zero the head of the slack frame in both planes (the allocation holds at least one slack frame, TensorInfo::frames_alloc).
+    const size_t head = static_cast<size_t>(std::min<int64_t>(64, t.stored_pix_per_frame())) * t.c_pad * sizeof(__nv_bfloat16);
+    cudaMemsetAsync(out.hi + total * t.c_pad, 0, head, s);
+    cudaMemsetAsync(out.lo + total * t.c_pad, 0, head, s);
 }
 
 template <typename T>

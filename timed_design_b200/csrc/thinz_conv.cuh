@@ -94,8 +94,8 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
 
     __shared__ __align__(8) uint64_t full_bar[kConvMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kConvMaxStages];
-    __shared__ __align__(8) uint64_t tfull_bar[2];
-    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ __align__(8) uint64_t tfull_bar[4];
+    __shared__ __align__(8) uint64_t tempty_bar[4];
     __shared__ __align__(8) uint64_t w_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_epi[3][128];
@@ -110,7 +110,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], kThinzEpiWarps);
         }
@@ -210,7 +210,7 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
         // are two issuers: warp 1 takes the even tiles of this CTA's sequence (stage 0), the last warp the odd ones (stage 1),
         // so the two streams never touch the same accumulator or input stage -- every output keeps a fixed accumulation
         // order -- and one fills the other's issue gaps (tools/mma_pattern_probe.cu: 193 -> 176 cycles per step pair).
-        const int n_iss = (acc_stages == 2 && p.issuers == 2) ? 2 : 1;
+        const int n_iss = (acc_stages >= 2 && (acc_stages & 1) == 0 && p.issuers == 2) ? 2 : 1;
         const int q = warp == 1 ? 0 : 1;
         int s = q, acc = q;                                   // stages >= 2
         uint32_t ph = 0, acc_ph = 0;
@@ -239,6 +239,38 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                     const uint32_t d_lo2 = d_lo + n_tile;
                     const uint32_t idesc1 = umma_idesc_bf16_m128(cnt * n2);
                     const uint32_t idesc2 = umma_idesc_bf16_m128(cnt * n2 - n_tile);
+                    if constexpr (POOL == 1) {
+                        // corrections into the main columns (see thinz_geometry): per step A_hi x W_hi, A_hi x W_lo, A_lo x W_hi,
+                        // each N = cnt * n_tile on the same accumulator columns; blocks [W_hi][W_lo] of kd*n_tile rows each
+                        const uint32_t rowm = static_cast<uint32_t>(kd - 1 - (i - j_lo)) * n_tile;
+                        const uint32_t dm = d_tile + static_cast<uint32_t>(j_lo) * n_tile;
+                        const uint32_t idm = umma_idesc_bf16_m128(cnt * n_tile);
+                        uint32_t bh = (w_base16 + rowm) | (b1_lbo << 16);
+                        uint32_t bl = (w_base16 + 2u * b1_lbo + rowm) | (b1_lbo << 16);
+                        const uint32_t stepm16 = 4u * b1_lbo;
+                        int st = 0;
+                        if (i < zt_eff) {
+                            // output plane i gets its first contribution (kd' = 0, the last W_hi block)
+                            const uint32_t a_hi = a_plane + s_step_a[0];
+                            const uint32_t bfm = (w_base16 + static_cast<uint32_t>(kd - 1) * n_tile) | (b1_lbo << 16);
+                            umma_bf16_desc(true, d_tile + static_cast<uint32_t>(i) * n_tile, a_hi, desc_hi, bfm, desc_hi,
+                                           umma_idesc_bf16_m128(n_tile), 0u);
+                            if (cnt > 1)
+                                umma_bf16_desc(true, dm, a_hi, desc_hi, bh, desc_hi, umma_idesc_bf16_m128((cnt - 1) * n_tile), 1u);
+                            umma_bf16_desc(true, dm, a_hi, desc_hi, bl, desc_hi, idm, 1u);
+                            umma_bf16_desc(true, dm, a_hi + plane16, desc_hi, bh, desc_hi, idm, 1u);
+                            bh += stepm16;
+                            bl += stepm16;
+                            st = 1;
+                        }
+                        for (; st < n_steps; ++st, bh += stepm16, bl += stepm16) {
+                            const uint32_t a_hi = a_plane + s_step_a[st];
+                            umma_bf16_desc(true, dm, a_hi, desc_hi, bh, desc_hi, idm, 1u);
+                            umma_bf16_desc(true, dm, a_hi, desc_hi, bl, desc_hi, idm, 1u);
+                            umma_bf16_desc(true, dm, a_hi + plane16, desc_hi, bh, desc_hi, idm, 1u);
+                        }
+                        continue;
+                    }
                     uint32_t b1 = (w_base16 + row0) | (b1_lbo << 16);
                     uint32_t b2 = (w_base16 + 2u * b1_lbo + row0) | (b2_lbo << 16);
                     int st = 0;
@@ -265,8 +297,8 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
             umma_commit(&tfull_bar[acc]);
             s += n_iss;
             if (s >= stages) { s -= stages; ph ^= 1u; }
-            if (n_iss == 2) acc_ph ^= 1u;                      // this issuer's stage, used every iteration
-            else if (++acc == acc_stages) { acc = 0; acc_ph ^= 1u; }
+            acc += n_iss;                                      // this issuer's accumulator stages: q, q + n_iss, ...
+            if (acc >= acc_stages) { acc -= acc_stages; acc_ph ^= 1u; }
         }
         }
         __syncwarp();
@@ -415,23 +447,20 @@ thinz_conv_kernel(const __grid_constant__ ThinZParams p) {
                         float v[8];
                         {
                             // both planes' loads in flight before the one wait (the phase is bound by TMEM round trips)
+                            // (this instantiation accumulates the corrections in the main columns: plane j at column j * n_tile)
                             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                                   static_cast<uint32_t>(acc * p.acc_cols + 2 * zp * 2 * p.n_tile + unit * 8);
-                            uint32_t rv0[8], rc0[8], rv1[8], rc1[8];
+                                                   static_cast<uint32_t>(acc * p.acc_cols + 2 * zp * p.n_tile + unit * 8);
+                            uint32_t rv0[8], rv1[8];
                             __syncwarp();
                             tmem_ld_32x32b_x8(tbase, rv0);
-                            tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(p.n_tile), rc0);
-                            if (two) {
-                                tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(2 * p.n_tile), rv1);
-                                tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(3 * p.n_tile), rc1);
-                            }
+                            if (two) tmem_ld_32x32b_x8(tbase + static_cast<uint32_t>(p.n_tile), rv1);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float x0 = __uint_as_float(__float_as_uint(__uint_as_float(rv0[i]) + __uint_as_float(rc0[i])) ^ xm[i]);
-                                v[i] = x0;
-                                if (two)
-                                    v[i] = fmaxf(x0, __uint_as_float(__float_as_uint(__uint_as_float(rv1[i]) + __uint_as_float(rc1[i])) ^ xm[i]));
+                                // acc_comp > 0 undoes the accumulator's truncation shrink (conv_umma.cuh); a positive factor
+                                // commutes with the maximum
+                                const float x0 = __uint_as_float(rv0[i] ^ xm[i]) * p.epi.acc_comp;
+                                v[i] = two ? fmaxf(x0, __uint_as_float(rv1[i] ^ xm[i]) * p.epi.acc_comp) : x0;
                             }
                         }
                         const int srow = (u0 + quad * 32 + lane) & 255;
