@@ -558,8 +558,10 @@ def main():
     traffic, traffic_source = None, None
     tp = ROOT / "profiles" / "r2p_dominant_kernel_ncu.json"
     if tp.exists() and args.config == "timed20" and B == 4096:
-        traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
-        traffic_source = f"from profile ({tp.relative_to(ROOT)}: one ncu --set full capture of this kernel at this batch), not measured in this run"
+        prof = json.loads(tp.read_text())
+        traffic = prof.get("dram_bytes_per_launch")
+        traffic_source = (f"from profile ({tp.relative_to(ROOT)}: {prof.get('source', 'ncu capture of this kernel at this batch')}), "
+                          f"not measured in this run")
     top_kernel = model.op_kernel(top["index"], chunk)
     mv = re.search(r"valid taps ([0-9.]+)", top_kernel)
     valid_taps = float(mv.group(1)) if mv else 1.0
