@@ -282,3 +282,36 @@ def test_tap_to_n_kw_in_n_variant(shape, monkeypatch):
     assert y_w.shape == y_direct.shape
     assert np.abs(y_w[:1] - ref).max() <= 1e-4 * np.abs(ref).max()
     assert np.abs(y_w - y_direct).max() <= 5e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("shape", [(3, 21, 128, 32, "linear"), (3, 9, 128, 32, "relu"), (5, 6, 64, 16, "elu"), (2, 7, 128, 32, "linear"),
+                                   (2, 11, 64, 32, "relu"), (1, 21, 160, 32, "linear")],
+                         ids=lambda s: f"n{s[0]}_s{s[1]}_c{s[2]}_n{s[3]}_{s[4]}")
+def test_col2im_over_kw_in_the_epilogue_is_bit_identical(shape, monkeypatch):
+    """kw-in-N tap-to-N convs with kw = 3, 'same', C_out = 16 / 32 (DenseCPD's growth convs) sum the three kw-shifted
+    column groups inside the GEMM epilogue on tiles of whole volume rows (ConvKernelParams::c2i) instead of writing the Z
+    matrix and launching col2im_kernel: same operations in the same order, so the two routes must agree to the last bit --
+    at tile seams (side 21: 6 rows per tile, tiles straddle planes and frames), lane-quadrant seams, the last partial tile,
+    and with the layer's bias / activation / BatchNorm affine applied by the GEMM epilogue.  And both against the oracle."""
+    n, side, ci, co, act = shape
+    rng = np.random.default_rng(side * ci + co)
+    x = rng.standard_normal((n, side, side, side, ci)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 3, ci, co)) * np.sqrt(2.0 / (27 * ci))).astype(np.float32)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, co).astype(np.float32)
+    sh = (rng.standard_normal(co) * 0.2).astype(np.float32)
+    monkeypatch.setenv("TIMED_B200_TAP2N_W", "1")
+    monkeypatch.setenv("TIMED_B200_TAP2N_MARGIN", "100")         # take the variant whatever the cost model says
+    y_fused = run_conv_gpu(x, w, bias=b, scale=sc, shift=sh, padding="same", act1=act)
+    monkeypatch.setenv("TIMED_B200_NO_C2I_FUSE", "1")
+    y_z = run_conv_gpu(x, w, bias=b, scale=sc, shift=sh, padding="same", act1=act)
+    assert y_fused.shape == y_z.shape == (n, side, side, side, co)
+    if act == "elu":        # the GEMM epilogue's branch-free ELU (SFU exp / series) vs col2im_kernel's expm1f: ~1e-7 apart
+        assert np.abs(y_fused - y_z).max() <= 1e-6
+    else:
+        assert np.array_equal(y_fused, y_z)
+    ref = ko.np_conv3d(x[:1].astype(np.float64), w.astype(np.float64), b.astype(np.float64), "same")
+    if act != "linear":
+        ref = ko.np_activation(ref, act)
+    ref = ref * sc + sh
+    assert np.abs(y_fused[:1] - ref).max() <= 1e-4 * np.abs(ref).max()

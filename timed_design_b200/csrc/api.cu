@@ -185,6 +185,11 @@ struct ConvPlan {
     // (96 for DenseCPD's 128 -> 32 growth convs: two N-folded MMAs of N = 192 / 96 per K step instead of N = 64 / 32 -- the
     // thin-N MMAs cost the same ~72 cycles -- for a Z matrix of only 384 bytes per pixel).
     bool t2n_w = false;
+    // t2n_w with kw = 3, 'same', C_out = 16 / 32: the col2im over kw runs in the GEMM's epilogue on tiles of whole volume
+    // rows (ConvKernelParams::c2i) -- no Z matrix in HBM, no col2im launch.  Not when the conv is the fused network head.
+    bool c2i = false;
+    int c2i_rows = 0;
+    bool c2i_active() const { return c2i && !fuse_head; }
     // network head: this tap-to-N conv is read only by GlobalPooling -> Softmax (the graph output): the col2im gather, the
     // pooling and the softmax run as ONE launch after the GEMM (head_col2im_pool_softmax_kernel) straight into `probs`
     bool fuse_head = false;
@@ -346,7 +351,7 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
     // wide tiles (no N-fold) of a precise graph: one M sub-tile, main and correction accumulators side by side
     const bool sep_corr = p.precise && !nfold && 2 * acc_cols <= 512;
     std::vector<int> mts;
-    if (!sep_corr && 2 * acc_cols <= 512 && static_cast<int64_t>(ceil_div(m_tiles, 2)) * p.n_tiles >= 2 * 148)
+    if (!sep_corr && !p.c2i_active() && 2 * acc_cols <= 512 && static_cast<int64_t>(ceil_div(m_tiles, 2)) * p.n_tiles >= 2 * 148)
         mts.push_back(2);
     mts.push_back(1);
     int best_score = INT_MIN;
@@ -1117,6 +1122,11 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
             p.t2n_w = variant == 2;
             p.z_cols = zc;
             p.z_ld = round_up(p.z_cols, 4);
+            if (p.t2n_w && p.kw == 3 && p.pad0[2] == 1 && p.Wo == p.Wi && (p.cout == 16 || p.cout == 32) && p.Wo <= 128 &&
+                !getenv("TIMED_B200_NO_C2I_FUSE")) {
+                const int rows = (128 / p.Wo) * p.Wo;        // whole rows of the volume per 128-row tile
+                if (rows >= 104) { p.c2i = true; p.c2i_rows = rows; }
+            }
         }
     }
     const int n_pad = round_up(p.gemm_n(), 16);
@@ -1154,18 +1164,20 @@ static int conv_plan_create(ConvPlan& p, const tb_op_desc& d, int Di, int Hi, in
     TB_CHECK_CUDA(cudaMemcpy(p.d_w, w.data(), 2 * plane * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     std::vector<float> b(p.n_alloc, 0.f), sc(p.n_alloc, 1.f), sh(p.n_alloc, 0.f);
     if (p.tap2n) {      // the GEMM epilogue is the identity; the col2im kernel applies bias/act/BN
-        std::vector<float> cb(p.cout, 0.f), cs(p.cout, 1.f), ch(p.cout, 0.f);
+        // n_alloc entries (identity past cout): the fused-col2im GEMM epilogue stages n_alloc of them
+        const int nv = std::max(p.cout, p.n_alloc);
+        std::vector<float> cb(nv, 0.f), cs(nv, 1.f), ch(nv, 0.f);
         for (int n = 0; n < p.cout; ++n) {
             if (d.bias) cb[n] = d.bias[n];
             if (d.scale) cs[n] = d.scale[n];
             if (d.shift) ch[n] = d.shift[n];
         }
-        TB_CHECK_CUDA(cudaMalloc(&p.d_c2i_bias, p.cout * sizeof(float)));
-        TB_CHECK_CUDA(cudaMalloc(&p.d_c2i_scale, p.cout * sizeof(float)));
-        TB_CHECK_CUDA(cudaMalloc(&p.d_c2i_shift, p.cout * sizeof(float)));
-        TB_CHECK_CUDA(cudaMemcpy(p.d_c2i_bias, cb.data(), p.cout * sizeof(float), cudaMemcpyHostToDevice));
-        TB_CHECK_CUDA(cudaMemcpy(p.d_c2i_scale, cs.data(), p.cout * sizeof(float), cudaMemcpyHostToDevice));
-        TB_CHECK_CUDA(cudaMemcpy(p.d_c2i_shift, ch.data(), p.cout * sizeof(float), cudaMemcpyHostToDevice));
+        TB_CHECK_CUDA(cudaMalloc(&p.d_c2i_bias, nv * sizeof(float)));
+        TB_CHECK_CUDA(cudaMalloc(&p.d_c2i_scale, nv * sizeof(float)));
+        TB_CHECK_CUDA(cudaMalloc(&p.d_c2i_shift, nv * sizeof(float)));
+        TB_CHECK_CUDA(cudaMemcpy(p.d_c2i_bias, cb.data(), nv * sizeof(float), cudaMemcpyHostToDevice));
+        TB_CHECK_CUDA(cudaMemcpy(p.d_c2i_scale, cs.data(), nv * sizeof(float), cudaMemcpyHostToDevice));
+        TB_CHECK_CUDA(cudaMemcpy(p.d_c2i_shift, ch.data(), nv * sizeof(float), cudaMemcpyHostToDevice));
     } else
     for (int n = 0; n < p.cout; ++n) {
         if (d.bias) b[n] = d.bias[n];
@@ -1269,7 +1281,7 @@ static size_t conv_scratch_bytes(const ConvPlan& p, int64_t n_frames) {
     if (p.gap_collapse)       // box sums (split planes) + pooled logits
         return static_cast<size_t>(round_up64(2 * n_frames * p.dense->cin_pad * 2, 1024) +
                                    round_up64(n_frames * round_up(p.cout, 4) * 4, 1024));
-    if (!p.tap2n) return 0;
+    if (!p.tap2n || p.c2i_active()) return 0;
     return static_cast<size_t>(round_up64(n_frames * p.Mo_d() * p.Mo_h() * p.Mo_w() * static_cast<int64_t>(p.z_ld) * 4, 1024));
 }
 
@@ -1321,7 +1333,8 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     if (p.thinz) return thinz_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream, out_info);
     if (p.thin) return thin_launch(p, in_base, in_frames_alloc, n_frames, final_out, stream);
     TView out = final_out;
-    if (p.tap2n) {
+    const bool c2i = p.c2i_active();
+    if (p.tap2n && !c2i) {
         TB_REQUIRE(scratch && scratch_bytes >= conv_scratch_bytes(p, n_frames), "conv: scratch too small");
         out = TView{};
         out.fmt = FMT_F32;
@@ -1353,6 +1366,15 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     const int m_tiles = static_cast<int>((m_total64 + 127) / 128);
     k.mt = cfg.mt;
     k.n_ctile_m = ceil_div(m_tiles, (cfg.cluster2 || cfg.pair) ? 2 : cfg.mt);   // cluster / pair mode: tiles are 256-row pair-tiles
+    if (c2i) {
+        TB_REQUIRE(cfg.mt == 1 && !cfg.cluster2 && !cfg.pair && p.n_tiles == 1 && p.n_tile == 3 * p.cout && p.c2i_rows > 0,
+                   "conv: fused col2im needs one 128-row sub-tile and N = 3 * C_out");
+        k.c2i = 1;
+        k.c2i_rows = p.c2i_rows;
+        k.c2i_w = p.Wo;
+        k.c2i_cout = p.cout;
+        k.n_ctile_m = static_cast<int32_t>((m_total64 + p.c2i_rows - 1) / p.c2i_rows);
+    }
     if (vox) {
         k.vox = 1;
         k.vox_frames = static_cast<int32_t>(n_frames);
@@ -1393,8 +1415,9 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
     k.row_bytes = cfg.kc * 2u;
     k.layout_type = cfg.swizzle_code;
     k.bias = p.d_bias; k.scale = p.d_scale; k.shift = p.d_shift;
+    if (c2i) { k.bias = p.d_c2i_bias; k.scale = p.d_c2i_scale; k.shift = p.d_c2i_shift; }   // the layer's own epilogue
     k.act1 = p.act1; k.act2 = p.act2; k.alpha1 = p.alpha1; k.alpha2 = p.alpha2;
-    if (p.tap2n) k.act1 = k.act2 = ACT_NONE;     // applied by the col2im kernel
+    if (p.tap2n && !c2i) k.act1 = k.act2 = ACT_NONE;     // applied by the col2im kernel
     k.out_fmt = out.fmt;
     k.out_f32 = out.f32; k.out_hi = out.hi; k.out_lo = out.lo;
     k.ldc = out.ld;
@@ -1451,7 +1474,7 @@ static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int6
                                     : launch_conv_instance<-1, -1, FMT_F32>(map_a, map_w, map_v, k, grid, cfg.smem_bytes, stream);
     if (rc) return rc;
     TB_CHECK_CUDA(cudaGetLastError());
-    if (p.tap2n) {
+    if (p.tap2n && !c2i) {
         Col2imParams cp;
         cp.Di = p.Mo_d(); cp.Hi = p.Mo_h(); cp.Wi = p.Mo_w(); cp.Do = p.Do; cp.Ho = p.Ho; cp.Wo = p.Wo;
         cp.kd = p.t2n_w ? 1 : p.kd; cp.kh = p.t2n_w ? 1 : p.kh;              // t2n_w: the GEMM already summed over (kd,kh)
@@ -1784,7 +1807,7 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 if (rc) return rc;
                 t.D = node.conv.Do; t.H = node.conv.Ho; t.W = node.conv.Wo; t.C = d.c_out;
                 g->flops += node.conv.flops_per_frame();
-                g->launches += node.conv.tap2n ? 2 : 1;
+                g->launches += (node.conv.tap2n && !node.conv.c2i) ? 2 : 1;     // GEMM + col2im, unless the col2im is in the epilogue
                 // thinz conv read only by a MaxPool(2,2,2; stride 2): the pooling runs in the conv epilogue and this
                 // op's tensor IS the pooled tensor (the pooling op becomes an alias of it)
                 // Round 1 staged ACTIVATED outputs over overlapping windows (+25 % MMA work) and measured neutral; round 2 pools
@@ -2014,13 +2037,14 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
                 c.gap_collapse = c.gap_softmax = true;
                 cudaFree(c.d_w);                                            // the per-voxel conv's packed weights are not used
                 c.d_w = nullptr;
-                g->launches += 3 - (c.tap2n ? 2 : 1);                       // box sums, dense GEMM, softmax
+                g->launches += 3 - ((c.tap2n && !c.c2i) ? 2 : 1);                       // box sums, dense GEMM, softmax
                 g->ops[j].pool_softmax = false;
                 g->ops[j].skip = true;
                 g->launches -= 1;
             } else
             if (ops[i].op == TB_OP_CONV3D && c.tap2n && readers(i) == 1 && c.cout % 4 == 0 && c.z_ld % 4 == 0 &&
                 smem <= kHeadSmemMax && g->tensors[i].fmt == FMT_F32) {
+                if (c.c2i) g->launches += 1;                                // the fused head takes the Z matrix route
                 c.fuse_head = true;
                 c.head_is_avg = ops[j].pool_kind;
                 g->ops[j].pool_softmax = false;
@@ -2395,7 +2419,7 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
                     snprintf(buf, sizeof(buf), "(voxel-stationary tiles, valid taps %.3f)", valid);
                     name += buf;
                 }
-                if (c.tap2n) name += c.fuse_head ? "+head_col2im_pool_softmax_kernel" : "+col2im_kernel";
+                if (c.tap2n) name += c.fuse_head ? "+head_col2im_pool_softmax_kernel" : c.c2i_active() ? "(col2im over kw in the epilogue)" : "+col2im_kernel";
             }
             break;
         }

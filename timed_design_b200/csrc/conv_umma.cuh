@@ -104,6 +104,16 @@ struct ConvKernelParams {
     int32_t* progress;
     int32_t window;
     int32_t Di, Hi, Wi;       // input extents (validity of a tap: 0 <= out + lc + tap < in)
+    // ---- col2im over kw in the epilogue (conv_umma_kernel, tap-to-N with the kw taps in N, kw = 3, 'same', stride 1):
+    // a tile is c2i_rows = (128 / Wo) * Wo consecutive output pixels, i.e. WHOLE rows of the volume, so the kw shift never
+    // leaves the tile: out[x] = Z[x-1][kw=0] + Z[x][kw=1] + Z[x+1][kw=2] is a lane shuffle of the accumulator chunks
+    // (plus one shared-memory exchange at the three lane-quadrant seams), and the layer's real epilogue (bias / act / BN /
+    // split) runs on the sum.  The (rows, kw*C_out) fp32 Z matrix never goes to HBM and the col2im kernel is not launched;
+    // same operations in the same order, so the results are bit-identical to GEMM + col2im_kernel.  mt = 1, C_out = 16 / 32.
+    int32_t c2i;
+    int32_t c2i_rows;
+    int32_t c2i_w;            // Wo
+    int32_t c2i_cout;
     // ---- bring-up / tuning only (env TIMED_B200_DBG): 1 = skip TMA loads, 2 = skip MMA issue,
     // 4 = skip epilogue math+stores.  Results are garbage; used to time each role in isolation.
     int32_t dbg;
@@ -436,7 +446,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             } else {
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi) {
-                    int m0 = p.cluster2 ? (m_ct * 2 + static_cast<int>(cta_rank)) * 128 : (m_ct * p.mt + mi) * 128;
+                    int m0 = p.cluster2 ? (m_ct * 2 + static_cast<int>(cta_rank)) * 128
+                           : p.c2i      ? m_ct * p.c2i_rows + mi * 128        // whole rows of the volume per tile
+                                        : (m_ct * p.mt + mi) * 128;
                     if (m0 >= p.m_total) m0 = 0;       // dummy sub-tile: rows are discarded later
                     const int q = m0 % p.Wo;
                     int t = m0 / p.Wo;
@@ -591,11 +603,90 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         const float* shift_v = epi_in_smem ? s_epi[2] : p.shift;
         int acc = 0;
         uint32_t acc_ph = 0;
+        int c2i_it = 0;
         for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
             const int m_ct = tile / p.n_tiles;
             const int n_idx = tile - m_ct * p.n_tiles;
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
+            if (p.c2i) {
+                // ---- col2im over kw on the accumulator (ConvKernelParams::c2i).  This warp: rows quad*32 .. +31, channels
+                // [16*half, 16*half + 16) of each of the three kw column groups.
+                // seam exchange buffers [tile parity][lane quadrant][column half][channel], aliased onto the unused tail of
+                // the staged epilogue vectors (n_alloc = 3 * C_out <= 96 of their 512 entries are in use; the static shared
+                // memory has no room left beside the 220 KB operand ring)
+                float (*s_left)[4][2][16] = reinterpret_cast<float (*)[4][2][16]>(&s_epi[0][256]);
+                float (*s_right)[4][2][16] = reinterpret_cast<float (*)[4][2][16]>(&s_epi[1][256]);
+                const int buf = c2i_it & 1;
+                ++c2i_it;
+                const bool active = half * 16 < p.c2i_cout;                // warp-uniform
+                const int64_t m = static_cast<int64_t>(m_ct) * p.c2i_rows + row_in_tile;
+                const bool row_ok = row_in_tile < p.c2i_rows && m < p.m_total && !TB_DBG(p.dbg, 8);
+                const int x = row_in_tile % p.c2i_w;                       // tiles start at x = 0
+                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                       static_cast<uint32_t>(acc * p.acc_cols);
+                const int corr = p.nfold ? p.n_tile : p.corr_off;
+                uint32_t z[3][16];
+                if (active) {
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < 3; ++t)
+                        tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(t * p.c2i_cout + half * 16), z[t]);
+                    if (corr) {
+                        uint32_t zc[3][16];
+#pragma unroll
+                        for (int t = 0; t < 3; ++t)
+                            tmem_ld_32x32b_x16(tbase + static_cast<uint32_t>(corr + t * p.c2i_cout + half * 16), zc[t]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int t = 0; t < 3; ++t)
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                z[t][i] = __float_as_uint(fmaf(__uint_as_float(z[t][i]), p.acc_comp, __uint_as_float(zc[t][i])));
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int t = 0; t < 3; ++t)
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) z[t][i] = __float_as_uint(__uint_as_float(z[t][i]) * p.acc_comp);
+                    }
+                }
+                // the accumulator stage is free again: the next tile's mainloop overlaps the exchange, math and stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (active) {
+                    if (lane == 31) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) s_left[buf][quad][half][i] = __uint_as_float(z[0][i]);
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) s_right[buf][quad][half][i] = __uint_as_float(z[2][i]);
+                    }
+                }
+                // all eight epilogue warps; the parity double buffer makes one barrier per tile enough (a warp that
+                // writes tile t+2's seams has passed tile t+1's barrier, which every reader of tile t's has reached)
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvEpilogueWarps) : "memory");
+                if (active && !TB_DBG(p.dbg, 4)) {
+                    uint32_t r[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float left = __shfl_up_sync(0xffffffffu, __uint_as_float(z[0][i]), 1);
+                        float right = __shfl_down_sync(0xffffffffu, __uint_as_float(z[2][i]), 1);
+                        if (lane == 0 && quad > 0) left = s_left[buf][quad - 1][half][i];
+                        if (lane == 31 && quad < 3) right = s_right[buf][quad + 1][half][i];
+                        float a = 0.0f;                                    // col2im_kernel's order: kw = 0, 1, 2
+                        if (x > 0) a += left;
+                        a += __uint_as_float(z[1][i]);
+                        if (x < p.c2i_w - 1) a += right;
+                        r[i] = __float_as_uint(a);
+                    }
+                    epilogue_chunk<ACT1, ACT2, FMT>(p, r, half * 16, m, row_ok, bias_v, scale_v, shift_v);
+                }
+                if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+                continue;
+            }
             for (int mi = 0; mi < p.mt && !TB_DBG(p.dbg, 4); ++mi) {
                 int64_t m = (p.cluster2 ? static_cast<int64_t>(m_ct * 2 + static_cast<int>(cta_rank))
                                         : static_cast<int64_t>(m_ct * p.mt + mi)) * 128 + row_in_tile;
