@@ -276,6 +276,10 @@ static double valid_tap_fraction(int in, int out, int k, int pad0) {
 static constexpr size_t kSmemDynamicMax = 220 * 1024;
 static constexpr size_t kHeadSmemMax = 96 * 1024;      // fused head: one frame's (pixels, classes) activation in shared memory
 static constexpr size_t kSmemBudget = kSmemDynamicMax - 1024;
+// conv_umma_kernel keeps its static shared memory under 2 KB (kUmmaEpiSmemN) and may use 225 KB of operand ring: exactly four
+// stages of the 56 KB k-blocks of DenseCPD's growth convs, which three stages left latency-bound
+static constexpr size_t kUmmaSmemDynamicMax = 225 * 1024;
+static constexpr size_t kUmmaSmemBudget = kUmmaSmemDynamicMax - 1024;
 
 // Pick (kc, mt, kg, stages) for a conv given the number of output rows.
 static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* cfg) {
@@ -362,9 +366,9 @@ static int choose_config(const ConvPlan& p, int64_t m_total, ConvPlan::Config* c
             const int n_kblocks = p.taps_eff() * (p.cin_pad / kc);
             int kg = std::max(1, 64 / kc);
             kg = std::min(kg, n_kblocks);
-            while (kg > 1 && kb * kg * 2 > kSmemBudget) --kg;
-            if (kb * kg * 2 > kSmemBudget) continue;   // cannot even double-buffer
-            int stages = static_cast<int>(std::min<size_t>(kConvMaxStages, kSmemBudget / (kb * kg)));
+            while (kg > 1 && kb * kg * 2 > kUmmaSmemBudget) --kg;
+            if (kb * kg * 2 > kUmmaSmemBudget) continue;   // cannot even double-buffer
+            int stages = static_cast<int>(std::min<size_t>(kConvMaxStages, kUmmaSmemBudget / (kb * kg)));
             // score: prefer >=3 stages, then mt=2, then wider kc; a single accumulator stage
             // serialises the epilogue with the mainloop, which only a long K loop amortises
             const int acc_stages_c = sep_corr ? 1 : std::min(2, 512 / (mt * acc_cols));
@@ -1202,7 +1206,7 @@ static int launch_conv_instance(const CUtensorMap& map_a, const CUtensorMap& map
     if (!attr_set) {
         TB_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<A1, A2, F>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(kSmemDynamicMax)));
+                                           static_cast<int>(kUmmaSmemDynamicMax)));
         attr_set = true;
     }
     if (k.cluster2) {

@@ -121,7 +121,11 @@ struct ConvKernelParams {
 
 #if defined(__CUDACC__)
 
-constexpr int kEpiSmemN = 512;   // epilogue vectors are staged in smem when n_alloc <= this
+constexpr int kEpiSmemN = 512;   // conv_pair_kernel: epilogue vectors are staged in smem when n_alloc <= this
+// conv_umma_kernel stages fewer: its static shared memory must stay under 2 KB so that FOUR 56 KB operand stages (DenseCPD's
+// growth convs: 128 x 64 A hi/lo + 96 x 64 W hi/lo) fit beside it -- with three, the 112 KB in flight covered ~55 % of the
+// L2 round trip and the tensor pipe idled the rest (profiles/r2c_densecpd_ncu_kernels.csv)
+constexpr int kUmmaEpiSmemN = 128;
 
 // ACT = -1 selects the runtime-dispatched activation (sigmoid/tanh/mixed cases).
 // ELU is branch-free: a divergent expm1f call per element made the epilogue as long as the
@@ -374,7 +378,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float s_epi[3][kEpiSmemN];
+    __shared__ __align__(16) float s_epi[3][kUmmaEpiSmemN];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -400,9 +404,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     const uint32_t cta_rank = p.cluster2 ? cluster_ctarank() : 0u;
     if (warp == 1) tmem_alloc_512(&tmem_base_slot);
     const int n_alloc = p.n_tiles * p.n_tile;
-    const bool epi_in_smem = n_alloc <= kEpiSmemN;
+    const bool epi_in_smem = n_alloc <= kUmmaEpiSmemN;
     if (epi_in_smem) {
-        for (int i = threadIdx.x; i < n_alloc; i += blockDim.x) {
+        for (int i = threadIdx.x; i < (p.c2i ? p.c2i_cout : n_alloc); i += blockDim.x) {
             s_epi[0][i] = p.bias[i];
             s_epi[1][i] = p.scale[i];
             s_epi[2][i] = p.shift[i];
@@ -603,7 +607,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         const float* shift_v = epi_in_smem ? s_epi[2] : p.shift;
         int acc = 0;
         uint32_t acc_ph = 0;
-        int c2i_it = 0;
         for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
             const int m_ct = tile / p.n_tiles;
             const int n_idx = tile - m_ct * p.n_tiles;
@@ -612,13 +615,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             if (p.c2i) {
                 // ---- col2im over kw on the accumulator (ConvKernelParams::c2i).  This warp: rows quad*32 .. +31, channels
                 // [16*half, 16*half + 16) of each of the three kw column groups.
-                // seam exchange buffers [tile parity][lane quadrant][column half][channel], aliased onto the unused tail of
-                // the staged epilogue vectors (n_alloc = 3 * C_out <= 96 of their 512 entries are in use; the static shared
-                // memory has no room left beside the 220 KB operand ring)
-                float (*s_left)[4][2][16] = reinterpret_cast<float (*)[4][2][16]>(&s_epi[0][256]);
-                float (*s_right)[4][2][16] = reinterpret_cast<float (*)[4][2][16]>(&s_epi[1][256]);
-                const int buf = c2i_it & 1;
-                ++c2i_it;
+                // seam exchange buffers [seam between quadrants s and s+1][column half][channel], aliased onto the tail of the
+                // staged epilogue vectors (C_out <= 32 of their 128 entries are in use; the static shared memory has no room
+                // left beside the operand ring)
+                float (*s_left)[2][16] = reinterpret_cast<float (*)[2][16]>(&s_epi[0][32]);     // last row of quadrant s, kw = 0
+                float (*s_right)[2][16] = reinterpret_cast<float (*)[2][16]>(&s_epi[1][32]);    // first row of quadrant s+1, kw = 2
                 const bool active = half * 16 < p.c2i_cout;                // warp-uniform
                 const int64_t m = static_cast<int64_t>(m_ct) * p.c2i_rows + row_in_tile;
                 const bool row_ok = row_in_tile < p.c2i_rows && m < p.m_total && !TB_DBG(p.dbg, 8);
@@ -656,34 +657,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (active) {
-                    if (lane == 31) {
+                    if (lane == 31 && quad < 3) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) s_left[buf][quad][half][i] = __uint_as_float(z[0][i]);
+                        for (int i = 0; i < 16; ++i) s_left[quad][half][i] = __uint_as_float(z[0][i]);
                     }
-                    if (lane == 0) {
+                    if (lane == 0 && quad > 0) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) s_right[buf][quad][half][i] = __uint_as_float(z[2][i]);
+                        for (int i = 0; i < 16; ++i) s_right[quad - 1][half][i] = __uint_as_float(z[2][i]);
                     }
                 }
-                // all eight epilogue warps; the parity double buffer makes one barrier per tile enough (a warp that
-                // writes tile t+2's seams has passed tile t+1's barrier, which every reader of tile t's has reached)
+                // all eight epilogue warps: seams written -> read ...
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvEpilogueWarps) : "memory");
-                if (active && !TB_DBG(p.dbg, 4)) {
-                    uint32_t r[16];
+                uint32_t r[16];
+                if (active) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float left = __shfl_up_sync(0xffffffffu, __uint_as_float(z[0][i]), 1);
                         float right = __shfl_down_sync(0xffffffffu, __uint_as_float(z[2][i]), 1);
-                        if (lane == 0 && quad > 0) left = s_left[buf][quad - 1][half][i];
-                        if (lane == 31 && quad < 3) right = s_right[buf][quad + 1][half][i];
+                        if (lane == 0 && quad > 0) left = s_left[quad - 1][half][i];
+                        if (lane == 31 && quad < 3) right = s_right[quad][half][i];
                         float a = 0.0f;                                    // col2im_kernel's order: kw = 0, 1, 2
                         if (x > 0) a += left;
                         a += __uint_as_float(z[1][i]);
                         if (x < p.c2i_w - 1) a += right;
                         r[i] = __float_as_uint(a);
                     }
-                    epilogue_chunk<ACT1, ACT2, FMT>(p, r, half * 16, m, row_ok, bias_v, scale_v, shift_v);
                 }
+                // ... and read -> the next tile's writes
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvEpilogueWarps) : "memory");
+                if (active && !TB_DBG(p.dbg, 4))
+                    epilogue_chunk<ACT1, ACT2, FMT>(p, r, half * 16, m, row_ok, bias_v, scale_v, shift_v);
                 if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
                 continue;
             }
