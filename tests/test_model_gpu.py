@@ -243,3 +243,30 @@ def test_linear_head_conv_gap_collapse(side, k, cin, classes, monkeypatch):
     assert np.abs(p - ref).max() <= PROB_TOL
     assert np.abs(p - p2).max() <= 2e-5
     assert any("gap_boxsum_kernel" in kk for kk in kernels), kernels
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("side,n_layers,frames", [(12, 2, 9), (21, 6, 3)])
+def test_densenet_preactivation_in_the_conv_operand_path_is_bit_identical(side, n_layers, frames, monkeypatch):
+    """DenseNet bottlenecks (BatchNorm -> ReLU -> 1x1x1 conv): the affine + ReLU + bf16 split of the concatenated fp32 tensor
+    run inside the conv's operand path (bnrelu_conv1x1_kernel: TMA-staged fp32 tile, transform warps, UMMA), the BatchNorm
+    launch and its split-plane copy of the tensor disappear.  Same arithmetic per element and the same MMA sequence as
+    affine_act_kernel + conv_umma_kernel => identical probabilities, one launch fewer per dense layer; and the growth convs'
+    col2im in the GEMM epilogue on top (the shipped DenseCPD path) against the Z-matrix route."""
+    from timed_design_b200.model import Model
+    cfg, w = standins.densecpd_standin(side=side, n_layers=n_layers, calib_frames=3)
+    X = standins.synthetic_frames(frames, side=side, seed=5)
+    m = Model(cfg, w)
+    fused = m.predict(X)
+    names = [m.op_kernel(i, frames) for i in range(len(m.graph.ops))]
+    n_fused = sum("bnrelu_conv1x1_kernel" in n for n in names)
+    assert n_fused >= 3 * n_layers - 1, names
+    monkeypatch.setenv("TIMED_B200_NO_XFORM", "1")
+    m2 = Model(cfg, w)
+    unfused = m2.predict(X)
+    assert m2.launches_per_forward == m.launches_per_forward + n_fused
+    monkeypatch.setenv("TIMED_B200_NO_C2I_FUSE", "1")
+    plain = Model(cfg, w).predict(X)
+    np.testing.assert_array_equal(fused, unfused)
+    np.testing.assert_array_equal(fused, plain)
+    assert np.abs(fused - ko.forward_torch(cfg, w, X)).max() <= PROB_TOL

@@ -24,6 +24,7 @@
 #include "thin_conv.cuh"
 #include "slab_conv.cuh"
 #include "thinz_conv.cuh"
+#include "xform_conv.cuh"
 #include "voxelise.cuh"
 
 namespace tb {
@@ -187,6 +188,13 @@ struct ConvPlan {
     bool t2n_w = false;
     // t2n_w with kw = 3, 'same', C_out = 16 / 32: the col2im over kw runs in the GEMM's epilogue on tiles of whole volume
     // rows (ConvKernelParams::c2i) -- no Z matrix in HBM, no col2im launch.  Not when the conv is the fused network head.
+    // 1x1x1 conv whose input is a BatchNorm -> ReLU of an fp32 tensor read by nothing else (DenseNet pre-activation): the
+    // affine + ReLU + bf16 split run in the conv's operand path (xform_conv.cuh), the AFFINE op is skipped and the conv reads
+    // tensor `xf_src` (the AFFINE's input).  xf_scale / xf_shift are owned by the AFFINE node.
+    bool xform = false;
+    int xf_src = -1;
+    const float* xf_scale = nullptr;
+    const float* xf_shift = nullptr;
     bool c2i = false;
     int c2i_rows = 0;
     bool c2i_active() const { return c2i && !fuse_head; }
@@ -1329,6 +1337,98 @@ static int gap_head_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, 
     return 0;
 }
 
+template <int A1, int A2, int F>
+static int launch_xform_instance(const CUtensorMap& map_x, const CUtensorMap& map_w, const ConvKernelParams& k,
+                                 const XformParams& xp, int grid, size_t smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+        TB_CHECK_CUDA(cudaFuncSetAttribute(bnrelu_conv1x1_kernel<A1, A2, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kSmemDynamicMax)));
+        attr_set = true;
+    }
+    bnrelu_conv1x1_kernel<A1, A2, F><<<grid, kXfThreads, smem_bytes, stream>>>(map_x, map_w, k, xp);
+    return 0;
+}
+
+// Can `c` (already planned) take its BatchNorm -> ReLU pre-activation in its own operand path?
+static bool xform_eligible(const ConvPlan& c, int c_in) {
+    return c.kd * c.kh * c.kw == 1 && !c.tap2n && !c.slab && !c.thin && !c.thinz && !c.wfold && !c.gap_collapse &&
+           c.n_tiles == 1 && c.n_tile % 16 == 0 && c.n_tile <= 128 && c.cin == c_in && c.cin_pad == c_in &&
+           c_in % kXfKc == 0 && c_in <= kXfMaxCin && !getenv("TIMED_B200_NO_NFOLD");
+}
+
+// BatchNorm -> ReLU -> 1x1x1 conv in one launch (ConvPlan::xform).  `x`: the fp32 tensor the BatchNorm reads (a channel-slice
+// view of a Concatenate buffer as a rule: x.ld >= x.c).
+static int xform_launch(ConvPlan& p, const TView& x, int64_t n_frames, const TView& out, cudaStream_t stream) {
+    TB_REQUIRE(x.fmt == FMT_F32 && x.c == p.cin && x.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x.f32) & 15) == 0,
+               "fused pre-activation: input must be a 16-byte aligned fp32 tensor");
+    const int64_t m_total64 = n_frames * p.Do * p.Ho * p.Wo;
+    TB_REQUIRE(m_total64 > 0 && m_total64 < (1ll << 31) - 512, "conv: too many output pixels per launch");
+    CUtensorMap map_w, map_x;
+    int rc = encode_w_map(p, kXfKc, CU_TENSOR_MAP_SWIZZLE_64B, &map_w, p.n_tile);
+    if (rc) return rc;
+    {
+        cuuint64_t dims[2] = {static_cast<cuuint64_t>(p.cin), static_cast<cuuint64_t>(m_total64)};
+        cuuint64_t strides[1] = {static_cast<cuuint64_t>(x.ld) * 4};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(kXfKc), 128};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode_tiled(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, x.f32, dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(fp32 activations) failed, CUresult=" + std::to_string(r));
+            return TB_ERR_CUDA;
+        }
+    }
+    ConvKernelParams k;
+    std::memset(&k, 0, sizeof(k));
+    k.m_total = static_cast<int32_t>(m_total64);
+    k.n_ctile_m = static_cast<int32_t>((m_total64 + 127) / 128);
+    k.mt = 1;
+    k.n_tiles = 1;
+    k.n_tile = p.n_tile;
+    k.acc_cols = round_up(2 * p.n_tile, 32);
+    k.acc_stages = 2;
+    k.nfold = 1;
+    k.n_kblocks = p.cin / kXfKc;
+    k.w_lo_rows = p.n_alloc;
+    k.w_sub_bytes = static_cast<uint32_t>(p.n_tile) * kXfKc * 2u;
+    const size_t stage = 128u * kXfKc * 4u + 2u * 128u * kXfKc * 2u + 2u * k.w_sub_bytes;
+    k.stages = static_cast<int>(std::min<size_t>(kXfMaxStages, (kSmemDynamicMax - 8 * 1024 - 1024) / stage));
+    k.stages = std::max(2, std::min(k.stages, std::max(2, k.n_kblocks)));
+    k.bias = p.d_bias; k.scale = p.d_scale; k.shift = p.d_shift;
+    k.act1 = p.act1; k.act2 = p.act2; k.alpha1 = p.alpha1; k.alpha2 = p.alpha2;
+    k.out_fmt = out.fmt;
+    k.out_f32 = out.f32; k.out_hi = out.hi; k.out_lo = out.lo;
+    k.ldc = out.ld;
+    k.c_store = out.fmt == FMT_SPLIT ? out.c_pad : out.c;
+    k.acc_comp = accum_comp(static_cast<double>(ceil_div(p.cin, 16)), 1.0);
+    TB_REQUIRE(out.fmt != FMT_SPLIT || (out.c_pad % 16 == 0 && out.c_pad <= p.n_alloc),
+               "conv: split output channel padding mismatch");
+    XformParams xp;
+    xp.in_scale = p.xf_scale;
+    xp.in_shift = p.xf_shift;
+    xp.c_in = p.cin;
+    const size_t smem_bytes = stage * k.stages + 1024;
+    const int grid = std::min(k.n_ctile_m, 148);
+    bool launched = false;
+#define TB_XF_CASE(A1, A2, F)                                                                  \
+    if (!launched && k.act1 == (A1) && k.act2 == (A2) && k.out_fmt == (F)) {                   \
+        rc = launch_xform_instance<A1, A2, F>(map_x, map_w, k, xp, grid, smem_bytes, stream);  \
+        launched = true;                                                                       \
+    }
+    TB_XF_CASE(ACT_NONE, ACT_RELU, FMT_SPLIT)
+    TB_XF_CASE(ACT_NONE, ACT_NONE, FMT_SPLIT)
+    TB_XF_CASE(ACT_RELU, ACT_NONE, FMT_SPLIT)
+#undef TB_XF_CASE
+    if (!launched)
+        rc = k.out_fmt == FMT_SPLIT ? launch_xform_instance<-1, -1, FMT_SPLIT>(map_x, map_w, k, xp, grid, smem_bytes, stream)
+                                    : launch_xform_instance<-1, -1, FMT_F32>(map_x, map_w, k, xp, grid, smem_bytes, stream);
+    if (rc) return rc;
+    TB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int conv_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, int64_t n_frames,
                        const TView& final_out, cudaStream_t stream, void* scratch,
                        size_t scratch_bytes, const TensorInfo* out_info) {
@@ -1639,6 +1739,11 @@ static const Layout& get_layout(tb_graph* g, int64_t n_frames) {
         if (g->ops[i].alias_of >= 0) {                 // fused pooling op: same storage as the conv output
             L.offset[i] = L.offset[g->ops[i].alias_of];
             live[i] = {L.offset[i], 0};
+            continue;
+        }
+        if (g->ops[i].skip && g->ops[i].d.op == TB_OP_AFFINE) {     // applied inside the conv that reads it: never materialised
+            L.offset[i] = 0;
+            live[i] = {0, 0};
             continue;
         }
         // zero-copy Concatenate: the first view to be produced places the root buffer; views themselves take no storage
@@ -2057,6 +2162,37 @@ static int graph_build(tb_graph* g, const tb_op_desc* ops, int n_ops) {
             }
         }
     }
+    // DenseNet pre-activation: AFFINE(+ReLU) (a) of an fp32 tensor, read only by a 1x1x1 conv (j): the conv applies it in
+    // its operand path (ConvPlan::xform, xform_conv.cuh), the AFFINE launch and its split-plane output disappear
+    if (!getenv("TIMED_B200_NO_XFORM")) {
+        for (int j = 1; j < n_ops; ++j) {
+            if (ops[j].op != TB_OP_CONV3D || g->ops[j].skip) continue;
+            const int a = ops[j].inputs[0];
+            if (ops[a].op != TB_OP_AFFINE || g->ops[a].skip || g->ops[a].alias_of >= 0) continue;
+            const tb_op_desc& ad = g->ops[a].d;
+            if (ad.act1 != ACT_NONE || ad.act2 != ACT_RELU) continue;
+            int n_readers = 0;
+            for (int q = 0; q < n_ops; ++q)
+                for (int b = 0; b < ops[q].n_inputs; ++b) n_readers += ops[q].inputs[b] == a;
+            const int src = ops[a].inputs[0];
+            const TensorInfo& ts = g->tensors[src];
+            ConvPlan& c = g->ops[j].conv;
+            if (n_readers != 1 || a == n_ops - 1 || ts.fmt != FMT_F32 || ts.cpv || ts.padvol || ts.wfold ||
+                g->tensors[a].view_of >= 0 || !xform_eligible(c, ts.C))
+                continue;
+            const int root = ts.view_of >= 0 ? ts.view_root : src;
+            if ((ts.view_of >= 0 ? g->tensors[root].C : ts.C) % 4 != 0 || (ts.view_of >= 0 && ts.view_c0 % 4 != 0)) continue;
+            c.xform = true;
+            c.xf_src = src;
+            c.xf_scale = g->ops[a].d_scale;
+            c.xf_shift = g->ops[a].d_shift;
+            g->ops[a].skip = true;
+            g->launches -= 1;
+            // the conv now reads the AFFINE's input: keep it (and the buffer it is a slice of) alive until then
+            g->tensors[src].last_use = std::max(g->tensors[src].last_use, j);
+            g->tensors[root].last_use = std::max(g->tensors[root].last_use, j);
+        }
+    }
     // conv inputs need 127 readable pixels past the last valid one (im2col column of 128)
     for (int i = 0; i < n_ops; ++i)
         if (ops[i].op == TB_OP_CONV3D) {
@@ -2184,6 +2320,12 @@ static int graph_forward(tb_graph* g, const void* d_frames, int dtype, int64_t n
                 else TB_REQUIRE(false, "unknown frames dtype");
                 break;
             case TB_OP_CONV3D: {
+                if (node.conv.xform) {
+                    const TView x = tensor_view(g, L, node.conv.xf_src, base, n_frames);
+                    int rc = xform_launch(node.conv, x, n_frames, out, s);
+                    if (rc) return rc;
+                    break;
+                }
                 TB_REQUIRE(ti0->fmt == FMT_SPLIT, "internal: conv input must be split planes");
                 if (node.conv.fuse_pool && t.cpv) {
                     const CpvGeom cg = make_cpv_geom(t, n_frames);
@@ -2412,6 +2554,7 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
             else if (c.slab) name = "slab_conv_kernel";
             else if (c.thinz) name = c.fuse_pool ? "thinz_conv_kernel(+maxpool)" : c.fuse_zpool ? "thinz_conv_kernel(+z-maxpool)" : "thinz_conv_kernel";
             else if (c.thin) name = "thin_conv_kernel";
+            else if (c.xform) name = "bnrelu_conv1x1_kernel(BatchNorm-ReLU in the operand path)";
             else {
                 ConvPlan::Config cfg;
                 const int rc = choose_config(c, n_frames * c.Mo_d() * c.Mo_h() * c.Mo_w(), &cfg);
@@ -2429,7 +2572,7 @@ int timed_b200_graph_op_kernel(const tb_graph* g, int32_t op, int64_t n_frames, 
         }
         case TB_OP_INPUT: name = g->tensors[op].cpv ? "input_convert_cpv_kernel" : g->tensors[op].padvol ? "input_convert_padvol_kernel" : "input_convert_kernel"; break;
         case TB_OP_POOL3D: name = node.alias_of >= 0 ? "(fused into the producing conv)" : g->tensors[op].cpv ? "pool3d_cpv_kernel" : "pool3d_vec8_kernel"; break;
-        case TB_OP_AFFINE: name = "affine_act_kernel"; break;
+        case TB_OP_AFFINE: name = node.skip ? "(applied in the operand path of the 1x1 conv that reads it)" : "affine_act_kernel"; break;
         case TB_OP_GPOOL: name = node.skip ? "(fused into the head conv's launch)" : node.pool_softmax ? "head_pool_softmax_kernel" : "gpool_kernel"; break;
         case TB_OP_SOFTMAX: name = node.skip ? "(fused into the pooling launch)" : "softmax_kernel"; break;
         case TB_OP_CONCAT: {
