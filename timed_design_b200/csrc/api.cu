@@ -1338,7 +1338,8 @@ static int gap_head_launch(ConvPlan& p, void* in_base, int64_t in_frames_alloc, 
 }
 
 template <int A1, int A2, int F>
-static int launch_xform_instance(const CUtensorMap& map_x, const CUtensorMap& map_w, const ConvKernelParams& k,
+static int launch_xform_instance(const CUtensorMap& map_x, const CUtensorMap& map_w, const CUtensorMap& map_ohi,
+                                 const CUtensorMap& map_olo, const ConvKernelParams& k,
                                  const XformParams& xp, int grid, size_t smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;       // per instantiation
     if (!attr_set) {
@@ -1346,7 +1347,7 @@ static int launch_xform_instance(const CUtensorMap& map_x, const CUtensorMap& ma
                                            static_cast<int>(kSmemDynamicMax)));
         attr_set = true;
     }
-    bnrelu_conv1x1_kernel<A1, A2, F><<<grid, kXfThreads, smem_bytes, stream>>>(map_x, map_w, k, xp);
+    bnrelu_conv1x1_kernel<A1, A2, F><<<grid, kXfThreads, smem_bytes, stream>>>(map_x, map_w, map_ohi, map_olo, k, xp);
     return 0;
 }
 
@@ -1393,9 +1394,34 @@ static int xform_launch(ConvPlan& p, const TView& x, int64_t n_frames, const TVi
     k.n_kblocks = p.cin / kXfKc;
     k.w_lo_rows = p.n_alloc;
     k.w_sub_bytes = static_cast<uint32_t>(p.n_tile) * kXfKc * 2u;
-    const size_t stage = 128u * kXfKc * 4u + 2u * 128u * kXfKc * 2u + 2u * k.w_sub_bytes;
-    k.stages = static_cast<int>(std::min<size_t>(kXfMaxStages, (kSmemDynamicMax - 8 * 1024 - 1024) / stage));
-    k.stages = std::max(2, std::min(k.stages, std::max(2, k.n_kblocks)));
+    // split-plane output through a shared-memory staging tile + bulk tensor stores (XformParams::tstore)
+    const bool tstore = out.fmt == FMT_SPLIT && p.n_tile % 64 == 0 && out.c_pad == p.n_tile && out.ld % 8 == 0 &&
+                        (reinterpret_cast<uintptr_t>(out.hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(out.lo) & 15) == 0 &&
+                        !getenv("TIMED_B200_NO_TSTORE");
+    CUtensorMap map_ohi = map_x, map_olo = map_x;
+    if (tstore) {
+        cuuint64_t dims[2] = {static_cast<cuuint64_t>(out.c_pad), static_cast<cuuint64_t>(m_total64)};
+        cuuint64_t strides[1] = {static_cast<cuuint64_t>(out.ld) * 2};
+        cuuint32_t box[2] = {64, 128};
+        cuuint32_t estr[2] = {1, 1};
+        for (int pl = 0; pl < 2; ++pl) {
+            CUresult r = g_encode_tiled(pl ? &map_olo : &map_ohi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl ? out.lo : out.hi, dims,
+                                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled(split output) failed, CUresult=" + std::to_string(r));
+                return TB_ERR_CUDA;
+            }
+        }
+    }
+    // operand ring: 3 stages of (A hi/lo + W hi/lo); output staging tile; fp32 ring: whatever is left
+    const size_t stage = 2u * 128u * kXfKc * 2u + 2u * k.w_sub_bytes, x_stage = 128u * kXfKc * 4u;
+    const size_t out_stage = tstore ? 2u * static_cast<size_t>(p.n_tile / 64) * 16384u : 0u;
+    k.stages = 3;
+    const size_t budget = kSmemDynamicMax - 8 * 1024 - 1024 - out_stage;
+    int x_stages = static_cast<int>(std::min<size_t>(kXfMaxXStages, (budget - stage * k.stages) / x_stage));
+    if (const char* e = getenv("TIMED_B200_XFORM_XSTAGES")) x_stages = std::max(k.stages, std::min(x_stages, atoi(e)));   // A/B
+    TB_REQUIRE(x_stages >= k.stages, "fused pre-activation: shared memory too small");
     k.bias = p.d_bias; k.scale = p.d_scale; k.shift = p.d_shift;
     k.act1 = p.act1; k.act2 = p.act2; k.alpha1 = p.alpha1; k.alpha2 = p.alpha2;
     k.out_fmt = out.fmt;
@@ -1409,12 +1435,14 @@ static int xform_launch(ConvPlan& p, const TView& x, int64_t n_frames, const TVi
     xp.in_scale = p.xf_scale;
     xp.in_shift = p.xf_shift;
     xp.c_in = p.cin;
-    const size_t smem_bytes = stage * k.stages + 1024;
+    xp.x_stages = x_stages;
+    xp.tstore = tstore ? 1 : 0;
+    const size_t smem_bytes = stage * k.stages + x_stage * x_stages + out_stage + 1024;
     const int grid = std::min(k.n_ctile_m, 148);
     bool launched = false;
 #define TB_XF_CASE(A1, A2, F)                                                                  \
     if (!launched && k.act1 == (A1) && k.act2 == (A2) && k.out_fmt == (F)) {                   \
-        rc = launch_xform_instance<A1, A2, F>(map_x, map_w, k, xp, grid, smem_bytes, stream);  \
+        rc = launch_xform_instance<A1, A2, F>(map_x, map_w, map_ohi, map_olo, k, xp, grid, smem_bytes, stream);  \
         launched = true;                                                                       \
     }
     TB_XF_CASE(ACT_NONE, ACT_RELU, FMT_SPLIT)
@@ -1422,8 +1450,8 @@ static int xform_launch(ConvPlan& p, const TView& x, int64_t n_frames, const TVi
     TB_XF_CASE(ACT_RELU, ACT_NONE, FMT_SPLIT)
 #undef TB_XF_CASE
     if (!launched)
-        rc = k.out_fmt == FMT_SPLIT ? launch_xform_instance<-1, -1, FMT_SPLIT>(map_x, map_w, k, xp, grid, smem_bytes, stream)
-                                    : launch_xform_instance<-1, -1, FMT_F32>(map_x, map_w, k, xp, grid, smem_bytes, stream);
+        rc = k.out_fmt == FMT_SPLIT ? launch_xform_instance<-1, -1, FMT_SPLIT>(map_x, map_w, map_ohi, map_olo, k, xp, grid, smem_bytes, stream)
+                                    : launch_xform_instance<-1, -1, FMT_F32>(map_x, map_w, map_ohi, map_olo, k, xp, grid, smem_bytes, stream);
     if (rc) return rc;
     TB_CHECK_CUDA(cudaGetLastError());
     return 0;
