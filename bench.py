@@ -583,6 +583,12 @@ def main():
         "per_op_ms": {f"{o['index']}:{o['name']}": round(o["ms"] / n_steps_timed, 4) for o in op_times},
         "per_op_kernel": {f"{o['index']}:{o['name']}": model.op_kernel(o["index"], chunk) for o in op_times},
     }
+    if "col2im over kw in the epilogue" in top_kernel:
+        # DenseCPD's growth convs (N = 3 x 32 columns): the tensor roofline is kept as the yardstick north_star names, but
+        # what paces the kernel is the SM's shared memory (profiles/r2c_densecpd_ncu_kernels.csv)
+        roofline["paced_by"] = ("shared-memory bandwidth: per 126-row tile 1.2 MB of tcgen05 operand reads (N <= 192 MMAs read "
+                                "17 KB per K = 16 step for 144 cycles of math) + 1.0 MB of TMA fills against 128 B/clk/SM; "
+                                "ncu: tensor pipe 53 %, L2 53 %, xbar->SM 40 %, DRAM bytes = algorithmic")
 
     cpu = None
     if not args.no_cpu_baseline:

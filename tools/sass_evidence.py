@@ -10,9 +10,10 @@ import sys
 from pathlib import Path
 
 LIB = Path(__file__).resolve().parents[1] / "timed_design_b200" / "libtimed_b200.so"
-KEEP = re.compile(r"^(UTCHMMA|UTMALDG|UBLKCP|LDTM|UTCBAR|UTCATOMSWS|USETMAXREG|STG\.E[A-Z0-9.]*\.256|BAR\.SYNC|REDG|REDUX|DFMA|SYNCS\.ARRIVE\.TRANS64\.RED)")
+KEEP = re.compile(r"^(UTCHMMA|UTMALDG|UTMASTG|FENCE\.VIEW\.ASYNC|UBLKCP|LDTM|UTCBAR|UTCATOMSWS|USETMAXREG|STG\.E[A-Z0-9.]*\.256|BAR\.SYNC|REDG|REDUX|DFMA|SYNCS\.ARRIVE\.TRANS64\.RED)")
 WANT = ("conv_umma_kernelILi2ELi0ELi1", "conv_pair_kernelILi2ELi0ELi1", "thin_conv_kernelILi0ELi0ELi0", "thinz_conv_kernelILi2ELi0ELi1ELi1",
-        "slab_conv_kernelILi2ELi0ELi0", "sample_tiled_kernelILi32", "voxelise_kernelE", "head_col2im_pool_softmax_kernel"
+        "slab_conv_kernelILi2ELi0ELi0", "sample_tiled_kernelILi32", "voxelise_kernelE", "head_col2im_pool_softmax_kernel",
+        "bnrelu_conv1x1_kernelILi0ELi1ELi1", "conv_umma_kernelILi0ELi0ELi0"
         )
 
 out = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True).stdout
@@ -31,7 +32,7 @@ for line in out.splitlines():
 print("# SASS evidence, round 2 (cuobjdump -sass timed_design_b200/libtimed_b200.so; instruction counts per kernel instantiation; "
       "`python tools/sass_evidence.py`)\n")
 print("`UTCHMMA` = tcgen05.mma (`.2CTA` = cta_group::2), `UTMALDG.*` = cp.async.bulk.tensor (TMA; `IM2COL` = im2col mode, plain = tiled: "
-      "the voxel-stationary boxes), `UBLKCP` = 1-D cp.async.bulk, `LDTM` = tcgen05.ld, `UTCBAR` = tcgen05.commit, `USETMAXREG` = "
+      "the voxel-stationary boxes), `UTMASTG` = cp.async.bulk.tensor store (shared -> global), `FENCE.VIEW.ASYNC` = fence.proxy.async, `UBLKCP` = 1-D cp.async.bulk, `LDTM` = tcgen05.ld, `UTCBAR` = tcgen05.commit, `USETMAXREG` = "
       "setmaxnreg, `STG.E.EF*.256` = 256-bit store with the L2 evict-first hint.\n")
 for k, c in counts.items():
     print(f"* `{k}`: " + ", ".join(f"{n} × {v}" for n, v in sorted(c.items())))
