@@ -1418,6 +1418,7 @@ static int xform_launch(ConvPlan& p, const TView& x, int64_t n_frames, const TVi
     const size_t stage = 2u * 128u * kXfKc * 2u + 2u * k.w_sub_bytes, x_stage = 128u * kXfKc * 4u;
     const size_t out_stage = tstore ? 2u * static_cast<size_t>(p.n_tile / 64) * 16384u : 0u;
     k.stages = 3;
+    if (const char* e = getenv("TIMED_B200_XFORM_AWSTAGES")) k.stages = std::max(2, std::min<int>(kXfMaxStages, atoi(e)));     // A/B
     const size_t budget = kSmemDynamicMax - 8 * 1024 - 1024 - out_stage;
     int x_stages = static_cast<int>(std::min<size_t>(kXfMaxXStages, (budget - stage * k.stages) / x_stage));
     if (const char* e = getenv("TIMED_B200_XFORM_XSTAGES")) x_stages = std::max(k.stages, std::min(x_stages, atoi(e)));   // A/B
