@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TIMED_B200_ABI_VERSION 3 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers; 3: predict_stats, float16 frames, voxelise (all additive) */
+#define TIMED_B200_ABI_VERSION 4 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers; 3: predict_stats, float16 frames, voxelise; 4: pdb_parse (all additive) */
 
 /* error codes */
 #define TB_OK 0
@@ -245,6 +245,26 @@ int timed_b200_format_csv_e18(const void* data, int32_t dtype, int64_t rows, int
  * No device work. */
 int timed_b200_parse_csv(const char* text, int64_t len, double* out, int64_t out_cap, int64_t* rows, int64_t* cols,
                          int32_t n_threads);
+
+/* ---- host-side structure files  (the aposteriori front end of /root/reference/ui.py:73-86, /root/reference/README.md:84-97:
+ * structure files -> residue frames) ---------------------------------------------------------------
+ * Read `n_paths` PDB files (plain or .gz) on `n_threads` host threads into per-state atom / residue tables: ATOM records
+ * only, states closed by ENDMDL (first state with atoms unless all_states), residues keyed by chain + resSeq + iCode in
+ * order of first appearance, alternate locations resolved per residue, first occurrence of an atom name wins, residue
+ * numbers repeated through insertion codes dropped (counted in state_dup).  No device work.
+ * timed_b200_pdb_sizes: totals over all files.  timed_b200_pdb_export fills caller-allocated arrays:
+ *   file_status[n_paths]        0 ok, 1 unreadable, 2 no ATOM record, 3 malformed coordinate field (such files have no state)
+ *   state_file[n_states], state_res_off / state_atom_off[n_states + 1], state_dup[n_states]
+ *   res_chain[n_res], res_id[n_res * 4], res_label[n_res * 3] (space padded), res_has_bb[n_res], res_bb[n_res * 9] (N, CA, C)
+ *   atom_xyz[n_atoms * 3], atom_name[n_atoms] (0 N, 1 CA, 2 C, 3 O, 4 OXT, 5 CB), atom_res[n_atoms] (index within its state)
+ * (only the backbone + C-beta atoms the frame encoders use are exported, in file order). */
+typedef struct tb_pdb_batch tb_pdb_batch;
+int timed_b200_pdb_parse(const char* const* paths, int32_t n_paths, int32_t all_states, int32_t n_threads, tb_pdb_batch** out);
+int timed_b200_pdb_sizes(const tb_pdb_batch* batch, int64_t* n_states, int64_t* n_res, int64_t* n_atoms);
+int timed_b200_pdb_export(const tb_pdb_batch* batch, int32_t* file_status, int32_t* state_file, int64_t* state_res_off,
+                          int64_t* state_atom_off, int32_t* state_dup, char* res_chain, char* res_id, char* res_label,
+                          uint8_t* res_has_bb, double* res_bb, double* atom_xyz, int32_t* atom_name, int32_t* atom_res);
+void timed_b200_pdb_free(tb_pdb_batch* batch);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.timed_b200_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.timed_b200_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_no_cpu_fallback_without_device(lib):

@@ -6,6 +6,7 @@ import json
 from pathlib import Path
 
 import numpy as np
+import pytest
 
 from oracle import voxelise_oracle as vo
 from timed_design_b200 import voxelise as vx
@@ -141,3 +142,78 @@ def test_vectorised_parser_equals_the_reference_parser():
         assert list(info.label) == [r.label for r in residues] and list(info.res_id) == [r.res_id for r in residues]
     states = vx.load_states([PDB, PDB])
     assert len(states) == 2 and len(vx.flat_map_of(states)) == 152
+
+
+def _same_tables(a, b):
+    (ta, ia), (tb, ib) = a, b
+    for f in ta._fields:
+        x, y = getattr(ta, f), getattr(tb, f)
+        if f == "channels":
+            assert list(x) == list(y)
+        elif x is None or y is None:
+            assert x is None and y is None, f
+        else:
+            assert np.asarray(x).dtype == np.asarray(y).dtype, f
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=f)
+    for f in ia._fields:
+        assert [str(v) for v in getattr(ia, f)] == [str(v) for v in getattr(ib, f)], f
+
+
+def _synthetic_pdb_lines():
+    """Records that exercise every selection rule: alternate locations (blank / first-seen / second), an insertion-code
+    duplicate, a blank chain id, HETATM, a non-standard residue, a missing backbone atom, OXT, a side-chain atom, a residue
+    whose records come back later in the file, two MODELs."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    lines, serial = ["HEADER    TEST", "MODEL        1"], [1]
+
+    def res(resn, chain, resi, icode=" ", alts=(" ",), names=("N", "CA", "C", "O", "CB"), rec="ATOM  "):
+        for nm in names:
+            for al in alts:
+                x, y, z = rng.uniform(-20, 20, 3)
+                name = nm if len(nm) == 4 else " " + nm.ljust(3)
+                lines.append(f"{rec}{serial[0]:5d} {name}{al}{resn:>3} {chain}{resi:4d}{icode}   {x:8.3f}{y:8.3f}{z:8.3f}  1.00  0.00")
+                serial[0] += 1
+
+    res("ALA", "A", 1); res("GLY", "A", 2, names=("N", "CA", "C", "O")); res("SER", "A", 3, alts=("A", "B"))
+    res("LYS", "A", 3, icode="A"); res("ASP", " ", 4); res("HOH", "A", 900, names=("O",), rec="HETATM")
+    res("MSE", "B", 10); res("TRP", "B", 11, names=("N", "CA", "O", "CB"))
+    res("GLU", "B", 12, names=("N", "CA", "C", "O", "OXT", "CB", "CG"))
+    res("ALA", "A", 1, names=("CB", "N")); res("VAL", "B", 13, alts=(" ", "A"))
+    lines += ["ENDMDL", "MODEL        2"]
+    res("ALA", "A", 1); res("CYS", "A", 2, alts=("B", "A"))
+    lines += ["ENDMDL", "END"]
+    return lines
+
+
+def test_native_pdb_reader_equals_the_python_parser(tmp_path):
+    """timed_b200_pdb_parse (host threads, zlib) + the shared numpy arithmetic = fast_tables, table for table: on 1ubq for
+    every codec, on synthetic records that hit every selection rule (plain, gzip + CRLF, first state / all states), batched
+    with other files; files it flags as unusual fall through to the Python parser and raise its errors."""
+    import gzip
+    import warnings
+    for codec in vx.CODECS:
+        _same_tables(vx.fast_tables(PDB, codec, 1.0)[0], vx.native_tables([PDB], codec, 1.0)[0][0])
+    lines = _synthetic_pdb_lines()
+    (tmp_path / "syn.pdb").write_text("\n".join(lines) + "\n")
+    with gzip.open(tmp_path / "syn2.pdb.gz", "wt", newline="") as f:
+        f.write("\r\n".join(lines))
+    for all_states in (False, True):
+        for name in ("syn.pdb", "syn2.pdb.gz"):
+            with warnings.catch_warnings(record=True) as w_py:
+                warnings.simplefilter("always")
+                a = vx.fast_tables(tmp_path / name, "CNOCBCAQ", 0.9, all_states=all_states)
+            with warnings.catch_warnings(record=True) as w_nat:
+                warnings.simplefilter("always")
+                b = vx.native_tables([PDB, tmp_path / name, PDB], "CNOCBCAQ", 0.9, all_states=all_states)[1]
+            assert len(a) == len(b) == (2 if all_states else 1)
+            for x, y in zip(a, b):
+                _same_tables(x, y)
+            assert [str(w.message) for w in w_py] == [str(w.message) for w in w_nat] and len(w_py) == 1
+            assert len(a[0][1].chain) == 8 and list(a[0][0].valid) == [0, 1, 2, 3, 4, 6, 7]
+    (tmp_path / "empty.pdb").write_text("HEADER\nEND\n")
+    with pytest.raises(ValueError, match="no ATOM records"):
+        vx.native_tables([PDB, tmp_path / "empty.pdb"], "CNOCBCA", 1.0)
+    with pytest.raises(FileNotFoundError):
+        vx.native_tables([tmp_path / "missing.pdb"], "CNOCBCA", 1.0)
+    assert vx.native_tables([], "CNOCBCA", 1.0) == []

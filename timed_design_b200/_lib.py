@@ -17,7 +17,7 @@ LIB_PATH = _HERE / "libtimed_b200.so"
 
 TB_MAX_INPUTS = 8
 DTYPE_F32, DTYPE_F64, DTYPE_U8, DTYPE_F16 = 0, 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class TimedB200Error(RuntimeError):
@@ -95,6 +95,10 @@ SYMBOLS = {
     "timed_b200_sample_uniforms": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64,
                                              C.c_void_p, C.c_void_p]),
     "timed_b200_argmax_fp16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "timed_b200_pdb_parse": (C.c_int, [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "timed_b200_pdb_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "timed_b200_pdb_export": (C.c_int, [C.c_void_p] + [C.c_void_p] * 13),
+    "timed_b200_pdb_free": (None, [C.c_void_p]),
 }
 
 _lib = None

@@ -25,6 +25,7 @@
 #include "slab_conv.cuh"
 #include "thinz_conv.cuh"
 #include "xform_conv.cuh"
+#include "pdb_parse.cuh"
 #include "voxelise.cuh"
 
 namespace tb {
@@ -3034,6 +3035,78 @@ int timed_b200_voxelise(const float* d_atoms_xyzs, const int32_t* d_atom_channel
     TB_CHECK_CUDA(cudaGetLastError());
     return TB_OK;
 }
+
+// ---- host-side structure files (pdb_parse.cuh): no device work
+int timed_b200_pdb_parse(const char* const* paths, int32_t n_paths, int32_t all_states, int32_t n_threads, tb_pdb_batch** out) {
+    TB_REQUIRE(paths && out && n_paths >= 0, "null argument");
+    tb_pdb_batch* b = new tb_pdb_batch;
+    b->files.resize(static_cast<size_t>(n_paths));
+    std::atomic<int32_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const int32_t i = next.fetch_add(1);
+            if (i >= n_paths) return;
+            pdb_parse_one(paths[i], i, all_states != 0, &b->files[i]);
+        }
+    };
+    const int nt = std::max(1, std::min<int>(n_threads, n_paths));
+    if (nt == 1) {
+        worker();
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+    *out = b;
+    return TB_OK;
+}
+
+int timed_b200_pdb_sizes(const tb_pdb_batch* b, int64_t* n_states, int64_t* n_res, int64_t* n_atoms) {
+    TB_REQUIRE(b && n_states && n_res && n_atoms, "null argument");
+    int64_t s = 0, r = 0, a = 0;
+    for (const auto& f : b->files)
+        for (const auto& st : f.states) { ++s; r += static_cast<int64_t>(st.res.size()); a += static_cast<int64_t>(st.atoms.size()); }
+    *n_states = s; *n_res = r; *n_atoms = a;
+    return TB_OK;
+}
+
+int timed_b200_pdb_export(const tb_pdb_batch* b, int32_t* file_status, int32_t* state_file, int64_t* state_res_off,
+                          int64_t* state_atom_off, int32_t* state_dup, char* res_chain, char* res_id, char* res_label,
+                          uint8_t* res_has_bb, double* res_bb, double* atom_xyz, int32_t* atom_name, int32_t* atom_res) {
+    TB_REQUIRE(b && file_status && state_file && state_res_off && state_atom_off && state_dup && res_chain && res_id &&
+               res_label && res_has_bb && res_bb && atom_xyz && atom_name && atom_res, "null argument");
+    int64_t s = 0, r = 0, a = 0;
+    for (size_t fi = 0; fi < b->files.size(); ++fi) {
+        const auto& f = b->files[fi];
+        file_status[fi] = f.status;
+        for (const auto& st : f.states) {
+            state_file[s] = static_cast<int32_t>(fi);
+            state_res_off[s] = r;
+            state_atom_off[s] = a;
+            state_dup[s] = st.n_dup;
+            for (const auto& pr : st.res) {
+                res_chain[r] = pr.chain;
+                std::memcpy(res_id + 4 * r, pr.res_id, 4);
+                std::memcpy(res_label + 3 * r, pr.label, 3);
+                res_has_bb[r] = pr.has_bb;
+                std::memcpy(res_bb + 9 * r, pr.bb, sizeof(pr.bb));
+                ++r;
+            }
+            for (const auto& pa : st.atoms) {
+                std::memcpy(atom_xyz + 3 * a, pa.xyz, sizeof(pa.xyz));
+                atom_name[a] = pa.name;
+                atom_res[a] = pa.res;
+                ++a;
+            }
+            ++s;
+        }
+    }
+    state_res_off[s] = r;
+    state_atom_off[s] = a;
+    return TB_OK;
+}
+
+void timed_b200_pdb_free(tb_pdb_batch* b) { delete b; }
 
 // ---- host-side frame I/O helper: no device work, no Python: inflate + unshuffle + scatter + cast on host threads
 int timed_b200_inflate_chunks(const uint8_t* file_base, int64_t n_chunks, const int64_t* src_off, const int64_t* src_size,

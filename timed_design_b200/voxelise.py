@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import gzip
+import os
 import typing as t
 import warnings
 from pathlib import Path
@@ -134,7 +135,8 @@ def fast_tables(path, codec: str, voxel_edge: float, all_states: bool = False):
     channels = CODECS[codec]
     prop_kind = channels[-1] if channels[-1] in ("Q", "P") else None
     path = Path(path)
-    raw = (gzip.open(path, "rb") if path.suffix == ".gz" else open(path, "rb")).read()
+    with (gzip.open(path, "rb") if path.suffix == ".gz" else open(path, "rb")) as fh:
+        raw = fh.read()
     lines = raw.split(b"\n")
     # state boundaries: ENDMDL closes a state
     out = []
@@ -230,6 +232,100 @@ def fast_tables(path, codec: str, voxel_edge: float, all_states: bool = False):
         out.append((tab, ResidueInfo(chain, res_id, label)))
     if not out:
         raise ValueError(f"{path}: no ATOM records")
+    return out
+
+
+_NATIVE_WARNED = False
+
+
+def native_tables(paths, codec: str, voxel_edge: float, all_states: bool = False, n_threads: t.Optional[int] = None):
+    """``[fast_tables(p, codec, voxel_edge, all_states) for p in paths]`` with the file reading, gunzip and record parsing done
+    by libtimed_b200's host-side PDB reader on a thread pool (``timed_b200_pdb_parse``, csrc/pdb_parse.cuh) and the float
+    arithmetic (frames, sigmas) by the same numpy expressions as ``fast_tables`` over ALL files at once: identical tables
+    (tests/test_voxelise_cpu.py), ~20x faster per structure -- the structure route of predict.py was bound by the parser.
+    A file the native reader reports as unusual (unreadable, no ATOM record, malformed field) goes through ``fast_tables``,
+    which raises / warns as before; so does everything when the library is not built (one RuntimeWarning)."""
+    global _NATIVE_WARNED
+    import ctypes as C
+    if codec not in CODECS:
+        raise ValueError(f"unknown codec {codec!r} (known: {sorted(CODECS)})")
+    paths = [Path(p) for p in paths]
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except Exception as e:  # noqa: BLE001 -- host-side helper: same tables from the Python parser, much slower
+        if not _NATIVE_WARNED:
+            warnings.warn(f"timed_b200_pdb_parse unavailable ({type(e).__name__}: {e}); using the Python PDB parser "
+                          "(identical tables, ~20x slower)", RuntimeWarning, stacklevel=2)
+            _NATIVE_WARNED = True
+        return [fast_tables(p, codec, voxel_edge, all_states) for p in paths]
+    if not paths:
+        return []
+    channels = CODECS[codec]
+    prop_kind = channels[-1] if channels[-1] in ("Q", "P") else None
+    arr = (C.c_char_p * len(paths))(*[os.fsencode(str(p)) for p in paths])
+    handle = C.c_void_p()
+    threads = n_threads or min(len(paths), max(1, os.cpu_count() or 1), 16)
+    _lib.check(lib.timed_b200_pdb_parse(arr, len(paths), int(bool(all_states)), int(threads), C.byref(handle)))
+    try:
+        ns, nr, na = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(lib.timed_b200_pdb_sizes(handle, C.byref(ns), C.byref(nr), C.byref(na)))
+        ns, nr, na = ns.value, nr.value, na.value
+        status = np.zeros(len(paths), np.int32)
+        st_file = np.zeros(ns, np.int32)
+        st_r = np.zeros(ns + 1, np.int64)
+        st_a = np.zeros(ns + 1, np.int64)
+        st_dup = np.zeros(ns, np.int32)
+        r_chain = np.zeros(nr, "S1")
+        r_id = np.zeros(nr, "S4")
+        r_label = np.zeros(nr, "S3")
+        r_has = np.zeros(nr, np.uint8)
+        r_bb = np.zeros((nr, 9), np.float64)
+        a_xyz = np.zeros((na, 3), np.float64)
+        a_name = np.zeros(na, np.int32)
+        a_res = np.zeros(na, np.int32)
+        ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        _lib.check(lib.timed_b200_pdb_export(handle, ptr(status), ptr(st_file), ptr(st_r), ptr(st_a), ptr(st_dup), ptr(r_chain),
+                                             ptr(r_id), ptr(r_label), ptr(r_has), ptr(r_bb), ptr(a_xyz), ptr(a_name), ptr(a_res)))
+    finally:
+        lib.timed_b200_pdb_free(handle)
+    # ---- the float arithmetic of fast_tables, once over all residues / atoms (row-wise: independent of the batch)
+    has = r_has.astype(bool)
+    frames = np.zeros((nr, 12), dtype=np.float32)
+    if has.any():
+        n_, ca, c_ = r_bb[has, 0:3], r_bb[has, 3:6], r_bb[has, 6:9]
+        ey = n_ - ca
+        ey /= np.linalg.norm(ey, axis=1, keepdims=True)
+        v = c_ - ca
+        ex = v - ey * np.sum(v * ey, axis=1, keepdims=True)
+        ex /= np.linalg.norm(ex, axis=1, keepdims=True)
+        ez = np.cross(ex, ey)
+        frames[has] = np.concatenate([ca, ex, ey, ez], axis=1).astype(np.float32)
+    chain = np.char.decode(r_chain, "ascii")
+    res_id = np.char.strip(np.char.decode(r_id, "ascii"))
+    label = np.char.strip(np.char.decode(r_label, "ascii"))
+    prop_all = None
+    if prop_kind:
+        one = [_THREE_TO_ONE.get(l, "X") for l in label]
+        prop_all = np.array([_CHARGE.get(o, 0) if prop_kind == "Q" else (1.0 if o in _POLAR else 0.0) for o in one], dtype=np.float32)
+    lab_of = ["N", "CA", "C", "O", "O", "CB"]                     # OXT is encoded as O
+    ch_lut = np.array([channels.index(x) for x in lab_of], dtype=np.int32)
+    sig_lut = np.array([VDW[x[0]] for x in lab_of], dtype=np.float64) / 2.3548 / voxel_edge
+    atoms = np.concatenate([a_xyz, sig_lut[a_name][:, None]], axis=1).astype(np.float32)
+    a_ch = ch_lut[a_name]
+    a_cb = (a_name == 5).astype(np.int32)
+    out: t.List[t.Optional[list]] = [[] if status[i] == 0 else None for i in range(len(paths))]
+    for s in range(ns):
+        r0, r1, a0, a1 = int(st_r[s]), int(st_r[s + 1]), int(st_a[s]), int(st_a[s + 1])
+        path = paths[int(st_file[s])]
+        if st_dup[s]:
+            warnings.warn(f"{path.name}: {int(st_dup[s])} residue(s) repeat a residue number (insertion code); skipped")
+        tab = AtomTables(atoms[a0:a1], a_ch[a0:a1], a_res[a0:a1], a_cb[a0:a1], frames[r0:r1],
+                         prop_all[r0:r1] if prop_all is not None else None, np.nonzero(has[r0:r1])[0].astype(np.int64), channels)
+        out[int(st_file[s])].append((tab, ResidueInfo(chain[r0:r1], res_id[r0:r1], label[r0:r1])))
+    for i, p in enumerate(paths):
+        if out[i] is None or not out[i]:
+            out[i] = fast_tables(p, codec, voxel_edge, all_states)          # raises / warns as the Python reader does
     return out
 
 
@@ -344,8 +440,7 @@ def load_states(paths, codec: str = "CNOCBCA", voxels_per_side: int = 21, frame_
     edge = float(frame_edge_length) / voxels_per_side
     out = []
     paths = [Path(p) for p in paths]
-    # (a thread pool is slower here: the parser is mostly small Python / numpy calls under the GIL -- measured 4.4 vs 3.3 ms)
-    parsed = [fast_tables(p, codec, edge, all_states=voxelise_all_states) for p in paths]
+    parsed = native_tables(paths, codec, edge, all_states=voxelise_all_states)
     for path, states in zip(paths, parsed):
         pdb_code = path.name.split(".pdb")[0]
         for si, (tab, info) in enumerate(states):

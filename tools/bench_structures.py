@@ -37,7 +37,13 @@ p = predict._forward_device_rows(m, fr)
 t2 = time.perf_counter()
 out = {"structures": n, "frames": int(fr.shape[0]),
        "structure_route": {"voxelise_s": t1 - t0, "network_s": t2 - t1, "frames_per_s": fr.shape[0] / (t2 - t0),
-                           "note": "PDB parsing in Python + timed_b200_voxelise + graph_forward, frames stay on the device"}}
+                           "note": "timed_b200_pdb_parse (host threads) + timed_b200_voxelise + graph_forward, frames stay on the device"}}
+t0 = time.perf_counter()
+states = voxelise.load_states(files, "CNOCBCA")
+out["structure_route"]["parse_s"] = time.perf_counter() - t0
+t0 = time.perf_counter()
+parsed = [voxelise.fast_tables(f, "CNOCBCA", 1.0) for f in files]
+out["structure_route"]["python_parser_s"] = time.perf_counter() - t0
 # (b) the dataset route on the same frames
 data = voxelise.make_frame_dataset(files, tmp, "data", codec="CNOCBCA")
 flat2, _ = frames.create_flat_dataset_map(data)
