@@ -217,3 +217,26 @@ def test_native_pdb_reader_equals_the_python_parser(tmp_path):
     with pytest.raises(FileNotFoundError):
         vx.native_tables([tmp_path / "missing.pdb"], "CNOCBCA", 1.0)
     assert vx.native_tables([], "CNOCBCA", 1.0) == []
+
+
+def test_dataset_order_chains_as_they_appear_numbers_as_integers():
+    """utils.py:367-371: chains in order of first appearance, residue ids sorted as INTEGERS (not strings), ties in file
+    order, residues without a backbone or with a non-standard name left out -- checked against the plain loop."""
+    ((tab, info),) = vx.fast_tables(PDB, "CNOCBCA", 1.0)
+    rng = np.random.default_rng(1)
+    n = len(info.chain)
+    chain = np.array(["B" if i % 3 else "A" for i in range(n)])
+    res_id = np.array([str(int(x) - 30) for x in rng.permutation(n)])          # -30 .. 45: "-5" < "10" < "9" as strings
+    label = np.array(info.label)
+    label[[4, 40]] = "MSE"
+    info2 = vx.ResidueInfo(chain, res_id, label)
+    tab2 = tab._replace(valid=np.delete(tab.valid, [7, 8]))
+    expect, chains = [], []
+    valid = [int(i) for i in tab2.valid if label[i] != "MSE"]
+    for i in valid:
+        if chain[i] not in chains:
+            chains.append(chain[i])
+    for ch in chains:
+        expect += sorted((i for i in valid if chain[i] == ch), key=lambda i: int(res_id[i]))
+    assert vx._dataset_order(tab2, info2) == expect and len(expect) == n - 4
+    assert vx._dataset_order(tab2._replace(valid=np.zeros(0, np.int64)), info2) == []

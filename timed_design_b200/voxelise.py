@@ -411,19 +411,23 @@ def voxelise_tables(tab: AtomTables, residues_idx: np.ndarray, voxels_per_side: 
     return host.astype(np.bool_) if dtype == np.bool_ else host
 
 
+_STD_LABELS = np.array(sorted(_THREE_TO_ONE))
+
+
 def _dataset_order(tab: AtomTables, info: ResidueInfo) -> t.List[int]:
     """Residues that get a frame, in dataset order: chains as they appear, residue ids sorted as integers
     (utils.py:367-371); residues without N/CA/C or with a non-standard name are left out."""
-    order, chains = [], []
-    valid = [int(i) for i in tab.valid if info.label[i] in _THREE_TO_ONE]
-    for i in valid:
-        if info.chain[i] not in chains:
-            chains.append(info.chain[i])
-    for ch in chains:
-        idx = [i for i in valid if info.chain[i] == ch]
-        idx.sort(key=lambda i: int(info.res_id[i]))
-        order.extend(idx)
-    return order
+    valid = np.asarray(tab.valid, dtype=np.int64)
+    if len(valid):
+        valid = valid[np.isin(np.asarray(info.label)[valid], _STD_LABELS)]
+    if not len(valid):
+        return []
+    chains = np.asarray(info.chain)[valid]
+    uniq, first, inv = np.unique(chains, return_index=True, return_inverse=True)
+    rank = np.empty(len(uniq), dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))           # chains in order of first appearance
+    res_no = np.asarray(info.res_id)[valid].astype(np.int64)                 # ValueError for a non-integer id, as int() gave
+    return valid[np.lexsort((res_no, rank[inv]))].tolist()                   # stable: equal numbers keep the file order
 
 
 class State(t.NamedTuple):
