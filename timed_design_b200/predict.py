@@ -171,12 +171,23 @@ def load_dataset_and_predict(
         if frame_model.n_classes != n_classes:
             raise ValueError(f"{m}: model has {frame_model.n_classes} outputs but "
                              f"{'--predict_rotamers' if predict_rotamers else 'residue mode'} expects {n_classes}")
-        def predict_rows(a: int, b: int):
-            """(probabilities, one-hot labels) of the frames [a, b) of the flat map."""
+        def predicted(ranges):
+            """Yields (probabilities, one-hot labels) of the frame ranges [a, b) of the flat map, in order.  On the .hdf5
+            route the NEXT range's frames are read (native inflater, host threads, no GIL) while the GPU predicts the current
+            one -- load_batch is ~80 % of that route."""
+            ranges = list(ranges)
             if source is not None:
-                return _forward_device_rows(frame_model, source.rows(a, b)), source.labels[a:b]
-            X_batch, y_true = load_batch(dataset_path, flat_dataset_map[a:b])
-            return frame_model.predict(X_batch), y_true
+                for a, b in ranges:
+                    yield _forward_device_rows(frame_model, source.rows(a, b)), source.labels[a:b]
+                return
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=1) as pool:
+                nxt = pool.submit(load_batch, dataset_path, flat_dataset_map[ranges[0][0]:ranges[0][1]]) if ranges else None
+                for k, (a, b) in enumerate(ranges):
+                    X_batch, y_true = nxt.result()
+                    nxt = (pool.submit(load_batch, dataset_path, flat_dataset_map[ranges[k + 1][0]:ranges[k + 1][1]])
+                           if k + 1 < len(ranges) else None)
+                    yield frame_model.predict(X_batch), y_true
 
         rot_out = path_to_output / f"{model_name}_rot.csv"
         model_out = rot_out if predict_rotamers else path_to_output / f"{model_name}.csv"
@@ -194,21 +205,21 @@ def load_dataset_and_predict(
             lo, hi = shard_range(n_total, rank, world)
             lo, hi = lo + first, hi + first
             preds, labels = [], []
-            for b0 in range(lo, hi, batch_size):
-                y_pred_b, y_true_b = predict_rows(b0, min(b0 + batch_size, hi))
+            for y_pred_b, y_true_b in predicted((b0, min(b0 + batch_size, hi)) for b0 in range(lo, hi, batch_size)):
                 preds.append(y_pred_b)
                 labels.append(np.asarray(y_true_b, dtype=np.float64))
             local_p = np.concatenate(preds) if preds else np.zeros((0, n_classes), np.float32)
             local_y = np.concatenate(labels) if labels else np.zeros((0, 20), np.float64)
             gathered = (_gather(local_p.astype(np.float32), n_total, local_rank), _gather(local_y, n_total, local_rank))
+        local = None if gathered is not None else predicted(
+            (index * batch_size, min((index + 1) * batch_size, len(flat_dataset_map))) for index in range(start_batch, n_batches))
         for index in range(start_batch, n_batches):
-            current_batch_map = flat_dataset_map[index * batch_size:(index + 1) * batch_size]
             if gathered is not None:
                 r0 = (index - start_batch) * batch_size
                 y_pred_batch = gathered[0][r0:r0 + batch_size]
                 y_true_batch = gathered[1][r0:r0 + batch_size]
             else:
-                y_pred_batch, y_true_batch = predict_rows(index * batch_size, min((index + 1) * batch_size, len(flat_dataset_map)))
+                y_pred_batch, y_true_batch = next(local)
             raw_rows.append(y_pred_batch)
             if rank != 0:
                 continue                               # only rank 0 touches the output directory
