@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TIMED_B200_ABI_VERSION 4 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers; 3: predict_stats, float16 frames, voxelise; 4: pdb_parse (all additive) */
+#define TIMED_B200_ABI_VERSION 4 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers; 3: predict_stats, float16 frames, voxelise; 4: pdb_parse, inflate_device (all additive) */
 
 /* error codes */
 #define TB_OK 0
@@ -232,6 +232,14 @@ int timed_b200_inflate_chunks(const uint8_t* file_base, int64_t n_chunks, const 
                               const int64_t* dst_frame, const int32_t* origin, int32_t rank, const int32_t* chunk_dims,
                               const int32_t* frame_dims, int32_t deflate, int32_t shuffle_elem_size, int32_t src_dtype,
                               int32_t dst_dtype, void* dst, int32_t n_threads);
+
+/* The same on the device, for datasets whose frames are stored as ONE deflate-filtered chunk each (no shuffle): the STORED
+ * bytes are shipped (18 KB instead of 222 KB per frame on real structures) and every zlib stream is inflated by its own warp
+ * (csrc/inflate.cuh) into d_out + s * out_bytes.  d_comp: the stored bytes; stream s occupies [d_off[s], d_off[s] + d_size[s]).
+ * d_status[s]: 0 ok, else the stream is malformed / truncated / does not inflate to exactly out_bytes (the caller then takes
+ * the host path).  All pointers are device pointers; asynchronous on cuda_stream. */
+int timed_b200_inflate_device(const uint8_t* d_comp, int64_t n_streams, const int64_t* d_off, const int64_t* d_size,
+                              int64_t out_bytes, void* d_out, int32_t* d_status, void* cuda_stream);
 
 /* Text of a (rows, cols) float32/float64 host matrix exactly as numpy.savetxt(..., delimiter=",") prints it ("%.18e",
  * comma separated, one line per row: the rotamer dump of predict.py:145-146), formatted on `n_threads` host threads.

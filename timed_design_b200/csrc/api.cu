@@ -26,6 +26,7 @@
 #include "thinz_conv.cuh"
 #include "xform_conv.cuh"
 #include "pdb_parse.cuh"
+#include "inflate.cuh"
 #include "voxelise.cuh"
 
 namespace tb {
@@ -3032,6 +3033,24 @@ int timed_b200_voxelise(const float* d_atoms_xyzs, const int32_t* d_atom_channel
     if (frames_dtype == TB_DTYPE_F32) voxelise_finalize_kernel<float><<<grid, 256, 0, s>>>(d_scratch, n, !as_gaussian, static_cast<float*>(d_frames));
     else if (frames_dtype == TB_DTYPE_F16) voxelise_finalize_kernel<__half><<<grid, 256, 0, s>>>(d_scratch, n, !as_gaussian, static_cast<__half*>(d_frames));
     else voxelise_finalize_kernel<uint8_t><<<grid, 256, 0, s>>>(d_scratch, n, 1, static_cast<uint8_t*>(d_frames));
+    TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+// ---- device-side inflate of stored HDF5 frame chunks (inflate.cuh)
+int timed_b200_inflate_device(const uint8_t* d_comp, int64_t n_streams, const int64_t* d_off, const int64_t* d_size,
+                              int64_t out_bytes, void* d_out, int32_t* d_status, void* cuda_stream) {
+    TB_REQUIRE(d_comp && d_off && d_size && d_out && d_status, "null argument");
+    TB_REQUIRE(n_streams >= 0 && out_bytes > 0, "bad stream count / output size");
+    if (n_streams == 0) return TB_OK;
+    if (timed_b200_device_count() <= 0) {
+        set_error("no CUDA device (libtimed_b200 has no CPU path)");
+        return TB_ERR_NO_DEVICE;
+    }
+    const int64_t blocks = (n_streams + kInflateWarps - 1) / kInflateWarps;
+    TB_REQUIRE(blocks < (1ll << 31), "too many streams per launch");
+    inflate_streams_kernel<<<static_cast<unsigned>(blocks), 32 * kInflateWarps, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        d_comp, d_off, d_size, n_streams, out_bytes, static_cast<uint8_t*>(d_out), d_status);
     TB_CHECK_CUDA(cudaGetLastError());
     return TB_OK;
 }
