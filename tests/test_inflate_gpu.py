@@ -73,3 +73,44 @@ def test_device_inflate_flags_bad_streams():
     assert status[1] == 1 and status[2] != 0 and status[3] == 5 and status[4] == 3
     _, st = _inflate_device([bytes(corrupt)], 5000)             # either detected or (rarely) a different valid stream: never a hang
     assert st[0] in (0, 2, 3, 4, 5)
+
+
+@pytest.mark.gpu
+def test_device_inflate_route_of_predict_equals_the_host_route(tmp_path, monkeypatch):
+    """frames.load_batch_device (stored gzip chunks -> GPU -> one warp per chunk) returns load_batch's frames and labels
+    byte for byte, and predict.py writes identical files whichever route reads the dataset
+    (TIMED_B200_NO_DEVICE_INFLATE = host route)."""
+    import json
+    from pathlib import Path
+
+    from timed_design_b200 import frames, predict, standins
+    from timed_design_b200.hdf5 import write_frame_dataset, write_keras_h5
+    ubq = json.loads((Path(__file__).parent / "golden" / "1ubq_chainA.json").read_text())
+    X = standins.synthetic_frames(76, seed=3)
+    X[X < 0.6] = 0.0                                              # sparse, as voxelised structures are
+    residues = {str(rid): (X[i], ubq["labels"][i]) for i, rid in enumerate(ubq["residue_ids"])}
+    write_frame_dataset(tmp_path / "data.hdf5", {"1ubq": {"A": residues}, "2xyz": {"B": dict(list(residues.items())[:9])}},
+                        (21, 21, 21, 6), compression="gzip")
+    flat, _ = frames.create_flat_dataset_map(tmp_path / "data.hdf5")
+    Xh, yh = frames.load_batch(tmp_path / "data.hdf5", flat)
+    dev = frames.load_batch_device(tmp_path / "data.hdf5", flat)
+    assert dev is not None, "gzip single-chunk float frames must take the device route"
+    assert np.array_equal(dev[0].cpu().numpy(), Xh) and np.array_equal(dev[1], yh)
+    some = [flat[i] for i in (80, 3, 41)]                         # scattered rows: chunks far apart in the file
+    d2 = frames.load_batch_device(tmp_path / "data.hdf5", some)
+    assert np.array_equal(d2[0].cpu().numpy(), frames.load_batch(tmp_path / "data.hdf5", some)[0])
+    cfg, w = standins.timed_standin(20, filters=(8, 16, 16, 24, 32), calib_frames=4)
+    write_keras_h5(tmp_path / "TIMED.h5", cfg, w)
+    monkeypatch.chdir(tmp_path)
+    outs = []
+    for name, env in (("dev", None), ("host", "1")):
+        if env:
+            monkeypatch.setenv("TIMED_B200_NO_DEVICE_INFLATE", env)
+        out = tmp_path / name
+        predict.cli(["--path_to_dataset", str(tmp_path / "data.hdf5"), "--path_to_model", str(tmp_path / "TIMED.h5"),
+                     "--path_to_output", str(out), "--path_to_datasetmap", str(out / "datasetmap.txt"), "--batch_size", "32",
+                     "--yes"])
+        outs.append({p.name: p.read_bytes() for p in sorted(out.iterdir())})
+    assert outs[0].keys() == outs[1].keys() and "TIMED.csv" in outs[0]
+    for k in outs[0]:
+        assert outs[0][k] == outs[1][k], k

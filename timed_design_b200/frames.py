@@ -184,3 +184,71 @@ def load_batch(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple]) -> t.T
         for i in range(n):
             one(i)
     return X, y
+
+
+def load_batch_device(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple], device: int = 0):
+    """``load_batch`` with the frames left ON THE DEVICE: for datasets whose gaussian frames are stored as one
+    deflate-filtered chunk each (what aposteriori / h5py write with ``compression='gzip'``), the STORED bytes of the batch go
+    to the GPU (18 KB instead of 222 KB per frame on real structures) and every chunk is inflated there by its own warp
+    (``timed_b200_inflate_device``, csrc/inflate.cuh) straight into the batch tensor the network reads.  Returns
+    ``(frames, y)`` -- frames a CUDA tensor (B, *frame_dims) of the stored dtype, the values ``load_batch`` returns, byte for
+    byte -- or ``None`` when the file is stored any other way, a stream does not inflate cleanly, or
+    ``TIMED_B200_NO_DEVICE_INFLATE`` is set: the caller then takes ``load_batch``."""
+    import ctypes as C
+    import os
+    if os.environ.get("TIMED_B200_NO_DEVICE_INFLATE"):
+        return None
+    import torch
+    from . import _lib
+    if not torch.cuda.is_available():
+        return None
+    f = _open(dataset_path)
+    dims = tuple(int(d) for d in f.attrs["frame_dims"])
+    n = len(data_point_batch)
+    if not n or not bool(f.attrs["voxels_as_gaussian"]):
+        return None                                     # boolean datasets are 1 byte per voxel already: host path
+    offs, sizes, objs, common = np.empty(n, np.int64), np.empty(n, np.int64), [], None
+    for i, row in enumerate(data_point_batch):
+        pdb_code, chain_id, residue_id = (str(v) for v in row[:3])
+        ds = f[pdb_code][chain_id][residue_id]
+        info = ds.chunk_table() if hasattr(ds, "chunk_table") else None
+        if info is None or tuple(ds.shape) != dims:
+            return None
+        cdims, table, deflate, shuffle, dtype = info
+        if len(table) != 1 or tuple(cdims) != dims or not deflate or shuffle or any(int(o) for o in table[0][0]):
+            return None
+        if common is None:
+            common = dtype
+        elif dtype != common:
+            return None
+        offs[i], sizes[i] = table[0][1], table[0][2]
+        objs.append(ds)
+    tdt = {("f", 4): torch.float32, ("f", 8): torch.float64, ("u", 1): torch.uint8}.get((common.kind, common.itemsize))
+    if tdt is None or common.byteorder == ">":
+        return None
+    base = np.frombuffer(f.buf, dtype=np.uint8)
+    lo, hi = int(offs.min()), int((offs + sizes).max())
+    if hi - lo <= 4 * int(sizes.sum()) + (1 << 20):     # the batch's chunks are (nearly) contiguous in the file: one copy
+        comp = torch.from_numpy(base[lo:hi]).to(f"cuda:{device}")
+        rel = offs - lo
+    else:
+        comp = torch.from_numpy(np.concatenate([base[o:o + s] for o, s in zip(offs, sizes)])).to(f"cuda:{device}")
+        rel = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+    d_off = torch.from_numpy(rel).to(comp.device)
+    d_size = torch.from_numpy(sizes).to(comp.device)
+    frames = torch.empty((n, *dims), dtype=tdt, device=comp.device)
+    status = torch.empty(n, dtype=torch.int32, device=comp.device)
+    out_bytes = int(np.prod(dims)) * common.itemsize
+    with torch.cuda.device(comp.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.load().timed_b200_inflate_device(
+            C.c_void_p(comp.data_ptr()), n, C.c_void_p(d_off.data_ptr()), C.c_void_p(d_size.data_ptr()), out_bytes,
+            C.c_void_p(frames.data_ptr()), C.c_void_p(status.data_ptr()), C.c_void_p(stream)))
+        if int(status.ne(0).sum().item()):
+            warnings.warn(f"{Path(dataset_path).name}: {int(status.ne(0).sum().item())} frame chunk(s) did not inflate on the "
+                          "device; reading the batch on the host", RuntimeWarning, stacklevel=2)
+            return None
+    y = np.zeros((n, 20), dtype=float)
+    for i, ds in enumerate(objs):
+        y[i] = ds.attrs["encoded_residue"]
+    return frames, y

@@ -383,10 +383,10 @@ class _Attrs:
 
 
 class _Object:
-    def __init__(self, f: File, addr: int, name: str):
+    def __init__(self, f: File, addr: int, name: str, msgs: Optional[List[_Message]] = None):
         self._f, self._addr, self.name = f, addr, name
         try:
-            self._msgs = f._messages(addr)
+            self._msgs = f._messages(addr) if msgs is None else msgs      # (the lookup that found the object parsed them)
         except (IndexError, struct.error) as e:        # reads past the end of the map
             raise Hdf5FormatError(f"{f.path}: truncated or corrupt file (object header of '{name}' at {addr})") from e
         self._attrs = None
@@ -399,8 +399,8 @@ class _Object:
 
 
 class Group(_Object):
-    def __init__(self, f, addr, name):
-        super().__init__(f, addr, name)
+    def __init__(self, f, addr, name, msgs=None):
+        super().__init__(f, addr, name, msgs)
         self._links: Optional[Dict[str, int]] = None
         self._groups: Dict[str, "Group"] = {}        # child groups already opened (their link tables are parsed once)
 
@@ -474,7 +474,7 @@ class Group(_Object):
             child_name = (node.name.rstrip("/") + "/" + part)
             msgs = self._f._messages(addr)
             is_dataset = any(m.type == 0x08 for m in msgs)
-            child = Dataset(self._f, addr, child_name) if is_dataset else Group(self._f, addr, child_name)
+            child = Dataset(self._f, addr, child_name, msgs) if is_dataset else Group(self._f, addr, child_name, msgs)
             if not is_dataset:
                 node._groups[part] = child
             node = child
@@ -482,8 +482,8 @@ class Group(_Object):
 
 
 class Dataset(_Object):
-    def __init__(self, f, addr, name):
-        super().__init__(f, addr, name)
+    def __init__(self, f, addr, name, msgs=None):
+        super().__init__(f, addr, name, msgs)
         self._type = self._shape = self._layout = None
         self._filters: List[Tuple[int, Tuple[int, ...]]] = []
         for m in self._msgs:

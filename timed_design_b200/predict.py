@@ -23,7 +23,7 @@ from pathlib import Path
 
 import numpy as np
 
-from .frames import create_flat_dataset_map, load_batch
+from .frames import create_flat_dataset_map, load_batch, load_batch_device
 from .model import load_model
 from .postprocess import (convert_dataset_map_for_srb, extract_sequence_from_pred_matrix,
                           get_pdb_keys_to_filter, get_rotamer_codec, rotamer_class_to_residue,
@@ -181,13 +181,20 @@ def load_dataset_and_predict(
                     yield _forward_device_rows(frame_model, source.rows(a, b)), source.labels[a:b]
                 return
             from concurrent.futures import ThreadPoolExecutor
+
+            def load(a, b):
+                """Frames of [a, b): stored chunks inflated on the device when the file allows it (frames.load_batch_device),
+                else load_batch on the host threads."""
+                rows = flat_dataset_map[a:b]
+                dev = load_batch_device(dataset_path, rows, local_rank)
+                return (True, *dev) if dev is not None else (False, *load_batch(dataset_path, rows))
+
             with ThreadPoolExecutor(max_workers=1) as pool:
-                nxt = pool.submit(load_batch, dataset_path, flat_dataset_map[ranges[0][0]:ranges[0][1]]) if ranges else None
-                for k, (a, b) in enumerate(ranges):
-                    X_batch, y_true = nxt.result()
-                    nxt = (pool.submit(load_batch, dataset_path, flat_dataset_map[ranges[k + 1][0]:ranges[k + 1][1]])
-                           if k + 1 < len(ranges) else None)
-                    yield frame_model.predict(X_batch), y_true
+                nxt = pool.submit(load, *ranges[0]) if ranges else None
+                for k in range(len(ranges)):
+                    on_device, X_batch, y_true = nxt.result()
+                    nxt = pool.submit(load, *ranges[k + 1]) if k + 1 < len(ranges) else None
+                    yield (_forward_device_rows(frame_model, X_batch) if on_device else frame_model.predict(X_batch)), y_true
 
         rot_out = path_to_output / f"{model_name}_rot.csv"
         model_out = rot_out if predict_rotamers else path_to_output / f"{model_name}.csv"

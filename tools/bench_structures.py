@@ -55,5 +55,22 @@ t2 = time.perf_counter()
 out["hdf5_route"] = {"load_batch_s": t1 - t0, "predict_s": t2 - t1, "frames_per_s": len(flat2) / (t2 - t0),
                      "file_MB": data.stat().st_size / 1e6, "note": "gzip float32 frames, native inflater on the host threads"}
 out["max_abs_diff_between_routes"] = float(np.abs(p - p2).max())
+# (c) the same file with the STORED chunks inflated on the device (frames.load_batch_device, csrc/inflate.cuh)
+import torch  # noqa: E402
+frames.load_batch_device(data, flat2[:64])                       # warm-up
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+dev = frames.load_batch_device(data, flat2)
+torch.cuda.synchronize()
+t1 = time.perf_counter()
+if dev is not None:
+    p3 = predict._forward_device_rows(m, dev[0])
+    t2 = time.perf_counter()
+    X3 = dev[0].cpu().numpy()
+    out["hdf5_device_inflate_route"] = {"load_s": t1 - t0, "predict_s": t2 - t1, "frames_per_s": len(flat2) / (t2 - t0),
+                                        "frames_equal_host_inflate": bool(np.array_equal(X3, X)) and bool(np.array_equal(dev[1], y)),
+                                        "max_abs_diff_vs_host_route": float(np.abs(p3 - p2).max()),
+                                        "note": "stored chunks H2D + one warp per chunk inflating on the device; load_s is the Python object walk + copy + inflate"}
+
 print(json.dumps(out))
 shutil.rmtree(tmp)
