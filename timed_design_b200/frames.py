@@ -229,7 +229,9 @@ def load_batch_device(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple],
     base = np.frombuffer(f.buf, dtype=np.uint8)
     lo, hi = int(offs.min()), int((offs + sizes).max())
     if hi - lo <= 4 * int(sizes.sum()) + (1 << 20):     # the batch's chunks are (nearly) contiguous in the file: one copy
-        comp = torch.from_numpy(base[lo:hi]).to(f"cuda:{device}")
+        with warnings.catch_warnings():                 # (a read-only view of the mapped file; it is only read)
+            warnings.filterwarnings("ignore", message="The given NumPy array is not writable")
+            comp = torch.from_numpy(base[lo:hi]).to(f"cuda:{device}")
         rel = offs - lo
     else:
         comp = torch.from_numpy(np.concatenate([base[o:o + s] for o, s in zip(offs, sizes)])).to(f"cuda:{device}")
