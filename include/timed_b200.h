@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TIMED_B200_ABI_VERSION 4 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers; 3: predict_stats, float16 frames, voxelise; 4: pdb_parse, inflate_device (all additive) */
+#define TIMED_B200_ABI_VERSION 4 /* 2: sample_chains, consensus, seq_metrics, op_kernel, host-side I/O helpers; 3: predict_stats, float16 frames, voxelise; 4: pdb_parse, inflate_device, hdf5_frame_index (all additive) */
 
 /* error codes */
 #define TB_OK 0
@@ -240,6 +240,21 @@ int timed_b200_inflate_chunks(const uint8_t* file_base, int64_t n_chunks, const 
  * the host path).  All pointers are device pointers; asynchronous on cuda_stream. */
 int timed_b200_inflate_device(const uint8_t* d_comp, int64_t n_streams, const int64_t* d_off, const int64_t* d_size,
                               int64_t out_bytes, void* d_out, int32_t* d_status, void* cuda_stream);
+
+/* Index of n frame datasets of a memory-mapped HDF5 file in one call (replaces the per-frame object lookups of
+ * design_utils/utils.py:514-529 on the device-inflate route): obj_addr[i] is the object-header address of frame i (from the
+ * chain group's link table).  The caller has parsed ONE frame of the batch in full and passes its raw dataspace / datatype /
+ * filter-pipeline messages, the header of its `encoded_residue` attribute message (everything before the attribute's data)
+ * and the data length; a frame is accepted only when those bytes are identical, its layout is version-3 chunked with exactly
+ * one unmasked chunk at the origin (one-leaf version-1 B-tree) and every read stays inside file_len.  Outputs: chunk_off /
+ * chunk_size (absolute offset and stored size of the chunk), attr_data (n * attr_data_len bytes), status[i] (0 ok; else the
+ * caller walks the batch with its own reader).  Version-1 object headers only.  Host threads, no device work. */
+int timed_b200_hdf5_frame_index(const uint8_t* file_base, int64_t file_len, int64_t base_addr, int64_t n,
+                                const int64_t* obj_addr, const uint8_t* tmpl_space, int32_t space_len,
+                                const uint8_t* tmpl_type, int32_t type_len, const uint8_t* tmpl_filters, int32_t filters_len,
+                                const uint8_t* tmpl_attr_hdr, int32_t attr_hdr_len, int32_t attr_data_len, int32_t rank,
+                                int64_t* chunk_off, int64_t* chunk_size, uint8_t* attr_data, int32_t* status,
+                                int32_t n_threads);
 
 /* Text of a (rows, cols) float32/float64 host matrix exactly as numpy.savetxt(..., delimiter=",") prints it ("%.18e",
  * comma separated, one line per row: the rotamer dump of predict.py:145-146), formatted on `n_threads` host threads.

@@ -159,3 +159,50 @@ def test_native_frame_inflater_reports_corrupt_chunks(tmp_path):
     bad.write_bytes(bytes(blob))
     with pytest.raises(_lib.TimedB200Error):
         F.load_batch(bad, [("1abc", "A", "2", "ALA")])
+
+
+def test_native_frame_index_equals_the_python_walk(tmp_path):
+    """timed_b200_hdf5_frame_index (one native call per batch: object headers, chunk B-trees, the encoded_residue attribute)
+    returns the chunk offsets / stored sizes / labels the Python reader finds frame by frame; files stored any other way,
+    or with one deviating frame, are refused (the caller then walks the batch with the Python reader)."""
+    from timed_design_b200 import frames as fr
+    from timed_design_b200.hdf5 import write_frame_dataset
+    from timed_design_b200.postprocess import standard_amino_acids
+    labs = list(standard_amino_acids.values())
+    rng = np.random.default_rng(0)
+    dims = (9, 9, 9, 6)
+    tree, k = {}, 0
+    for c in range(3):
+        for r in range(40):
+            x = np.where(rng.random(dims) < 0.05, rng.random(dims), 0).astype(np.float32)
+            tree.setdefault("1abc" if c < 2 else "2xyz", {}).setdefault("ABC"[c], {})[str(r - 3)] = (x, labs[k % 20])
+            k += 1
+    p = tmp_path / "x.hdf5"
+    write_frame_dataset(p, tree, dims, compression="gzip")
+    flat, _ = fr.create_flat_dataset_map(p)
+    rows = [flat[i] for i in rng.permutation(len(flat))]                       # any order, any subset
+    f = fr._open(p)
+    fast = fr._fast_frame_index(f, rows, dims)
+    assert fast is not None
+    offs, sizes, y, dtype = fast
+    assert dtype == np.float32 and y.shape == (len(rows), 20) and (y.sum(1) == 1).all()
+    for i, row in enumerate(rows):
+        ds = f[str(row[0])][str(row[1])][str(row[2])]
+        (org, off, size), = ds.chunk_table()[1]
+        assert (off, size) == (offs[i], sizes[i]) and np.array_equal(ds.attrs["encoded_residue"], y[i])
+    # stored without compression: not this route
+    q = tmp_path / "plain.hdf5"
+    write_frame_dataset(q, {"1abc": {"A": {"1": tree["1abc"]["A"]["1"]}}}, dims, compression=None)
+    fq, _ = fr.create_flat_dataset_map(q)
+    assert fr._fast_frame_index(fr._open(q), fq, dims) is None
+    # one frame's object header damaged: the whole batch is refused
+    raw = bytearray(p.read_bytes())
+    addr = f["1abc"]["B"]._load()["5"] + f.base_addr
+    assert raw[addr] == 1
+    raw[addr] = 7
+    bad = tmp_path / "bad.hdf5"
+    bad.write_bytes(bytes(raw))
+    assert fr._fast_frame_index(fr._open(bad), [r for r in flat if not (r[1] == "B" and r[2] == "5")][:20], dims) is not None
+    assert fr._fast_frame_index(fr._open(bad), flat, dims) is None
+    # a row that does not exist
+    assert fr._fast_frame_index(f, [("1abc", "A", "999", "ALA")], dims) is None

@@ -95,6 +95,9 @@ SYMBOLS = {
     "timed_b200_sample_uniforms": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64,
                                              C.c_void_p, C.c_void_p]),
     "timed_b200_argmax_fp16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "timed_b200_hdf5_frame_index": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_char_p, C.c_int32,
+                                              C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "timed_b200_inflate_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
     "timed_b200_pdb_parse": (C.c_int, [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),

@@ -27,6 +27,7 @@
 #include "xform_conv.cuh"
 #include "pdb_parse.cuh"
 #include "inflate.cuh"
+#include "hdf5_index.cuh"
 #include "voxelise.cuh"
 
 namespace tb {
@@ -3034,6 +3035,39 @@ int timed_b200_voxelise(const float* d_atoms_xyzs, const int32_t* d_atom_channel
     else if (frames_dtype == TB_DTYPE_F16) voxelise_finalize_kernel<__half><<<grid, 256, 0, s>>>(d_scratch, n, !as_gaussian, static_cast<__half*>(d_frames));
     else voxelise_finalize_kernel<uint8_t><<<grid, 256, 0, s>>>(d_scratch, n, 1, static_cast<uint8_t*>(d_frames));
     TB_CHECK_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+// ---- host-side index of many HDF5 frame datasets (hdf5_index.cuh): no device work
+int timed_b200_hdf5_frame_index(const uint8_t* file_base, int64_t file_len, int64_t base_addr, int64_t n,
+                                const int64_t* obj_addr, const uint8_t* tmpl_space, int32_t space_len,
+                                const uint8_t* tmpl_type, int32_t type_len, const uint8_t* tmpl_filters, int32_t filters_len,
+                                const uint8_t* tmpl_attr_hdr, int32_t attr_hdr_len, int32_t attr_data_len, int32_t rank,
+                                int64_t* chunk_off, int64_t* chunk_size, uint8_t* attr_data, int32_t* status,
+                                int32_t n_threads) {
+    TB_REQUIRE(file_base && obj_addr && tmpl_space && tmpl_type && tmpl_attr_hdr && chunk_off && chunk_size && attr_data && status,
+               "null argument");
+    TB_REQUIRE(file_len > 0 && n >= 0 && space_len > 0 && type_len > 0 && filters_len >= 0 && (filters_len == 0 || tmpl_filters) &&
+               attr_hdr_len > 0 && attr_data_len > 0 && rank >= 1 && rank <= 8, "bad template / sizes");
+    H5Template t{tmpl_space, space_len, tmpl_type, type_len, tmpl_filters, filters_len, tmpl_attr_hdr, attr_hdr_len, attr_data_len, rank};
+    std::atomic<int64_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const int64_t i0 = next.fetch_add(256);
+            if (i0 >= n) return;
+            for (int64_t i = i0; i < std::min(n, i0 + 256); ++i)
+                status[i] = h5_index_one(file_base, file_len, base_addr, obj_addr[i], t, chunk_off + i, chunk_size + i,
+                                         attr_data + i * attr_data_len);
+        }
+    };
+    const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_threads, (n + 255) / 256)));
+    if (nt == 1) {
+        worker();
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k) th.emplace_back(worker);
+        for (auto& x : th) x.join();
+    }
     return TB_OK;
 }
 

@@ -186,6 +186,76 @@ def load_batch(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple]) -> t.T
     return X, y
 
 
+def _attr_header(d: bytes) -> t.Tuple[bytes, int]:
+    """(name, offset of the data) of a raw HDF5 attribute message (versions 1-3), as hdf5/reader.py::_Attrs walks it."""
+    import struct
+    version = d[0]
+    nsz, tsz, ssz = struct.unpack_from("<HHH", d, 2)
+    if version == 1:
+        p, pad = 8, (lambda x: (x + 7) // 8 * 8)
+    elif version in (2, 3):
+        p, pad = (8 if version == 2 else 9), (lambda x: x)
+    else:
+        raise ValueError("attribute message version")
+    name = d[p:p + nsz].split(b"\x00")[0]
+    return name, p + pad(nsz) + pad(tsz) + pad(ssz)
+
+
+def _fast_frame_index(f: File, rows, dims):
+    """(chunk offsets, stored sizes, labels (n, 20), stored dtype) of the frames of ``rows`` through ONE native call
+    (``timed_b200_hdf5_frame_index``: object headers / chunk B-trees walked on host threads), the first frame parsed by the
+    Python reader as the template every other frame must match byte for byte.  None when the file is not stored as one
+    unshuffled deflate chunk per gaussian frame in version-1 object headers, or any frame deviates: the caller then walks the
+    batch frame by frame."""
+    import ctypes as C
+    from . import _lib
+    n = len(rows)
+    groups: t.Dict[t.Tuple[str, str], dict] = {}
+    addrs = np.empty(n, np.int64)
+    try:
+        for i, row in enumerate(rows):
+            key = (str(row[0]), str(row[1]))
+            links = groups.get(key)
+            if links is None:
+                links = groups[key] = f[key[0]][key[1]]._load()
+            addrs[i] = links[str(row[2])]
+        ds0 = f[str(rows[0][0])][str(rows[0][1])][str(rows[0][2])]
+        info = ds0.chunk_table() if hasattr(ds0, "chunk_table") else None
+        if info is None or tuple(ds0.shape) != tuple(dims):
+            return None
+        cdims, table, deflate, shuffle, dtype = info
+        if len(table) != 1 or tuple(cdims) != tuple(dims) or not deflate or shuffle or any(int(o) for o in table[0][0]):
+            return None
+        raw = {m.type: bytes(m.data) for m in ds0._msgs if m.type in (0x01, 0x03, 0x0B)}
+        hdr = None
+        for m in ds0._msgs:
+            if m.type == 0x0C:
+                d = bytes(m.data)
+                name, p = _attr_header(d)
+                if name == b"encoded_residue":
+                    hdr, data_len = d[:p], len(d) - p
+                    want = np.asarray(ds0.attrs["encoded_residue"], dtype=np.float64)
+                    if data_len != 160 or want.shape != (20,) or not np.array_equal(np.frombuffer(d[p:], "<f8"), want):
+                        return None
+        if hdr is None or 0x01 not in raw or 0x03 not in raw or 0x0B not in raw:
+            return None
+    except (KeyError, AttributeError, ValueError, IndexError):
+        return None
+    base = np.frombuffer(f.buf, dtype=np.uint8)
+    offs, sizes = np.empty(n, np.int64), np.empty(n, np.int64)
+    labels = np.empty((n, 20), np.float64)
+    status = np.empty(n, np.int32)
+    rc = _lib.load().timed_b200_hdf5_frame_index(
+        C.c_void_p(base.ctypes.data), len(base), int(f.base_addr), n, C.c_void_p(addrs.ctypes.data),
+        raw[0x01], len(raw[0x01]), raw[0x03], len(raw[0x03]), raw[0x0B], len(raw[0x0B]), hdr, len(hdr), 160, len(dims),
+        C.c_void_p(offs.ctypes.data), C.c_void_p(sizes.ctypes.data), C.c_void_p(labels.ctypes.data),
+        C.c_void_p(status.ctypes.data), _loader_threads())
+    _lib.check(rc)
+    if status.any():
+        return None
+    return offs, sizes, labels, dtype
+
+
 def load_batch_device(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple], device: int = 0):
     """``load_batch`` with the frames left ON THE DEVICE: for datasets whose gaussian frames are stored as one
     deflate-filtered chunk each (what aposteriori / h5py write with ``compression='gzip'``), the STORED bytes of the batch go
@@ -207,8 +277,11 @@ def load_batch_device(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple],
     n = len(data_point_batch)
     if not n or not bool(f.attrs["voxels_as_gaussian"]):
         return None                                     # boolean datasets are 1 byte per voxel already: host path
+    fast = None if os.environ.get("TIMED_B200_NO_FAST_INDEX") else _fast_frame_index(f, data_point_batch, dims)
     offs, sizes, objs, common = np.empty(n, np.int64), np.empty(n, np.int64), [], None
-    for i, row in enumerate(data_point_batch):
+    if fast is not None:
+        offs, sizes, y_fast, common = fast
+    for i, row in enumerate(data_point_batch if fast is None else ()):
         pdb_code, chain_id, residue_id = (str(v) for v in row[:3])
         ds = f[pdb_code][chain_id][residue_id]
         info = ds.chunk_table() if hasattr(ds, "chunk_table") else None
@@ -250,6 +323,8 @@ def load_batch_device(dataset_path: Path, data_point_batch: t.Sequence[t.Tuple],
             warnings.warn(f"{Path(dataset_path).name}: {int(status.ne(0).sum().item())} frame chunk(s) did not inflate on the "
                           "device; reading the batch on the host", RuntimeWarning, stacklevel=2)
             return None
+    if fast is not None:
+        return frames, y_fast
     y = np.zeros((n, 20), dtype=float)
     for i, ds in enumerate(objs):
         y[i] = ds.attrs["encoded_residue"]
