@@ -29,7 +29,7 @@ static inline uint16_t h5_u16(const uint8_t* p) { uint16_t v; std::memcpy(&v, p,
 // template or is missing, 5 layout is not one unmasked chunk at the origin in a one-leaf B-tree
 static int h5_index_one(const uint8_t* base, int64_t flen, int64_t base_addr, int64_t obj, const H5Template& t,
                         int64_t* chunk_off, int64_t* chunk_size, uint8_t* attr_out) {
-    auto ok = [&](int64_t off, int64_t len) { return off >= 0 && len >= 0 && off + len <= flen; };
+    auto ok = [&](int64_t off, int64_t len) { return off >= 0 && len >= 0 && off <= flen && len <= flen - off; };   // (no overflow)
     int64_t a = obj + base_addr;
     if (!ok(a, 16)) return 1;
     if (base[a] != 1) return 2;
