@@ -206,3 +206,47 @@ def test_native_frame_index_equals_the_python_walk(tmp_path):
     assert fr._fast_frame_index(fr._open(bad), flat, dims) is None
     # a row that does not exist
     assert fr._fast_frame_index(f, [("1abc", "A", "999", "ALA")], dims) is None
+
+
+def test_native_frame_index_survives_corrupt_files(tmp_path):
+    """Random byte damage in and around the object headers, truncated lengths: the native index refuses frames (status != 0)
+    or returns chunks that lie inside the file -- it never reads outside the mapping."""
+    import ctypes as C
+
+    from timed_design_b200 import _lib
+    from timed_design_b200 import frames as fr
+    from timed_design_b200.hdf5 import write_frame_dataset
+    rng = np.random.default_rng(0)
+    dims = (7, 7, 7, 6)
+    tree = {"1abc": {ch: {str(r + 1): (np.where(rng.random(dims) < 0.05, rng.random(dims), 0).astype(np.float32), "ALA")
+                          for r in range(30)} for ch in "AB"}}
+    p = tmp_path / "x.hdf5"
+    write_frame_dataset(p, tree, dims, compression="gzip")
+    flat, _ = fr.create_flat_dataset_map(p)
+    f = fr._open(p)
+    assert fr._fast_frame_index(f, flat, dims) is not None
+    ds0 = f[flat[0][0]][flat[0][1]][flat[0][2]]
+    raw_m = {m.type: bytes(m.data) for m in ds0._msgs if m.type in (1, 3, 0x0B)}
+    hdr = next(bytes(m.data)[:fr._attr_header(bytes(m.data))[1]] for m in ds0._msgs
+               if m.type == 0x0C and fr._attr_header(bytes(m.data))[0] == b"encoded_residue")
+    addrs = np.array([f[r[0]][r[1]]._load()[r[2]] for r in flat], np.int64)
+    raw0, n, lib = p.read_bytes(), len(flat), _lib.load()
+    refused = 0
+    for _ in range(300):
+        raw = bytearray(raw0)
+        for _ in range(rng.integers(1, 6)):
+            a = int(addrs[rng.integers(n)]) + int(rng.integers(0, 400)) if rng.random() < 0.7 else int(rng.integers(0, len(raw)))
+            if a < len(raw):
+                raw[a] = int(rng.integers(0, 256))
+        buf = np.frombuffer(bytes(raw), np.uint8)
+        flen = len(buf) if rng.random() < 0.8 else int(rng.integers(1, len(buf)))
+        offs, sizes, lab, st = np.empty(n, np.int64), np.empty(n, np.int64), np.empty((n, 20)), np.empty(n, np.int32)
+        rc = lib.timed_b200_hdf5_frame_index(
+            C.c_void_p(buf.ctypes.data), flen, 0, n, C.c_void_p(addrs.ctypes.data), raw_m[1], len(raw_m[1]), raw_m[3],
+            len(raw_m[3]), raw_m[0x0B], len(raw_m[0x0B]), hdr, len(hdr), 160, len(dims), C.c_void_p(offs.ctypes.data),
+            C.c_void_p(sizes.ctypes.data), C.c_void_p(lab.ctypes.data), C.c_void_p(st.ctypes.data), 2)
+        assert rc == 0
+        ok = st == 0
+        assert ((offs[ok] >= 0) & (sizes[ok] > 0) & (offs[ok] + sizes[ok] <= flen)).all()
+        refused += int((~ok).sum())
+    assert refused > 0
