@@ -240,3 +240,58 @@ def test_dataset_order_chains_as_they_appear_numbers_as_integers():
         expect += sorted((i for i in valid if chain[i] == ch), key=lambda i: int(res_id[i]))
     assert vx._dataset_order(tab2, info2) == expect and len(expect) == n - 4
     assert vx._dataset_order(tab2._replace(valid=np.zeros(0, np.int64)), info2) == []
+
+
+def test_native_pdb_reader_equals_the_python_parser_on_mutated_files(tmp_path):
+    """Structured damage to the 1ubq records (atom names / altLoc / residue keys rewritten, lines duplicated, dropped,
+    truncated, turned into HETATM / ANISOU, ENDMDL inserted, CR added): the native reader and the Python parser build the same
+    tables or raise the same exception."""
+    import gzip
+    import warnings
+    lines0 = gzip.open(PDB, "rb").read().split(b"\n")
+    rng = np.random.default_rng(2)
+    compared = 0
+    for it in range(120):
+        lines = list(lines0)
+        for _ in range(rng.integers(1, 8)):
+            i = int(rng.integers(0, len(lines)))
+            ln = bytearray(lines[i])
+            r = rng.random()
+            if r < 0.35 and len(ln) > 27:
+                ln[int(rng.integers(12, 27))] = int(rng.choice(list(b" ABC12NOX")))
+            elif r < 0.5:
+                lines.insert(i, lines[int(rng.integers(0, len(lines)))])
+                continue
+            elif r < 0.6:
+                del lines[i]
+                continue
+            elif r < 0.7:
+                lines.insert(i, b"ENDMDL")
+                continue
+            elif r < 0.8:
+                ln = ln[:int(rng.integers(0, len(ln) + 1))]
+            elif r < 0.9 and len(ln) > 6:
+                ln[0:6] = bytes(rng.choice([b"ATOM  ", b"HETATM", b"ANISOU"]))
+            else:
+                ln += b"\r"
+            lines[i] = bytes(ln)
+        fn = tmp_path / f"m{it % 4}.pdb"
+        fn.write_bytes(b"\n".join(lines))
+        got = []
+        for parse in (lambda: vx.fast_tables(fn, "CNOCBCAQ", 1.0, all_states=bool(it % 2)),
+                      lambda: vx.native_tables([fn], "CNOCBCAQ", 1.0, all_states=bool(it % 2))[0]):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                try:
+                    got.append(parse())
+                except Exception as e:  # noqa: BLE001
+                    got.append(type(e).__name__)
+        a, b = got
+        if isinstance(a, str) or isinstance(b, str):
+            assert a == b, (it, a, b)
+            continue
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            _same_tables(x, y)
+        compared += 1
+    assert compared > 60
