@@ -173,28 +173,40 @@ def load_dataset_and_predict(
                              f"{'--predict_rotamers' if predict_rotamers else 'residue mode'} expects {n_classes}")
         def predicted(ranges):
             """Yields (probabilities, one-hot labels) of the frame ranges [a, b) of the flat map, in order.  On the .hdf5
-            route the NEXT range's frames are read (native inflater, host threads, no GIL) while the GPU predicts the current
-            one -- load_batch is ~80 % of that route."""
+            route consecutive ranges are read and predicted together in groups of >= 2048 frames -- one index call, one copy
+            of the stored chunks, one inflate launch, one forward for many of the CLI's (small: default 12) batches; the
+            probabilities of a frame do not depend on how frames are grouped (tests/test_properties_gpu.py) -- and the NEXT
+            group is read while the GPU predicts the current one."""
             ranges = list(ranges)
             if source is not None:
                 for a, b in ranges:
                     yield _forward_device_rows(frame_model, source.rows(a, b)), source.labels[a:b]
                 return
             from concurrent.futures import ThreadPoolExecutor
+            group_frames = max(int(batch_size), 2048)
+            groups = []                                   # lists of consecutive (a, b) ranges
+            for a, b in ranges:
+                if groups and groups[-1][-1][1] == a and b - groups[-1][0][0] <= group_frames:
+                    groups[-1].append((a, b))
+                else:
+                    groups.append([(a, b)])
 
-            def load(a, b):
-                """Frames of [a, b): stored chunks inflated on the device when the file allows it (frames.load_batch_device),
-                else load_batch on the host threads."""
-                rows = flat_dataset_map[a:b]
+            def load(grp):
+                """Frames of a group: stored chunks inflated on the device when the file allows it
+                (frames.load_batch_device), else load_batch on the host threads."""
+                rows = flat_dataset_map[grp[0][0]:grp[-1][1]]
                 dev = load_batch_device(dataset_path, rows, local_rank)
                 return (True, *dev) if dev is not None else (False, *load_batch(dataset_path, rows))
 
             with ThreadPoolExecutor(max_workers=1) as pool:
-                nxt = pool.submit(load, *ranges[0]) if ranges else None
-                for k in range(len(ranges)):
-                    on_device, X_batch, y_true = nxt.result()
-                    nxt = pool.submit(load, *ranges[k + 1]) if k + 1 < len(ranges) else None
-                    yield (_forward_device_rows(frame_model, X_batch) if on_device else frame_model.predict(X_batch)), y_true
+                nxt = pool.submit(load, groups[0]) if groups else None
+                for k, grp in enumerate(groups):
+                    on_device, X_grp, y_grp = nxt.result()
+                    nxt = pool.submit(load, groups[k + 1]) if k + 1 < len(groups) else None
+                    p_grp = _forward_device_rows(frame_model, X_grp) if on_device else frame_model.predict(X_grp)
+                    a0 = grp[0][0]
+                    for a, b in grp:
+                        yield p_grp[a - a0:b - a0], y_grp[a - a0:b - a0]
 
         rot_out = path_to_output / f"{model_name}_rot.csv"
         model_out = rot_out if predict_rotamers else path_to_output / f"{model_name}.csv"
