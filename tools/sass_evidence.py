@@ -10,10 +10,10 @@ import sys
 from pathlib import Path
 
 LIB = Path(__file__).resolve().parents[1] / "timed_design_b200" / "libtimed_b200.so"
-KEEP = re.compile(r"^(UTCHMMA|UTMALDG|UTMASTG|FENCE\.VIEW\.ASYNC|UBLKCP|LDTM|UTCBAR|UTCATOMSWS|USETMAXREG|STG\.E[A-Z0-9.]*\.256|BAR\.SYNC|REDG|REDUX|DFMA|SYNCS\.ARRIVE\.TRANS64\.RED)")
+KEEP = re.compile(r"^(UTCHMMA|UTMALDG|UTMASTG|FENCE\.VIEW\.ASYNC|UBLKCP|LDTM|UTCBAR|UTCATOMSWS|USETMAXREG|STG\.E[A-Z0-9.]*\.256|BAR\.SYNC|REDG|REDUX|DFMA|SHFL|WARPSYNC|SYNCS\.ARRIVE\.TRANS64\.RED)")
 WANT = ("conv_umma_kernelILi2ELi0ELi1", "conv_pair_kernelILi2ELi0ELi1", "thin_conv_kernelILi0ELi0ELi0", "thinz_conv_kernelILi2ELi0ELi1ELi1",
         "slab_conv_kernelILi2ELi0ELi0", "sample_tiled_kernelILi32", "voxelise_kernelE", "head_col2im_pool_softmax_kernel",
-        "bnrelu_conv1x1_kernelILi0ELi1ELi1", "conv_umma_kernelILi0ELi0ELi0"
+        "bnrelu_conv1x1_kernelILi0ELi1ELi1", "conv_umma_kernelILi0ELi0ELi0", "inflate_streams_kernel"
         )
 
 out = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True).stdout
