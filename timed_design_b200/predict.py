@@ -232,6 +232,7 @@ def load_dataset_and_predict(
             gathered = (_gather(local_p.astype(np.float32), n_total, local_rank), _gather(local_y, n_total, local_rank))
         local = None if gathered is not None else predicted(
             (index * batch_size, min((index + 1) * batch_size, len(flat_dataset_map))) for index in range(start_batch, n_batches))
+        pend_pred, pend_true, pend_rows = [], [], 0
         for index in range(start_batch, n_batches):
             if gathered is not None:
                 r0 = (index - start_batch) * batch_size
@@ -242,12 +243,20 @@ def load_dataset_and_predict(
             raw_rows.append(y_pred_batch)
             if rank != 0:
                 continue                               # only rank 0 touches the output directory
-            if predict_rotamers:
-                with open(rot_out, "a") as f:
-                    savetxt_e18(f, y_pred_batch)
-                y_pred_batch = np.eye(20, dtype=int)[cls_to_res[np.argmax(y_pred_batch, axis=1)]]
-            save_outputs_to_file(list(y_true_batch), {i: list(y_pred_batch)}, flat_dataset_map, i, model_name,
-                                 path_to_output)
+            # The files are appended row by row, so writing several of the CLI's batches at once leaves the same bytes; the
+            # rows are flushed every >= 2048 frames (whole batches: the files always end on a batch boundary, which is what
+            # --start_batch resumes from) instead of once per 12-frame batch.
+            pend_pred.append(np.asarray(y_pred_batch))
+            pend_true.append(np.asarray(y_true_batch))
+            pend_rows += len(pend_pred[-1])
+            if pend_rows >= 2048 or index == n_batches - 1:
+                yp, yt = np.concatenate(pend_pred), np.concatenate(pend_true)
+                pend_pred, pend_true, pend_rows = [], [], 0
+                if predict_rotamers:
+                    with open(rot_out, "a") as f:
+                        savetxt_e18(f, yp)
+                    yp = np.eye(20, dtype=int)[cls_to_res[np.argmax(yp, axis=1)]]
+                save_outputs_to_file(list(yt), {i: list(yp)}, flat_dataset_map, i, model_name, path_to_output)
         frame_model.close()
         flat_dataset_map = np.array(flat_dataset_map)
         if rank == 0:
